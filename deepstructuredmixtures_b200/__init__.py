@@ -1,0 +1,20 @@
+"""deepstructuredmixtures_b200 -- B200-native (sm_100a) drop-in for the data-parallel hot path of
+DeepStructuredMixtures.jl: the batched per-expert GP computation over the leaves of the region graph.
+
+All numerics run in `libdsmgp.so` (hand-written CUDA, include/dsmgp.h).  Importing this package loads the
+library and fails loudly when it is missing; there is no CPU fallback.
+"""
+from . import _native
+from ._native import DsmgpError, PosDefException
+
+_native.lib()   # fail at import time when libdsmgp.so has not been built
+
+from .kernels import ArdLinear, ArdSE, IsoLinear, IsoSE, KernelFunction, kernelmatrix  # noqa: E402
+from .linalg import chol_continue_, chol_delete_rows, potrf_  # noqa: E402
+from .model import (DSMGP, GaussianProcess, LeafGP, Model, PoE, buildBCM, buildDSMGP, buildPoE, evaluate, fit_,  # noqa: E402
+                    fit_naive_, gPoE, grad_mll, leftGP, mll, mll_nodes, params, predict, prediction, rBCM, rightGP,
+                    setparams_, stats, update_, update_cholesky_)
+from .structure import ConstMean, GPNode, GPSplitNode, GPSumNode, getLeaves, getOverlap  # noqa: E402
+from .train import ADAM, Descent, RMSProp, finetune_, train_, train_gp_  # noqa: E402
+
+__all__ = [n for n in dir() if not n.startswith("_")]

@@ -1,0 +1,1181 @@
+// libdsmgp.so : C ABI implementation (include/dsmgp.h).  sm_100a only, no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "../../include/dsmgp.h"
+#include "args.h"
+#include "tree_host.h"
+
+using namespace dsm;
+
+static thread_local std::string g_create_error;
+
+#define CUDA_TRY(h, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                            \
+      return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA;                  \
+    }                                                                                           \
+  } while (0)
+
+namespace {
+
+struct Batch {
+  int s0 = 0, s1 = 0, max_nb = 0;
+  std::vector<int> cnt;                  // cnt[J]: slots of the batch that own block column J (slots sorted by size)
+  int64_t f_doubles = 0, w_doubles = 0, ntiles = 0, trpart_doubles = 0, gpart_doubles = 0;
+  int64_t* d_tile_off = nullptr;
+  int64_t* d_trpart_off = nullptr;
+  int64_t* d_gpart_off = nullptr;
+  int2* d_trtri_tasks = nullptr; int n_trtri = 0;
+  int4* d_lauum_tasks = nullptr; int n_lauum = 0;
+  double potrf_flops = 0, gram_bytes = 0;
+};
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) {
+    free();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    return cudaMalloc(&p, count * sizeof(T));
+  }
+  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct dsmgp_handle {
+  int64_t N = 0, D = 0, L = 0;
+  int nk = 0;
+  std::vector<dsmgp_kernel_desc> kernels;
+  std::vector<int64_t> koff;      // theta offset per kernel
+  std::vector<int32_t> knp;       // nparams per kernel
+  int64_t H = 0; int Hmax = 0; int row_width = 0; int pstride = 0;
+  std::vector<int64_t> leaf_ptr;
+  std::vector<int32_t> leaf_kid;
+  std::vector<double> leaf_mean;
+  HostTree tree;
+  dsmgp_opts opts;
+  std::vector<int32_t> owner;
+  std::vector<int> slot_leaf;     // slot -> global leaf
+  std::vector<int> leaf_slot;     // global leaf -> slot or -1
+  std::vector<LeafMeta> meta;     // per slot
+  std::vector<Batch> batches;
+  std::vector<double> theta_leaf; // L x Hmax
+  std::vector<double> h_prm;      // nslots x pstride
+  std::vector<double> h_rows;     // L x row_width
+  std::vector<double> node_lml;
+  std::vector<int32_t> h_info;    // L
+  std::vector<double> sum_logw;   // CSR by child_ptr (update!)
+  bool have_weights = false;
+  bool fitted = false, have_rows = false, have_grad = false, rows_complete = false;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {};
+  bool profiling = false;
+  dsmgp_timings tm = {};
+  // device
+  DevBuf<LeafMeta> d_meta;
+  DevBuf<double> d_xg, d_y, d_z, d_alpha, d_F, d_W, d_WT, d_prm, d_trpart, d_gpart, d_rows, d_leaf_mean;
+  DevBuf<LeafScal> d_scal;
+  DevBuf<int> d_counter;
+  double* pin_rows = nullptr;
+  LeafScal* pin_scal = nullptr;
+  std::string err;
+
+  ~dsmgp_handle() {
+    for (auto& b : batches) {
+      cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
+      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks);
+    }
+    d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
+    d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
+    if (pin_rows) cudaFreeHost(pin_rows);
+    if (pin_scal) cudaFreeHost(pin_scal);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+static bool g_attr_done = false;
+static cudaError_t engine_attrs() {
+  if (g_attr_done) return cudaSuccess;
+  cudaError_t e;
+  if ((e = init_potrf_kernels())) return e;
+  if ((e = init_trtri_kernels())) return e;
+  if ((e = init_lauum_kernels())) return e;
+  if ((e = init_predict_kernels())) return e;
+  g_attr_done = true;
+  return cudaSuccess;
+}
+
+static int num_sms(int device) {
+  int n = 148;
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
+  return n;
+}
+
+template <typename T>
+static cudaError_t upload(T** dptr, const std::vector<T>& v) {
+  *dptr = nullptr;
+  if (v.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc(dptr, v.size() * sizeof(T));
+  if (e) return e;
+  return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static void shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* owner) {
+  std::vector<int64_t> order(L);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+    return (leaf_ptr[a + 1] - leaf_ptr[a]) > (leaf_ptr[b + 1] - leaf_ptr[b]);
+  });
+  std::vector<double> load(world, 0.0);
+  for (int64_t l : order) {
+    int best = 0;
+    for (int r = 1; r < world; r++) if (load[r] < load[best]) best = r;
+    const double n = (double)(leaf_ptr[l + 1] - leaf_ptr[l]);
+    load[best] += n * n * n;
+    owner[l] = best;
+  }
+}
+
+static void derive_params(const dsmgp_handle* h, int kid, const double* th, double* prm) {
+  const int type = h->kernels[kid].type, np = h->kernels[kid].nparams, nl = np - 2;
+  const bool se = (type == DSMGP_ISO_SE || type == DSMGP_ARD_SE);
+  const double logs = th[nl], logn = th[nl + 1];
+  prm[PRM_V] = se ? std::exp(2.0 * logs) : 1.0;                   // kernels.jl:68,118,181,216
+  prm[PRM_S] = se ? std::exp(logs) : 1.0;                         // kernels.jl:69,119,182,217
+  prm[PRM_ETA] = std::exp(2.0 * logn);                            // gaussianprocess.jl:39
+  prm[PRM_C] = prm[PRM_ETA] + 1e-8;                               // gaussianprocess.jl:94, DeepStructuredMixtures.jl:27
+  for (int d = 0; d < nl; d++) {
+    const double l = std::exp(th[d]);
+    const double l2 = l * l;                                      // kernels.jl:22,41
+    prm[PRM_COEF + d] = se ? -0.5 / l2 : 1.0 / l2;                // kernels.jl:78,189
+  }
+}
+
+static void upload_params(dsmgp_handle* h) {
+  const int ns = (int)h->slot_leaf.size();
+  for (int s = 0; s < ns; s++) {
+    const int l = h->slot_leaf[s];
+    derive_params(h, h->leaf_kid[l], &h->theta_leaf[(size_t)l * h->Hmax], &h->h_prm[(size_t)s * h->pstride]);
+  }
+  if (ns) cudaMemcpyAsync(h->d_prm.p, h->h_prm.data(), h->h_prm.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// create / destroy
+// ------------------------------------------------------------------------------------------
+extern "C" void dsmgp_default_opts(dsmgp_opts* o) {
+  memset(o, 0, sizeof(*o));
+  o->as_written_grads = 1;
+  o->keep_factors = 1;
+  o->rank = 0; o->world = 1;
+  o->device = -1;
+  o->strict_pd = 0;
+  o->arena_bytes = 0;
+}
+
+extern "C" const char* dsmgp_last_error(const dsmgp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" void dsmgp_destroy(dsmgp_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* leaf_obs, const double* y_centered) {
+  const int64_t L = h->L;
+  // local slots sorted by size (descending), ties by leaf number
+  std::vector<int> loc;
+  for (int64_t l = 0; l < L; l++) if (h->owner[l] == h->opts.rank) loc.push_back((int)l);
+  std::stable_sort(loc.begin(), loc.end(), [&](int a, int b) {
+    return (h->leaf_ptr[a + 1] - h->leaf_ptr[a]) > (h->leaf_ptr[b + 1] - h->leaf_ptr[b]);
+  });
+  h->slot_leaf = loc;
+  h->leaf_slot.assign(L, -1);
+  const int ns = (int)loc.size();
+  h->meta.resize(ns);
+  h->pstride = PRM_COEF + (int)std::max<int64_t>(h->D, 1);
+  int64_t voff = 0, xoff = 0;
+  for (int s = 0; s < ns; s++) {
+    const int l = loc[s];
+    h->leaf_slot[l] = s;
+    LeafMeta& m = h->meta[s];
+    m.n = (int32_t)(h->leaf_ptr[l + 1] - h->leaf_ptr[l]);
+    m.np = (m.n + PAD - 1) / PAD * PAD;
+    m.nb = (m.np + BLK - 1) / BLK;
+    m.kid = h->leaf_kid[l];
+    m.ktype = h->kernels[m.kid].type;
+    m.nl = h->kernels[m.kid].nparams - 2;
+    m.leaf = l;
+    m.pad_ = 0;
+    m.voff = voff; voff += m.np;
+    m.xoff = xoff; xoff += (int64_t)m.np * h->D;
+    m.poff = (int64_t)s * h->pstride;
+    m.foff = 0; m.woff = 0;
+  }
+  // arena budget
+  size_t free_b = 0, total_b = 0;
+  CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+  const int64_t fixed = (voff * 4 + xoff) * 8 + (64ll << 20);
+  int64_t budget = h->opts.arena_bytes > 0 ? h->opts.arena_bytes : (int64_t)(free_b * 0.85) - fixed;
+  // per leaf bytes in a batch: factor np^2 + W/WT 2*nb*BLK^2
+  auto leaf_bytes = [&](const LeafMeta& m) { return ((int64_t)m.np * m.np + 2ll * m.nb * BLK * BLK) * 8; };
+  int64_t need_all = 0;
+  for (auto& m : h->meta) need_all += leaf_bytes(m);
+  if (h->opts.keep_factors && need_all > budget) {
+    h->err = "keep_factors=1 but the factors of the local leaves (" + std::to_string(need_all >> 20) +
+             " MiB) exceed the arena budget (" + std::to_string(budget >> 20) + " MiB); use keep_factors=0";
+    return DSMGP_ERR_OOM;
+  }
+  // streaming batches: cap the arena so that several batches pipeline well but each one still fills the GPU
+  if (!h->opts.keep_factors && h->opts.arena_bytes == 0) budget = std::min<int64_t>(budget, 48ll << 30);
+  h->batches.clear();
+  {
+    int s = 0;
+    while (s < ns) {
+      Batch b; b.s0 = s;
+      int64_t used = 0, fo = 0, wo = 0;
+      while (s < ns) {
+        const int64_t lb = leaf_bytes(h->meta[s]);
+        if (used > 0 && used + lb > budget) break;
+        if (lb > budget) { h->err = "one expert's factor exceeds the arena budget"; return DSMGP_ERR_OOM; }
+        h->meta[s].foff = fo; fo += (int64_t)h->meta[s].np * h->meta[s].np;
+        h->meta[s].woff = wo; wo += (int64_t)h->meta[s].nb * BLK * BLK;
+        used += lb; s++;
+      }
+      b.s1 = s; b.f_doubles = fo; b.w_doubles = wo;
+      h->batches.push_back(b);
+    }
+  }
+  int64_t maxF = 0, maxW = 0, maxTr = 0, maxG = 0;
+  for (auto& b : h->batches) {
+    const int nb_s = b.s1 - b.s0;
+    b.max_nb = 0;
+    for (int s = b.s0; s < b.s1; s++) b.max_nb = std::max(b.max_nb, h->meta[s].nb);
+    b.cnt.assign(b.max_nb, 0);
+    std::vector<int64_t> tile_off(nb_s + 1, 0), trp(nb_s, 0), gp(nb_s, 0);
+    std::vector<int2> tt; std::vector<int4> lt;
+    int64_t tro = 0, go = 0;
+    for (int s = b.s0; s < b.s1; s++) {
+      const LeafMeta& m = h->meta[s];
+      for (int J = 0; J < m.nb; J++) b.cnt[J]++;
+      const int64_t t64 = m.np / GT;
+      tile_off[s - b.s0 + 1] = tile_off[s - b.s0] + t64 * (t64 + 1) / 2;
+      trp[s - b.s0] = tro; tro += 2 * m.nb;
+      gp[s - b.s0] = go; go += (int64_t)(m.nb * (m.nb + 1) / 2) * m.nl;
+      for (int J = 0; J < m.nb; J++) tt.push_back(make_int2(s - b.s0, J));
+      int idx = 0;
+      for (int I = 0; I < m.nb; I++) for (int J = 0; J <= I; J++) lt.push_back(make_int4(s - b.s0, I, J, idx++));
+      const double n = m.n;
+      b.potrf_flops += n * n * n / 3.0 + n * n / 2.0 + n / 6.0;
+      b.gram_bytes += 8.0 * (n * (n + 1) / 2.0) + 8.0 * n * h->D;
+    }
+    // cost-descending task order (dynamic LPT through the atomic task counter)
+    std::stable_sort(tt.begin(), tt.end(), [&](const int2& a, const int2& c) {
+      const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
+    std::stable_sort(lt.begin(), lt.end(), [&](const int4& a, const int4& c) {
+      const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
+    b.ntiles = tile_off.back(); b.trpart_doubles = tro; b.gpart_doubles = go;
+    b.n_trtri = (int)tt.size(); b.n_lauum = (int)lt.size();
+    CUDA_TRY(h, upload(&b.d_tile_off, tile_off));
+    CUDA_TRY(h, upload(&b.d_trpart_off, trp));
+    CUDA_TRY(h, upload(&b.d_gpart_off, gp));
+    CUDA_TRY(h, upload(&b.d_trtri_tasks, tt));
+    CUDA_TRY(h, upload(&b.d_lauum_tasks, lt));
+    maxF = std::max(maxF, b.f_doubles); maxW = std::max(maxW, b.w_doubles);
+    maxTr = std::max(maxTr, tro); maxG = std::max(maxG, go);
+  }
+  CUDA_TRY(h, h->d_meta.alloc(ns));
+  if (ns) CUDA_TRY(h, cudaMemcpy(h->d_meta.p, h->meta.data(), ns * sizeof(LeafMeta), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, h->d_xg.alloc(xoff));
+  CUDA_TRY(h, h->d_y.alloc(voff));
+  CUDA_TRY(h, h->d_z.alloc(voff));
+  CUDA_TRY(h, h->d_alpha.alloc(voff));
+  CUDA_TRY(h, h->d_F.alloc(maxF));
+  CUDA_TRY(h, h->d_W.alloc(maxW));
+  CUDA_TRY(h, h->d_WT.alloc(maxW));
+  CUDA_TRY(h, h->d_prm.alloc((size_t)ns * h->pstride));
+  CUDA_TRY(h, h->d_trpart.alloc(maxTr));
+  CUDA_TRY(h, h->d_gpart.alloc(std::max<int64_t>(maxG, 1)));
+  CUDA_TRY(h, h->d_rows.alloc((size_t)L * h->row_width));
+  CUDA_TRY(h, h->d_scal.alloc(ns));
+  CUDA_TRY(h, h->d_counter.alloc(16));
+  CUDA_TRY(h, h->d_leaf_mean.alloc(L));
+  CUDA_TRY(h, cudaMemcpy(h->d_leaf_mean.p, h->leaf_mean.data(), L * sizeof(double), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemset(h->d_rows.p, 0, (size_t)L * h->row_width * sizeof(double)));
+  CUDA_TRY(h, cudaMallocHost(&h->pin_rows, (size_t)L * h->row_width * sizeof(double)));
+  CUDA_TRY(h, cudaMallocHost(&h->pin_scal, std::max(ns, 1) * sizeof(LeafScal)));
+  h->h_prm.assign((size_t)ns * h->pstride, 0.0);
+  h->h_rows.assign((size_t)L * h->row_width, 0.0);
+  h->h_info.assign(L, 0);
+
+  // y (zero padded) and gathered inputs
+  {
+    std::vector<double> yv(voff, 0.0);
+    std::vector<int64_t> obs, obs_off(ns + 1, 0);
+    for (int s = 0; s < ns; s++) {
+      const int l = loc[s];
+      const int64_t b0 = h->leaf_ptr[l], n = h->meta[s].n;
+      std::copy(y_centered + b0, y_centered + b0 + n, yv.begin() + h->meta[s].voff);
+      obs.insert(obs.end(), leaf_obs + b0, leaf_obs + b0 + n);
+      obs_off[s + 1] = obs_off[s] + n;
+    }
+    if (voff) CUDA_TRY(h, cudaMemcpy(h->d_y.p, yv.data(), voff * sizeof(double), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemset(h->d_z.p, 0, voff * sizeof(double)));
+    CUDA_TRY(h, cudaMemset(h->d_alpha.p, 0, voff * sizeof(double)));
+    if (ns) {
+      double* d_x = nullptr; int64_t* d_obs = nullptr; int64_t* d_obs_off = nullptr;
+      CUDA_TRY(h, cudaMalloc(&d_x, (size_t)h->N * h->D * sizeof(double)));
+      CUDA_TRY(h, cudaMemcpy(d_x, x, (size_t)h->N * h->D * sizeof(double), cudaMemcpyHostToDevice));
+      CUDA_TRY(h, upload(&d_obs, obs));
+      CUDA_TRY(h, upload(&d_obs_off, obs_off));
+      GatherArgs ga{h->d_meta.p, d_x, h->N, (int)h->D, d_obs, d_obs_off, h->d_xg.p};
+      launch_gather(ga, h->meta[0].np, ns, h->stream);
+      CUDA_TRY(h, cudaGetLastError());
+      CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+      cudaFree(d_x); cudaFree(d_obs); cudaFree(d_obs_off);
+    }
+  }
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_create(const double* x, int64_t N, int64_t D, int64_t L, const int64_t* leaf_ptr,
+                                const int64_t* leaf_obs, const double* y_centered, const double* leaf_mean,
+                                const int32_t* leaf_kernel_id, const dsmgp_kernel_desc* kernels, int32_t n_kernels,
+                                const dsmgp_tree* tree, const dsmgp_opts* opts, dsmgp_handle** out) {
+  if (out) *out = nullptr;
+  auto fail = [&](int32_t code, const std::string& msg) { g_create_error = msg; return code; };
+  if (!x || !leaf_ptr || !leaf_obs || !y_centered || !leaf_mean || !leaf_kernel_id || !kernels || !tree || !out)
+    return fail(DSMGP_ERR_ARG, "null argument");
+  if (N <= 0 || D <= 0 || L <= 0 || n_kernels <= 0) return fail(DSMGP_ERR_ARG, "N, D, L, n_kernels must be positive");
+  if (D > 32) return fail(DSMGP_ERR_ARG, "D > 32 is not supported by the staged point tiles");
+  dsmgp_handle* h = new dsmgp_handle();
+  if (opts) h->opts = *opts; else dsmgp_default_opts(&h->opts);
+  if (h->opts.world <= 0 || h->opts.rank < 0 || h->opts.rank >= h->opts.world) { delete h; return fail(DSMGP_ERR_ARG, "bad rank/world"); }
+  h->N = N; h->D = D; h->L = L; h->nk = n_kernels;
+  h->kernels.assign(kernels, kernels + n_kernels);
+  h->koff.resize(n_kernels); h->knp.resize(n_kernels);
+  for (int k = 0; k < n_kernels; k++) {
+    const int t = kernels[k].type, np = kernels[k].nparams;
+    const int nl = (t == DSMGP_ISO_SE || t == DSMGP_ISO_LINEAR) ? 1 : (int)D;
+    if (t < 0 || t > 3 || np != nl + 2) { delete h; return fail(DSMGP_ERR_ARG, "kernel desc: bad type or nparams != len(logl)+2"); }
+    h->koff[k] = h->H; h->knp[k] = np; h->H += np; h->Hmax = std::max(h->Hmax, np);
+  }
+  h->row_width = 1 + h->Hmax;
+  h->leaf_ptr.assign(leaf_ptr, leaf_ptr + L + 1);
+  h->leaf_kid.assign(leaf_kernel_id, leaf_kernel_id + L);
+  h->leaf_mean.assign(leaf_mean, leaf_mean + L);
+  if (leaf_ptr[0] != 0) { delete h; return fail(DSMGP_ERR_ARG, "leaf_ptr[0] != 0"); }
+  for (int64_t l = 0; l < L; l++) {
+    if (leaf_ptr[l + 1] <= leaf_ptr[l]) { delete h; return fail(DSMGP_ERR_ARG, "empty leaf"); }
+    if (leaf_kernel_id[l] < 0 || leaf_kernel_id[l] >= n_kernels) { delete h; return fail(DSMGP_ERR_ARG, "leaf_kernel_id out of range"); }
+    for (int64_t i = leaf_ptr[l]; i < leaf_ptr[l + 1]; i++)
+      if (leaf_obs[i] < 1 || leaf_obs[i] > N) { delete h; return fail(DSMGP_ERR_ARG, "leaf_obs must be 1-based rows in 1..N"); }
+  }
+  std::string terr;
+  if (!h->tree.load(tree, L, terr)) { delete h; return fail(DSMGP_ERR_ARG, terr); }
+  h->node_lml.assign(h->tree.n_nodes, 0.0);
+  h->owner.assign(L, 0);
+  if (h->opts.world > 1) shard_lpt(L, leaf_ptr, h->opts.world, h->owner.data());
+  // default parameters: zeros (IsoSE(0,0)-like); callers always set_params before fit
+  h->theta_leaf.assign((size_t)L * h->Hmax, 0.0);
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    delete h;
+    return fail(DSMGP_ERR_CUDA, std::string("no CUDA device: libdsmgp has no CPU fallback (") + cudaGetErrorString(ce) + ")");
+  }
+  if (h->opts.device >= 0) h->device = h->opts.device; else cudaGetDevice(&h->device);
+  if ((ce = cudaSetDevice(h->device)) != cudaSuccess) { delete h; return fail(DSMGP_ERR_CUDA, cudaGetErrorString(ce)); }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, h->device);
+  if (prop.major != 10) {
+    delete h;
+    return fail(DSMGP_ERR_CUDA, "libdsmgp is built for sm_100a (B200) only; found compute capability " +
+                                    std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  }
+  if ((ce = engine_attrs()) != cudaSuccess) { delete h; return fail(DSMGP_ERR_CUDA, cudaGetErrorString(ce)); }
+  cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  for (auto& e : h->ev) cudaEventCreate(&e);
+  int32_t rc = plan_and_alloc(h, x, leaf_obs, y_centered);
+  if (rc != DSMGP_OK) { g_create_error = h->err; delete h; return rc; }
+  *out = h;
+  return DSMGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameters
+// ------------------------------------------------------------------------------------------
+extern "C" int64_t dsmgp_nparams(const dsmgp_handle* h) { return h ? h->H : -1; }
+extern "C" int64_t dsmgp_n_leaves(const dsmgp_handle* h) { return h ? h->L : -1; }
+extern "C" int64_t dsmgp_n_nodes(const dsmgp_handle* h) { return h ? h->tree.n_nodes : -1; }
+extern "C" int64_t dsmgp_row_width(const dsmgp_handle* h) { return h ? h->row_width : -1; }
+extern "C" int64_t dsmgp_leaf_size(const dsmgp_handle* h, int64_t leaf) {
+  if (!h || leaf < 0 || leaf >= h->L) return -1;
+  return h->leaf_ptr[leaf + 1] - h->leaf_ptr[leaf];
+}
+
+extern "C" int32_t dsmgp_set_params(dsmgp_handle* h, const double* theta, int64_t n) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!theta || n != h->H) { h->err = "set_params: theta length must equal nparams"; return DSMGP_ERR_ARG; }
+  for (int64_t l = 0; l < h->L; l++) {
+    const int k = h->leaf_kid[l];
+    std::copy(theta + h->koff[k], theta + h->koff[k] + h->knp[k], h->theta_leaf.begin() + (size_t)l * h->Hmax);
+  }
+  cudaSetDevice(h->device);
+  upload_params(h);
+  h->fitted = false; h->have_rows = false; h->have_grad = false;
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_set_leaf_params(dsmgp_handle* h, int64_t leaf, const double* theta, int64_t n) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (leaf < 0 || leaf >= h->L || !theta || n != h->knp[h->leaf_kid[leaf]]) { h->err = "set_leaf_params: bad leaf or length"; return DSMGP_ERR_ARG; }
+  std::copy(theta, theta + n, h->theta_leaf.begin() + (size_t)leaf * h->Hmax);
+  cudaSetDevice(h->device);
+  upload_params(h);
+  h->fitted = false; h->have_rows = false; h->have_grad = false;
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_get_leaf_params(const dsmgp_handle* h, int64_t leaf, double* theta, int64_t n) {
+  if (!h || leaf < 0 || leaf >= h->L || !theta || n != h->knp[h->leaf_kid[leaf]]) return DSMGP_ERR_ARG;
+  std::copy(h->theta_leaf.begin() + (size_t)leaf * h->Hmax, h->theta_leaf.begin() + (size_t)leaf * h->Hmax + n, theta);
+  return DSMGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// the device pipeline
+// ------------------------------------------------------------------------------------------
+static bool needs_lauum(const dsmgp_handle* h) {
+  for (int k = 0; k < h->nk; k++) {
+    const int t = h->kernels[k].type;
+    if (t == DSMGP_ISO_SE || t == DSMGP_ARD_LINEAR) return true;
+    if (t == DSMGP_ARD_SE && !h->opts.as_written_grads) return true;
+  }
+  return false;
+}
+
+static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+// gram -> potrf -> solves (-> inverse -> lauum) -> rows, batch by batch
+static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
+  cudaStream_t st = h->stream;
+  const int sms = num_sms(h->device);
+  const bool lau = with_grad && needs_lauum(h);
+  h->tm = dsmgp_timings{};
+  const bool prof = h->profiling;
+  CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
+  for (auto& b : h->batches) {
+    const int nsl = b.s1 - b.s0;
+    if (nsl == 0) continue;
+    const LeafMeta* meta = h->d_meta.p + b.s0;
+    LeafScal* scal = h->d_scal.p + b.s0;
+    CUDA_TRY(h, cudaMemsetAsync(scal, 0, nsl * sizeof(LeafScal), st));
+    if (prof) cudaEventRecord(h->ev[1], st);
+    GramArgs ga{meta, h->d_xg.p, h->d_prm.p, h->d_F.p, b.d_tile_off, nsl, (int)h->D};
+    launch_gram_fit(ga, b.ntiles, st);
+    h->tm.launches++;
+    if (prof) cudaEventRecord(h->ev[2], st);
+    CholArgs ca{meta, h->d_F.p, h->d_W.p, h->d_WT.p, scal, h->d_trpart.p, b.d_trpart_off, 0, 0};
+    for (int J = 0; J < b.max_nb; J++) {
+      ca.step = J;
+      launch_potrf_diag(ca, b.cnt[J], st);
+      h->tm.launches++;
+      if (J + 1 < b.max_nb) {
+        launch_potrf_panel(ca, b.max_nb - J - 1, b.cnt[J + 1], st);
+        h->tm.launches++;
+      }
+    }
+    if (prof) cudaEventRecord(h->ev[3], st);
+    SolveArgs sa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, scal};
+    launch_solve(sa, nsl, st);
+    h->tm.launches++;
+    if (prof) cudaEventRecord(h->ev[4], st);
+    if (with_grad) {
+      CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
+      TrtriArgs ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_trpart.p, b.d_trpart_off, b.d_trtri_tasks, b.n_trtri, h->d_counter.p};
+      launch_trtri(ta, std::min(sms, b.n_trtri), st);
+      h->tm.launches++;
+      if (prof) cudaEventRecord(h->ev[5], st);
+      if (lau) {
+        LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
+                     h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D};
+        launch_lauum(la, std::min(sms, b.n_lauum), st);
+        h->tm.launches++;
+      }
+    } else if (prof) cudaEventRecord(h->ev[5], st);
+    if (prof) cudaEventRecord(h->ev[6], st);
+    RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,
+                h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0};
+    launch_rows(ra, nsl, st);
+    h->tm.launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    h->tm.potrf_flops += b.potrf_flops;
+    h->tm.inverse_flops += with_grad ? b.potrf_flops * (lau ? 2.0 : 1.0) : 0.0;
+    h->tm.gram_bytes += b.gram_bytes;
+    if (prof) {
+      cudaEventRecord(h->ev[7], st);
+      CUDA_TRY(h, cudaEventSynchronize(h->ev[7]));
+      h->tm.gram_ms += ev_ms(h->ev[1], h->ev[2]);
+      h->tm.potrf_ms += ev_ms(h->ev[2], h->ev[3]);
+      h->tm.solve_ms += ev_ms(h->ev[3], h->ev[4]);
+      h->tm.inverse_ms += ev_ms(h->ev[4], h->ev[5]);
+      h->tm.grad_ms += ev_ms(h->ev[5], h->ev[7]);
+    }
+  }
+  const int ns = (int)h->slot_leaf.size();
+  if (ns) CUDA_TRY(h, cudaMemcpyAsync(h->pin_scal, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaEventRecord(h->ev[7], st));
+  CUDA_TRY(h, cudaEventSynchronize(h->ev[7]));
+  h->tm.total_ms = ev_ms(h->ev[0], h->ev[7]);
+  std::fill(h->h_info.begin(), h->h_info.end(), 0);
+  for (int s = 0; s < ns; s++) {
+    int info = h->pin_scal[s].info;
+    if (info > h->meta[s].n) info = 0;     // padding rows are identity
+    h->h_info[h->slot_leaf[s]] = info;
+  }
+  h->fitted = true; h->have_rows = true; h->have_grad = with_grad; h->rows_complete = (h->opts.world == 1);
+  return DSMGP_OK;
+}
+
+static int32_t fetch_rows(dsmgp_handle* h) {
+  const size_t bytes = (size_t)h->L * h->row_width * sizeof(double);
+  CUDA_TRY(h, cudaMemcpyAsync(h->pin_rows, h->d_rows.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  memcpy(h->h_rows.data(), h->pin_rows, bytes);
+  return DSMGP_OK;
+}
+
+static int32_t check_pd(dsmgp_handle* h) {
+  if (!h->opts.strict_pd) return DSMGP_OK;
+  for (int64_t l = 0; l < h->L; l++)
+    if (h->h_info[l] != 0) {
+      h->err = "PosDefException: leaf " + std::to_string(l) + " not positive definite at pivot " + std::to_string(h->h_info[l]);
+      return DSMGP_ERR_NOT_PD;
+    }
+  return DSMGP_OK;
+}
+
+static void tree_grad(dsmgp_handle* h, const double* leaf_scale, double* grad) {
+  std::fill(grad, grad + h->H, 0.0);
+  DownCtx c{&h->tree, h->h_rows.data(), h->row_width, h->node_lml.data(), h->node_lml[h->tree.root],
+            leaf_scale, h->leaf_kid.data(), h->koff.data(), h->knp.data(), grad};
+  // a model with a single kernel writes at offset 0; kernel mixtures slice inside down_pass
+  down_pass(c, h->tree.root, 0.0, 0.0, 0);
+}
+
+extern "C" int32_t dsmgp_fit(dsmgp_handle* h, int32_t* info, double* seconds) {
+  if (!h) return DSMGP_ERR_ARG;
+  cudaSetDevice(h->device);
+  int32_t rc = run_pipeline(h, false);
+  if (rc) return rc;
+  if ((rc = fetch_rows(h))) return rc;
+  if (info) std::copy(h->h_info.begin(), h->h_info.end(), info);
+  if (seconds) *seconds = h->tm.total_ms * 1e-3;
+  return check_pd(h);
+}
+
+extern "C" int32_t dsmgp_lml(dsmgp_handle* h, double* node_lml) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!h->have_rows) { h->err = "lml: call fit or eval first"; return DSMGP_ERR_STATE; }
+  if (!h->rows_complete) { h->err = "lml: rows of other ranks missing (all-reduce the rows, then eval_finish_dev)"; return DSMGP_ERR_STATE; }
+  up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
+  if (node_lml) std::copy(h->node_lml.begin(), h->node_lml.end(), node_lml);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_grad(dsmgp_handle* h, const double* leaf_scale, double* grad) {
+  if (!h || !grad) return DSMGP_ERR_ARG;
+  cudaSetDevice(h->device);
+  int32_t rc;
+  if (!h->have_grad) {
+    if ((rc = run_pipeline(h, true))) return rc;
+    if ((rc = fetch_rows(h))) return rc;
+  }
+  if (!h->rows_complete) { h->err = "grad: rows of other ranks missing"; return DSMGP_ERR_STATE; }
+  up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
+  tree_grad(h, leaf_scale, grad);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_eval(dsmgp_handle* h, const double* theta, int64_t n, const double* leaf_scale,
+                              double* lml, double* grad, double* node_lml) {
+  if (!h) return DSMGP_ERR_ARG;
+  int32_t rc;
+  if (theta && (rc = dsmgp_set_params(h, theta, n))) return rc;
+  cudaSetDevice(h->device);
+  if ((rc = run_pipeline(h, grad != nullptr))) return rc;
+  if ((rc = fetch_rows(h))) return rc;
+  if (!h->rows_complete) { h->err = "eval: world > 1 needs eval_local_dev + all-reduce + eval_finish_dev"; return DSMGP_ERR_STATE; }
+  up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
+  if (lml) *lml = h->node_lml[h->tree.root];
+  if (node_lml) std::copy(h->node_lml.begin(), h->node_lml.end(), node_lml);
+  if (grad) tree_grad(h, leaf_scale, grad);
+  return check_pd(h);
+}
+
+extern "C" int32_t dsmgp_eval_local_dev(dsmgp_handle* h, const double* theta, int64_t n, double** rows_dev) {
+  if (!h || !rows_dev) return DSMGP_ERR_ARG;
+  int32_t rc;
+  if (theta && (rc = dsmgp_set_params(h, theta, n))) return rc;
+  cudaSetDevice(h->device);
+  if ((rc = run_pipeline(h, true))) return rc;
+  *rows_dev = h->d_rows.p;
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_eval_finish_dev(dsmgp_handle* h, const double* leaf_scale, double* lml, double* grad, double* node_lml) {
+  if (!h) return DSMGP_ERR_ARG;
+  cudaSetDevice(h->device);
+  int32_t rc;
+  CUDA_TRY(h, cudaDeviceSynchronize());   // the caller's collective ran on its own stream
+  if ((rc = fetch_rows(h))) return rc;
+  h->rows_complete = true;
+  up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
+  if (lml) *lml = h->node_lml[h->tree.root];
+  if (node_lml) std::copy(h->node_lml.begin(), h->node_lml.end(), node_lml);
+  if (grad) tree_grad(h, leaf_scale, grad);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_rows(const dsmgp_handle* h, double* rows) {
+  if (!h || !rows) return DSMGP_ERR_ARG;
+  if (!h->have_rows) return DSMGP_ERR_STATE;
+  std::copy(h->h_rows.begin(), h->h_rows.end(), rows);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_owner(const dsmgp_handle* h, int32_t* owner) {
+  if (!h || !owner) return DSMGP_ERR_ARG;
+  std::copy(h->owner.begin(), h->owner.end(), owner);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_info(const dsmgp_handle* h, int32_t* info) {
+  if (!h || !info) return DSMGP_ERR_ARG;
+  std::copy(h->h_info.begin(), h->h_info.end(), info);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_update_weights(dsmgp_handle* h, double* sum_logweights, double* z) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!h->have_rows || !h->rows_complete) { h->err = "update_weights: call fit or eval first"; return DSMGP_ERR_STATE; }
+  h->sum_logw.assign(h->tree.child_ptr[h->tree.n_nodes], 0.0);
+  update_weights(h->tree, h->h_rows.data(), h->row_width, h->sum_logw.data(), z);
+  h->have_weights = true;
+  if (sum_logweights) std::copy(h->sum_logw.begin(), h->sum_logw.end(), sum_logweights);
+  return DSMGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// accessors
+// ------------------------------------------------------------------------------------------
+static int32_t need_resident(const dsmgp_handle* h, int64_t leaf, int* slot) {
+  if (!h || leaf < 0 || leaf >= h->L) return DSMGP_ERR_ARG;
+  if (!h->fitted) return DSMGP_ERR_STATE;
+  if (!h->opts.keep_factors || h->batches.size() != 1) return DSMGP_ERR_STATE;
+  *slot = h->leaf_slot[leaf];
+  if (*slot < 0) return DSMGP_ERR_STATE;    // owned by another rank
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_alpha(const dsmgp_handle* h, int64_t leaf, double* alpha) {
+  int slot; int32_t rc = need_resident(h, leaf, &slot);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  const LeafMeta& m = h->meta[slot];
+  if (cudaMemcpy(alpha, h->d_alpha.p + m.voff, m.n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return DSMGP_ERR_CUDA;
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_factor(const dsmgp_handle* h, int64_t leaf, double* Lfac) {
+  int slot; int32_t rc = need_resident(h, leaf, &slot);
+  if (rc) return rc;
+  cudaSetDevice(h->device);
+  const LeafMeta& m = h->meta[slot];
+  if (cudaMemcpy2D(Lfac, (size_t)m.n * 8, h->d_F.p + m.foff, (size_t)m.np * 8, (size_t)m.n * 8, m.n, cudaMemcpyDeviceToHost) != cudaSuccess)
+    return DSMGP_ERR_CUDA;
+  for (int64_t c = 1; c < m.n; c++) for (int64_t r = 0; r < c; r++) Lfac[c * m.n + r] = 0.0;
+  return DSMGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// prediction
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Router {
+  const HostTree& t; const double* x; int64_t T;
+  std::vector<std::vector<int64_t>> pts;   // per leaf
+  bool bad = false;
+  Router(const HostTree& tt, const double* xx, int64_t TT, int64_t L) : t(tt), x(xx), T(TT), pts(L) {}
+  void route(int64_t node, const std::vector<int64_t>& idx, bool poe) {
+    const int ty = t.type[node];
+    if (ty == DSMGP_NODE_LEAF) { auto& v = pts[t.leaf_of_node[node]]; v.insert(v.end(), idx.begin(), idx.end()); return; }
+    if (ty == DSMGP_NODE_SPLIT && !poe) {
+      std::vector<std::vector<int64_t>> sub(t.nchild(node));
+      for (int64_t p : idx) { const int64_t k = getchild(t, node, x, T, p); if (k < 0) { bad = true; return; } sub[k].push_back(p); }
+      for (int64_t k = 0; k < t.nchild(node); k++) if (!sub[k].empty()) route(t.child(node, k), sub[k], poe);
+      return;
+    }
+    for (int64_t k = 0; k < t.nchild(node); k++) route(t.child(node, k), idx, poe);
+  }
+};
+
+// common.jl mixing on the host.  Leaf predictions are stored per leaf in routing order; `cursor` replays it.
+struct Mixer {
+  const HostTree& t; const double* x; int64_t T;
+  const std::vector<std::vector<double>>& mu; const std::vector<std::vector<double>>& var;
+  const std::vector<double>& logw;
+  std::vector<size_t> cursor;
+  Mixer(const HostTree& tt, const double* xx, int64_t TT, const std::vector<std::vector<double>>& m,
+        const std::vector<std::vector<double>>& v, const std::vector<double>& lw)
+      : t(tt), x(xx), T(TT), mu(m), var(v), logw(lw), cursor(m.size(), 0) {}
+  void reset() { std::fill(cursor.begin(), cursor.end(), 0); }
+
+  // _minpredict common.jl:151-173
+  void minpredict(int64_t node, const std::vector<int64_t>& idx, std::vector<double>& out) {
+    const int ty = t.type[node];
+    out.assign(idx.size(), 0.0);
+    if (ty == DSMGP_NODE_LEAF) {
+      const int64_t l = t.leaf_of_node[node];
+      for (size_t i = 0; i < idx.size(); i++) out[i] = mu[l][cursor[l] + i];
+      cursor[l] += idx.size();
+    } else if (ty == DSMGP_NODE_SPLIT) {
+      std::vector<std::vector<int64_t>> sub(t.nchild(node)); std::vector<std::vector<size_t>> pos(t.nchild(node));
+      for (size_t i = 0; i < idx.size(); i++) { const int64_t k = getchild(t, node, x, T, idx[i]); sub[k].push_back(idx[i]); pos[k].push_back(i); }
+      std::vector<double> o;
+      for (int64_t k = 0; k < t.nchild(node); k++) {
+        if (sub[k].empty()) continue;
+        minpredict(t.child(node, k), sub[k], o);
+        for (size_t i = 0; i < o.size(); i++) out[pos[k][i]] = o[i];
+      }
+    } else {
+      std::fill(out.begin(), out.end(), std::numeric_limits<double>::infinity());
+      std::vector<double> o;
+      for (int64_t k = 0; k < t.nchild(node); k++) {
+        minpredict(t.child(node, k), idx, o);
+        for (size_t i = 0; i < o.size(); i++) out[i] = std::min(out[i], o[i]);
+      }
+    }
+  }
+  // _predict common.jl:134-143,181-196,275-292 : log(mu - mumin), log(mu^2), log(sigma^2)
+  void predict(int64_t node, const std::vector<int64_t>& idx, const std::vector<double>& mumin,
+               std::vector<double>& lm, std::vector<double>& lm2, std::vector<double>& ls) {
+    const int ty = t.type[node];
+    const size_t n = idx.size();
+    lm.assign(n, 0.0); lm2.assign(n, 0.0); ls.assign(n, 0.0);
+    if (ty == DSMGP_NODE_LEAF) {
+      const int64_t l = t.leaf_of_node[node];
+      for (size_t i = 0; i < n; i++) {
+        const double m = mu[l][cursor[l] + i];
+        double s2 = var[l][cursor[l] + i];
+        if (s2 <= 0) s2 = 1e-8;                                  // common.jl:137
+        lm[i] = std::log(m - mumin[i]); lm2[i] = std::log(m * m); ls[i] = std::log(s2);
+      }
+      cursor[l] += n;
+    } else if (ty == DSMGP_NODE_SPLIT) {
+      std::vector<std::vector<int64_t>> sub(t.nchild(node)); std::vector<std::vector<size_t>> pos(t.nchild(node));
+      std::vector<std::vector<double>> mm(t.nchild(node));
+      for (size_t i = 0; i < n; i++) {
+        const int64_t k = getchild(t, node, x, T, idx[i]);
+        sub[k].push_back(idx[i]); pos[k].push_back(i); mm[k].push_back(mumin[i]);
+      }
+      std::vector<double> a, b, c;
+      for (int64_t k = 0; k < t.nchild(node); k++) {
+        if (sub[k].empty()) continue;
+        predict(t.child(node, k), sub[k], mm[k], a, b, c);
+        for (size_t i = 0; i < a.size(); i++) { lm[pos[k][i]] = a[i]; lm2[pos[k][i]] = b[i]; ls[pos[k][i]] = c[i]; }
+      }
+    } else {
+      const int64_t K = t.nchild(node);
+      std::vector<std::vector<double>> A(K), B(K), C(K);
+      for (int64_t k = 0; k < K; k++) predict(t.child(node, k), idx, mumin, A[k], B[k], C[k]);
+      const double* lw = logw.data() + t.child_ptr[node];
+      auto lse = [&](std::vector<std::vector<double>>& M, size_t i) {   // common.jl:309-313
+        double m = -std::numeric_limits<double>::infinity();
+        for (int64_t k = 0; k < K; k++) m = std::max(m, M[k][i] + lw[k]);
+        double s = 0.0;
+        for (int64_t k = 0; k < K; k++) s += std::exp((M[k][i] + lw[k]) - m);
+        return std::log(s) + m;
+      };
+      for (size_t i = 0; i < n; i++) { lm[i] = lse(A, i); lm2[i] = lse(B, i); ls[i] = lse(C, i); }
+    }
+  }
+  // _predictPoE common.jl:145-149,198-208 : (mu, precision)
+  bool poe(int64_t node, const std::vector<int64_t>& idx, std::vector<double>& m, std::vector<double>& tau) {
+    const int ty = t.type[node];
+    const size_t n = idx.size();
+    if (ty == DSMGP_NODE_LEAF) {
+      const int64_t l = t.leaf_of_node[node];
+      m.resize(n); tau.resize(n);
+      for (size_t i = 0; i < n; i++) { m[i] = mu[l][cursor[l] + i]; tau[i] = 1.0 / var[l][cursor[l] + i]; }
+      cursor[l] += n;
+      return true;
+    }
+    if (ty != DSMGP_NODE_SPLIT) return false;    // MethodError in the reference
+    m.assign(n, 0.0); tau.assign(n, 0.0);
+    std::vector<double> m_, t_;
+    for (int64_t k = 0; k < t.nchild(node); k++) {
+      if (!poe(t.child(node, k), idx, m_, t_)) return false;
+      for (size_t i = 0; i < n; i++) { tau[i] += t_[i]; m[i] += t_[i] * m_[i]; }
+    }
+    for (size_t i = 0; i < n; i++) m[i] = m[i] / tau[i];
+    return true;
+  }
+};
+}  // namespace
+
+// Device prediction of every leaf on its routed points.  pts[l] = test rows routed to leaf l.
+static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, const std::vector<std::vector<int64_t>>& pts,
+                              std::vector<std::vector<double>>& mu, std::vector<std::vector<double>>& var) {
+  if (!h->fitted) { h->err = "predict: call fit first"; return DSMGP_ERR_STATE; }
+  if (!h->opts.keep_factors || h->batches.size() != 1) { h->err = "predict needs keep_factors=1"; return DSMGP_ERR_STATE; }
+  const int64_t L = h->L, D = h->D;
+  mu.assign(L, {}); var.assign(L, {});
+  std::vector<PredLeaf> pls; std::vector<int2> tasks; std::vector<int64_t> pl_leaf;
+  int64_t xto = 0, vto = 0, oo = 0;
+  for (int64_t l = 0; l < L; l++) {
+    if (pts[l].empty()) continue;
+    const int slot = h->leaf_slot[l];
+    if (slot < 0) { h->err = "predict: leaf owned by another rank"; return DSMGP_ERR_STATE; }
+    PredLeaf p; p.slot = slot; p.T = (int32_t)pts[l].size(); p.Tp = (p.T + BLK - 1) / BLK * BLK; p.pad_ = 0;
+    p.xtoff = xto; xto += (int64_t)p.Tp * D;
+    p.vtoff = vto; vto += (int64_t)p.Tp * h->meta[slot].np;
+    p.ooff = oo; oo += p.Tp;
+    for (int q = 0; q < p.Tp / BLK; q++) tasks.push_back(make_int2((int)pls.size(), q));
+    pls.push_back(p); pl_leaf.push_back(l);
+  }
+  if (pls.empty()) return DSMGP_OK;
+  std::stable_sort(tasks.begin(), tasks.end(), [&](const int2& a, const int2& b) {
+    return h->meta[pls[a.x].slot].np > h->meta[pls[b.x].slot].np; });
+  std::vector<double> xt(xto, 0.0);
+  for (size_t i = 0; i < pls.size(); i++) {
+    const auto& pv = pts[pl_leaf[i]];
+    for (int64_t d = 0; d < D; d++)
+      for (size_t q = 0; q < pv.size(); q++) xt[pls[i].xtoff + d * pls[i].Tp + q] = xtest[d * T + pv[q]];
+  }
+  DevBuf<double> d_xt, d_VT, d_mu, d_var; DevBuf<PredLeaf> d_pl; DevBuf<int2> d_tasks;
+  auto cleanup = [&]() { d_xt.free(); d_VT.free(); d_mu.free(); d_var.free(); d_pl.free(); d_tasks.free(); };
+#define PTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { h->err = std::string(#expr) + ": " + cudaGetErrorString(e_); cleanup(); \
+    return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA; } } while (0)
+  PTRY(d_xt.alloc(xto)); PTRY(d_VT.alloc(vto)); PTRY(d_mu.alloc(oo)); PTRY(d_var.alloc(oo));
+  PTRY(d_pl.alloc(pls.size())); PTRY(d_tasks.alloc(tasks.size()));
+  PTRY(cudaMemcpyAsync(d_xt.p, xt.data(), xto * 8, cudaMemcpyHostToDevice, h->stream));
+  PTRY(cudaMemcpyAsync(d_pl.p, pls.data(), pls.size() * sizeof(PredLeaf), cudaMemcpyHostToDevice, h->stream));
+  PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
+  PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
+              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D};
+  launch_predict(pa, std::min(num_sms(h->device), (int)tasks.size()), h->stream);
+  h->tm.launches++;
+  PTRY(cudaGetLastError());
+  std::vector<double> hmu(oo), hvar(oo);
+  PTRY(cudaMemcpyAsync(hmu.data(), d_mu.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
+  PTRY(cudaMemcpyAsync(hvar.data(), d_var.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
+  PTRY(cudaStreamSynchronize(h->stream));
+#undef PTRY
+  for (size_t i = 0; i < pls.size(); i++) {
+    const int64_t l = pl_leaf[i];
+    mu[l].assign(hmu.begin() + pls[i].ooff, hmu.begin() + pls[i].ooff + pls[i].T);
+    var[l].assign(hvar.begin() + pls[i].ooff, hvar.begin() + pls[i].ooff + pls[i].T);
+  }
+  cleanup();
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_predict(dsmgp_handle* h, int64_t leaf, const double* xtest, int64_t T, double* mu, double* var) {
+  if (!h || leaf < 0 || leaf >= h->L || !xtest || T <= 0 || !mu || !var) return DSMGP_ERR_ARG;
+  cudaSetDevice(h->device);
+  std::vector<std::vector<int64_t>> pts(h->L);
+  pts[leaf].resize(T);
+  std::iota(pts[leaf].begin(), pts[leaf].end(), 0);
+  std::vector<std::vector<double>> m, v;
+  int32_t rc = predict_leaves(h, xtest, T, pts, m, v);
+  if (rc) return rc;
+  std::copy(m[leaf].begin(), m[leaf].end(), mu);
+  std::copy(v[leaf].begin(), v[leaf].end(), var);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!xtest || T <= 0 || !mu || !var || mode < 0 || mode > 3) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
+  for (int64_t i = 0; i < T * h->D; i++) if (!std::isfinite(xtest[i])) { h->err = "predict: non-finite input"; return DSMGP_ERR_ARG; }
+  cudaSetDevice(h->device);
+  const HostTree& t = h->tree;
+  const bool poe = mode != DSMGP_PREDICT_DSMGP;
+  if (poe && t.type[t.root] != DSMGP_NODE_SPLIT) { h->err = "predict: PoE/gPoE/rBCM need a split root (buildPoE/buildBCM model)"; return DSMGP_ERR_ARG; }
+  if (!poe && !h->have_weights) {
+    // the reference predicts with whatever logweights the sum nodes hold (uniform -log K after build)
+    h->sum_logw.assign(t.child_ptr[t.n_nodes], 0.0);
+    for (int64_t i = 0; i < t.n_nodes; i++)
+      if (t.type[i] >= DSMGP_NODE_SUM) for (int64_t c = t.child_ptr[i]; c < t.child_ptr[i + 1]; c++) h->sum_logw[c] = -std::log((double)t.nchild(i));
+  }
+  std::vector<int64_t> all(T);
+  std::iota(all.begin(), all.end(), 0);
+  Router r(t, xtest, T, h->L);
+  r.route(t.root, all, poe);
+  if (r.bad) { h->err = "predict: a test point lies outside every split interval"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<double>> lmu, lvar;
+  int32_t rc = predict_leaves(h, xtest, T, r.pts, lmu, lvar);
+  if (rc) return rc;
+  Mixer mx(t, xtest, T, lmu, lvar, h->sum_logw);
+  if (mode == DSMGP_PREDICT_DSMGP) {
+    // predict(node) common.jl:175-179 (leaf), :243-254 (split root), :294-302 (sum root)
+    struct Rec {
+      Mixer& mx; const HostTree& t; double* mu; double* var; const double* x; int64_t T;
+      void run(int64_t node, const std::vector<int64_t>& idx) {
+        if (t.type[node] == DSMGP_NODE_SPLIT) {
+          std::vector<std::vector<int64_t>> sub(t.nchild(node));
+          for (int64_t p : idx) sub[getchild(t, node, x, T, p)].push_back(p);
+          for (int64_t k = 0; k < t.nchild(node); k++) if (!sub[k].empty()) run(t.child(node, k), sub[k]);
+          return;
+        }
+        // leaf or sum: two traversals of the subtree -> replay cursors must restart for this subtree.
+        std::vector<size_t> save = mx.cursor;
+        std::vector<double> mumin, lm, lm2, ls;
+        mx.minpredict(node, idx, mumin);
+        mx.cursor = save;
+        for (auto& v : mumin) v -= 1.0;
+        mx.predict(node, idx, mumin, lm, lm2, ls);
+        for (size_t i = 0; i < idx.size(); i++) {
+          const double m = std::exp(lm[i]) + mumin[i];
+          mu[idx[i]] = m;
+          var[idx[i]] = (t.type[node] == DSMGP_NODE_LEAF) ? std::exp(ls[i]) : std::exp(ls[i]) + (std::exp(lm2[i]) - m * m);
+        }
+      }
+    } rec{mx, t, mu, var, xtest, T};
+    rec.run(t.root, all);
+    return DSMGP_OK;
+  }
+  const int64_t K = t.nchild(t.root);
+  std::vector<double> m_, t_;
+  if (mode == DSMGP_PREDICT_POE) {
+    if (!mx.poe(t.root, all, m_, t_)) { h->err = "predictPoE: sum node below a split (MethodError in the reference)"; return DSMGP_ERR_ARG; }
+    for (int64_t i = 0; i < T; i++) { mu[i] = m_[i]; var[i] = 1.0 / t_[i]; }
+  } else if (mode == DSMGP_PREDICT_GPOE) {       // common.jl:211-222
+    const double beta = 1.0 / (double)K;
+    std::vector<double> M(T, 0.0), Tt(T, 0.0);
+    for (int64_t k = 0; k < K; k++) {
+      if (!mx.poe(t.child(t.root, k), all, m_, t_)) { h->err = "predictgPoE: sum node below a split"; return DSMGP_ERR_ARG; }
+      for (int64_t i = 0; i < T; i++) { Tt[i] += beta * t_[i]; M[i] += beta * t_[i] * m_[i]; }
+    }
+    for (int64_t i = 0; i < T; i++) { mu[i] = M[i] / Tt[i]; var[i] = 1.0 / Tt[i]; }
+  } else {                                       // rBCM common.jl:224-241
+    int64_t nd = t.root;
+    while (t.type[nd] != DSMGP_NODE_LEAF) nd = t.child(nd, 0);
+    const int64_t l0 = t.leaf_of_node[nd];
+    const int k0 = h->leaf_kid[l0];
+    std::vector<double> prm(h->pstride);
+    derive_params(h, k0, &h->theta_leaf[(size_t)l0 * h->Hmax], prm.data());
+    const int type = h->kernels[k0].type;
+    std::vector<double> s(T), C(T), M(T, 0.0);
+    for (int64_t i = 0; i < T; i++) {
+      double ktt;
+      if (type == DSMGP_ISO_SE) ktt = prm[PRM_V];
+      else if (type == DSMGP_ARD_SE) ktt = prm[PRM_V] * (double)h->D;
+      else {
+        ktt = 0.0;
+        for (int64_t d = 0; d < h->D; d++) { const double xv = xtest[d * T + i]; ktt += (type == DSMGP_ISO_LINEAR ? prm[PRM_COEF] : prm[PRM_COEF + d]) * xv * xv; }
+      }
+      s[i] = ktt + prm[PRM_ETA];
+      C[i] = 1.0 / s[i];
+    }
+    for (int64_t k = 0; k < K; k++) {
+      if (!mx.poe(t.child(t.root, k), all, m_, t_)) { h->err = "predictrBCM: sum node below a split"; return DSMGP_ERR_ARG; }
+      for (int64_t i = 0; i < T; i++) {
+        const double s_ = 1.0 / t_[i];
+        const double beta = 0.5 * (std::log(s[i]) - std::log(s_));
+        C[i] = C[i] + (beta * t_[i]) - (beta / s[i]);
+        M[i] = M[i] + m_[i] * (beta * t_[i]);
+      }
+    }
+    for (int64_t i = 0; i < T; i++) { mu[i] = M[i] / C[i]; var[i] = 1.0 / C[i]; }
+  }
+  return DSMGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host-only helpers
+// ------------------------------------------------------------------------------------------
+extern "C" int32_t dsmgp_host_shard(int64_t L, const int64_t* leaf_ptr, int32_t world, int32_t* owner) {
+  if (L <= 0 || !leaf_ptr || world <= 0 || !owner) return DSMGP_ERR_ARG;
+  shard_lpt(L, leaf_ptr, world, owner);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_host_tree_eval(const dsmgp_tree* tree, int64_t L, const int32_t* leaf_kernel_id,
+                                        const dsmgp_kernel_desc* kernels, int32_t n_kernels, const double* rows,
+                                        int64_t row_width, const double* leaf_scale, double* node_lml, double* grad,
+                                        double* sum_logweights, double* z) {
+  if (!tree || !leaf_kernel_id || !kernels || !rows || !node_lml || L <= 0 || n_kernels <= 0) return DSMGP_ERR_ARG;
+  HostTree t; std::string err;
+  if (!t.load(tree, L, err)) { g_create_error = err; return DSMGP_ERR_ARG; }
+  std::vector<int64_t> koff(n_kernels); std::vector<int32_t> knp(n_kernels);
+  int64_t H = 0;
+  for (int k = 0; k < n_kernels; k++) { koff[k] = H; knp[k] = kernels[k].nparams; H += knp[k]; }
+  up_pass(t, rows, row_width, node_lml);
+  if (grad) {
+    std::fill(grad, grad + H, 0.0);
+    DownCtx c{&t, rows, row_width, node_lml, node_lml[t.root], leaf_scale, leaf_kernel_id, koff.data(), knp.data(), grad};
+    down_pass(c, t.root, 0.0, 0.0, 0);
+  }
+  if (sum_logweights || z) {
+    std::vector<double> lw(t.child_ptr[t.n_nodes], 0.0);
+    double zz = 0;
+    update_weights(t, rows, row_width, lw.data(), &zz);
+    if (sum_logweights) std::copy(lw.begin(), lw.end(), sum_logweights);
+    if (z) *z = zz;
+  }
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_get_timings(const dsmgp_handle* h, dsmgp_timings* t) {
+  if (!h || !t) return DSMGP_ERR_ARG;
+  *t = h->tm;
+  return DSMGP_OK;
+}
+extern "C" int32_t dsmgp_set_profiling(dsmgp_handle* h, int32_t on) {
+  if (!h) return DSMGP_ERR_ARG;
+  h->profiling = on != 0;
+  return DSMGP_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// stand-alone operators
+// ------------------------------------------------------------------------------------------
+static int32_t standalone_device_check(std::string& err) {
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) { err = std::string("no CUDA device: libdsmgp has no CPU fallback (") + cudaGetErrorString(ce) + ")"; return DSMGP_ERR_CUDA; }
+  if ((ce = engine_attrs()) != cudaSuccess) { err = cudaGetErrorString(ce); return DSMGP_ERR_CUDA; }
+  return DSMGP_OK;
+}
+#define SA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_create_error = std::string(#expr) + ": " + cudaGetErrorString(e_); rc = DSMGP_ERR_CUDA; goto done; } } while (0)
+
+extern "C" int32_t dsmgp_kernelmatrix(int32_t kernel_type, const double* theta, int64_t D, const double* x1, int64_t n1,
+                                      const double* x2, int64_t n2, double* K) {
+  if (kernel_type < 0 || kernel_type > 3 || !theta || !x1 || !x2 || !K || D <= 0 || n1 <= 0 || n2 <= 0) return DSMGP_ERR_ARG;
+  int32_t rc = standalone_device_check(g_create_error);
+  if (rc) return rc;
+  const bool iso = (kernel_type == DSMGP_ISO_SE || kernel_type == DSMGP_ISO_LINEAR);
+  const bool se = (kernel_type == DSMGP_ISO_SE || kernel_type == DSMGP_ARD_SE);
+  const int nl = iso ? 1 : (int)D;
+  std::vector<double> prm(PRM_COEF + D, 0.0);
+  prm[PRM_V] = se ? std::exp(2.0 * theta[nl]) : 1.0;
+  prm[PRM_S] = se ? std::exp(theta[nl]) : 1.0;
+  for (int d = 0; d < nl; d++) { const double l = std::exp(theta[d]); prm[PRM_COEF + d] = se ? -0.5 / (l * l) : 1.0 / (l * l); }
+  double *d1 = nullptr, *d2 = nullptr, *dk = nullptr, *dp = nullptr;
+  SA_TRY(cudaMalloc(&d1, n1 * D * 8)); SA_TRY(cudaMalloc(&d2, n2 * D * 8)); SA_TRY(cudaMalloc(&dk, n1 * n2 * 8));
+  SA_TRY(cudaMalloc(&dp, prm.size() * 8));
+  SA_TRY(cudaMemcpy(d1, x1, n1 * D * 8, cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemcpy(d2, x2, n2 * D * 8, cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemcpy(dp, prm.data(), prm.size() * 8, cudaMemcpyHostToDevice));
+  {
+    GramRectArgs ga{kernel_type, (int)D, dp, d1, n1, (int)n1, d2, n2, (int)n2, dk, n1};
+    launch_gram_rect(ga, 0);
+    SA_TRY(cudaGetLastError());
+    SA_TRY(cudaMemcpy(K, dk, n1 * n2 * 8, cudaMemcpyDeviceToHost));
+  }
+done:
+  cudaFree(d1); cudaFree(d2); cudaFree(dk); cudaFree(dp);
+  return rc;
+}
+
+// potrf / chol_continue on one host matrix.  k = number of leading rows/cols that already hold a valid factor.
+static int32_t chol_host_matrix(double* A, int64_t n, int64_t k, int32_t* info) {
+  int32_t rc = standalone_device_check(g_create_error);
+  if (rc) return rc;
+  const int64_t kp = (k + BLK - 1) / BLK * BLK;          // leading part padded to a block boundary
+  const int64_t nn = kp + (n - k);
+  LeafMeta m{};
+  m.n = (int32_t)nn; m.np = (int32_t)((nn + PAD - 1) / PAD * PAD); m.nb = (m.np + BLK - 1) / BLK;
+  const int64_t np = m.np;
+  std::vector<double> P((size_t)np * np, 0.0);
+  auto map = [&](int64_t i) { return i < k ? i : kp + (i - k); };
+  for (int64_t i = 0; i < np; i++) P[i * np + i] = 1.0;
+  for (int64_t c = 0; c < n; c++)
+    for (int64_t r = c; r < n; r++) P[map(c) * np + map(r)] = A[c * n + r];
+  double *dF = nullptr, *dW = nullptr, *dWT = nullptr, *dtr = nullptr; LeafMeta* dm = nullptr; LeafScal* ds = nullptr; int64_t* doff = nullptr;
+  LeafScal sc{};
+  const int64_t zero = 0;
+  SA_TRY(cudaMalloc(&dF, np * np * 8)); SA_TRY(cudaMalloc(&dW, (size_t)m.nb * BLK * BLK * 8)); SA_TRY(cudaMalloc(&dWT, (size_t)m.nb * BLK * BLK * 8));
+  SA_TRY(cudaMalloc(&dtr, 2 * m.nb * 8)); SA_TRY(cudaMalloc(&dm, sizeof(LeafMeta))); SA_TRY(cudaMalloc(&ds, sizeof(LeafScal)));
+  SA_TRY(cudaMalloc(&doff, 8));
+  SA_TRY(cudaMemcpy(dF, P.data(), np * np * 8, cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemcpy(dm, &m, sizeof(m), cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemset(ds, 0, sizeof(LeafScal)));
+  SA_TRY(cudaMemcpy(doff, &zero, 8, cudaMemcpyHostToDevice));
+  {
+    CholArgs ca{dm, dF, dW, dWT, ds, dtr, doff, 0, (int)(kp / BLK)};
+    for (int J = 0; J < m.nb; J++) {
+      ca.step = J;
+      launch_potrf_diag(ca, 1, 0);
+      if (J + 1 < m.nb) launch_potrf_panel(ca, m.nb - J - 1, 1, 0);
+    }
+    SA_TRY(cudaGetLastError());
+    SA_TRY(cudaMemcpy(P.data(), dF, np * np * 8, cudaMemcpyDeviceToHost));
+    SA_TRY(cudaMemcpy(&sc, ds, sizeof(sc), cudaMemcpyDeviceToHost));
+  }
+  for (int64_t c = 0; c < n; c++)
+    for (int64_t r = 0; r < n; r++) A[c * n + r] = (r >= c) ? P[map(c) * np + map(r)] : 0.0;    // tril!
+  if (info) {
+    int64_t i = sc.info;                       // 1-based pivot in padded coordinates
+    if (i > 0) { i = (i - 1 >= kp) ? (i - 1 - kp) + 1 : i; if (i > n - k) i = 0; }
+    *info = (int32_t)i;                        // relative to the trailing block, as LAPACK.potrf!(C) reports it
+  }
+done:
+  cudaFree(dF); cudaFree(dW); cudaFree(dWT); cudaFree(dtr); cudaFree(dm); cudaFree(ds); cudaFree(doff);
+  return rc;
+}
+
+extern "C" int32_t dsmgp_potrf(double* A, int64_t n, int32_t* info) {
+  if (!A || n <= 0) return DSMGP_ERR_ARG;
+  return chol_host_matrix(A, n, 0, info);
+}
+
+extern "C" int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t* info) {
+  if (!A || n <= 0 || ki < 1 || ki > n) return DSMGP_ERR_ARG;
+  return chol_host_matrix(A, n, ki - 1, info);
+}
+
+extern "C" int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, int64_t nrows, double* out) {
+  if (!A || n <= 0 || !rows || nrows < 0 || nrows >= n || !out) return DSMGP_ERR_ARG;
+  for (int64_t q = 0; q < nrows; q++)
+    if (rows[q] < 1 || rows[q] > n || (q > 0 && rows[q] <= rows[q - 1])) { g_create_error = "delete_rows: rows must be 1-based ascending"; return DSMGP_ERR_ARG; }
+  int32_t rc = standalone_device_check(g_create_error);
+  if (rc) return rc;
+  double *dL = nullptr, *dv = nullptr; int64_t* dr = nullptr;
+  std::vector<double> P((size_t)n * n);
+  SA_TRY(cudaMalloc(&dL, n * n * 8)); SA_TRY(cudaMalloc(&dv, n * 8)); SA_TRY(cudaMalloc(&dr, std::max<int64_t>(nrows, 1) * 8));
+  SA_TRY(cudaMemcpy(dL, A, n * n * 8, cudaMemcpyHostToDevice));
+  if (nrows) SA_TRY(cudaMemcpy(dr, rows, nrows * 8, cudaMemcpyHostToDevice));
+  launch_delete_rows(dL, (int)n, dr, (int)nrows, dv, 0);
+  SA_TRY(cudaGetLastError());
+  SA_TRY(cudaMemcpy(P.data(), dL, n * n * 8, cudaMemcpyDeviceToHost));
+  {
+    std::vector<int64_t> keep;
+    for (int64_t i = 0, q = 0; i < n; i++) { if (q < nrows && rows[q] - 1 == i) { q++; continue; } keep.push_back(i); }
+    const int64_t m = (int64_t)keep.size();
+    for (int64_t c = 0; c < m; c++)
+      for (int64_t r = 0; r < m; r++) out[c * m + r] = (r >= c) ? P[keep[c] * n + keep[r]] : 0.0;
+  }
+done:
+  cudaFree(dL); cudaFree(dv); cudaFree(dr);
+  return rc;
+}

@@ -1,0 +1,144 @@
+// Kernel argument blocks and host-side launchers (one translation unit per kernel family so the library
+// builds in parallel; api.cu sees only this header).
+#pragma once
+#include "common.cuh"
+
+namespace dsm {
+
+constexpr int GT = 64;       // gram tile
+constexpr int GDC = 16;      // dimensions staged per pass
+
+struct CholArgs {
+  const LeafMeta* meta;
+  double* F;          // factor arena
+  double* W;          // inverse diagonal blocks, per leaf nb blocks of BLK*BLK (column-major, ld BLK)
+  double* WT;         // their transposes
+  LeafScal* scal;
+  double* trpart;     // per (leaf, block column) partial of tr(F^{-1}); leaf l at trpart_off[l]
+  const int64_t* trpart_off;
+  int step;           // block column J (potrf kernels)
+  int jstart;         // chol_continue: block columns < jstart already hold a valid factor
+};
+
+struct TrtriArgs {
+  const LeafMeta* meta;
+  double* F;
+  const double* W;
+  const double* WT;
+  double* trpart;
+  const int64_t* trpart_off;
+  const int2* tasks;     // (leaf slot, J)
+  int ntasks;
+  int* counter;
+};
+
+struct SolveArgs {
+  const LeafMeta* meta;
+  const double* F;
+  const double* W;
+  const double* WT;
+  const double* y;
+  double* z;
+  double* alpha;
+  LeafScal* scal;
+};
+
+struct GramArgs {
+  const LeafMeta* meta;
+  const double* xg;
+  const double* prm;
+  double* F;
+  const int64_t* tile_off;   // [nleaves+1] prefix sum of lower-triangular GT tiles per leaf
+  int nleaves;
+  int D;
+};
+
+struct GramRectArgs {
+  int ktype, D;
+  const double* prm;
+  const double* xa; int64_t sa; int na;
+  const double* xb; int64_t sb; int nb;
+  double* out; int64_t ldo;
+};
+
+struct GatherArgs {
+  const LeafMeta* meta;
+  const double* x; int64_t N; int D;
+  const int64_t* obs;        // concatenated 1-based rows (local leaves)
+  const int64_t* obs_off;    // [nleaves+1]
+  double* xg;
+};
+
+struct LauumArgs {
+  const LeafMeta* meta;
+  const double* F;
+  const double* WT;
+  const double* xg;
+  const double* alpha;
+  const double* prm;
+  const int4* tasks;        // (leaf slot, I, J, index of this task within the leaf)
+  int ntasks;
+  int* counter;
+  double* gpart;            // [gpart_off[slot] + task_in_leaf * nl + h]
+  const int64_t* gpart_off;
+  int D;
+};
+
+struct RowsArgs {
+  const LeafMeta* meta;
+  const LeafScal* scal_in;
+  LeafScal* scal;
+  const double* prm;
+  const double* trpart; const int64_t* trpart_off;
+  const double* gpart; const int64_t* gpart_off;   // may be null when no LAUUM pass ran
+  double* rows; int row_width;
+  int as_written; int with_grad; int lauum_ran;
+};
+
+struct PredLeaf {     // per leaf with routed points
+  int32_t slot;       // leaf slot (LeafMeta index)
+  int32_t T;          // routed points
+  int32_t Tp;         // padded to BLK
+  int32_t pad_;
+  int64_t xtoff;      // xt: D columns of length Tp
+  int64_t vtoff;      // VT scratch: Tp x np (ld = Tp)
+  int64_t ooff;       // output offset (mu / var), length Tp
+};
+
+struct PredArgs {
+  const LeafMeta* meta;
+  const PredLeaf* pl;
+  const int2* tasks;       // (pred leaf index, Q)
+  int ntasks;
+  int* counter;
+  const double* F;
+  const double* W;
+  const double* xg;
+  const double* alpha;
+  const double* prm;
+  const double* leaf_mean;  // per global leaf
+  const double* xt;
+  double* VT;
+  double* mu;
+  double* var;
+  int D;
+};
+
+// ---- launchers (defined next to their kernels) ------------------------------------------------
+cudaError_t init_potrf_kernels();
+cudaError_t init_trtri_kernels();
+cudaError_t init_lauum_kernels();
+cudaError_t init_predict_kernels();
+void launch_potrf_diag(const CholArgs& a, int nleaves, cudaStream_t st);
+void launch_potrf_panel(const CholArgs& a, int ntile_rows, int nleaves, cudaStream_t st);
+void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
+void launch_trtri(const TrtriArgs& a, int nctas, cudaStream_t st);
+void launch_lauum(const LauumArgs& a, int nctas, cudaStream_t st);
+void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
+void launch_predict(const PredArgs& a, int nctas, cudaStream_t st);
+void launch_gram_fit(const GramArgs& a, int64_t ntiles, cudaStream_t st);
+void launch_gram_rect(const GramRectArgs& a, cudaStream_t st);
+void launch_gather(const GatherArgs& a, int maxnp, int nleaves, cudaStream_t st);
+void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
+
+}  // namespace dsm

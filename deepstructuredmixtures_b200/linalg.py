@@ -1,0 +1,36 @@
+"""Stand-alone dense operators of the `AdvancedCholesky` sub-module (src/AdvancedCholeskey.jl), on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence, Tuple
+
+import numpy as np
+
+from . import _native as nat
+
+
+def potrf_(A: np.ndarray) -> Tuple[np.ndarray, int]:
+    """LAPACK.potrf!('L', A) as used at gaussianprocess.jl:101: returns (lower factor, info)."""
+    A = np.array(A, dtype=np.float64, order="F")
+    info = C.c_int32(0)
+    nat.check(nat.lib().dsmgp_potrf(nat.p_d(A), A.shape[0], C.byref(info)))
+    return A, info.value
+
+
+def chol_continue_(A: np.ndarray, ki: int) -> Tuple[np.ndarray, int]:
+    """chol_continue!(A, ki) AdvancedCholeskey.jl:152-174 (ki 1-based): rows/cols < ki hold a valid lower factor."""
+    A = np.array(A, dtype=np.float64, order="F")
+    info = C.c_int32(0)
+    nat.check(nat.lib().dsmgp_chol_continue(nat.p_d(A), A.shape[0], int(ki), C.byref(info)))
+    return A, info.value
+
+
+def chol_delete_rows(Lf: np.ndarray, rows: Sequence[int]) -> np.ndarray:
+    """Factor of A[keep, keep] from the factor of A (the row-deletion fit.jl:179-195 builds from lowrankupdate!,
+    AdvancedCholeskey.jl:20-59 -- implemented correctly).  `rows` 1-based ascending."""
+    Lf = np.array(Lf, dtype=np.float64, order="F")
+    rows = np.ascontiguousarray(sorted(rows), dtype=np.int64)
+    n = Lf.shape[0]
+    out = np.zeros((n - rows.size, n - rows.size), order="F")
+    nat.check(nat.lib().dsmgp_chol_delete_rows(nat.p_d(Lf), n, nat.p_i64(rows), rows.size, nat.p_d(out)))
+    return out

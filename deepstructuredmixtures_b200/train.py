@@ -1,0 +1,171 @@
+"""Training drivers (host orchestration): train_ / finetune_ and Flux-style optimisers.
+
+Mirrors /root/reference/src/optimisers.jl:4-145 and src/finetuning.jl:3-88.  These are the CALLERS of the hot
+path: every iteration is one `dsmgp_eval` (setparams! -> fit! -> mll! -> updategradients! -> ∇mll!).
+
+Flux semantics that matter: `Flux.Optimise.apply!(opt, x, Δ)` turns Δ into the step in place
+with optimiser state keyed by the IDENTITY of `x`; the reference then rebinds `hyp += grad`, so the state is
+fresh every iteration and an ADAM step degenerates to η·Δ/(|Δ|+ϵ).  `state_by_identity=True` (default)
+reproduces that; `False` keeps one state per optimiser (textbook behaviour).  The update is gradient ASCENT.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from .model import LeafGP, Model, fit_, leftGP, update_cholesky_
+
+
+class _Optimiser:
+    def __init__(self, state_by_identity: bool = True):
+        self.state_by_identity = state_by_identity
+        self._state: Dict[int, tuple] = {}
+
+    def _get(self, x: np.ndarray, init):
+        key = id(x) if self.state_by_identity else 0
+        ent = self._state.get(key)
+        if ent is None or (self.state_by_identity and ent[0] is not x):
+            ent = (x, init())
+            self._state[key] = ent
+        return ent[1]
+
+    def _put(self, x: np.ndarray, st):
+        self._state[id(x) if self.state_by_identity else 0] = (x, st)
+
+
+class Descent(_Optimiser):
+    def __init__(self, eta: float = 0.1, **kw):
+        super().__init__(**kw); self.eta = eta
+
+    def apply_(self, x, delta):
+        delta *= self.eta
+        return delta
+
+
+class ADAM(_Optimiser):
+    """Flux.ADAM(η=0.001, β=(0.9, 0.999)), ϵ = 1e-8."""
+
+    def __init__(self, eta: float = 0.001, beta=(0.9, 0.999), **kw):
+        super().__init__(**kw); self.eta, self.beta = eta, beta
+
+    def apply_(self, x, delta):
+        b1, b2 = self.beta
+        mt, vt, bp = self._get(x, lambda: (np.zeros_like(x), np.zeros_like(x), [b1, b2]))
+        mt = b1 * mt + (1 - b1) * delta
+        vt = b2 * vt + (1 - b2) * delta ** 2
+        delta[:] = mt / (1 - bp[0]) / (np.sqrt(vt / (1 - bp[1])) + 1e-8) * self.eta
+        self._put(x, (mt, vt, [bp[0] * b1, bp[1] * b2]))
+        return delta
+
+
+class RMSProp(_Optimiser):
+    """Flux.RMSProp(η=0.001, ρ=0.9), ϵ = 1e-8."""
+
+    def __init__(self, eta: float = 0.001, rho: float = 0.9, **kw):
+        super().__init__(**kw); self.eta, self.rho = eta, rho
+
+    def apply_(self, x, delta):
+        acc = self._get(x, lambda: np.zeros_like(x))
+        acc = self.rho * acc + (1 - self.rho) * delta ** 2
+        delta[:] = delta * (self.eta / (np.sqrt(acc) + 1e-8))
+        self._put(x, acc)
+        return delta
+
+
+def _current_hyp(model: Model) -> np.ndarray:
+    gp = leftGP(model)
+    gps = gp if isinstance(gp, list) else [gp]
+    out = []
+    for g in gps:
+        l, s, n = g.params(logscale=True)
+        out.append(np.concatenate([np.atleast_1d(l), [s, n]]))
+    return np.concatenate(out)
+
+
+def train_(model, optim=None, *, iterations: int = 10_000, lam: float = 0.05, randinit: bool = True,
+           earlystop: int = 10, rng=None, callback=None):
+    """train!(model, optim; iterations, λ, randinit, earlystop) optimisers.jl:4-87.
+    Returns (model, ℓ) with ℓ the LML trace.  For a single `GaussianProcess` see `train_gp_`."""
+    if isinstance(model, LeafGP):
+        return train_gp_(model, optim=optim, iterations=iterations, lam=lam, rng=rng)
+    optim = ADAM() if optim is None else optim
+    rng = np.random.default_rng() if rng is None else (np.random.default_rng(rng) if isinstance(rng, int) else rng)
+    n = model.nparams
+    hyp = rng.standard_normal(n) if randinit else _current_hyp(model)      # :18
+    ell = np.zeros(iterations)
+    c = 0
+    delta = np.inf
+    for it in range(iterations):
+        lml, grad = model.handle.eval(hyp)                                  # :43-49, 68-77
+        ell[it] = lml
+        delta = abs(ell[it] - np.mean(ell[it - 9:it])) if it >= 10 else np.inf   # :53
+        c = c + 1 if delta < lam else 0                                     # :57-61
+        if callback is not None:
+            callback(it, lml, grad, hyp)
+        if c >= earlystop:                                                  # :63-66 (returns before the update)
+            model._mirror_params(hyp)
+            return model, ell[:it + 1]
+        optim.apply_(hyp, grad)                                             # :78
+        hyp = hyp + grad                                                    # :79 (rebinding; gradient ASCENT)
+    model.setparams_(hyp)                                                   # :82-83
+    fit_(model)
+    return model, ell
+
+
+def train_gp_(gp: LeafGP, *, optim=None, iterations: int = 10_000, lam: float = 0.1, rng=None):
+    """train!(gp; iterations, optim, λ) optimisers.jl:89-145 (single exact GP, rolls back on NaN)."""
+    optim = RMSProp() if optim is None else optim
+    rng = np.random.default_rng() if rng is None else (np.random.default_rng(rng) if isinstance(rng, int) else rng)
+    model = gp.model
+    n = model.nparams
+    hyp = rng.standard_normal(n)
+    oldhyp = hyp
+    ell = np.zeros(iterations)
+    for it in range(iterations):
+        lml, grad = model.handle.eval(hyp)
+        ell[it] = lml
+        if np.isnan(lml):                                                   # :115-119
+            gp.setparams_(oldhyp); update_cholesky_(gp)
+            return gp, ell[:it + 1]
+        delta = abs(ell[it] - np.mean(ell[it - 9:it])) if it >= 10 else np.inf
+        if delta < lam:                                                     # :125-128
+            model._mirror_params(hyp)
+            return gp, ell[:it + 1]
+        oldhyp = hyp.copy()
+        optim.apply_(hyp, grad)
+        hyp = hyp + grad
+    gp.setparams_(hyp); update_cholesky_(gp)
+    return gp, ell
+
+
+def finetune_(model: Model, optim=None, *, iterations: int = 1000, lam: float = 0.5):
+    """finetune!(model, optim; iterations, λ) finetuning.jl:3-88: per-leaf hyper-parameters.  For every leaf g the
+    WHOLE model is evaluated under θ_g and the leaf gradients are weighted by the overlap row D[g,:]
+    (optimize.jl:92-102; the diagonal of D is 0, so a leaf's own gradient has weight 0).
+    Kernel mixtures raise, as in the reference (App. B Q10)."""
+    optim = ADAM() if optim is None else optim
+    if len(model.kernels) != 1:
+        raise IndexError("finetune! with a kernel vector is a BoundsError in the reference (finetuning.jl:41)")
+    L = len(model.leaves)
+    D = model.D
+    hyp = [model.handle.get_leaf_params(g).copy() for g in range(L)]         # :24
+    ell = np.zeros(iterations)
+    c = 0
+    node_of_leaf = [lf.id for lf in model.leaves]
+    for it in range(iterations):
+        l = 0.0
+        for g in range(L):
+            lml, grad, nodes = model.handle.eval(hyp[g], leaf_scale=D[g, :], want_nodes=True)   # :41-54
+            l += nodes[node_of_leaf[g]]                                      # :51
+            optim.apply_(hyp[g], grad)
+            hyp[g] = hyp[g] + grad
+        ell[it] = l
+        delta = abs(ell[it] - np.mean(ell[it - 9:it])) if it >= 10 else np.inf
+        c = c + 1 if delta < lam else 0
+        if c >= 10:
+            break
+    for g in range(L):                                                       # :75-84
+        model.handle.set_leaf_params(g, hyp[g])
+    fit_(model)
+    return model, ell

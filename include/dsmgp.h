@@ -1,0 +1,199 @@
+/* libdsmgp.so -- C ABI of the B200-native (sm_100a) DSMGP per-expert GP hot path.
+ *
+ * The reference (trappmartin/DeepStructuredMixtures, Julia) has no FFI/plugin layer: its hot
+ * path is ordinary Julia methods calling LAPACK/BLAS.  This header is therefore the boundary a
+ * maintainer binds with `ccall`; every entry point names the reference
+ * method(s) whose body it replaces (file:line under /root/reference/src).
+ *
+ * Rules
+ *   - plain C, `extern "C"`, no C++/torch types; every pointer is a HOST pointer unless the
+ *     name ends in `_dev`;  all matrices are column-major FP64 (Julia layout);  indices that
+ *     come from Julia (`leaf_obs`) are Int64 1-based, everything else is 0-based.
+ *   - the caller owns every buffer; the library copies inputs at `dsmgp_create` and keeps no
+ *     host pointer.  All calls are synchronous on return.  A handle is not thread-safe.
+ *   - every function returns a status (0 = ok); `dsmgp_last_error` gives the message.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     DSMGP_ERR_CUDA.  The pure host helpers (tree passes, sharding) are marked HOST-ONLY.
+ *
+ * Hyper-parameter layout (gaussianprocess.jl:153-161, optimize.jl:188-198): per kernel
+ *   theta_k = [ logl (1 for Iso*, D for Ard*) , log sigma , logNoise ]   (nparams = len(logl)+2)
+ * and for a kernel mixture `KernelFunction[...]` the concatenation over kernels.  The gradient
+ * uses the same layout (gaussianprocess.jl:206-217).  Linear kernels ignore the log sigma slot
+ * (kernels.jl:181-183,201) and report 0 gradient there.
+ */
+#ifndef DSMGP_H
+#define DSMGP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DSMGP_VERSION 100
+
+typedef struct dsmgp_handle dsmgp_handle;
+
+enum { DSMGP_OK = 0, DSMGP_ERR_ARG = 1, DSMGP_ERR_CUDA = 2, DSMGP_ERR_COMM = 3, DSMGP_ERR_OOM = 4,
+       DSMGP_ERR_NOT_PD = 5, DSMGP_ERR_STATE = 6 };
+
+/* kernels.jl:59-64 (IsoSE), :109-114 (ArdSE), :174-177 (IsoLinear), :209-212 (ArdLinear) */
+enum { DSMGP_ISO_SE = 0, DSMGP_ARD_SE = 1, DSMGP_ISO_LINEAR = 2, DSMGP_ARD_LINEAR = 3 };
+
+typedef struct {
+  int32_t type;      /* DSMGP_ISO_SE ... */
+  int32_t nparams;   /* len(logl) + 2  (gaussianprocess.jl:139-145) */
+} dsmgp_kernel_desc;
+
+/* node types: GPNode (DeepStructuredMixtures.jl:61-71), GPSplitNode (:52-59), GPSumNode{T,SPNNode}
+ * (:40-45) and the kernel-mixture GPSumNode{T,GPNode} built by _buildGP (treeStructure.jl:258-286) */
+enum { DSMGP_NODE_LEAF = 0, DSMGP_NODE_SPLIT = 1, DSMGP_NODE_SUM = 2, DSMGP_NODE_KSUM = 3 };
+
+/* Flattened region graph.  Nodes are numbered so that children precede parents. */
+typedef struct {
+  int64_t n_nodes;
+  const int32_t* node_type;    /* [n_nodes] */
+  const int64_t* child_ptr;    /* [n_nodes+1] CSR into child_idx, reference child order */
+  const int64_t* child_idx;
+  const int64_t* leaf_of_node; /* [n_nodes] leaf number (getLeaves / gpmap order, fit.jl:9-10) or -1 */
+  const int32_t* split_dim;    /* [n_nodes] 0-based split dimension of a split node, else -1 */
+  const int64_t* split_ptr;    /* [n_nodes+1] CSR into split_val */
+  const double*  split_val;    /* thresholds s_1..s_K of GPSplitNode.split; the last one is upperBound[d] */
+  int64_t root;
+} dsmgp_tree;
+
+enum { DSMGP_GRAD_AS_WRITTEN = 1, DSMGP_GRAD_MATHEMATICAL = 0 };
+
+typedef struct {
+  int32_t as_written_grads; /* 1 (default): gradients exactly as kernels.jl:85-99,146-164,196-200 compute them
+                               (extra exp(log sigma) factor, ArdSE length-scale gradient == 0);  0: true dLML/dtheta */
+  int32_t keep_factors;     /* 1: keep every leaf's Cholesky factor resident after fit (needed by predict and the
+                               per-leaf accessors); 0: stream (factor -> reduce -> discard), for models whose
+                               factors exceed HBM (cfg5) */
+  int32_t rank, world;      /* leaf sharding for one-process-per-GPU runs; (0,1) = everything local */
+  int32_t device;           /* CUDA device ordinal, -1 = current */
+  int32_t strict_pd;        /* 1: a non-positive pivot makes fit/eval return DSMGP_ERR_NOT_PD */
+  int64_t arena_bytes;      /* cap for the factor arena; 0 = choose from free HBM */
+  int32_t reserved[8];
+} dsmgp_opts;
+
+void dsmgp_default_opts(dsmgp_opts* o);
+
+/* ---- lifetime -------------------------------------------------------------------------------
+ * Replaces the per-leaf state built by GaussianProcess(x, y; ...) gaussianprocess.jl:50-80 for every
+ * leaf of buildTree (treeStructure.jl:245-307): x is the GLOBAL N x D input matrix, `leaf_obs` the
+ * ascending 1-based rows of each leaf (GPNode.obs), `y_centered` the leaves' mean-subtracted targets
+ * concatenated in leaf order (apply_subtract!, means.jl:11-14), `leaf_mean` the ConstMean value m.
+ * The distance tensor P (gaussianprocess.jl:57) is never materialised. */
+int32_t dsmgp_create(const double* x, int64_t N, int64_t D,
+                     int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
+                     const double* y_centered, const double* leaf_mean,
+                     const int32_t* leaf_kernel_id,
+                     const dsmgp_kernel_desc* kernels, int32_t n_kernels,
+                     const dsmgp_tree* tree, const dsmgp_opts* opts,
+                     dsmgp_handle** out);
+void dsmgp_destroy(dsmgp_handle* h);
+const char* dsmgp_last_error(const dsmgp_handle* h); /* h may be NULL: last create error */
+
+/* ---- parameters ----------------------------------------------------------------------------
+ * setparams!(spn, hyp) optimize.jl:188-198 -> setparams!(gp, hyper) gaussianprocess.jl:153-161:
+ * ONE global theta (sum of nparams over the kernels) broadcast to every leaf of the matching kernel id. */
+int32_t dsmgp_set_params(dsmgp_handle* h, const double* theta, int64_t n);
+/* per-leaf theta (finetune! ends with setparams!(gp.dist, hyp[gp.id]), finetuning.jl:75-84) */
+int32_t dsmgp_set_leaf_params(dsmgp_handle* h, int64_t leaf, const double* theta, int64_t n);
+int32_t dsmgp_get_leaf_params(const dsmgp_handle* h, int64_t leaf, double* theta, int64_t n);
+int64_t dsmgp_nparams(const dsmgp_handle* h);        /* n in train!, optimisers.jl:15-17 */
+int64_t dsmgp_n_leaves(const dsmgp_handle* h);
+int64_t dsmgp_n_nodes(const dsmgp_handle* h);
+int64_t dsmgp_leaf_size(const dsmgp_handle* h, int64_t leaf);
+
+/* ---- fit -----------------------------------------------------------------------------------
+ * fit!(spn, D, gpmap; tau) fit.jl:71-122 / fit_naive! :294-304 -> update_cholesky! gaussianprocess.jl:82-108
+ * for every (local) leaf:  F = K + (exp(2 logNoise) + 1e-8) I ; L = potrf('L', F) ; alpha = L' \ (L \ y).
+ * `info[L]` (may be NULL): LAPACK potrf convention per leaf (0 ok, k>0 first non-positive pivot, 1-based;
+ * chol_continue! returns the same, AdvancedCholeskey.jl:171-173).  `seconds` (may be NULL): device time of
+ * the call, the value fit! returns (fit.jl:88,121). */
+int32_t dsmgp_fit(dsmgp_handle* h, int32_t* info, double* seconds);
+
+/* mll!(spn, L) optimize.jl:27-39 (leaf: mll(gp) gaussianprocess.jl:163): fills the per-node table
+ * (AxisArray keyed by node id -> node_lml[n_nodes]); returns the root value in node_lml[root]. */
+int32_t dsmgp_lml(dsmgp_handle* h, double* node_lml);
+
+/* updategradients!(spn) fit.jl:306-311 (per leaf: gaussianprocess.jl:165-178, 219-226 and the kernel's
+ * updategradients! kernels.jl:85-99,146-164,196-200) followed by the down-pass
+ * nabla-mll!(spn, 0, 0, L, L[root], grad) optimize.jl:42-89.  `leaf_scale` = NULL, or the row D[g,:]
+ * of the overlap matrix for the finetune variant optimize.jl:92-150.  grad[dsmgp_nparams] is OVERWRITTEN
+ * (the reference zero-fills it first, optimisers.jl:76). */
+int32_t dsmgp_grad(dsmgp_handle* h, const double* leaf_scale, double* grad);
+
+/* One LML+gradient evaluation = optimisers.jl:43-77 minus the Flux step:
+ * setparams! -> fit! -> mll! -> updategradients! -> nabla-mll!.  The benchmarked call.
+ * theta may be NULL (keep current parameters); node_lml may be NULL. */
+int32_t dsmgp_eval(dsmgp_handle* h, const double* theta, int64_t n, const double* leaf_scale,
+                   double* lml, double* grad, double* node_lml);
+
+/* Per-leaf rows of the last eval: rows[l*(1+Hmax) + 0] = mll(gp_l), [1..] = nabla-mll(gp_l)
+ * (gaussianprocess.jl:185-217).  Hmax = max nparams over kernels.  Also the multi-GPU exchange unit:
+ * a rank fills only its own leaves, rows of other ranks are 0, so a SUM all-reduce assembles them. */
+int64_t dsmgp_row_width(const dsmgp_handle* h);
+int32_t dsmgp_eval_local_dev(dsmgp_handle* h, const double* theta, int64_t n, double** rows_dev);
+int32_t dsmgp_eval_finish_dev(dsmgp_handle* h, const double* leaf_scale, double* lml, double* grad, double* node_lml);
+int32_t dsmgp_leaf_rows(const dsmgp_handle* h, double* rows);
+int32_t dsmgp_leaf_owner(const dsmgp_handle* h, int32_t* owner); /* rank owning each leaf (LPT on n^3) */
+
+/* ---- posterior weights and prediction --------------------------------------------------------
+ * update!(spn) common.jl:323-334: sum_logweights receives, for every sum node in node order, its
+ * normalised child log-weights (CSR by child_ptr; pass NULL to skip), *z the root evidence. */
+int32_t dsmgp_update_weights(dsmgp_handle* h, double* sum_logweights, double* z);
+
+enum { DSMGP_PREDICT_DSMGP = 0, DSMGP_PREDICT_POE = 1, DSMGP_PREDICT_GPOE = 2, DSMGP_PREDICT_RBCM = 3 };
+/* predict(model, x) common.jl:294-307 -> prediction(gp, xtest) gaussianprocess.jl:110-137.
+ * xtest is T x D column-major.  Requires keep_factors and a preceding fit/eval (+ update_weights for
+ * the DSMGP mode, like the reference). */
+int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var);
+
+/* prediction(gp, xtest) of ONE leaf: mu[T] and diag(Sigma)[T] (gaussianprocess.jl:110-137) */
+int32_t dsmgp_leaf_predict(dsmgp_handle* h, int64_t leaf, const double* xtest, int64_t T, double* mu, double* var);
+
+/* ---- per-leaf accessors (gp.alpha, gp.cK.factors stay readable from Julia) -------------------- */
+int32_t dsmgp_leaf_alpha(const dsmgp_handle* h, int64_t leaf, double* alpha /* n */);
+int32_t dsmgp_leaf_factor(const dsmgp_handle* h, int64_t leaf, double* Lfac /* n x n col-major, lower; upper = 0 */);
+int32_t dsmgp_leaf_info(const dsmgp_handle* h, int32_t* info /* L */);
+
+/* ---- stand-alone operators ------------------------------------------------------------------
+ * kernelmatrix(kernel, x1, x2) kernels.jl:15-18.  theta = [logl..., log sigma] (noise not used).
+ * x1: n1 x D, x2: n2 x D, K: n1 x n2, all column-major. */
+int32_t dsmgp_kernelmatrix(int32_t kernel_type, const double* theta, int64_t D,
+                           const double* x1, int64_t n1, const double* x2, int64_t n2, double* K);
+/* AdvancedCholesky.chol_continue!(A, ki) AdvancedCholeskey.jl:152-174 (ki 1-based): A n x n column-major in/out. */
+int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t* info);
+/* Row/column deletion from a lower Cholesky factor: the operation fit.jl:179-195 composes from
+ * lowrankupdate! (AdvancedCholeskey.jl:20-59), implemented CORRECTLY.
+ * A: n x n in, (n-nrows) x (n-nrows) factor written to `out` (column-major, ld = n-nrows). rows 1-based ascending. */
+int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, int64_t nrows, double* out);
+/* plain batched-size-1 potrf('L') on a host matrix (LAPACK.potrf! as used at gaussianprocess.jl:101) */
+int32_t dsmgp_potrf(double* A, int64_t n, int32_t* info);
+
+/* ---- HOST-ONLY helpers (no GPU needed; used by the multi-process plumbing and its CPU tests) ---
+ * Tree passes over a table of per-leaf rows (layout of dsmgp_leaf_rows): up-pass mll! optimize.jl:27-39,
+ * down-pass nabla-mll! :42-150, update! common.jl:323-334. */
+int32_t dsmgp_host_tree_eval(const dsmgp_tree* tree, int64_t L, const int32_t* leaf_kernel_id,
+                             const dsmgp_kernel_desc* kernels, int32_t n_kernels,
+                             const double* rows, int64_t row_width, const double* leaf_scale,
+                             double* node_lml, double* grad, double* sum_logweights, double* z);
+/* LPT bin packing of leaves by n^3 onto `world` ranks (deterministic). */
+int32_t dsmgp_host_shard(int64_t L, const int64_t* leaf_ptr, int32_t world, int32_t* owner);
+
+/* ---- instrumentation ------------------------------------------------------------------------ */
+typedef struct {
+  double gram_ms, potrf_ms, solve_ms, inverse_ms, grad_ms, tree_ms, total_ms;
+  double potrf_flops, inverse_flops, gram_bytes;   /* algorithmic work of the last eval (local leaves) */
+  int64_t launches;                                 /* kernels launched by the last call */
+} dsmgp_timings;
+int32_t dsmgp_get_timings(const dsmgp_handle* h, dsmgp_timings* t);
+int32_t dsmgp_set_profiling(dsmgp_handle* h, int32_t on); /* per-phase CUDA events (adds syncs) */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DSMGP_H */

