@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- LML+gradient evaluations/sec of a DSMGP on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg3|cfg3b|cfg2|cfg4|cfg5] [--impl reference]
+
+A "step" is ONE LML+gradient evaluation of the whole model = optimisers.jl:43-77 of the reference without the
+Flux step (setparams! -> fit! -> mll! -> updategradients! -> nabla-mll!) = one `dsmgp_eval`.
+
+* value    device time (CUDA events on the library's stream, max over ranks), inputs resident in HBM.
+* e2e      the same evaluation through the public API (`handle.eval(theta)`): host theta in, host (lml, grad) out,
+           wall clock including the per-step host->device parameter upload, the device->host read of the per-leaf
+           rows and the host tree passes.
+* N > 1    the SAME model, leaves sharded over the ranks by LPT on n^3 (strong scaling); one NCCL all-reduce (SUM) of
+           the L x (1+H) per-leaf row table per evaluation, then every rank finishes the O(L) tree passes.
+* roofline FP64: the dominant kernel's algorithmic flops / its CUDA-event time, against the FP64 DGEMM rate measured
+           on this pool's B200 (tools/fp64_peaks.cu; MEASURED_PEAKS.json has no FP64 entry).
+* --impl reference   the reference's CPU path: Julia is not installed, so the oracle port in the reference's
+           algorithmic shape (oracle/reference_shape.py), all host threads, on a bounded sample of leaves.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# FP64 roofs measured on this pool's B200 with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json)
+FP64_DGEMM_TFLOPS = 35.9     # cuBLAS DGEMM 8192^3 (burst == sustained: FP64 is not power capped)
+FP64_DMMA_TFLOPS = 37.2      # DMMA.8x8x4 issue roof
+
+WORKLOADS = {
+    # name: (N, D, kernel, V, K, M, depth, eps, seed)   SURVEY §8(d)
+    "cfg1": dict(N=100, D=1, kernel="isose", V=3, K=4, M=10, depth=2, eps=0.5, seed=1),
+    "cfg2": dict(N=10_000, D=1, kernel="isose", V=3, K=4, M=100, depth=2, eps=0.5, seed=2),
+    "cfg3": dict(N=40_000, D=8, kernel="ardse", V=3, K=4, M=500, depth=2, eps=0.5, seed=3),
+    "cfg3b": dict(N=40_000, D=8, kernel="ardse", V=3, K=4, M=500, depth=2, eps=0.0, seed=3),
+    "cfg4": dict(N=45_730, D=9, kernel="isose+isolinear", V=4, K=4, M=1000, depth=2, eps=0.5, seed=4),
+    "cfg5": dict(N=1_000_000, D=8, kernel="ardse", V=3, K=4, M=2000, depth=4, eps=0.1, seed=5),
+}
+
+
+def make_data(w):
+    rng = np.random.default_rng(w["seed"])
+    x = rng.random((w["N"], w["D"]))
+    if w["D"] == 1:
+        x = np.sort(x, axis=0)
+    wv = rng.standard_normal(w["D"])
+    y = np.sin(2 * np.pi * (x @ wv)) + 0.1 * rng.standard_normal(w["N"])
+    return x, y
+
+
+def thetas(nparams_per_kernel, seed):
+    rng = np.random.default_rng(1000 + seed)
+    base = []
+    for npk in nparams_per_kernel:
+        base.extend([0.0] * (npk - 2) + [0.0, -1.0])
+    base = np.array(base)
+    return [base] + [base + 0.3 * rng.standard_normal(base.size) * (np.arange(base.size) >= 0) for _ in range(3)]
+
+
+def sample_clocks(stop, out):
+    q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    dev = os.environ.get("LOCAL_RANK", "0")
+    while not stop.is_set():
+        try:
+            r = subprocess.run(["nvidia-smi", "-i", dev, f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                               capture_output=True, text=True, timeout=5)
+            out.append([s.strip() for s in r.stdout.strip().split(",")])
+        except Exception:
+            pass
+        stop.wait(0.2)
+
+
+def clocks_summary(samples):
+    sm = [float(s[0]) for s in samples if len(s) >= 6 and s[0].replace(".", "").isdigit()]
+    mx = [float(s[1]) for s in samples if len(s) >= 6 and s[1].replace(".", "").isdigit()]
+    reasons = set()
+    for s in samples:
+        if len(s) >= 6:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+    return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+            "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class _DevPtr:
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+
+def oracle_kernel(w):
+    from oracle import dsm_oracle as orc
+    if w["kernel"] == "isose":
+        return [orc.IsoSE(0.0, 0.0)]
+    if w["kernel"] == "ardse":
+        return [orc.ArdSE(np.zeros(w["D"]), 0.0)]
+    return [orc.IsoSE(0.0, 0.0), orc.IsoLinear(0.0)]
+
+
+def build_structure(w):
+    """Region graph on the host (no GPU): returns x, y, root, kernels (product types)."""
+    from deepstructuredmixtures_b200 import kernels as kr, structure as st
+    x, y = make_data(w)
+    if w["kernel"] == "isose":
+        kern = kr.IsoSE(0.0, 0.0)
+    elif w["kernel"] == "ardse":
+        kern = kr.ArdSE(np.zeros(w["D"]), 0.0)
+    else:
+        kern = [kr.IsoSE(0.0, 0.0), kr.IsoLinear(0.0)]
+    cfg = st.DSMGPConfig(None, kern, -1.0, w["M"], w["K"], w["V"], w["depth"], w["eps"], True)
+    root = st.buildTree(x, y, cfg, np.random.default_rng(w["seed"]))
+    return x, y, root, kern
+
+
+def cpu_baseline(w, x, y, root, budget_s, optimised=False, threads=None):
+    from deepstructuredmixtures_b200 import structure as st
+    from oracle import reference_shape as rs
+    leaves = st.getLeaves(root)
+    ok = oracle_kernel(w)
+    # mixtures: time the first kernel's leaves and the second's separately through their own kernel objects
+    res_total = 0.0
+    used = []
+    for kid, k in enumerate(ok):
+        lv = [lf for lf in leaves if lf.kernelid - 1 == kid]
+        r = rs.sample_model_time(x, y, [lf.obs - 1 for lf in lv], [lf.mean for lf in lv], k, -1.0,
+                                 budget_s=budget_s / len(ok), optimised=optimised)
+        res_total += r["seconds_per_eval"]; used.extend(r["sample_sizes"])
+    return {"value": 1.0 / res_total, "unit": "evals/s", "cores": threads or os.cpu_count(),
+            "kind": "port",
+            "sample": f"oracle port in the reference's algorithmic shape (2x update_cholesky!, potrs(-I)+GEMM traces, "
+                      f"gradients twice; SciPy/OpenBLAS) on leaves of size {used}, extrapolated by sum n^3 to all "
+                      f"{len(leaves)} leaves; seconds/eval={res_total:.1f}"}
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    x, y, root, _ = build_structure(w)
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        vals.append(cpu_baseline(w, x, y, root, budget_s=max(10.0, 60.0 / max(1, min(args.steps, 3)))))
+    best = max(vals, key=lambda r: r["value"])
+    v = float(np.mean([r["value"] for r in vals]))
+    line = {"impl": "reference", "metric": "DSMGP LML+gradient evals/sec", "value": v, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.workload, w),
+            "cpu_baseline": dict(best, value=v),
+            "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "Julia is not installed in this image: the reference arm is the oracle port timed in the "
+                    "reference's algorithmic shape on the host cores"}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, w):
+    return {"workload": f"{name}: synthetic {w['N']}x{w['D']} {w['kernel']} DSMGP V={w['V']} K={w['K']} M={w['M']} "
+                        f"depth={w['depth']} eps={w['eps']} (SURVEY 8d)",
+            "l2": "factor arena (GBs) >> 126 MB L2, no flush needed", "theta": "4 fixed hyper-parameter vectors cycled"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mathematical", action="store_true", help="true gradients instead of as-written")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, w)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libdsmgp has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import model as mdl
+
+    t_build0 = time.perf_counter()
+    x, y, root, kern = build_structure(w)
+    klist = kern if isinstance(kern, list) else [kern]
+    t_tree = time.perf_counter() - t_build0
+    keep = args.workload != "cfg5"
+    t0 = time.perf_counter()
+    model = mdl.DSMGP(root, x, y, [k.copy() for k in klist], -1.0, rank=rank, world=world, device=local,
+                      keep_factors=keep, as_written_grads=not args.mathematical)
+    t_create = time.perf_counter() - t0
+    H = model.handle
+    ths = thetas([k.nparams for k in klist], w["seed"])
+    L = len(model.leaves)
+    sizes = np.array([lf.nobs for lf in model.leaves], dtype=np.float64)
+
+    def step_device(i):
+        """device-resident inputs; returns device ms of this rank"""
+        if world == 1:
+            H.eval(ths[i % len(ths)])
+        else:
+            ptr = H.eval_local_dev(ths[i % len(ths)])
+            rows = torch.as_tensor(_DevPtr(ptr, (L * H.row_width,)), device=f"cuda:{local}")
+            dist.all_reduce(rows)
+            torch.cuda.synchronize()
+            H.eval_finish_dev()
+        return H.timings()
+
+    for i in range(args.warmup):
+        step_device(i)
+    samples, stop = [], threading.Event()
+    th = threading.Thread(target=sample_clocks, args=(stop, samples), daemon=True)
+    th.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    phase = {k: 0.0 for k in ("gram_ms", "potrf_ms", "solve_ms", "inverse_ms", "grad_ms", "total_ms")}
+    launches = 0
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        tm = step_device(args.warmup + i)
+        for k in phase:
+            phase[k] += tm[k]
+        launches += int(tm["launches"])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall = time.perf_counter() - t_wall0
+    stop.set(); th.join(timeout=2)
+    dev_ms = phase["total_ms"]
+    # e2e through the public API on host buffers (world == 1: the same call; world > 1: the wall clock above)
+    tt = torch.tensor([dev_ms, t_wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(tt[0]), float(tt[1])
+    if rank == 0:
+        value = args.steps / (dev_ms * 1e-3)
+        e2e = args.steps / (wall_ms * 1e-3)
+        potrf_fl, inv_fl = tm["potrf_flops"], tm["inverse_flops"]
+        potrf_tf = potrf_fl * args.steps / (phase["potrf_ms"] * 1e-3) * 1e-12 if phase["potrf_ms"] > 0 else 0.0
+        inv_tf = inv_fl * args.steps / (phase["inverse_ms"] * 1e-3) * 1e-12 if phase["inverse_ms"] > 0 else 0.0
+        gram_gbs = tm["gram_bytes"] * args.steps / (phase["gram_ms"] * 1e-3) * 1e-9 if phase["gram_ms"] > 0 else 0.0
+        dom = "trtri_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf_panel_kernel+potrf_diag_kernel"
+        ach = inv_tf if dom == "trtri_kernel" else potrf_tf
+        ns_local = int(np.sum(H.leaf_owner() == 0))
+        line = {
+            "metric": "DSMGP LML+gradient evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args.workload, w), leaves=L, n_min=int(sizes.min()),
+                           n_median=int(np.median(sizes)), n_max=int(sizes.max()), sum_n3=float(np.sum(sizes ** 3)),
+                           grads="mathematical" if args.mathematical else "as-written", parallelism=f"leaf-shard x{world}"),
+            "e2e": {"value": e2e, "unit": "evals/s",
+                    "h2d_bytes_per_step": int(ns_local * (4 + w["D"]) * 8),
+                    "d2h_bytes_per_step": int(L * H.row_width * 8 + ns_local * 48)},
+            "gpu_launches": launches,
+            "cholesky_gflops": potrf_tf * 1e3,
+            "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
+                         "frac": ach / FP64_DGEMM_TFLOPS, "traffic": None,
+                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (tools/fp64_peaks.cu, profiles/); "
+                                        "MEASURED_PEAKS.json has no FP64 entry; DMMA issue roof 37.2",
+                         "potrf_tflops": potrf_tf, "inverse_tflops": inv_tf, "gram_gbs": gram_gbs,
+                         "gram_frac_hbm": gram_gbs / 6458.4},
+            "clocks": clocks_summary(samples),
+            "host": {"tree_build_s": t_tree, "create_upload_s": t_create},
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line["cpu_baseline"] = cpu_baseline(w, x, y, root, args.cpu_budget)
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -78,7 +78,7 @@ struct dsmgp_handle {
   bool fitted = false, have_rows = false, have_grad = false, rows_complete = false;
   int device = 0;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev[8] = {};
+  std::vector<cudaEvent_t> ev;     // 8 per batch: phase boundaries, always recorded (no extra syncs)
   bool profiling = false;
   dsmgp_timings tm = {};
   // device
@@ -410,9 +410,10 @@ extern "C" int32_t dsmgp_create(const double* x, int64_t N, int64_t D, int64_t L
   }
   if ((ce = engine_attrs()) != cudaSuccess) { delete h; return fail(DSMGP_ERR_CUDA, cudaGetErrorString(ce)); }
   cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
-  for (auto& e : h->ev) cudaEventCreate(&e);
   int32_t rc = plan_and_alloc(h, x, leaf_obs, y_centered);
   if (rc != DSMGP_OK) { g_create_error = h->err; delete h; return rc; }
+  h->ev.assign(8 * std::max<size_t>(h->batches.size(), 1), nullptr);
+  for (auto& e : h->ev) cudaEventCreate(&e);
   *out = h;
   return DSMGP_OK;
 }
@@ -478,19 +479,24 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
   const int sms = num_sms(h->device);
   const bool lau = with_grad && needs_lauum(h);
   h->tm = dsmgp_timings{};
-  const bool prof = h->profiling;
-  CUDA_TRY(h, cudaEventRecord(h->ev[0], st));
-  for (auto& b : h->batches) {
+  if (h->batches.empty()) {   // a rank that owns no leaf
+    h->fitted = true; h->have_rows = true; h->have_grad = with_grad; h->rows_complete = (h->opts.world == 1);
+    return DSMGP_OK;
+  }
+  for (size_t bi = 0; bi < h->batches.size(); bi++) {
+    Batch& b = h->batches[bi];
+    cudaEvent_t* ev = h->ev.data() + 8 * bi;
     const int nsl = b.s1 - b.s0;
-    if (nsl == 0) continue;
+    CUDA_TRY(h, cudaEventRecord(ev[0], st));
+    if (nsl == 0) { for (int k = 1; k < 8; k++) cudaEventRecord(ev[k], st); continue; }
     const LeafMeta* meta = h->d_meta.p + b.s0;
     LeafScal* scal = h->d_scal.p + b.s0;
     CUDA_TRY(h, cudaMemsetAsync(scal, 0, nsl * sizeof(LeafScal), st));
-    if (prof) cudaEventRecord(h->ev[1], st);
+    cudaEventRecord(ev[1], st);
     GramArgs ga{meta, h->d_xg.p, h->d_prm.p, h->d_F.p, b.d_tile_off, nsl, (int)h->D};
     launch_gram_fit(ga, b.ntiles, st);
     h->tm.launches++;
-    if (prof) cudaEventRecord(h->ev[2], st);
+    cudaEventRecord(ev[2], st);
     CholArgs ca{meta, h->d_F.p, h->d_W.p, h->d_WT.p, scal, h->d_trpart.p, b.d_trpart_off, 0, 0};
     for (int J = 0; J < b.max_nb; J++) {
       ca.step = J;
@@ -501,48 +507,47 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
         h->tm.launches++;
       }
     }
-    if (prof) cudaEventRecord(h->ev[3], st);
+    cudaEventRecord(ev[3], st);
     SolveArgs sa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, scal};
     launch_solve(sa, nsl, st);
     h->tm.launches++;
-    if (prof) cudaEventRecord(h->ev[4], st);
+    cudaEventRecord(ev[4], st);
     if (with_grad) {
       CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
       TrtriArgs ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_trpart.p, b.d_trpart_off, b.d_trtri_tasks, b.n_trtri, h->d_counter.p};
       launch_trtri(ta, std::min(sms, b.n_trtri), st);
       h->tm.launches++;
-      if (prof) cudaEventRecord(h->ev[5], st);
-      if (lau) {
-        LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
-                     h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D};
-        launch_lauum(la, std::min(sms, b.n_lauum), st);
-        h->tm.launches++;
-      }
-    } else if (prof) cudaEventRecord(h->ev[5], st);
-    if (prof) cudaEventRecord(h->ev[6], st);
+    }
+    cudaEventRecord(ev[5], st);
+    if (lau) {
+      LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
+                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D};
+      launch_lauum(la, std::min(sms, b.n_lauum), st);
+      h->tm.launches++;
+    }
+    cudaEventRecord(ev[6], st);
     RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,
                 h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0};
     launch_rows(ra, nsl, st);
     h->tm.launches++;
     CUDA_TRY(h, cudaGetLastError());
+    cudaEventRecord(ev[7], st);
     h->tm.potrf_flops += b.potrf_flops;
     h->tm.inverse_flops += with_grad ? b.potrf_flops * (lau ? 2.0 : 1.0) : 0.0;
     h->tm.gram_bytes += b.gram_bytes;
-    if (prof) {
-      cudaEventRecord(h->ev[7], st);
-      CUDA_TRY(h, cudaEventSynchronize(h->ev[7]));
-      h->tm.gram_ms += ev_ms(h->ev[1], h->ev[2]);
-      h->tm.potrf_ms += ev_ms(h->ev[2], h->ev[3]);
-      h->tm.solve_ms += ev_ms(h->ev[3], h->ev[4]);
-      h->tm.inverse_ms += ev_ms(h->ev[4], h->ev[5]);
-      h->tm.grad_ms += ev_ms(h->ev[5], h->ev[7]);
-    }
   }
   const int ns = (int)h->slot_leaf.size();
   if (ns) CUDA_TRY(h, cudaMemcpyAsync(h->pin_scal, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(h, cudaEventRecord(h->ev[7], st));
-  CUDA_TRY(h, cudaEventSynchronize(h->ev[7]));
-  h->tm.total_ms = ev_ms(h->ev[0], h->ev[7]);
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  for (size_t bi = 0; bi < h->batches.size(); bi++) {
+    cudaEvent_t* ev = h->ev.data() + 8 * bi;
+    h->tm.gram_ms += ev_ms(ev[1], ev[2]);
+    h->tm.potrf_ms += ev_ms(ev[2], ev[3]);
+    h->tm.solve_ms += ev_ms(ev[3], ev[4]);
+    h->tm.inverse_ms += ev_ms(ev[4], ev[5]);
+    h->tm.grad_ms += ev_ms(ev[5], ev[7]);
+  }
+  h->tm.total_ms = ev_ms(h->ev[0], h->ev[8 * (h->batches.size() - 1) + 7]);
   std::fill(h->h_info.begin(), h->h_info.end(), 0);
   for (int s = 0; s < ns; s++) {
     int info = h->pin_scal[s].info;

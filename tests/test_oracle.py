@@ -1,0 +1,155 @@
+"""The oracle restatement pinned against itself: finite differences, mpmath, LAPACK identities, the reference's
+in-source self tests restated (AdvancedCholeskey.jl:61-135), and the committed golden vectors.
+(The reference ships no tests or fixtures -- SURVEY §4 -- so these are the pin.)"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg as sla
+
+from conftest import orc, synth
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+KERNELS = {
+    "isose": lambda D: orc.IsoSE(0.1, -0.2),
+    "ardse": lambda D: orc.ArdSE(np.linspace(-0.3, 0.2, D), -0.2),
+    "isolin": lambda D: orc.IsoLinear(0.2),
+    "ardlin": lambda D: orc.ArdLinear(np.linspace(-0.1, 0.2, D)),
+}
+
+
+def fd_grad(x, y, k, logn, h=1e-6):
+    th0 = np.concatenate([k.logl, [k.logs, logn]])
+
+    def f(th):
+        g = orc.GaussianProcess(x, y, kernel=k, logNoise=logn)
+        g.setparams(th)
+        return g.update_cholesky().mll()
+
+    return np.array([(f(th0 + h * e) - f(th0 - h * e)) / (2 * h) for e in np.eye(th0.size)])
+
+
+@pytest.mark.parametrize("name", list(KERNELS))
+def test_mathematical_gradient_matches_finite_differences(name):
+    x, y = synth(40, 3, 1)
+    k = KERNELS[name](3)
+    gp = orc.GaussianProcess(x, y, kernel=k, logNoise=-0.5, run_cholesky=True)
+    fd = fd_grad(x, y, k, -0.5)
+    g = gp.grad_mll(mathematical=True)
+    assert np.allclose(g, fd, rtol=2e-6, atol=2e-6)
+
+
+def test_as_written_quirks_q2_q3():
+    """Q2 extra exp(log sigma) factor on kernel gradients; Q3 ArdSE length-scale gradient == 0;
+    the noise gradient is exact."""
+    x, y = synth(40, 3, 2)
+    s = math.exp(-0.2)
+    k = KERNELS["isose"](3)
+    gp = orc.GaussianProcess(x, y, kernel=k, logNoise=-0.5, run_cholesky=True)
+    fd = fd_grad(x, y, k, -0.5)
+    g = gp.grad_mll(as_written_dense=True)
+    assert np.allclose(g[:2], s * fd[:2], rtol=2e-6) and np.isclose(g[2], fd[2], rtol=2e-6)
+    k = KERNELS["ardse"](3)
+    gp = orc.GaussianProcess(x, y, kernel=k, logNoise=-0.5, run_cholesky=True)
+    fd = fd_grad(x, y, k, -0.5)
+    g = gp.grad_mll(as_written_dense=True)
+    assert np.all(g[:3] == 0.0) and np.all(np.abs(fd[:3]) > 1e-3)
+    assert np.isclose(g[3], s * fd[3], rtol=2e-6) and np.isclose(g[4], fd[4], rtol=2e-6)
+
+
+@pytest.mark.parametrize("name", list(KERNELS))
+def test_fast_gradient_equals_dense_as_written(name):
+    x, y = synth(60, 3, 3)
+    k = KERNELS[name](3)
+    gp = orc.GaussianProcess(x, y, kernel=k, logNoise=-0.7, run_cholesky=True)
+    a = gp.grad_mll(as_written_dense=True).copy()
+    b = gp.grad_mll().copy()
+    assert np.allclose(a, b, rtol=1e-10, atol=1e-11)
+
+
+def test_ardse_is_additive_q1():
+    x, _ = synth(10, 4, 4)
+    k = orc.ArdSE(np.zeros(4), 0.3)
+    K = orc.kernelmatrix(k, x)
+    assert np.allclose(np.diag(K), 4 * math.exp(0.6))
+    ref = sum(np.exp(-0.5 * (x[:, None, d] - x[None, :, d]) ** 2) for d in range(4)) * math.exp(0.6)
+    assert np.allclose(K, ref, rtol=1e-15)
+
+
+def test_lml_against_mpmath():
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 50
+    x, y = synth(12, 2, 5)
+    k = orc.IsoSE(0.3, 0.1)
+    gp = orc.GaussianProcess(x, y, kernel=k, logNoise=-0.4, run_cholesky=True)
+    n = 12
+    F = mp.matrix(n, n)
+    l2 = mp.e ** (2 * mp.mpf(0.3)); v = mp.e ** (2 * mp.mpf(0.1)); c = mp.e ** (2 * mp.mpf(-0.4)) + mp.mpf("1e-8")
+    for i in range(n):
+        for j in range(n):
+            r2 = sum((mp.mpf(float(x[i, d])) - mp.mpf(float(x[j, d]))) ** 2 for d in range(2))
+            F[i, j] = v * mp.e ** (-r2 / (2 * l2)) + (c if i == j else 0)
+    yc = mp.matrix([mp.mpf(float(t)) for t in gp.y])
+    alpha = mp.lu_solve(F, yc)
+    lml = -((yc.T * alpha)[0] + mp.log(mp.det(F)) + n * mp.log(2 * mp.pi)) / 2
+    assert abs(float(lml) - gp.mll()) < 1e-11 * abs(float(lml))
+
+
+def test_chol_continue_restated():
+    """test_chol_continue AdvancedCholeskey.jl:121-135."""
+    rng = np.random.default_rng(6)
+    S = orc.gen_cov(100, rng)
+    A = S.copy()
+    A[:10, :10] = sla.cholesky(S[:10, :10], lower=True)
+    out, info = orc.chol_continue(A, 11)
+    assert info == 0
+    assert np.sum(np.abs(out - sla.cholesky(S, lower=True))) < 1e-10
+
+
+def test_lrtest_restated_corrected_and_as_written():
+    """lrtest AdvancedCholeskey.jl:61-110: the corrected row deletion matches a fresh factorisation; the loop as
+    written (App. B Q7) does not."""
+    rng = np.random.default_rng(7)
+    D = 60
+    S = orc.gen_cov(D, rng)
+    missing = np.sort(rng.permutation(D - 1)[:5])
+    keep = np.setdiff1d(np.arange(D), missing)
+    Lf = sla.cholesky(S, lower=True)
+    ref = sla.cholesky(S[np.ix_(keep, keep)], lower=True)
+    good = orc.chol_delete_rows(Lf, missing.tolist())
+    assert np.sum(np.abs(good - ref)) < 1e-11
+    CC = Lf.copy()
+    for r in missing:       # 0-based r -> reference call lowrankupdate!(CC, view(CC, r+1:D, r), r+1) with 1-based r
+        CC = orc.lowrankupdate_as_written(CC, CC[r + 1:, r].copy(), r + 2)
+    bad = np.tril(CC)[np.ix_(keep, keep)]
+    assert np.sum(np.abs(bad - ref)) > 1e-3
+
+
+def test_prediction_matches_direct_formula():
+    x, y = synth(50, 2, 8)
+    k = orc.ArdSE([0.1, -0.1], 0.2)
+    gp = orc.GaussianProcess(x, y, kernel=k, logNoise=-0.6, run_cholesky=True)
+    xt = np.random.default_rng(1).random((7, 2))
+    mu, s2 = gp.prediction(xt)
+    mu2, S = gp.prediction(xt, full_cov=True)
+    F = orc.kernelmatrix(k, x) + (gp.noise() + 1e-8) * np.eye(50)
+    Knt = orc.kernelmatrix(k, x, xt)
+    assert np.allclose(mu, gp.mean + Knt.T @ np.linalg.solve(F, gp.y), rtol=1e-10)
+    assert np.allclose(s2, np.diag(S), rtol=1e-12)
+    assert np.allclose(np.diag(S), np.diag(orc.kernelmatrix(k, xt) - Knt.T @ np.linalg.solve(F, Knt)) + gp.noise(), rtol=1e-9)
+
+
+def test_golden_vectors():
+    """Committed outputs of the oracle (tests/golden/make_golden.py) guard against silent drift of the checker."""
+    from golden.make_golden import CASES, run_case
+    with open(os.path.join(GOLD, "golden.json")) as f:
+        gold = json.load(f)
+    for name in CASES:
+        out = run_case(name)
+        g = gold[name]
+        assert abs(out["lml"] - g["lml"]) <= 1e-11 * abs(g["lml"]), name
+        assert np.allclose(out["grad"], g["grad"], rtol=1e-9, atol=1e-9), name
+        assert np.allclose(out["mu"], g["mu"], rtol=1e-10) and np.allclose(out["var"], g["var"], rtol=1e-9), name
