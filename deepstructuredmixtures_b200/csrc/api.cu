@@ -8,6 +8,7 @@
 
 #include "../../include/dsmgp.h"
 #include "args.h"
+#include "potrf2_args.h"
 #include "tree_host.h"
 
 using namespace dsm;
@@ -34,6 +35,8 @@ struct Batch {
   int64_t* d_gpart_off = nullptr;
   int2* d_trtri_tasks = nullptr; int n_trtri = 0;
   int4* d_lauum_tasks = nullptr; int n_lauum = 0;
+  int4* d_potrf2_tasks = nullptr; int n_potrf2 = 0;     // engine v2: tile tasks in look-ahead order
+  int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
 };
 
@@ -86,6 +89,8 @@ struct dsmgp_handle {
   DevBuf<double> d_xg, d_y, d_z, d_alpha, d_F, d_W, d_WT, d_prm, d_trpart, d_gpart, d_rows, d_leaf_mean;
   DevBuf<LeafScal> d_scal;
   DevBuf<int> d_counter;
+  DevBuf<int> d_flags;
+  DevBuf<double> d_ldpart, d_zzpart;
   double* pin_rows = nullptr;
   LeafScal* pin_scal = nullptr;
   std::string err;
@@ -93,9 +98,10 @@ struct dsmgp_handle {
   ~dsmgp_handle() {
     for (auto& b : batches) {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
-      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks);
+      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_flag_off);
     }
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
+    d_flags.free(); d_ldpart.free(); d_zzpart.free();
     d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
     if (pin_rows) cudaFreeHost(pin_rows);
     if (pin_scal) cudaFreeHost(pin_scal);
@@ -111,10 +117,9 @@ static bool g_attr_done = false;
 static cudaError_t engine_attrs() {
   if (g_attr_done) return cudaSuccess;
   cudaError_t e;
-  if ((e = init_potrf_kernels())) return e;
-  if ((e = init_trtri_kernels())) return e;
   if ((e = init_lauum_kernels())) return e;
   if ((e = init_predict_kernels())) return e;
+  if ((e = init_v2_kernels())) return e;
   g_attr_done = true;
   return cudaSuccess;
 }
@@ -220,7 +225,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     m.ktype = h->kernels[m.kid].type;
     m.nl = h->kernels[m.kid].nparams - 2;
     m.leaf = l;
-    m.pad_ = 0;
+    m.nkc = m.np / KC;
     m.voff = voff; voff += m.np;
     m.xoff = xoff; xoff += (int64_t)m.np * h->D;
     m.poff = (int64_t)s * h->pstride;
@@ -232,7 +237,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   const int64_t fixed = (voff * 4 + xoff) * 8 + (64ll << 20);
   int64_t budget = h->opts.arena_bytes > 0 ? h->opts.arena_bytes : (int64_t)(free_b * 0.85) - fixed;
   // per leaf bytes in a batch: factor np^2 + W/WT 2*nb*BLK^2
-  auto leaf_bytes = [&](const LeafMeta& m) { return ((int64_t)m.np * m.np + 2ll * m.nb * BLK * BLK) * 8; };
+  auto leaf_bytes = [&](const LeafMeta& m) { return (tiled_doubles(m.np) + 2ll * m.nb * WBLK_D) * 8; };
   int64_t need_all = 0;
   for (auto& m : h->meta) need_all += leaf_bytes(m);
   if (h->opts.keep_factors && need_all > budget) {
@@ -252,15 +257,15 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         const int64_t lb = leaf_bytes(h->meta[s]);
         if (used > 0 && used + lb > budget) break;
         if (lb > budget) { h->err = "one expert's factor exceeds the arena budget"; return DSMGP_ERR_OOM; }
-        h->meta[s].foff = fo; fo += (int64_t)h->meta[s].np * h->meta[s].np;
-        h->meta[s].woff = wo; wo += (int64_t)h->meta[s].nb * BLK * BLK;
+        h->meta[s].foff = fo; fo += tiled_doubles(h->meta[s].np);
+        h->meta[s].woff = wo; wo += (int64_t)h->meta[s].nb * WBLK_D;
         used += lb; s++;
       }
       b.s1 = s; b.f_doubles = fo; b.w_doubles = wo;
       h->batches.push_back(b);
     }
   }
-  int64_t maxF = 0, maxW = 0, maxTr = 0, maxG = 0;
+  int64_t maxF = 0, maxW = 0, maxTr = 0, maxG = 0, maxFlags = 0;
   for (auto& b : h->batches) {
     const int nb_s = b.s1 - b.s0;
     b.max_nb = 0;
@@ -288,6 +293,34 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
     std::stable_sort(lt.begin(), lt.end(), [&](const int4& a, const int4& c) {
       const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
+    {   // engine v2 tile tasks: topological order with look-ahead, columns shifted so that all experts end together
+      struct TK { int s, grp, slot, I, J; };
+      std::vector<TK> tk;
+      std::vector<int64_t> foff(nb_s, 0);
+      int64_t fo = 0;
+      for (int s = b.s0; s < b.s1; s++) {
+        const LeafMeta& m = h->meta[s];
+        const int sl = s - b.s0, shift = b.max_nb - m.nb;
+        foff[sl] = fo; fo += (int64_t)m.nb * (m.nb + 1) / 2;
+        tk.push_back({shift - 1, 1, sl, 0, 0});
+        for (int J = 0; J + 1 < m.nb; J++) {
+          tk.push_back({J + shift, 0, sl, J + 1, J});
+          tk.push_back({J + shift, 1, sl, J + 1, J + 1});
+          for (int I = J + 2; I < m.nb; I++) tk.push_back({J + shift, 2, sl, I, J});
+        }
+      }
+      std::stable_sort(tk.begin(), tk.end(), [](const TK& a, const TK& c) {
+        if (a.s != c.s) return a.s < c.s;
+        if (a.grp != c.grp) return a.grp < c.grp;
+        if (a.slot != c.slot) return a.slot < c.slot;
+        return a.I < c.I; });
+      std::vector<int4> pt(tk.size());
+      for (size_t i = 0; i < tk.size(); i++) pt[i] = make_int4(tk[i].slot, tk[i].I, tk[i].J, 0);
+      b.n_potrf2 = (int)pt.size(); b.flag_ints = fo;
+      CUDA_TRY(h, upload(&b.d_potrf2_tasks, pt));
+      CUDA_TRY(h, upload(&b.d_flag_off, foff));
+      maxFlags = std::max(maxFlags, fo);
+    }
     b.ntiles = tile_off.back(); b.trpart_doubles = tro; b.gpart_doubles = go;
     b.n_trtri = (int)tt.size(); b.n_lauum = (int)lt.size();
     CUDA_TRY(h, upload(&b.d_tile_off, tile_off));
@@ -313,6 +346,9 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   CUDA_TRY(h, h->d_rows.alloc((size_t)L * h->row_width));
   CUDA_TRY(h, h->d_scal.alloc(ns));
   CUDA_TRY(h, h->d_counter.alloc(16));
+  CUDA_TRY(h, h->d_flags.alloc(std::max<int64_t>(maxFlags, 1)));
+  CUDA_TRY(h, h->d_ldpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
+  CUDA_TRY(h, h->d_zzpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
   CUDA_TRY(h, h->d_leaf_mean.alloc(L));
   CUDA_TRY(h, cudaMemcpy(h->d_leaf_mean.p, h->leaf_mean.data(), L * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemset(h->d_rows.p, 0, (size_t)L * h->row_width * sizeof(double)));
@@ -497,26 +533,27 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     launch_gram_fit(ga, b.ntiles, st);
     h->tm.launches++;
     cudaEventRecord(ev[2], st);
-    CholArgs ca{meta, h->d_F.p, h->d_W.p, h->d_WT.p, scal, h->d_trpart.p, b.d_trpart_off, 0, 0};
-    for (int J = 0; J < b.max_nb; J++) {
-      ca.step = J;
-      launch_potrf_diag(ca, b.cnt[J], st);
+    {
+      CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
+      CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
+      Potrf2Args pa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, scal, h->d_trpart.p, b.d_trpart_off,
+                    h->d_ldpart.p, h->d_zzpart.p, h->d_flags.p, b.d_flag_off, b.d_potrf2_tasks, b.n_potrf2,
+                    h->d_counter.p + 4, h->d_counter.p + 8, 0};
+      launch_potrf2(pa, std::min(sms, b.n_potrf2), st);
       h->tm.launches++;
-      if (J + 1 < b.max_nb) {
-        launch_potrf_panel(ca, b.max_nb - J - 1, b.cnt[J + 1], st);
+      cudaEventRecord(ev[3], st);
+      if (!with_grad) {       // fit only: alpha by block back-substitution (the forward solve was fused above)
+        SolveArgs sa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, scal, 1};
+        launch_solve(sa, nsl, st);
         h->tm.launches++;
       }
-    }
-    cudaEventRecord(ev[3], st);
-    SolveArgs sa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, scal};
-    launch_solve(sa, nsl, st);
-    h->tm.launches++;
-    cudaEventRecord(ev[4], st);
-    if (with_grad) {
-      CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
-      TrtriArgs ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_trpart.p, b.d_trpart_off, b.d_trtri_tasks, b.n_trtri, h->d_counter.p};
-      launch_trtri(ta, std::min(sms, b.n_trtri), st);
-      h->tm.launches++;
+      cudaEventRecord(ev[4], st);
+      if (with_grad) {
+        Trtri2Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
+                      b.d_trtri_tasks, b.n_trtri, h->d_counter.p, h->d_counter.p + 8};
+        launch_trtri2(ta, std::min(sms, b.n_trtri), st);
+        h->tm.launches++;
+      }
     }
     cudaEventRecord(ev[5], st);
     if (lau) {
@@ -527,7 +564,8 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     }
     cudaEventRecord(ev[6], st);
     RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,
-                h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0};
+                h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0,
+                h->d_ldpart.p, h->d_zzpart.p, h->d_alpha.p};
     launch_rows(ra, nsl, st);
     h->tm.launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -538,7 +576,10 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
   }
   const int ns = (int)h->slot_leaf.size();
   if (ns) CUDA_TRY(h, cudaMemcpyAsync(h->pin_scal, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, st));
+  int gerr = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&gerr, h->d_counter.p + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (gerr != 0) { h->err = "device scheduler timeout (code " + std::to_string(gerr) + ")"; return DSMGP_ERR_STATE; }
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
     cudaEvent_t* ev = h->ev.data() + 8 * bi;
     h->tm.gram_ms += ev_ms(ev[1], ev[2]);
@@ -713,9 +754,13 @@ extern "C" int32_t dsmgp_leaf_factor(const dsmgp_handle* h, int64_t leaf, double
   if (rc) return rc;
   cudaSetDevice(h->device);
   const LeafMeta& m = h->meta[slot];
-  if (cudaMemcpy2D(Lfac, (size_t)m.n * 8, h->d_F.p + m.foff, (size_t)m.np * 8, (size_t)m.n * 8, m.n, cudaMemcpyDeviceToHost) != cudaSuccess)
-    return DSMGP_ERR_CUDA;
-  for (int64_t c = 1; c < m.n; c++) for (int64_t r = 0; r < c; r++) Lfac[c * m.n + r] = 0.0;
+  double* tmp = nullptr;
+  if (cudaMalloc(&tmp, (size_t)m.n * m.n * 8) != cudaSuccess) return DSMGP_ERR_OOM;
+  launch_untile(h->d_F.p + m.foff, m.nkc, m.n, tmp, h->stream);
+  cudaError_t ce = cudaMemcpyAsync(Lfac, tmp, (size_t)m.n * m.n * 8, cudaMemcpyDeviceToHost, h->stream);
+  if (ce == cudaSuccess) ce = cudaStreamSynchronize(h->stream);
+  cudaFree(tmp);
+  if (ce != cudaSuccess) return DSMGP_ERR_CUDA;
   return DSMGP_OK;
 }
 
@@ -1103,49 +1148,65 @@ done:
 }
 
 // potrf / chol_continue on one host matrix.  k = number of leading rows/cols that already hold a valid factor.
+// Runs the same persistent tile scheduler as the batched path (potrf2_kernel) on a one-expert batch.
 static int32_t chol_host_matrix(double* A, int64_t n, int64_t k, int32_t* info) {
   int32_t rc = standalone_device_check(g_create_error);
   if (rc) return rc;
   const int64_t kp = (k + BLK - 1) / BLK * BLK;          // leading part padded to a block boundary
   const int64_t nn = kp + (n - k);
   LeafMeta m{};
-  m.n = (int32_t)nn; m.np = (int32_t)((nn + PAD - 1) / PAD * PAD); m.nb = (m.np + BLK - 1) / BLK;
-  const int64_t np = m.np;
-  std::vector<double> P((size_t)np * np, 0.0);
+  m.n = (int32_t)nn; m.np = (int32_t)((nn + PAD - 1) / PAD * PAD); m.nb = (m.np + BLK - 1) / BLK; m.nkc = m.np / KC;
+  const int np = m.np, nkc = m.nkc;
+  const int64_t fd = tiled_doubles(np);
+  std::vector<double> P((size_t)fd, 0.0);
   auto map = [&](int64_t i) { return i < k ? i : kp + (i - k); };
-  for (int64_t i = 0; i < np; i++) P[i * np + i] = 1.0;
+  for (int i = 0; i < np; i++) P[tidx(i, i, nkc)] = 1.0;
   for (int64_t c = 0; c < n; c++)
-    for (int64_t r = c; r < n; r++) P[map(c) * np + map(r)] = A[c * n + r];
-  double *dF = nullptr, *dW = nullptr, *dWT = nullptr, *dtr = nullptr; LeafMeta* dm = nullptr; LeafScal* ds = nullptr; int64_t* doff = nullptr;
-  LeafScal sc{};
-  const int64_t zero = 0;
-  SA_TRY(cudaMalloc(&dF, np * np * 8)); SA_TRY(cudaMalloc(&dW, (size_t)m.nb * BLK * BLK * 8)); SA_TRY(cudaMalloc(&dWT, (size_t)m.nb * BLK * BLK * 8));
-  SA_TRY(cudaMalloc(&dtr, 2 * m.nb * 8)); SA_TRY(cudaMalloc(&dm, sizeof(LeafMeta))); SA_TRY(cudaMalloc(&ds, sizeof(LeafScal)));
-  SA_TRY(cudaMalloc(&doff, 8));
-  SA_TRY(cudaMemcpy(dF, P.data(), np * np * 8, cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemcpy(dm, &m, sizeof(m), cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemset(ds, 0, sizeof(LeafScal)));
-  SA_TRY(cudaMemcpy(doff, &zero, 8, cudaMemcpyHostToDevice));
-  {
-    CholArgs ca{dm, dF, dW, dWT, ds, dtr, doff, 0, (int)(kp / BLK)};
-    for (int J = 0; J < m.nb; J++) {
-      ca.step = J;
-      launch_potrf_diag(ca, 1, 0);
-      if (J + 1 < m.nb) launch_potrf_panel(ca, m.nb - J - 1, 1, 0);
-    }
-    SA_TRY(cudaGetLastError());
-    SA_TRY(cudaMemcpy(P.data(), dF, np * np * 8, cudaMemcpyDeviceToHost));
-    SA_TRY(cudaMemcpy(&sc, ds, sizeof(sc), cudaMemcpyDeviceToHost));
+    for (int64_t r = c; r < n; r++) P[tidx((int)map(r), (int)map(c), nkc)] = A[c * n + r];
+  std::vector<int4> tasks;
+  tasks.push_back(make_int4(0, 0, 0, 0));
+  for (int J = 0; J + 1 < m.nb; J++) {
+    tasks.push_back(make_int4(0, J + 1, J, 0));
+    tasks.push_back(make_int4(0, J + 1, J + 1, 0));
+    for (int I = J + 2; I < m.nb; I++) tasks.push_back(make_int4(0, I, J, 0));
   }
+  const int64_t nflags = (int64_t)m.nb * (m.nb + 1) / 2;
+  double *dF = nullptr, *dW = nullptr, *dWT = nullptr, *dtr = nullptr, *dv = nullptr; LeafMeta* dm = nullptr; LeafScal* ds = nullptr;
+  int64_t* doff = nullptr; int* dflags = nullptr; int* dcnt = nullptr; int4* dtasks = nullptr;
+  LeafScal sc{}; int gerr = 0;
+  const int64_t zero[2] = {0, 0};
+  int sms = 148;
+  SA_TRY(cudaMalloc(&dF, fd * 8)); SA_TRY(cudaMalloc(&dW, (size_t)m.nb * WBLK_D * 8)); SA_TRY(cudaMalloc(&dWT, (size_t)m.nb * WBLK_D * 8));
+  SA_TRY(cudaMalloc(&dtr, 4 * m.nb * 8)); SA_TRY(cudaMalloc(&dv, 2 * (size_t)np * 8)); SA_TRY(cudaMalloc(&dm, sizeof(LeafMeta)));
+  SA_TRY(cudaMalloc(&ds, sizeof(LeafScal))); SA_TRY(cudaMalloc(&doff, 16)); SA_TRY(cudaMalloc(&dflags, nflags * 4));
+  SA_TRY(cudaMalloc(&dcnt, 64)); SA_TRY(cudaMalloc(&dtasks, tasks.size() * sizeof(int4)));
+  SA_TRY(cudaMemcpy(dF, P.data(), fd * 8, cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemcpy(dm, &m, sizeof(m), cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemset(ds, 0, sizeof(LeafScal))); SA_TRY(cudaMemset(dflags, 0, nflags * 4)); SA_TRY(cudaMemset(dcnt, 0, 64));
+  SA_TRY(cudaMemset(dv, 0, 2 * (size_t)np * 8));
+  SA_TRY(cudaMemcpy(doff, zero, 16, cudaMemcpyHostToDevice));
+  SA_TRY(cudaMemcpy(dtasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  {
+    Potrf2Args pa{dm, dF, dW, dWT, dv, dv + np, ds, dtr, doff, dtr + 2 * m.nb, dtr + 3 * m.nb, dflags, doff + 1, dtasks,
+                  (int)tasks.size(), dcnt, dcnt + 8, (int)(kp / BLK)};
+    launch_potrf2(pa, std::min(sms, (int)tasks.size()), 0);
+    SA_TRY(cudaGetLastError());
+    SA_TRY(cudaMemcpy(P.data(), dF, fd * 8, cudaMemcpyDeviceToHost));
+    SA_TRY(cudaMemcpy(&sc, ds, sizeof(sc), cudaMemcpyDeviceToHost));
+    SA_TRY(cudaMemcpy(&gerr, dcnt + 8, sizeof(int), cudaMemcpyDeviceToHost));
+  }
+  if (gerr != 0) { g_create_error = "device scheduler timeout"; rc = DSMGP_ERR_STATE; goto done; }
   for (int64_t c = 0; c < n; c++)
-    for (int64_t r = 0; r < n; r++) A[c * n + r] = (r >= c) ? P[map(c) * np + map(r)] : 0.0;    // tril!
+    for (int64_t r = 0; r < n; r++) A[c * n + r] = (r >= c) ? P[tidx((int)map(r), (int)map(c), nkc)] : 0.0;    // tril!
   if (info) {
     int64_t i = sc.info;                       // 1-based pivot in padded coordinates
     if (i > 0) { i = (i - 1 >= kp) ? (i - 1 - kp) + 1 : i; if (i > n - k) i = 0; }
     *info = (int32_t)i;                        // relative to the trailing block, as LAPACK.potrf!(C) reports it
   }
 done:
-  cudaFree(dF); cudaFree(dW); cudaFree(dWT); cudaFree(dtr); cudaFree(dm); cudaFree(ds); cudaFree(doff);
+  cudaFree(dF); cudaFree(dW); cudaFree(dWT); cudaFree(dtr); cudaFree(dv); cudaFree(dm); cudaFree(ds); cudaFree(doff);
+  cudaFree(dflags); cudaFree(dcnt); cudaFree(dtasks);
   return rc;
 }
 

@@ -8,29 +8,7 @@ namespace dsm {
 constexpr int GT = 64;       // gram tile
 constexpr int GDC = 16;      // dimensions staged per pass
 
-struct CholArgs {
-  const LeafMeta* meta;
-  double* F;          // factor arena
-  double* W;          // inverse diagonal blocks, per leaf nb blocks of BLK*BLK (column-major, ld BLK)
-  double* WT;         // their transposes
-  LeafScal* scal;
-  double* trpart;     // per (leaf, block column) partial of tr(F^{-1}); leaf l at trpart_off[l]
-  const int64_t* trpart_off;
-  int step;           // block column J (potrf kernels)
-  int jstart;         // chol_continue: block columns < jstart already hold a valid factor
-};
 
-struct TrtriArgs {
-  const LeafMeta* meta;
-  double* F;
-  const double* W;
-  const double* WT;
-  double* trpart;
-  const int64_t* trpart_off;
-  const int2* tasks;     // (leaf slot, J)
-  int ntasks;
-  int* counter;
-};
 
 struct SolveArgs {
   const LeafMeta* meta;
@@ -41,6 +19,7 @@ struct SolveArgs {
   double* z;
   double* alpha;
   LeafScal* scal;
+  int skip_forward;      // 1: z (and z'z) already produced by the fused forward solve of potrf2
 };
 
 struct GramArgs {
@@ -93,6 +72,8 @@ struct RowsArgs {
   const double* gpart; const int64_t* gpart_off;   // may be null when no LAUUM pass ran
   double* rows; int row_width;
   int as_written; int with_grad; int lauum_ran;
+  const double* ldpart; const double* zzpart;   // engine v2: per block-column partials of logdet and z'z (else null)
+  const double* alpha;                          // alpha'alpha is reduced here
 };
 
 struct PredLeaf {     // per leaf with routed points
@@ -125,20 +106,21 @@ struct PredArgs {
 };
 
 // ---- launchers (defined next to their kernels) ------------------------------------------------
-cudaError_t init_potrf_kernels();
-cudaError_t init_trtri_kernels();
 cudaError_t init_lauum_kernels();
 cudaError_t init_predict_kernels();
-void launch_potrf_diag(const CholArgs& a, int nleaves, cudaStream_t st);
-void launch_potrf_panel(const CholArgs& a, int ntile_rows, int nleaves, cudaStream_t st);
 void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
-void launch_trtri(const TrtriArgs& a, int nctas, cudaStream_t st);
 void launch_lauum(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
 void launch_predict(const PredArgs& a, int nctas, cudaStream_t st);
 void launch_gram_fit(const GramArgs& a, int64_t ntiles, cudaStream_t st);
 void launch_gram_rect(const GramRectArgs& a, cudaStream_t st);
 void launch_gather(const GatherArgs& a, int maxnp, int nleaves, cudaStream_t st);
+struct Potrf2Args;
+struct Trtri2Args;
+cudaError_t init_v2_kernels();
+void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st);
+void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st);
+void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st);
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
 
 }  // namespace dsm

@@ -23,6 +23,21 @@ static_assert(BLK * LDS == REGION0, "resident tile must alias the two-operand pi
 
 enum KernelType : int { ISO_SE = 0, ARD_SE = 1, ISO_LINEAR = 2, ARD_LINEAR = 3 };
 
+// ---- chunk-tiled matrix layout -----------------------------------------------------------------
+// Factors live in HBM as a grid of TILES: tile (rb, kc) = rows [128 rb, 128 rb + 128) x columns [16 kc, 16 kc + 16),
+// stored k-major with the shared-memory row stride:  tile[kk * LDS + r].  A tile is therefore the exact image of one
+// operand chunk of a pipeline stage and moves global -> shared with ONE bulk copy (cp.async.bulk, 16,896 B).
+// Tiles of one row block are contiguous in kc (the streaming direction of every contraction).
+constexpr int TILE_D = KC * LDS;                 // doubles per tile (== CHUNK)
+constexpr int TILE_BYTES = TILE_D * 8;
+constexpr int WBLK_D = (BLK / KC) * TILE_D;      // a 128 x 128 diagonal-block inverse: 8 tiles
+__host__ __device__ __forceinline__ int64_t tiled_doubles(int np) { return (int64_t)((np + BLK - 1) / BLK) * (np / KC) * TILE_D; }
+__host__ __device__ __forceinline__ int64_t tidx(int r, int c, int nkc) {
+  return ((int64_t)(r >> 7) * nkc + (c >> 4)) * TILE_D + (c & 15) * LDS + (r & 127);
+}
+__host__ __device__ __forceinline__ int64_t tile_off(int rb, int kc, int nkc) { return ((int64_t)rb * nkc + kc) * TILE_D; }
+__host__ __device__ __forceinline__ int widx(int r, int k) { return (k >> 4) * TILE_D + (k & 15) * LDS + r; }   // inside a W block
+
 // Per-leaf metadata, device resident.  Offsets are in doubles.
 struct LeafMeta {
   int32_t n;        // expert size
@@ -32,11 +47,11 @@ struct LeafMeta {
   int32_t ktype;    // KernelType
   int32_t leaf;     // global leaf number
   int32_t nl;       // number of length-scale parameters (1 or D)
-  int32_t pad_;
-  int64_t foff;     // factor arena offset
+  int32_t nkc;      // np / 16: column chunks per row block of the tiled factor
+  int64_t foff;     // factor arena offset (tiled layout, tiled_doubles(np) doubles)
   int64_t voff;     // y / z / alpha offset (length np, zero padded)
   int64_t xoff;     // gathered inputs: D columns of length np
-  int64_t woff;     // inverse-diagonal-block buffers W / WT: nb blocks of BLK*BLK
+  int64_t woff;     // inverse-diagonal-block buffers W / WT: nb blocks of WBLK_D doubles (tiled)
   int64_t poff;     // derived parameter block
 };
 

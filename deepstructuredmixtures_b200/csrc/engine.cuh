@@ -27,13 +27,15 @@ __device__ __forceinline__ void acc_zero(Acc& acc) {
 // RES = 0: A and B streamed from global (stages in `sA`/`sB`, stage strides strideA/strideB doubles)
 // RES = 1: A resident in smem at sA as [k][LDS]; B streamed
 // RES = 2: B resident in smem at sB as [k][LDS]; A streamed
+// Operand element (r, k) of chunk c (k in [16c, 16c+16)) is at  P[c*cs + (k - 16c)*ld + r]: column-major operands
+// use (ld, cs) = (lda, 16*lda), operands in the chunk-tiled layout (common.cuh) use (LDS, TILE_D).
 // mrows / ncols: valid rows of A / B (64 or 128).  K: multiple of KC.
 // tri = 1: skip warp tiles strictly above the diagonal (symmetric result, lower part wanted).
 // klim_rows = 1 (RES==2 only): A is lower triangular in (r,k): rows of warp-half wm only need k < wm*64+64.
 // klim_cols = 1 (RES==1 only): B is lower triangular in (c,k): cols of warp wn only need k < wn*32+32.
 template <int RES>
-__device__ __forceinline__ void mma_run(Acc& acc, const double* __restrict__ A, int64_t lda,
-                                        const double* __restrict__ B, int64_t ldb, int K,
+__device__ __forceinline__ void mma_run(Acc& acc, const double* __restrict__ A, int64_t lda, int64_t csa,
+                                        const double* __restrict__ B, int64_t ldb, int64_t csb, int K,
                                         int mrows, int ncols, bool tri,
                                         double* sA, int strideA, double* sB, int strideB,
                                         bool klim_rows = false, bool klim_cols = false) {
@@ -49,7 +51,7 @@ __device__ __forceinline__ void mma_run(Acc& acc, const double* __restrict__ A, 
     const int st = c % NST;
     if (RES != 1) {
       double* dst = sA + st * strideA;
-      const double* src = A + (int64_t)c * KC * lda;
+      const double* src = A + (int64_t)c * csa;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int u = tid + q * NTHREADS, kk = u >> 6, r2 = (u & 63) << 1;
@@ -58,7 +60,7 @@ __device__ __forceinline__ void mma_run(Acc& acc, const double* __restrict__ A, 
     }
     if (RES != 2) {
       double* dst = sB + st * strideB;
-      const double* src = B + (int64_t)c * KC * ldb;
+      const double* src = B + (int64_t)c * csb;
 #pragma unroll
       for (int q = 0; q < 4; q++) {
         const int u = tid + q * NTHREADS, kk = u >> 6, r2 = (u & 63) << 1;

@@ -1,0 +1,154 @@
+// FP64 macro-tile contraction engine v2:  OUT(128 x 128) += A(128 x K) * B(128 x K)^T  on DMMA.8x8x4.
+//
+// Warp w owns the ROW SLAB  rows [16w, 16w+16) x all 128 columns  of the macro tile (2 x 16 DMMA tiles = 64 FP64
+// accumulators per thread).  Because a warp holds complete rows, the triangular right-multiplication that follows
+// every contraction in this code base (TRSM by the inverse diagonal block:  OUT <- OUT * M^T,  M lower triangular)
+// runs entirely in registers: OUT's accumulator fragments are re-shaped into A fragments with quad shuffles and the
+// only shared-memory operand is M, streamed through the same ring as everything else.  No staging tile, no block
+// barrier.  (v1 staged OUT through a 135 KB shared tile and synchronised the block twice per tile.)
+//
+// Accumulator element (mb, nb, e) of a thread:  row = 16*warp + 8*mb + lane/4 ,  col = 8*nb + 2*(lane%4) + e.
+#pragma once
+#include "pipe.cuh"
+
+namespace dsm {
+
+typedef double Acc2[2][16][2];
+
+__device__ __forceinline__ void acc2_zero(Acc2& acc) {
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int n = 0; n < 16; n++) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
+}
+
+// One 16-k chunk of the contraction; NG = number of 4-tile column groups that are live (cols < 32*NG).
+template <int NG>
+__device__ __forceinline__ void mma_chunk(Acc2& acc, const double* __restrict__ sA, const double* __restrict__ sB, int r0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double* pa = sA + t * LDS + r0 + g;
+  const double* pb = sB + t * LDS + g;
+#pragma unroll
+  for (int ks = 0; ks < KC / 4; ks++) {
+    const double a0 = pa[ks * 4 * LDS], a1 = pa[ks * 4 * LDS + 8];
+#pragma unroll
+    for (int n = 0; n < 4 * NG; n++) {
+      const double b = pb[ks * 4 * LDS + n * 8];
+      dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+      dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+    }
+  }
+}
+
+// A-fragment (row = lane/4, k = lane%4) of k-step `ks2` (0/1: columns 0-3 / 4-7) of accumulator tile (c0, c1).
+__device__ __forceinline__ double acc_to_afrag(double c0, double c1, int ks2) {
+  const int lane = threadIdx.x & 31;
+  const int src = (lane & ~3) | (2 * ks2 + ((lane & 3) >> 1));
+  const double v0 = __shfl_sync(0xffffffffu, c0, src);
+  const double v1 = __shfl_sync(0xffffffffu, c1, src);
+  return (lane & 1) ? v1 : v0;
+}
+
+// One epilogue chunk: pass P (output columns [32P, 32P+32)), k-chunk J (k in [16J, 16J+16)); M rows of the pass
+// are in the B part of the stage at row offset 32P:  sB[k][32P + c] = M[32P + c][16J + k].
+template <int P, int J>
+__device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2], const double* __restrict__ sB) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double* pb = sB + t * LDS + 32 * P + g;
+#pragma unroll
+  for (int ks = 0; ks < 4; ks++) {
+    const int n_src = 2 * J + (ks >> 1);                // accumulator tile that holds k = 16J + 4ks .. +3
+    const double a0 = acc_to_afrag(acc[0][n_src][0], acc[0][n_src][1], ks & 1);
+    const double a1 = acc_to_afrag(acc[1][n_src][0], acc[1][n_src][1], ks & 1);
+#pragma unroll
+    for (int n = 0; n < 4; n++) {
+      const double b = pb[ks * 4 * LDS + n * 8];
+      dmma884(o[0][n][0], o[0][n][1], a0, b);
+      dmma884(o[1][n][0], o[1][n][1], a1, b);
+    }
+  }
+}
+
+// Producer top-up: warp 0 issues every chunk the generator can deliver while the ring has room.
+template <class Gen>
+__device__ __forceinline__ void topup(Pipe& p, Gen& gen) {
+  ChunkDesc d;
+  while (p.can_issue() && gen.next(d)) p.issue(d);
+}
+
+// Triangular epilogue  OUT <- scale * OUT * M^T  (M lower triangular, 32*NP x 32*NP) in registers.
+// M arrives as NE = 2*NP/... epilogue stages: stage e carries M's k-tiles 2e (A part) and 2e+1 (B part); all of them
+// stay resident while the passes run (descending column groups, so the update is in place).
+template <int P, int J>
+struct TriPass {
+  __device__ static __forceinline__ void run(const Pipe& p, uint32_t q0, const Acc2& acc, double (&o)[2][4][2]) {
+    TriPass<P, J - 1>::run(p, q0, acc, o);
+    const int st = (q0 + (J >> 1)) % NS2;
+    tri_chunk<P, J>(acc, o, (J & 1) ? p.B(st) : p.A(st));
+  }
+};
+template <int P>
+struct TriPass<P, -1> {
+  __device__ static __forceinline__ void run(const Pipe&, uint32_t, const Acc2&, double (&)[2][4][2]) {}
+};
+
+template <int P>
+__device__ __forceinline__ void tri_pass(const Pipe& p, uint32_t q0, Acc2& acc, double scale) {
+  double o[2][4][2];
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int n = 0; n < 4; n++) { o[m][n][0] = 0.0; o[m][n][1] = 0.0; }
+  TriPass<P, 2 * P + 1>::run(p, q0, acc, o);
+#pragma unroll
+  for (int m = 0; m < 2; m++)
+#pragma unroll
+    for (int n = 0; n < 4; n++) { acc[m][4 * P + n][0] = scale * o[m][n][0]; acc[m][4 * P + n][1] = scale * o[m][n][1]; }
+}
+
+__host__ __device__ __forceinline__ int tri_epilogue_nstages(int npass) { return npass; }   // 8 (4) k-tiles, 2 per stage
+
+template <class Gen>
+__device__ __forceinline__ void tri_epilogue(Pipe& p, Gen& gen, Acc2& acc, int npass, bool active, double scale) {
+  const uint32_t q0 = p.q_cons;
+  for (int e = 0; e < npass; e++) {                 // wait for every epilogue stage (they stay resident)
+    if ((threadIdx.x >> 5) == 0) topup(p, gen);
+    const uint32_t q = q0 + e;
+    p.wait_bar(&p.full[q % NS2], (q / NS2) & 1, 4);
+  }
+  if (active) {
+    if (npass == 4) { tri_pass<3>(p, q0, acc, scale); tri_pass<2>(p, q0, acc, scale); }
+    tri_pass<1>(p, q0, acc, scale);
+    tri_pass<0>(p, q0, acc, scale);
+  }
+  for (int e = 0; e < npass; e++) p.release();
+}
+
+// Descriptor of epilogue stage `e` for a tiled W block (k-tiles 2e and 2e+1).
+__device__ __forceinline__ ChunkDesc tri_epilogue_chunk(const double* Wblk, int e, const int* flag) {
+  ChunkDesc d;
+  d.a = Wblk + (2 * e) * TILE_D; d.abytes = TILE_BYTES;
+  d.b = Wblk + (2 * e + 1) * TILE_D; d.bbytes = TILE_BYTES;
+  d.flag0 = (e == 0) ? flag : nullptr; d.flag1 = nullptr;
+  return d;
+}
+
+// Store OUT (rows r < mrows, cols c < ncols) into the tiled matrix at (row0 + r, col0 + c).
+__device__ __forceinline__ void acc2_store(const Acc2& acc, double* Fm, int nkc, int row0, int col0, int mrows, int ncols) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int r0 = 16 * warp;
+  if (r0 >= mrows) return;
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    if (8 * n < ncols) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        double* col = Fm + tidx(row0 + r0 + g, col0 + 8 * n + 2 * t + e, nkc);
+        col[0] = acc[0][n][e];
+        col[8] = acc[1][n][e];
+      }
+    }
+  }
+}
+
+}  // namespace dsm

@@ -35,21 +35,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lauum_trace_kernel(LauumArgs a) {
     const int I = tk.y, J = tk.z;
     const int wi = blk_width(m.np, I), wj = blk_width(m.np, J);
     const int64_t lda = m.np;
+    const int nkc = m.nkc;
     const int i0 = I * BLK, j0 = J * BLK;
     const double* F = a.F + m.foff;
-    const double* WTi = a.WT + m.woff + (int64_t)I * BLK * BLK;
+    const double* WTi = a.WT + m.woff + (int64_t)I * WBLK_D;
     Acc acc;
     acc_zero(acc);
     // K = I block: A[i][k] = X_II[k][i] = WT_I[i + k*BLK];  B[j][k] = X_IJ[k][j]
     if (I == J)
-      mma_run<0>(acc, WTi, BLK, WTi, BLK, wi, wi, wj, false, smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
+      mma_run<0>(acc, WTi, LDS, TILE_D, WTi, LDS, TILE_D, wi, wi, wj, false, smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
     else
-      mma_run<0>(acc, WTi, BLK, F + j0 + (int64_t)i0 * lda, lda, wi, wi, wj, false,
+      mma_run<0>(acc, WTi, LDS, TILE_D, F + tile_off(J, i0 / KC, nkc), LDS, TILE_D, wi, wi, wj, false,
                  smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
     const int k1 = i0 + wi;
     if (m.np > k1)
-      mma_run<0>(acc, F + i0 + (int64_t)k1 * lda, lda, F + j0 + (int64_t)k1 * lda, lda, m.np - k1, wi, wj, false,
-                 smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
+      mma_run<0>(acc, F + tile_off(I, k1 / KC, nkc), LDS, TILE_D, F + tile_off(J, k1 / KC, nkc), LDS, TILE_D, m.np - k1,
+                 wi, wj, false, smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
     // ---- fused epilogue -------------------------------------------------------------------
     const double* prm = a.prm + m.poff;
     const double* x = a.xg + m.xoff;
@@ -126,6 +127,17 @@ __global__ void rows_kernel(RowsArgs a) {
   const double* prm = a.prm + m.poff;
   double* row = a.rows + (int64_t)m.leaf * a.row_width;
   const double n = (double)m.n;
+  if (a.ldpart != nullptr) {      // engine v2: ordered sums of the per-block-column partials
+    double l = 0.0, zq = 0.0;
+    for (int i = tid; i < m.nb; i += blockDim.x) { l += a.ldpart[a.trpart_off[slot] / 2 + i]; zq += a.zzpart[a.trpart_off[slot] / 2 + i]; }
+    sc.logdet = block_sum(l, red);
+    sc.zz = block_sum(zq, red);
+  }
+  if (a.alpha != nullptr && a.with_grad) {
+    double q = 0.0;
+    for (int i = tid; i < m.n; i += blockDim.x) { const double v = a.alpha[m.voff + i]; q = fma(v, v, q); }
+    sc.aa = block_sum(q, red);
+  }
   double lml = -(sc.zz + sc.logdet + 1.8378770664093453 * n) / 2.0;   // log(2 pi)
   if (sc.info != 0) lml = nan("");
   if (!a.with_grad) {

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NTHREADS) gram_fit_kernel(GramArgs a) {
       else if (r == c) k += cnoise;
       v[i] = k;
     }
-    double* dst = F + (int64_t)c * m.np + ti * GT + tx * 4;
+    double* dst = F + tidx(ti * GT + tx * 4, c, m.nkc);
     *reinterpret_cast<double2*>(dst) = make_double2(v[0], v[1]);
     *reinterpret_cast<double2*>(dst + 2) = make_double2(v[2], v[3]);
   }

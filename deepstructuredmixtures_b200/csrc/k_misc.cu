@@ -29,6 +29,12 @@ __global__ void __launch_bounds__(NTHREADS) delete_rows_kernel(double* Lf, int n
   }
 }
 
+// tiled factor -> dense column-major n x n (lower triangle; upper zero)
+__global__ void untile_kernel(const double* Ft, int nkc, int n, double* out) {
+  const int c = blockIdx.x;
+  for (int r = threadIdx.x; r < n; r += blockDim.x) out[(int64_t)c * n + r] = (r >= c) ? Ft[tidx(r, c, nkc)] : 0.0;
+}
+void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st) { untile_kernel<<<n, 256, 0, st>>>(Ft, nkc, n, out); }
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st) {
   delete_rows_kernel<<<1, NTHREADS, 0, st>>>(Lf, n, rows, nrows, v);
 }

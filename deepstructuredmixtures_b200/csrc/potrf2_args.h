@@ -1,0 +1,27 @@
+// Argument blocks of the engine-v2 kernels (host-visible).
+#pragma once
+#include "common.cuh"
+namespace dsm {
+struct Potrf2Args {
+  const LeafMeta* meta;
+  double* F; double* W; double* WT;
+  const double* y; double* z;
+  LeafScal* scal;
+  double* trpart; const int64_t* trpart_off;      // [2*nb] per leaf: diag-block partials of tr(F^-1) in the first half
+  double* ldpart; double* zzpart;                  // [nb] per leaf at trpart_off/2: logdet and z'z partials
+  int* flags; const int64_t* flag_off;             // per leaf nb(nb+1)/2 tile flags
+  const int4* tasks; int ntasks;                   // (slot, I, J, unused)
+  int* counter; int* gerr;
+  int jstart;                                      // chol_continue: block columns < jstart hold a valid factor
+};
+
+struct Trtri2Args {
+  const LeafMeta* meta;
+  double* F; const double* W; const double* WT;
+  const double* z; double* alpha;
+  double* trpart; const int64_t* trpart_off;    // second half [nb + J]
+  const int2* tasks; int ntasks;
+  int* counter; int* gerr;
+};
+
+}  // namespace dsm

@@ -74,7 +74,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) predict_kernel(PredArgs a) {
       Acc acc;
       acc_zero(acc);
       if (i0 > 0)
-        mma_run<0>(acc, F + i0, lda, VT + q0, ldv, i0, wi, wq, false, smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
+        mma_run<0>(acc, F + tile_off(I, 0, m.nkc), LDS, TILE_D, VT + q0, ldv, (int64_t)KC * ldv, i0, wi, wq, false,
+                   smem, 2 * CHUNK, smem + CHUNK, 2 * CHUNK);
       // stage point tiles (REGION1 is idle between engine runs)
       for (int u = tid; u < D * BLK; u += NTHREADS) {
         const int d = u / BLK, p = u % BLK;
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) predict_kernel(PredArgs a) {
       acc_store_rowmajor(acc, S, 1.0);
       __syncthreads();
       acc_zero(acc);
-      const double* Wi = a.W + m.woff + (int64_t)I * BLK * BLK;
-      mma_run<2>(acc, Wi, BLK, nullptr, 0, wi, wi, wq, false, smem + REGION0, CHUNK, S, 0, true, false);
+      const double* Wi = a.W + m.woff + (int64_t)I * WBLK_D;
+      mma_run<2>(acc, Wi, LDS, TILE_D, nullptr, 0, 0, wi, wi, wq, false, smem + REGION0, CHUNK, S, 0, true, false);
       // V_IQ -> VT[(q0 + c) + (i0 + r) * ldv] ; column sums of squares
       double spart[8];
 #pragma unroll
