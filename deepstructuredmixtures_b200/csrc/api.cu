@@ -79,6 +79,7 @@ struct dsmgp_handle {
   std::vector<double> sum_logw;   // CSR by child_ptr (update!)
   bool have_weights = false;
   bool fitted = false, have_rows = false, have_grad = false, rows_complete = false;
+  bool alpha_exact = false;       // alpha from back-substitution (fit path); the gradient path leaves X^T z
   int device = 0;
   cudaStream_t stream = nullptr;
   std::vector<cudaEvent_t> ev;     // 8 per batch: phase boundaries, always recorded (no extra syncs)
@@ -596,6 +597,24 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     h->h_info[h->slot_leaf[s]] = info;
   }
   h->fitted = true; h->have_rows = true; h->have_grad = with_grad; h->rows_complete = (h->opts.world == 1);
+  h->alpha_exact = !with_grad;
+  return DSMGP_OK;
+}
+
+// alpha = L^-T z by block back-substitution (gaussianprocess.jl:105).  The gradient path leaves alpha = X^T z, which is
+// what tr(W) needs but carries the rounding of the explicit inverse; consumers of alpha itself (predict, accessors)
+// get the back-substituted vector, exactly like the reference.
+static int32_t refine_alpha(dsmgp_handle* h) {
+  if (h->alpha_exact || !h->fitted || h->batches.size() != 1) return DSMGP_OK;
+  Batch& b = h->batches[0];
+  const int nsl = b.s1 - b.s0;
+  if (nsl > 0) {
+    SolveArgs sa{h->d_meta.p, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, h->d_scal.p, 1};
+    launch_solve(sa, nsl, h->stream);
+    CUDA_TRY(h, cudaGetLastError());
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  h->alpha_exact = true;
   return DSMGP_OK;
 }
 
@@ -744,6 +763,7 @@ extern "C" int32_t dsmgp_leaf_alpha(const dsmgp_handle* h, int64_t leaf, double*
   int slot; int32_t rc = need_resident(h, leaf, &slot);
   if (rc) return rc;
   cudaSetDevice(h->device);
+  if (refine_alpha(const_cast<dsmgp_handle*>(h))) return DSMGP_ERR_CUDA;
   const LeafMeta& m = h->meta[slot];
   if (cudaMemcpy(alpha, h->d_alpha.p + m.voff, m.n * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return DSMGP_ERR_CUDA;
   return DSMGP_OK;
@@ -895,6 +915,7 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
                               std::vector<std::vector<double>>& mu, std::vector<std::vector<double>>& var) {
   if (!h->fitted) { h->err = "predict: call fit first"; return DSMGP_ERR_STATE; }
   if (!h->opts.keep_factors || h->batches.size() != 1) { h->err = "predict needs keep_factors=1"; return DSMGP_ERR_STATE; }
+  { int32_t rr = refine_alpha(h); if (rr) return rr; }
   const int64_t L = h->L, D = h->D;
   mu.assign(L, {}); var.assign(L, {});
   std::vector<PredLeaf> pls; std::vector<int2> tasks; std::vector<int64_t> pl_leaf;

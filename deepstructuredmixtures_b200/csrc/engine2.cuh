@@ -7,13 +7,21 @@
 // only shared-memory operand is M, streamed through the same ring as everything else.  No staging tile, no block
 // barrier.  (v1 staged OUT through a 135 KB shared tile and synchronised the block twice per tile.)
 //
-// Accumulator element (mb, nb, e) of a thread:  row = 16*warp + 8*mb + lane/4 ,  col = 8*nb + 2*(lane%4) + e.
+// Accumulator element (mb, nb, e) of thread (g = lane/4, t = lane%4) in warp w -- INTERLEAVED mapping:
+//     row = 16 w + 2 g + mb                      (the two m-tiles own the even / odd rows of the slab)
+//     col = 16 (nb/2) + 2 (2 t + e) + (nb % 2)   (tiles 2m, 2m+1 own the even / odd columns of a 16-column group)
+// so that the fragments of a tile PAIR are adjacent in shared memory and one LDS.128 feeds two DMMAs' operands:
+// 9 shared loads per k-step (1 for A, 8 for B) instead of 18.  Any consistent permutation of rows / columns is
+// legal for a contraction; only the stores and the epilogues have to agree with it.
 #pragma once
 #include "pipe.cuh"
 
 namespace dsm {
 
 typedef double Acc2[2][16][2];
+
+__device__ __forceinline__ int acc_row(int mb) { return 16 * (threadIdx.x >> 5) + 2 * ((threadIdx.x & 31) >> 2) + mb; }
+__device__ __forceinline__ int acc_col(int nb, int e) { return 16 * (nb >> 1) + 2 * (2 * (threadIdx.x & 3) + e) + (nb & 1); }
 
 __device__ __forceinline__ void acc2_zero(Acc2& acc) {
 #pragma unroll
@@ -26,45 +34,66 @@ __device__ __forceinline__ void acc2_zero(Acc2& acc) {
 template <int NG>
 __device__ __forceinline__ void mma_chunk(Acc2& acc, const double* __restrict__ sA, const double* __restrict__ sB, int r0) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const double* pa = sA + t * LDS + r0 + g;
-  const double* pb = sB + t * LDS + g;
+  const double* pa = sA + t * LDS + r0 + 2 * g;
+  const double* pb = sB + t * LDS + 2 * g;
 #pragma unroll
   for (int ks = 0; ks < KC / 4; ks++) {
-    const double a0 = pa[ks * 4 * LDS], a1 = pa[ks * 4 * LDS + 8];
+    const double2 a = *reinterpret_cast<const double2*>(pa + ks * 4 * LDS);
 #pragma unroll
-    for (int n = 0; n < 4 * NG; n++) {
-      const double b = pb[ks * 4 * LDS + n * 8];
-      dmma884(acc[0][n][0], acc[0][n][1], a0, b);
-      dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+    for (int m2 = 0; m2 < 2 * NG; m2++) {
+      const double2 b = *reinterpret_cast<const double2*>(pb + ks * 4 * LDS + 16 * m2);
+      dmma884(acc[0][2 * m2][0], acc[0][2 * m2][1], a.x, b.x);
+      dmma884(acc[1][2 * m2][0], acc[1][2 * m2][1], a.y, b.x);
+      dmma884(acc[0][2 * m2 + 1][0], acc[0][2 * m2 + 1][1], a.x, b.y);
+      dmma884(acc[1][2 * m2 + 1][0], acc[1][2 * m2 + 1][1], a.y, b.y);
     }
   }
 }
 
-// A-fragment (row = lane/4, k = lane%4) of k-step `ks2` (0/1: columns 0-3 / 4-7) of accumulator tile (c0, c1).
-__device__ __forceinline__ double acc_to_afrag(double c0, double c1, int ks2) {
-  const int lane = threadIdx.x & 31;
-  const int src = (lane & ~3) | (2 * ks2 + ((lane & 3) >> 1));
-  const double v0 = __shfl_sync(0xffffffffu, c0, src);
-  const double v1 = __shfl_sync(0xffffffffu, c1, src);
-  return (lane & 1) ? v1 : v0;
+// acc -= T for the 16-column group m2 of the macro tile, T = a [16][LDS] tile image in shared memory (columns
+// 16 m2 .. 16 m2 + 15 of the 128 x 128 block, rows = block rows).
+__device__ __forceinline__ void acc2_sub_tile(Acc2& acc, const double* __restrict__ sT, int r0, const int M2) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int p = 0; p < 2; p++)
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const double2 v = *reinterpret_cast<const double2*>(sT + (2 * (2 * t + e) + p) * LDS + r0 + 2 * g);
+      acc[0][2 * M2 + p][e] -= v.x;
+      acc[1][2 * M2 + p][e] -= v.y;
+    }
 }
 
-// One epilogue chunk: pass P (output columns [32P, 32P+32)), k-chunk J (k in [16J, 16J+16)); M rows of the pass
-// are in the B part of the stage at row offset 32P:  sB[k][32P + c] = M[32P + c][16J + k].
+// A-fragment (row = lane/4, k = lane%4) for k = 16 J + 4 ks + t, taken from the accumulator tiles 2J / 2J+1 of m-tile mb:
+// column k lives in tile 2J + (t & 1), lane t'' = ks, element e = t >> 1.
+template <int J>
+__device__ __forceinline__ double acc_to_afrag(const Acc2& acc, int mb, int ks) {
+  const int lane = threadIdx.x & 31;
+  const int src = (lane & ~3) | ks;
+  const double v00 = __shfl_sync(0xffffffffu, acc[mb][2 * J][0], src);
+  const double v01 = __shfl_sync(0xffffffffu, acc[mb][2 * J][1], src);
+  const double v10 = __shfl_sync(0xffffffffu, acc[mb][2 * J + 1][0], src);
+  const double v11 = __shfl_sync(0xffffffffu, acc[mb][2 * J + 1][1], src);
+  const double ve = (lane & 2) ? v01 : v00, vo = (lane & 2) ? v11 : v10;
+  return (lane & 1) ? vo : ve;
+}
+
+// One epilogue k-tile: pass P (output columns [32P, 32P+32)), k-tile J (k in [16J, 16J+16)):  sM[k][c] = M[c][16J + k].
 template <int P, int J>
-__device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2], const double* __restrict__ sB) {
+__device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2], const double* __restrict__ sM) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const double* pb = sB + t * LDS + 32 * P + g;
+  const double* pb = sM + t * LDS + 32 * P + 2 * g;
 #pragma unroll
   for (int ks = 0; ks < 4; ks++) {
-    const int n_src = 2 * J + (ks >> 1);                // accumulator tile that holds k = 16J + 4ks .. +3
-    const double a0 = acc_to_afrag(acc[0][n_src][0], acc[0][n_src][1], ks & 1);
-    const double a1 = acc_to_afrag(acc[1][n_src][0], acc[1][n_src][1], ks & 1);
+    const double a0 = acc_to_afrag<J>(acc, 0, ks);
+    const double a1 = acc_to_afrag<J>(acc, 1, ks);
 #pragma unroll
-    for (int n = 0; n < 4; n++) {
-      const double b = pb[ks * 4 * LDS + n * 8];
-      dmma884(o[0][n][0], o[0][n][1], a0, b);
-      dmma884(o[1][n][0], o[1][n][1], a1, b);
+    for (int m2 = 0; m2 < 2; m2++) {
+      const double2 b = *reinterpret_cast<const double2*>(pb + ks * 4 * LDS + 16 * m2);
+      dmma884(o[0][2 * m2][0], o[0][2 * m2][1], a0, b.x);
+      dmma884(o[1][2 * m2][0], o[1][2 * m2][1], a1, b.x);
+      dmma884(o[0][2 * m2 + 1][0], o[0][2 * m2 + 1][1], a0, b.y);
+      dmma884(o[1][2 * m2 + 1][0], o[1][2 * m2 + 1][1], a1, b.y);
     }
   }
 }
@@ -135,17 +164,15 @@ __device__ __forceinline__ ChunkDesc tri_epilogue_chunk(const double* Wblk, int 
 
 // Store OUT (rows r < mrows, cols c < ncols) into the tiled matrix at (row0 + r, col0 + c).
 __device__ __forceinline__ void acc2_store(const Acc2& acc, double* Fm, int nkc, int row0, int col0, int mrows, int ncols) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
-  const int r0 = 16 * warp;
+  const int r0 = 16 * (threadIdx.x >> 5);
   if (r0 >= mrows) return;
 #pragma unroll
   for (int n = 0; n < 16; n++) {
     if (8 * n < ncols) {
 #pragma unroll
       for (int e = 0; e < 2; e++) {
-        double* col = Fm + tidx(row0 + r0 + g, col0 + 8 * n + 2 * t + e, nkc);
-        col[0] = acc[0][n][e];
-        col[8] = acc[1][n][e];
+        double* dst = Fm + tidx(row0 + acc_row(0), col0 + acc_col(n, e), nkc);        // rows 2g, 2g+1 are adjacent
+        *reinterpret_cast<double2*>(dst) = make_double2(acc[0][n][e], acc[1][n][e]);
       }
     }
   }

@@ -12,7 +12,7 @@
 // producer warp issues the bulk copies of the k-block that reads it).
 #pragma once
 #include "engine2.cuh"
-#include "engine.cuh"   // potrf_smem / trtri_smem
+#include "diag_block.cuh"
 #include "args.h"
 #include "potrf2_args.h"
 
@@ -23,24 +23,29 @@ __device__ __forceinline__ int tile_flag_index(int I, int J) { return I * (I + 1
 struct PotrfGen {
   const double* F; const double* z; const double* Wj; const int* flags;
   int nkc, I, J, wj;
-  int nmain, nepi, c;
+  int nc, nmain, nepi, c;                          // stages: F_IJ itself, contraction chunks, W_J (panel tiles only)
   bool diag;
   __device__ __forceinline__ bool next(ChunkDesc& d) {
-    if (c >= nmain + nepi) return false;
-    if (c < nmain) {
-      const int Kb = c >> 3;                       // 8 chunks per 128-wide k-block
-      const bool first = (c & 7) == 0;
-      d.a = F + tile_off(I, c, nkc); d.abytes = TILE_BYTES;
-      if (diag) {             // B operand == A operand; the B part of the stage carries z[16c .. 16c+16)
-        d.b = z + KC * c; d.bbytes = KC * 8;
+    if (c >= nc + nmain + nepi) return false;
+    if (c < nc) {                                  // the tile being updated: 2 column tiles per stage, no dependency
+      d.a = F + tile_off(I, J * 8 + 2 * c, nkc); d.abytes = TILE_BYTES;
+      d.b = F + tile_off(I, J * 8 + 2 * c + 1, nkc); d.bbytes = TILE_BYTES;
+      d.flag0 = nullptr; d.flag1 = nullptr;
+    } else if (c < nc + nmain) {
+      const int cc = c - nc;
+      const int Kb = cc >> 3;                      // 8 chunks per 128-wide k-block
+      const bool first = (cc & 7) == 0;
+      d.a = F + tile_off(I, cc, nkc); d.abytes = TILE_BYTES;
+      if (diag) {             // B operand == A operand; the B part of the stage carries z[16cc .. 16cc+16)
+        d.b = z + KC * cc; d.bbytes = KC * 8;
         d.flag0 = first ? flags + tile_flag_index(J, Kb) : nullptr; d.flag1 = nullptr;
       } else {
-        d.b = F + tile_off(J, c, nkc); d.bbytes = TILE_BYTES;
+        d.b = F + tile_off(J, cc, nkc); d.bbytes = TILE_BYTES;
         d.flag0 = first ? flags + tile_flag_index(I, Kb) : nullptr;
         d.flag1 = first ? flags + tile_flag_index(J, Kb) : nullptr;
       }
     } else {
-      d = tri_epilogue_chunk(Wj, c - nmain, flags + tile_flag_index(J, J));
+      d = tri_epilogue_chunk(Wj, c - nc - nmain, flags + tile_flag_index(J, J));
     }
     c++;
     return true;
@@ -52,7 +57,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
   __shared__ int s_task;
   __shared__ double s_red[16];
   __shared__ double s_v[BLK];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  __shared__ int s_info;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = 16 * warp;
   Pipe p;
   p.init(smem, a.gerr);
@@ -83,22 +89,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     gen.wj = wj; gen.I = I; gen.J = J; gen.diag = diag; gen.c = 0;
     gen.nmain = (diag && prefactored) ? 0 : j0 / KC;
     gen.nepi = diag ? 0 : tri_epilogue_nstages(wj / 32);
+    gen.nc = wj / 32;
 
-    // acc = -F_IJ (loads overlap the pipeline fill); the contraction then leaves acc = -(F_IJ - sum) = -C
+    // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
     Acc2 acc;
+    acc2_zero(acc);
 #pragma unroll
-    for (int n = 0; n < 16; n++)
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const int c = 8 * n + 2 * t + e;
-        double v0 = 0.0, v1 = 0.0;
-        if (active && c < wj && !(diag && prefactored)) {
-          const double* col = F + tidx(i0 + r0 + g, j0 + c, nkc);
-          if (!diag || r0 + g >= c) v0 = -col[0];
-          if (!diag || r0 + 8 + g >= c) v1 = -col[8];
-        }
-        acc[0][n][e] = v0; acc[1][n][e] = v1;
+    for (int e = 0; e < 4; e++) {
+      if (e < gen.nc) {
+        if (warp == 0) topup(p, gen);
+        const int st = p.wait();
+        if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
+        p.release();
       }
+    }
 
     if (!diag) {
       // ---------------- panel tile ----------------
@@ -150,26 +154,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       for (int n = 0; n < 16; n++)
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          const int c = 8 * n + 2 * t + e;
-          if (c < wj) {
-            if (prefactored) {
-              const double* col = F + tidx(j0 + r0 + g, j0 + c, nkc);
-              S[c * LDS + r0 + g] = (r0 + g >= c) ? col[0] : 0.0;
-              S[c * LDS + r0 + 8 + g] = (r0 + 8 + g >= c) ? col[8] : 0.0;
-            } else {
-              S[c * LDS + r0 + g] = -acc[0][n][e];
-              S[c * LDS + r0 + 8 + g] = -acc[1][n][e];
-            }
-          }
+          const int c = acc_col(n, e);
+          if (c < wj) *reinterpret_cast<double2*>(S + c * LDS + acc_row(0)) = make_double2(-acc[0][n][e], -acc[1][n][e]);
         }
       if (lane < 16) s_v[r0 + lane] = gemv;
     }
-    if (tid == 0) { aux[0] = 0.0; aux[1] = 0.0; }
     __syncthreads();
-    const LeafScal* scp = a.scal + tk.x; (void)scp;
-    if (!prefactored) {
-      const int info = potrf_smem(S, wj, aux);
+    {
+      const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info);
       if (tid == 0 && info != 0) atomicCAS(&a.scal[tk.x].info, 0, j0 + info);
+    }
+    const double* DI = aux;
+    if (!prefactored) {
       for (int c = warp; c < wj; c += NTHREADS / 32) {
         double* dst = F + tidx(j0, j0 + c, nkc);
         for (int r = lane; r < wj; r += 32)
@@ -180,21 +176,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     for (int r = tid; r < wj; r += NTHREADS)
       if (j0 + r < m.n) ld += log(S[r * LDS + r]);
     ld = block_sum(ld, s_red);
-    trtri_smem(S, wj, aux + 16);
-    // W_J, W_J^T (zero filled) and the diagonal-block partial of tr(F^-1)
+    // W_J, W_J^T (zero filled, tiled) and the diagonal-block partial of tr(F^-1)
     double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;
     double tr = 0.0;
     for (int c = warp; c < BLK; c += NTHREADS / 32)
       for (int r = lane; r < BLK; r += 32) {
         double v = 0.0;
-        if (r < wj && c < wj && r >= c) v = S[c * LDS + r];
+        if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
         Wj[widx(r, c)] = v;
         if (j0 + r < m.n && j0 + c < m.n) tr += v * v;
       }
     for (int r = warp; r < BLK; r += NTHREADS / 32)
       for (int c = lane; c < BLK; c += 32) {
         double v = 0.0;
-        if (r < wj && c < wj && r >= c) v = S[c * LDS + r];
+        if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
         WTj[widx(c, r)] = v;
       }
     tr = block_sum(tr, s_red);
@@ -206,7 +201,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       const int r = tid >> 1, h = tid & 1;              // 2 threads per row
       double s = 0.0;
       if (r < wj)
-        for (int k = h; k <= r; k += 2) s = fma(S[k * LDS + r], s_v[k], s);
+        for (int k = h; k <= r; k += 2) s = fma(diag_W(S, DI, r, k), s_v[k], s);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       if (r < wj && h == 0) {
         a.z[m.voff + j0 + r] = s;

@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
   __shared__ int s_task;
   __shared__ double s_red[16];
   __shared__ double s_al[BLK];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = 16 * warp;
   Pipe p;
   p.init(smem, a.gerr);
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
     gen.F = F; gen.W = a.W + m.woff; gen.WT = a.WT + m.woff; gen.np = m.np; gen.nb = m.nb; gen.nkc = m.nkc;
     gen.J = J; gen.I = J + 1; gen.c = 0; gen.stored = J;
     double tr = 0.0;
-    double al0 = 0.0, al1 = 0.0;       // alpha partial of rows r0 + g and r0 + 8 + g (valid in lanes with t == 0)
+    double al0 = 0.0, al1 = 0.0;       // alpha partial of rows acc_row(0) / acc_row(1) (valid in lanes with t == 0)
     for (int I = J + 1; I < m.nb; I++) {
       const int wi = blk_width(m.np, I), i0 = I * BLK;
       const int nmain = (i0 - j0) / KC;
@@ -83,13 +83,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
       acc2_store(acc, F, m.nkc, j0, i0, BLK, wi);
       // fused reductions: ||X_IJ||_F^2 over real rows/cols, alpha_J += X_IJ^T z_I
       double p0 = 0.0, p1 = 0.0;
-      const bool row0 = (j0 + r0 + g) < m.n, row1 = (j0 + r0 + 8 + g) < m.n;
+      const bool row0 = (j0 + acc_row(0)) < m.n, row1 = (j0 + acc_row(1)) < m.n;
 #pragma unroll
       for (int n = 0; n < 16; n++) {
         if (8 * n < wi) {
 #pragma unroll
           for (int e = 0; e < 2; e++) {
-            const int col = i0 + 8 * n + 2 * t + e;
+            const int col = i0 + acc_col(n, e);
             if (col < m.n) {
               const double zi = z[col];
               const double v0 = acc[0][n][e], v1 = acc[1][n][e];
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
       if (warp == 0) { fence_proxy_async(); gen.stored = I; }
     }
     // alpha_J = W_J^T z_J + sum_I X_IJ^T z_I
-    if (t == 0) { s_al[r0 + g] = al0; s_al[r0 + 8 + g] = al1; }
+    if ((lane & 3) == 0) { s_al[acc_row(0)] = al0; s_al[acc_row(1)] = al1; }
     __syncthreads();
     if (tid < wj) {
       const double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;

@@ -15,9 +15,12 @@ GRAD_TOL = 1e-9
 PRED_TOL = 1e-8
 
 
-def grad_scale(root, leaf_rows_oracle):
-    """per-component scale max(|a' dK a|, |tr(F^-1 dK)|) is bounded below by |g|; use max(|g|, sum_leaf |g_leaf| w)"""
-    return None
+def pred_close(mu, omu, var, ovar, yscale):
+    """Predictions within PRED_TOL relative.  The mean m + K' alpha is a sum of large cancelling terms whose rounding
+    error scales with the data, not with the (possibly ~0) value, so |mu| is floored by the scale of the targets."""
+    ok_mu = np.all(np.abs(mu - omu) <= PRED_TOL * np.maximum(np.abs(omu), yscale))
+    ok_var = np.all(np.abs(var - ovar) <= PRED_TOL * np.abs(ovar))
+    return bool(ok_mu and ok_var)
 
 
 def check_eval(model, theta, mathematical=False, leaf_scale=None):
@@ -57,7 +60,7 @@ def test_single_gp_isose():
     xt = np.random.default_rng(5).random((77, 2))
     mu, var = gp.prediction(xt)
     omu, ovar = o.prediction(xt)
-    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+    assert pred_close(mu, omu, var, ovar, float(np.std(y)))
 
 
 @pytest.mark.parametrize("ktype", ["isose", "ardse", "isolin", "ardlin"])
@@ -79,7 +82,7 @@ def test_single_gp_sizes(ktype, n):
     xt = np.random.default_rng(n).random((50, D))
     mu, var = gp.prediction(xt)
     omu, ovar = o.prediction(xt)
-    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+    assert pred_close(mu, omu, var, ovar, float(np.std(y)))
 
 
 def test_cfg1_readme_dsmgp():
@@ -100,7 +103,7 @@ def test_cfg1_readme_dsmgp():
     xt = np.linspace(0.0, 1.0, 173).reshape(-1, 1)
     mu, var = dsm.predict(model, xt)
     omu, ovar = orc.predict_dsmgp(root, xt)
-    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+    assert pred_close(mu, omu, var, ovar, float(np.std(y)))
 
 
 @pytest.mark.parametrize("mathematical", [False, True])
@@ -145,7 +148,7 @@ def test_poe_family_predict(mode):
     mu, var = dsm.predict(model, xt)
     f = {"poe": orc.predict_poe, "gpoe": orc.predict_gpoe, "rbcm": orc.predict_rbcm}[mode]
     omu, ovar = f(root, xt)
-    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+    assert pred_close(mu, omu, var, ovar, float(np.std(y)))
 
 
 def test_kernelmatrix_operator():
@@ -221,7 +224,7 @@ def test_single_gp_multiblock(n, ktype):
     xt = np.random.default_rng(n).random((300, D))
     mu, var = gp.prediction(xt)
     omu, ovar = o.prediction(xt)
-    assert relerr(mu, omu) < PRED_TOL and relerr(var, ovar) < PRED_TOL
+    assert pred_close(mu, omu, var, ovar, float(np.std(y)))
 
 
 def test_dsmgp_medium_leaves():
