@@ -34,8 +34,8 @@ struct PotrfStep {
     PotrfStep<J - 1>::run(a, r, info);
     const double d = __shfl_sync(0xffffffffu, a[J], J);
     if (!(d > 0.0) && info == 0) info = J + 1;
-    const double piv = sqrt(d);
-    const double inv = 1.0 / piv;
+    const double inv = rsqrt(d);                 // one long-latency op on the pivot chain instead of sqrt + divide
+    const double piv = d * inv;
     a[J] = (r == J) ? piv : a[J] * inv;
 #pragma unroll
     for (int c = J + 1; c < PW; c++) {

@@ -137,11 +137,11 @@ __device__ __forceinline__ void tri_pass(const Pipe& p, uint32_t q0, Acc2& acc, 
 
 __host__ __device__ __forceinline__ int tri_epilogue_nstages(int npass) { return npass; }   // 8 (4) k-tiles, 2 per stage
 
-template <class Gen>
-__device__ __forceinline__ void tri_epilogue(Pipe& p, Gen& gen, Acc2& acc, int npass, bool active, double scale) {
+template <class Pump>
+__device__ __forceinline__ void tri_epilogue(Pipe& p, Pump&& pump, Acc2& acc, int npass, bool active, double scale) {
   const uint32_t q0 = p.q_cons;
   for (int e = 0; e < npass; e++) {                 // wait for every epilogue stage (they stay resident)
-    if ((threadIdx.x >> 5) == 0) topup(p, gen);
+    if ((threadIdx.x >> 5) == 0) pump();
     const uint32_t q = q0 + e;
     p.wait_bar(&p.full[q % NS2], (q / NS2) & 1, 4);
   }

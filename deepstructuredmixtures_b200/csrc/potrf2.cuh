@@ -20,35 +20,97 @@ namespace dsm {
 
 __device__ __forceinline__ int tile_flag_index(int I, int J) { return I * (I + 1) / 2 + J; }
 
+// non-blocking test of a tile flag by a whole warp (lane 0 reads, result broadcast)
+__device__ __forceinline__ bool flag_is_set(const int* f) {
+  int v = 1;
+  if ((threadIdx.x & 31) == 0) v = ld_acquire(f);
+  return __shfl_sync(0xffffffffu, v, 0) != 0;
+}
+
+// Chunk generator of one tile task.  Stage order: the tile F_IJ itself (2 column tiles per stage, no dependency), the
+// contraction chunks (k-block Kb needs tiles (I,Kb) and (J,Kb)), then W_J for the TRSM epilogue (panel tiles only).
 struct PotrfGen {
   const double* F; const double* z; const double* Wj; const int* flags;
-  int nkc, I, J, wj;
-  int nc, nmain, nepi, c;                          // stages: F_IJ itself, contraction chunks, W_J (panel tiles only)
-  bool diag;
-  __device__ __forceinline__ bool next(ChunkDesc& d) {
+  int nkc, I, J;
+  int nc, nmain, nepi, c;
+  bool diag, allready;       // allready: every k-block is known to be complete (tile (.,J-1) done implies all before it)
+  __device__ __forceinline__ int total() const { return nc + nmain + nepi; }
+
+  __device__ __forceinline__ void load(const Potrf2Args& a, int ti) {
+    c = 0; nc = nmain = nepi = 0; diag = false; allready = false;
+    if (ti >= a.ntasks) return;
+    const int4 tk = a.tasks[ti];
+    const LeafMeta m = a.meta[tk.x];
+    I = tk.y; J = tk.z; diag = (I == J);
+    if (!diag && I < a.jstart) return;                    // tile already final (chol_continue)
+    nkc = m.nkc;
+    F = a.F + m.foff; z = a.z + m.voff; Wj = a.W + m.woff + (int64_t)J * WBLK_D;
+    flags = a.flags + a.flag_off[tk.x];
+    const int wj = blk_width(m.np, J);
+    nc = wj / 32;
+    nmain = (diag && J < a.jstart) ? 0 : (J * BLK) / KC;
+    nepi = diag ? 0 : tri_epilogue_nstages(wj / 32);
+  }
+
+  // block = true: dependencies are attached to the descriptor and Pipe::issue waits for them;
+  // block = false (prefetch of the NEXT task): a chunk whose dependency is not yet complete is not delivered.
+  __device__ __forceinline__ bool next(ChunkDesc& d, bool block) {
     if (c >= nc + nmain + nepi) return false;
-    if (c < nc) {                                  // the tile being updated: 2 column tiles per stage, no dependency
+    d.flag0 = nullptr; d.flag1 = nullptr;
+    if (c < nc) {
       d.a = F + tile_off(I, J * 8 + 2 * c, nkc); d.abytes = TILE_BYTES;
       d.b = F + tile_off(I, J * 8 + 2 * c + 1, nkc); d.bbytes = TILE_BYTES;
-      d.flag0 = nullptr; d.flag1 = nullptr;
     } else if (c < nc + nmain) {
-      const int cc = c - nc;
-      const int Kb = cc >> 3;                      // 8 chunks per 128-wide k-block
-      const bool first = (cc & 7) == 0;
-      d.a = F + tile_off(I, cc, nkc); d.abytes = TILE_BYTES;
-      if (diag) {             // B operand == A operand; the B part of the stage carries z[16cc .. 16cc+16)
-        d.b = z + KC * cc; d.bbytes = KC * 8;
-        d.flag0 = first ? flags + tile_flag_index(J, Kb) : nullptr; d.flag1 = nullptr;
-      } else {
-        d.b = F + tile_off(J, cc, nkc); d.bbytes = TILE_BYTES;
-        d.flag0 = first ? flags + tile_flag_index(I, Kb) : nullptr;
-        d.flag1 = first ? flags + tile_flag_index(J, Kb) : nullptr;
+      const int cc = c - nc, Kb = cc >> 3;
+      if ((cc & 7) == 0 && !allready) {
+        if (cc == 0 && J > 1) {                           // fast path: the last k-block's tiles complete => all are
+          const bool l0 = flag_is_set(flags + tile_flag_index(I, J - 1));
+          const bool l1 = diag ? true : flag_is_set(flags + tile_flag_index(J, J - 1));
+          allready = l0 && l1;
+        }
+        if (!allready) {
+          const int* f0 = flags + tile_flag_index(I, Kb);
+          const int* f1 = diag ? nullptr : flags + tile_flag_index(J, Kb);
+          if (block) { d.flag0 = f0; d.flag1 = f1; }
+          else if (!flag_is_set(f0) || (f1 != nullptr && !flag_is_set(f1))) return false;
+        }
       }
+      d.a = F + tile_off(I, cc, nkc); d.abytes = TILE_BYTES;
+      if (diag) { d.b = z + KC * cc; d.bbytes = KC * 8; }          // B operand == A operand; B part carries z[16cc..]
+      else { d.b = F + tile_off(J, cc, nkc); d.bbytes = TILE_BYTES; }
     } else {
-      d = tri_epilogue_chunk(Wj, c - nc - nmain, flags + tile_flag_index(J, J));
+      const int e = c - nc - nmain;
+      const int* f = (e == 0) ? flags + tile_flag_index(J, J) : nullptr;
+      if (f != nullptr && !block && !flag_is_set(f)) return false;
+      d = tri_epilogue_chunk(Wj, e, block ? f : nullptr);
     }
     c++;
     return true;
+  }
+};
+
+// Warp-0 scheduler state: the generator of the running task and of the NEXT task, which is claimed as soon as the
+// running task has issued its last chunk so that its first stages are already in flight at the task boundary.
+struct PotrfSched {
+  PotrfGen cur, nxt;
+  int nxt_ti;
+  bool have_next;
+  __device__ __forceinline__ void claim(const Potrf2Args& a) {
+    int t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
+    nxt_ti = __shfl_sync(0xffffffffu, t, 0);
+    nxt.load(a, nxt_ti);
+    have_next = true;
+  }
+  __device__ __forceinline__ void pump(Pipe& p, const Potrf2Args& a) {
+    ChunkDesc d;
+    while (p.can_issue()) {
+      if (cur.next(d, true)) { p.issue(d); continue; }
+      if (cur.diag) break;        // a diagonal tile reuses the ring as scratch: nothing may be in flight behind it
+      if (!have_next) claim(a);
+      if (!nxt.next(d, false)) break;
+      p.issue(d);
+    }
   }
 };
 
@@ -62,11 +124,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
   const int r0 = 16 * warp;
   Pipe p;
   p.init(smem, a.gerr);
+  PotrfSched sch;
+  sch.have_next = false; sch.nxt_ti = 0;
+  if (tid == 0) s_task = atomicAdd(a.counter, 1);
+  __syncthreads();
+  int ti = s_task;
+  if (warp == 0) sch.cur.load(a, ti);
   for (;;) {
-    if (tid == 0) s_task = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const int ti = s_task;
-    __syncthreads();
     if (ti >= a.ntasks) return;
     const int4 tk = a.tasks[ti];
     const LeafMeta m = a.meta[tk.x];
@@ -80,24 +144,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     const bool diag = (I == J);
     const bool active = r0 < wi;
     const bool prefactored = (J < a.jstart);     // chol_continue: column already final, diag only rebuilds W
-    if (!diag && I < a.jstart) {                  // tile already final
-      if (tid == 0) st_release(flags + tile_flag_index(I, J), 1);
-      continue;
-    }
-    PotrfGen gen;
-    gen.F = F; gen.z = a.z + m.voff; gen.Wj = Wj; gen.flags = flags; gen.nkc = nkc;
-    gen.wj = wj; gen.I = I; gen.J = J; gen.diag = diag; gen.c = 0;
-    gen.nmain = (diag && prefactored) ? 0 : j0 / KC;
-    gen.nepi = diag ? 0 : tri_epilogue_nstages(wj / 32);
-    gen.nc = wj / 32;
+    const bool trivial = (!diag && I < a.jstart); // tile already final
+    const int n_c = trivial ? 0 : wj / 32;
+    const int n_main = (trivial || (diag && prefactored)) ? 0 : j0 / KC;
 
     // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
     Acc2 acc;
     acc2_zero(acc);
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      if (e < gen.nc) {
-        if (warp == 0) topup(p, gen);
+      if (e < n_c) {
+        if (warp == 0) sch.pump(p, a);
         const int st = p.wait();
         if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
         p.release();
@@ -106,28 +163,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
 
     if (!diag) {
       // ---------------- panel tile ----------------
-      const int nmain = gen.nmain;
-      for (int c = 0; c < nmain; c++) {
-        if (warp == 0) topup(p, gen);
-        const int st = p.wait();
-        if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
-        p.release();
+      if (!trivial) {
+        for (int c = 0; c < n_main; c++) {
+          if (warp == 0) sch.pump(p, a);
+          const int st = p.wait();
+          if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
+          p.release();
+        }
+        // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
+        tri_epilogue(p, [&]() { sch.pump(p, a); }, acc, wj / 32, active, -1.0);
+        acc2_store(acc, F, nkc, i0, j0, wi, wj);
       }
-      // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
-      tri_epilogue(p, gen, acc, wj / 32, active, -1.0);
-      acc2_store(acc, F, nkc, i0, j0, wi, wj);
-      __syncthreads();
-      if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
-      continue;
-    }
-
+    } else {
     // ---------------- diagonal tile ----------------
     double gemv = 0.0;                                  // row r0 + (lane & 15), k-half lane >> 4
     {
-      const int nmain = gen.nmain;
       const int ng = min(wj / 32, warp / 2 + 1);        // lower triangle only: columns <= 16*warp + 15
-      for (int c = 0; c < nmain; c++) {
-        if (warp == 0) topup(p, gen);
+      for (int c = 0; c < n_main; c++) {
+        if (warp == 0) sch.pump(p, a);
         const int st = p.wait();
         if (active) {
           const double* sA = p.A(st);
@@ -216,8 +269,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       a.zzpart[po / 2 + J] = zz;
     }
     fence_proxy_async();                                 // generic writes to the stages precede the next bulk copies
+    }   // diagonal tile
+    // ---------------- task boundary: publish the tile, hand over to the (possibly already prefetched) next task
     __syncthreads();
-    if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(J, J), 1); }
+    if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
+    if (warp == 0) {
+      if (!sch.have_next) sch.claim(a);
+      sch.cur = sch.nxt; sch.have_next = false;
+      if (lane == 0) s_task = sch.nxt_ti;
+    }
+    __syncthreads();
+    ti = s_task;
   }
 }
 

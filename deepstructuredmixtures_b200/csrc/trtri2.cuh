@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
         if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
         p.release();
       }
-      tri_epilogue(p, gen, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
+      tri_epilogue(p, [&]() { topup(p, gen); }, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
       acc2_store(acc, F, m.nkc, j0, i0, BLK, wi);
       // fused reductions: ||X_IJ||_F^2 over real rows/cols, alpha_J += X_IJ^T z_I
       double p0 = 0.0, p1 = 0.0;
