@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
   __shared__ int s_task;
   __shared__ double s_red[16];
   __shared__ double s_al[BLK];
+  __shared__ __align__(32) double s_z[NTHREADS / 32][BLK];     // per-warp copy of z_I (prefetched at the start of an iteration)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int r0 = 16 * warp;
   Pipe p;
@@ -73,6 +74,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
       const int nmain = (i0 - j0) / KC;
       Acc2 acc;
       acc2_zero(acc);
+      {   // z_I for the fused alpha reduction: latency hidden behind the contraction
+        const double4 zv = (4 * lane < wi) ? *reinterpret_cast<const double4*>(z + i0 + 4 * lane) : make_double4(0.0, 0.0, 0.0, 0.0);
+        __syncwarp();
+        *reinterpret_cast<double4*>(&s_z[warp][4 * lane]) = zv;
+        __syncwarp();
+      }
       for (int c = 0; c < nmain; c++) {
         if (warp == 0) topup(p, gen);
         const int st = p.wait();
@@ -91,7 +98,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
           for (int e = 0; e < 2; e++) {
             const int col = i0 + acc_col(n, e);
             if (col < m.n) {
-              const double zi = z[col];
+              const double zi = s_z[warp][col - i0];
               const double v0 = acc[0][n][e], v1 = acc[1][n][e];
               if (row0) { tr = fma(v0, v0, tr); p0 = fma(v0, zi, p0); }
               if (row1) { tr = fma(v1, v1, tr); p1 = fma(v1, zi, p1); }

@@ -261,3 +261,25 @@ def test_golden_vectors_gpu(name):
     assert abs(z - gold["z"]) <= LML_TOL * abs(gold["z"])
     mu, var = dsm.predict(model, test_points(case))
     assert relerr(mu, np.array(gold["mu"])) < PRED_TOL and relerr(var, np.array(gold["var"])) < PRED_TOL
+
+
+def test_streaming_batches_match_resident():
+    """keep_factors=0 with a tiny arena: the experts are processed in several batches that reuse the factor arena
+    (the cfg5 path: factor -> reduce -> discard).  Must give the same LML and gradient as the resident run."""
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import model as mdl, structure as st
+    x, y = synth(6000, 5, 31)
+    kern = dsm.ArdSE(np.zeros(5), 0.0)
+    cfg = st.DSMGPConfig(None, kern, -1.0, 120, 4, 3, 2, 0.5, True)
+    root = st.buildTree(x, y, cfg, np.random.default_rng(31))
+    th = np.array([0.1, -0.1, 0.2, 0.0, -0.2, 0.1, -1.0])
+    ma = mdl.DSMGP(root, x, y, [kern.copy()], -1.0)
+    lml_a, g_a = ma.handle.eval(th)
+    ma.close()
+    root = st.buildTree(x, y, cfg, np.random.default_rng(31))
+    mb = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, keep_factors=False, arena_bytes=24 << 20)
+    lml_b, g_b = mb.handle.eval(th)
+    assert lml_a == lml_b and np.array_equal(g_a, g_b)
+    with pytest.raises(dsm.DsmgpError):
+        dsm.predict(mb, x[:10])
+    mb.close()
