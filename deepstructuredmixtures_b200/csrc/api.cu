@@ -539,8 +539,18 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
       CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
       Potrf2Args pa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, scal, h->d_trpart.p, b.d_trpart_off,
                     h->d_ldpart.p, h->d_zzpart.p, h->d_flags.p, b.d_flag_off, b.d_potrf2_tasks, b.n_potrf2,
-                    h->d_counter.p + 4, h->d_counter.p + 8, 0};
+                    h->d_counter.p + 4, h->d_counter.p + 8, 0, nullptr};
+      long long* d_trace = nullptr;
+      const char* trace_file = getenv("DSMGP_TRACE_FILE");
+      if (trace_file) { cudaMalloc(&d_trace, (size_t)b.n_potrf2 * 64); cudaMemsetAsync(d_trace, 0, (size_t)b.n_potrf2 * 64, st); pa.trace = d_trace; }
       launch_potrf2(pa, std::min(sms, b.n_potrf2), st);
+      if (trace_file) {
+        std::vector<long long> tr((size_t)b.n_potrf2 * 8);
+        cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        if (FILE* f = fopen(trace_file, "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+        cudaFree(d_trace);
+      }
       h->tm.launches++;
       cudaEventRecord(ev[3], st);
       if (!with_grad) {       // fit only: alpha by block back-substitution (the forward solve was fused above)
@@ -1210,7 +1220,7 @@ static int32_t chol_host_matrix(double* A, int64_t n, int64_t k, int32_t* info) 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   {
     Potrf2Args pa{dm, dF, dW, dWT, dv, dv + np, ds, dtr, doff, dtr + 2 * m.nb, dtr + 3 * m.nb, dflags, doff + 1, dtasks,
-                  (int)tasks.size(), dcnt, dcnt + 8, (int)(kp / BLK)};
+                  (int)tasks.size(), dcnt, dcnt + 8, (int)(kp / BLK), nullptr};
     launch_potrf2(pa, std::min(sms, (int)tasks.size()), 0);
     SA_TRY(cudaGetLastError());
     SA_TRY(cudaMemcpy(P.data(), dF, fd * 8, cudaMemcpyDeviceToHost));

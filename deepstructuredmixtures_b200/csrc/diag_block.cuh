@@ -2,23 +2,25 @@
 //
 // This is the serial link of the left-looking factorisation (every panel tile of a block column waits for it), so
 // it is blocked for latency, not for throughput:
-//   * 32-wide panels.  The 32 x 32 diagonal block of a panel is factored AND inverted by one warp entirely in
+//   * 16-wide panels.  The 16 x 16 diagonal block of a panel is factored AND inverted by one warp entirely in
 //     registers (lane r holds row r; the rank-1 updates fetch the pivot column with warp shuffles) -- no shared-memory
-//     round trips and no block barriers inside the 32 pivot steps.
-//   * panel TRSM (A21 * D^-T), trailing SYRK and the block forward substitution that builds W = L^-1 run on
-//     DMMA.8x8x4 with operands straight from the tile.
+//     round trips and no block barriers inside the pivot steps.  (The register routine costs O(PW^2) shuffles per
+//     panel, i.e. O(m PW) per tile: 16 beat 32 by 3x in the per-task clock stamps.)
+//   * panel TRSM (A21 * D^-T) and the trailing SYRK run on DMMA.8x8x4 with operands straight from the tile.
+//   * W = L^-1 by block forward substitution, one WARP PER BLOCK COLUMN: column j of W depends only on L and on
+//     itself, so the eight columns proceed without any block barrier (DMMA + a per-warp 16 x 16 scratch).
 // Layout: S[c * LDS + r] column-major.  On return the lower triangle (incl. diagonal) holds L, the strict upper
-// triangle of the OFF-diagonal 32-blocks holds W^T (W[r][c] at S[r * LDS + c]) and DI[P] holds the inverse of the
-// P-th 32 x 32 diagonal block as DI[P][k * DLD + x] = W[x][k] (zero for x < k).
+// triangle of the OFF-diagonal 16-blocks holds W^T (W[r][c] at S[r * LDS + c]) and DI[P] holds the inverse of the
+// P-th 16 x 16 diagonal block as DI[P][k * DLD + x] = W[x][k] (zero for x < k).
 #pragma once
 #include "common.cuh"
 
 namespace dsm {
 
-constexpr int PW = 32;            // panel width
-constexpr int DLD = 36;           // leading dimension of the 32 x 32 scratch blocks (36 % 16 == 4: conflict-free fragments)
+constexpr int PW = 16;            // panel width
+constexpr int DLD = 20;           // leading dimension of the 16 x 16 scratch blocks (20 % 16 == 4: conflict-free fragments)
 constexpr int DBLK = PW * DLD;    // doubles per scratch block
-constexpr int DIAG_AUX_DOUBLES = 4 * DBLK + 3 * DBLK;   // DI[4] + T[3]
+constexpr int DIAG_AUX_DOUBLES = (BLK / PW) * DBLK + (NTHREADS / 32) * DBLK + BLK;   // DI[8] + one T block per warp + 1/diag
 
 // W[r][k] (r >= k) after diag_factor_invert
 __device__ __forceinline__ double diag_W(const double* S, const double* DI, int r, int k) {
@@ -69,28 +71,39 @@ struct InvStep<-1> {
   __device__ static __forceinline__ void run(const double (&)[PW], double (&)[PW], int, double) {}
 };
 
-// Warp-level Cholesky + inverse of the 32 x 32 block at (c0, c0).  Executed by ONE warp.  Returns the 1-based local
-// pivot index of the first non-positive pivot (0 = ok).
-__device__ __forceinline__ int warp_potrf_inv32(double* S, int c0, double* DIp, bool factor) {
-  const int r = threadIdx.x & 31;
+// Warp-level Cholesky of the PW x PW block at (c0, c0) (lanes 16..31 mirror lanes 0..15): L is written back to S,
+// the reciprocals of its diagonal to rdiag[c0 ..].  Returns the 1-based local index of the first non-positive pivot.
+__device__ __forceinline__ int warp_potrf16(double* S, int c0, double* rdiag) {
+  const int r = threadIdx.x & (PW - 1);
+  const bool writer = (threadIdx.x & 31) < PW;
   double a[PW];
 #pragma unroll
   for (int c = 0; c < PW; c++) a[c] = S[(c0 + c) * LDS + c0 + r];      // row r (entries c > r are never used)
   int info = 0;
-  if (factor) {
-    PotrfStep<PW - 1>::run(a, r, info);
+  PotrfStep<PW - 1>::run(a, r, info);
 #pragma unroll
-    for (int c = 0; c < PW; c++)
-      if (r >= c) S[(c0 + c) * LDS + c0 + r] = a[c];
+  for (int c = 0; c < PW; c++) {
+    if (writer && r >= c) S[(c0 + c) * LDS + c0 + r] = a[c];
+    if (writer && r == c) rdiag[c0 + c] = 1.0 / a[c];
   }
+  return info;
+}
+
+// Warp-level inverse of the lower-triangular PW x PW block at (c0, c0) into the scratch block DIp.
+__device__ __forceinline__ void warp_inv16(const double* S, int c0, double* DIp) {
+  const int r = threadIdx.x & (PW - 1);
+  const bool writer = (threadIdx.x & 31) < PW;
+  double a[PW];
+#pragma unroll
+  for (int c = 0; c < PW; c++) a[c] = S[(c0 + c) * LDS + c0 + r];
   double w[PW];
   double rinv = 1.0;
 #pragma unroll
   for (int k = 0; k < PW; k++) { w[k] = 0.0; if (k == r) rinv = 1.0 / a[k]; }     // 1 / l_rr without dynamic indexing
   InvStep<PW - 1>::run(a, w, r, rinv);
 #pragma unroll
-  for (int k = 0; k < PW; k++) DIp[r * DLD + k] = w[k];   // DI[k = column r][x = k] = W[k][r]  -> row `r` of the scratch
-  return info;
+  for (int k = 0; k < PW; k++)
+    if (writer) DIp[r * DLD + k] = w[k];                  // DI[k = column r][x = k] = W[k][r]  -> row `r` of the scratch
 }
 
 __device__ __forceinline__ void dmma_tile(double& c0, double& c1, double a, double b) { dmma884(c0, c1, a, b); }
@@ -100,38 +113,33 @@ __device__ __forceinline__ void dmma_tile(double& c0, double& c1, double a, doub
 __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux, bool factor, int* s_info) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   double* DI = aux;
-  double* T = aux + 4 * DBLK;
+  double* Tw = aux + (BLK / PW) * DBLK + warp * DBLK;       // this warp's 16 x 16 scratch
   const int np = m / PW;
   if (tid == 0) *s_info = 0;
   __syncthreads();
-  for (int P = 0; P < np; P++) {
+  double* rdiag = aux + (BLK / PW) * DBLK + (NTHREADS / 32) * DBLK;     // 1 / l_cc of the tile
+  for (int P = 0; P < np && factor; P++) {
     const int c0 = P * PW, r1 = c0 + PW, nrem = m - r1;
     if (warp == 0) {
-      const int info = warp_potrf_inv32(S, c0, DI + P * DBLK, factor);
+      const int info = warp_potrf16(S, c0, rdiag);
       if (lane == 0 && info != 0 && *s_info == 0) *s_info = c0 + info;
     }
     __syncthreads();
-    if (!factor || nrem == 0) continue;
-    // ---- panel TRSM: X = A21 * DI_P^T  (rows r1..m, 32 columns), in place
-    for (int rt = warp; rt < nrem / 8; rt += NTHREADS / 32) {
-      const int rr = r1 + 8 * rt;
-      double a[8];
+    if (nrem == 0) continue;
+    // ---- panel TRSM: X = A21 * L11^-T by forward substitution, one thread per row (needs L11 only, not its inverse)
+    if (tid < nrem) {
+      const int rr = r1 + tid;
+      double x[PW];
 #pragma unroll
-      for (int kb = 0; kb < 8; kb++) a[kb] = S[(c0 + 4 * kb + t) * LDS + rr + g];
-      double x[4][2];
+      for (int c = 0; c < PW; c++) x[c] = S[(c0 + c) * LDS + rr];
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        x[nb][0] = 0.0; x[nb][1] = 0.0;
+      for (int c = 0; c < PW; c++) {
+        x[c] *= rdiag[c0 + c];
 #pragma unroll
-        for (int kb = 0; kb < 8; kb++)
-          if (kb <= 2 * nb + 1) dmma_tile(x[nb][0], x[nb][1], a[kb], DI[P * DBLK + (4 * kb + t) * DLD + 8 * nb + g]);
+        for (int k = c + 1; k < PW; k++) x[k] = fma(-x[c], S[(c0 + c) * LDS + c0 + k], x[k]);     // l_kc (broadcast read)
       }
-      __syncwarp();
 #pragma unroll
-      for (int nb = 0; nb < 4; nb++) {
-        S[(c0 + 8 * nb + 2 * t) * LDS + rr + g] = x[nb][0];
-        S[(c0 + 8 * nb + 2 * t + 1) * LDS + rr + g] = x[nb][1];
-      }
+      for (int c = 0; c < PW; c++) S[(c0 + c) * LDS + rr] = x[c];
     }
     __syncthreads();
     // ---- trailing update: A22 -= X X^T  (lower 8 x 8 tiles)
@@ -145,7 +153,7 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
         double* cp = S + (r1 + 8 * tj + 2 * t) * LDS + r1 + 8 * ti + g;
         double c0v = cp[0], c1v = cp[LDS];
 #pragma unroll
-        for (int kb = 0; kb < 8; kb++) {
+        for (int kb = 0; kb < PW / 4; kb++) {
           const double av = -S[(c0 + 4 * kb + t) * LDS + r1 + 8 * ti + g];
           const double bv = S[(c0 + 4 * kb + t) * LDS + r1 + 8 * tj + g];
           dmma_tile(c0v, c1v, av, bv);
@@ -155,36 +163,60 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
     }
     __syncthreads();
   }
-  // ---- W = L^-1 by block forward substitution: row block P, column blocks j < P
-  for (int P = 1; P < np; P++) {
-    // T_j = sum_{k = 32 j}^{32 P - 1} L[32P + r][k] * W[k][32 j + c]      (16 tiles per j)
-    for (int q = warp; q < 16 * P; q += NTHREADS / 32) {
-      const int j = q >> 4, mb = (q >> 2) & 3, nb = q & 3;
-      double c0v = 0.0, c1v = 0.0;
-      for (int kb = 0; kb < 8 * (P - j); kb++) {
-        const int kg = PW * j + 4 * kb + t;                       // global k of this lane's fragment element
-        const double av = S[kg * LDS + PW * P + 8 * mb + g];
-        const double bv = (kb < 8) ? DI[j * DBLK + (8 * nb + g) * DLD + 4 * kb + t]     // W[k][c] inside diagonal block j
-                                   : S[kg * LDS + PW * j + 8 * nb + g];                  // W^T stored in the upper part
-        dmma_tile(c0v, c1v, av, bv);
-      }
-      double* tp = T + j * DBLK + (8 * mb + g) * DLD + 8 * nb + 2 * t;   // T[k = row][c]
-      tp[0] = c0v; tp[1] = c1v;
-    }
-    __syncthreads();
-    // W_Pj = -DI_P * T_j   -> stored transposed: W[r][c] at S[r_global * LDS + c_global]
-    for (int q = warp; q < 16 * P; q += NTHREADS / 32) {
-      const int j = q >> 4, mb = (q >> 2) & 3, nb = q & 3;
-      double c0v = 0.0, c1v = 0.0;
+  // ---- inverses of the diagonal blocks: eight independent 16 x 16 problems, one warp each
+  for (int P = warp; P < np; P += NTHREADS / 32) warp_inv16(S, P * PW, DI + P * DBLK);
+  __syncthreads();
+  // ---- W = L^-1: warp j owns block column j; row blocks P = j+1 .. np-1 in sequence, no block barrier
+  for (int j = warp; j < np; j += NTHREADS / 32) {
+    for (int P = j + 1; P < np; P++) {
+      // T = sum_{k = PW j}^{PW P - 1} L[PW P + r][k] * W[k][PW j + c]        (2 x 2 tiles)
+      double c[2][2][2];
 #pragma unroll
-      for (int kb = 0; kb < 8; kb++)
-        if (kb <= 2 * mb + 1)
-          dmma_tile(c0v, c1v, DI[P * DBLK + (4 * kb + t) * DLD + 8 * mb + g], T[j * DBLK + (4 * kb + t) * DLD + 8 * nb + g]);
-      double* wp = S + (PW * P + 8 * mb + g) * LDS + PW * j + 8 * nb + 2 * t;
-      wp[0] = -c0v; wp[1] = -c1v;
+      for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++) { c[mb][nb][0] = 0.0; c[mb][nb][1] = 0.0; }
+      for (int kb = 0; kb < (PW / 4) * (P - j); kb++) {
+        const int kg = PW * j + 4 * kb + t;
+        const double a0 = S[kg * LDS + PW * P + g], a1 = S[kg * LDS + PW * P + 8 + g];
+        double b0, b1;
+        if (kb < PW / 4) {            // W[k][c] inside diagonal block j
+          b0 = DI[j * DBLK + g * DLD + 4 * kb + t];
+          b1 = DI[j * DBLK + (8 + g) * DLD + 4 * kb + t];
+        } else {                       // W^T stored in the upper part (written by this warp in earlier iterations)
+          b0 = S[kg * LDS + PW * j + g];
+          b1 = S[kg * LDS + PW * j + 8 + g];
+        }
+        dmma_tile(c[0][0][0], c[0][0][1], a0, b0);
+        dmma_tile(c[0][1][0], c[0][1][1], a0, b1);
+        dmma_tile(c[1][0][0], c[1][0][1], a1, b0);
+        dmma_tile(c[1][1][0], c[1][1][1], a1, b1);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++) {
+          double* tp = Tw + (8 * mb + g) * DLD + 8 * nb + 2 * t;         // T[k = row][c]
+          tp[0] = c[mb][nb][0]; tp[1] = c[mb][nb][1];
+        }
+      __syncwarp();
+      // W_Pj = -DI_P * T  -> stored transposed: W[r][c] at S[r_global * LDS + c_global]
+#pragma unroll
+      for (int mb = 0; mb < 2; mb++)
+#pragma unroll
+        for (int nb = 0; nb < 2; nb++) {
+          double w0 = 0.0, w1 = 0.0;
+#pragma unroll
+          for (int kb = 0; kb < PW / 4; kb++)
+            if (kb <= 2 * mb + 1)
+              dmma_tile(w0, w1, DI[P * DBLK + (4 * kb + t) * DLD + 8 * mb + g], Tw[(4 * kb + t) * DLD + 8 * nb + g]);
+          double* wp = S + (PW * P + 8 * mb + g) * LDS + PW * j + 8 * nb + 2 * t;
+          wp[0] = -w0; wp[1] = -w1;
+        }
+      __syncwarp();
     }
-    __syncthreads();
   }
+  __syncthreads();
   return *s_info;
 }
 

@@ -34,10 +34,11 @@ struct PotrfGen {
   int nkc, I, J;
   int nc, nmain, nepi, c;
   bool diag, allready;       // allready: every k-block is known to be complete (tile (.,J-1) done implies all before it)
+  bool stalled;              // a non-blocking dependency test failed: do not poll again until the task is current
   __device__ __forceinline__ int total() const { return nc + nmain + nepi; }
 
   __device__ __forceinline__ void load(const Potrf2Args& a, int ti) {
-    c = 0; nc = nmain = nepi = 0; diag = false; allready = false;
+    c = 0; nc = nmain = nepi = 0; diag = false; allready = false; stalled = false;
     if (ti >= a.ntasks) return;
     const int4 tk = a.tasks[ti];
     const LeafMeta m = a.meta[tk.x];
@@ -56,6 +57,7 @@ struct PotrfGen {
   // block = false (prefetch of the NEXT task): a chunk whose dependency is not yet complete is not delivered.
   __device__ __forceinline__ bool next(ChunkDesc& d, bool block) {
     if (c >= nc + nmain + nepi) return false;
+    if (!block && stalled) return false;
     d.flag0 = nullptr; d.flag1 = nullptr;
     if (c < nc) {
       d.a = F + tile_off(I, J * 8 + 2 * c, nkc); d.abytes = TILE_BYTES;
@@ -64,15 +66,18 @@ struct PotrfGen {
       const int cc = c - nc, Kb = cc >> 3;
       if ((cc & 7) == 0 && !allready) {
         if (cc == 0 && J > 1) {                           // fast path: the last k-block's tiles complete => all are
-          const bool l0 = flag_is_set(flags + tile_flag_index(I, J - 1));
-          const bool l1 = diag ? true : flag_is_set(flags + tile_flag_index(J, J - 1));
-          allready = l0 && l1;
+          int v0 = 1, v1 = 1;                             // both loads in flight before either is consumed
+          if ((threadIdx.x & 31) == 0) {
+            v0 = ld_acquire(flags + tile_flag_index(I, J - 1));
+            if (!diag) v1 = ld_acquire(flags + tile_flag_index(J, J - 1));
+          }
+          allready = __shfl_sync(0xffffffffu, (v0 != 0) && (v1 != 0) ? 1 : 0, 0) != 0;
         }
         if (!allready) {
           const int* f0 = flags + tile_flag_index(I, Kb);
           const int* f1 = diag ? nullptr : flags + tile_flag_index(J, Kb);
           if (block) { d.flag0 = f0; d.flag1 = f1; }
-          else if (!flag_is_set(f0) || (f1 != nullptr && !flag_is_set(f1))) return false;
+          else if (!flag_is_set(f0) || (f1 != nullptr && !flag_is_set(f1))) { stalled = true; return false; }
         }
       }
       d.a = F + tile_off(I, cc, nkc); d.abytes = TILE_BYTES;
@@ -81,7 +86,7 @@ struct PotrfGen {
     } else {
       const int e = c - nc - nmain;
       const int* f = (e == 0) ? flags + tile_flag_index(J, J) : nullptr;
-      if (f != nullptr && !block && !flag_is_set(f)) return false;
+      if (f != nullptr && !block && !flag_is_set(f)) { stalled = true; return false; }
       d = tri_epilogue_chunk(Wj, e, block ? f : nullptr);
     }
     c++;
@@ -147,6 +152,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     const bool trivial = (!diag && I < a.jstart); // tile already final
     const int n_c = trivial ? 0 : wj / 32;
     const int n_main = (trivial || (diag && prefactored)) ? 0 : j0 / KC;
+    long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)ti * 8 : nullptr;
+    if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = sm; trc[6] = I; trc[7] = J; }
 
     // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
     Acc2 acc;
@@ -161,6 +168,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       }
     }
 
+    if (trc) trc[1] = clock64();
     if (!diag) {
       // ---------------- panel tile ----------------
       if (!trivial) {
@@ -170,8 +178,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
           if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
           p.release();
         }
+        if (trc) trc[2] = clock64();
         // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
         tri_epilogue(p, [&]() { sch.pump(p, a); }, acc, wj / 32, active, -1.0);
+        if (trc) trc[3] = clock64();
         acc2_store(acc, F, nkc, i0, j0, wi, wj);
       }
     } else {
@@ -198,6 +208,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
         p.release();
       }
     }
+    if (trc) trc[2] = clock64();
     gemv += __shfl_xor_sync(0xffffffffu, gemv, 16);
     __syncthreads();                                     // every warp is done with the ring: stages become scratch
     double* S = smem;                                    // resident tile [c][LDS] (stages 0..3)
@@ -217,6 +228,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info);
       if (tid == 0 && info != 0) atomicCAS(&a.scal[tk.x].info, 0, j0 + info);
     }
+    if (trc) trc[3] = clock64();
     const double* DI = aux;
     if (!prefactored) {
       for (int c = warp; c < wj; c += NTHREADS / 32) {
@@ -279,6 +291,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       if (lane == 0) s_task = sch.nxt_ti;
     }
     __syncthreads();
+    if (trc) trc[4] = clock64();
     ti = s_task;
   }
 }

@@ -13,6 +13,7 @@ struct Potrf2Args {
   const int4* tasks; int ntasks;                   // (slot, I, J, unused)
   int* counter; int* gerr;
   int jstart;                                      // chol_continue: block columns < jstart hold a valid factor
+  long long* trace;                                // optional [ntasks][8] clock stamps (DSMGP_TRACE_FILE), else null
 };
 
 struct Trtri2Args {
