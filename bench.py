@@ -35,6 +35,7 @@ sys.path.insert(0, ROOT)
 # FP64 roofs measured on this pool's B200 with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json)
 FP64_DGEMM_TFLOPS = 35.9     # cuBLAS DGEMM 8192^3 (burst == sustained: FP64 is not power capped)
 FP64_DMMA_TFLOPS = 37.2      # DMMA.8x8x4 issue roof
+NCU_TRAFFIC_GB = {("cfg3", 1, "potrf2_kernel"): 53.85, ("cfg3", 1, "trtri2_kernel"): 78.47}
 
 WORKLOADS = {
     # name: (N, D, kernel, V, K, M, depth, eps, seed)   SURVEY §8(d)
@@ -248,10 +249,15 @@ def main():
     stop.set(); th.join(timeout=2)
     dev_ms = phase["total_ms"]
     # e2e through the public API on host buffers (world == 1: the same call; world > 1: the wall clock above)
-    tt = torch.tensor([dev_ms, t_wall * 1e3], dtype=torch.float64, device=f"cuda:{local}")
+    tt = torch.tensor([dev_ms, t_wall * 1e3, phase["potrf_ms"], phase["inverse_ms"], phase["gram_ms"]], dtype=torch.float64,
+                      device=f"cuda:{local}")
+    fl = torch.tensor([tm["potrf_flops"], tm["inverse_flops"], tm["gram_bytes"]], dtype=torch.float64, device=f"cuda:{local}")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms = float(tt[0]), float(tt[1])
+    phase["potrf_ms"], phase["inverse_ms"], phase["gram_ms"] = float(tt[2]), float(tt[3]), float(tt[4])
+    tm = dict(tm, potrf_flops=float(fl[0]), inverse_flops=float(fl[1]), gram_bytes=float(fl[2]))
     if rank == 0:
         value = args.steps / (dev_ms * 1e-3)
         e2e = args.steps / (wall_ms * 1e-3)
@@ -259,8 +265,10 @@ def main():
         potrf_tf = potrf_fl * args.steps / (phase["potrf_ms"] * 1e-3) * 1e-12 if phase["potrf_ms"] > 0 else 0.0
         inv_tf = inv_fl * args.steps / (phase["inverse_ms"] * 1e-3) * 1e-12 if phase["inverse_ms"] > 0 else 0.0
         gram_gbs = tm["gram_bytes"] * args.steps / (phase["gram_ms"] * 1e-3) * 1e-9 if phase["gram_ms"] > 0 else 0.0
-        dom = "trtri_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf_panel_kernel+potrf_diag_kernel"
-        ach = inv_tf if dom == "trtri_kernel" else potrf_tf
+        dom = "trtri2_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf2_kernel"
+        ach = inv_tf if dom == "trtri2_kernel" else potrf_tf
+        # DRAM bytes per launch from `ncu --set full` (profiles/ncu_full_*_r01e.csv); only known for the profiled config
+        traffic = NCU_TRAFFIC_GB.get((args.workload, world, dom))
         ns_local = int(np.sum(H.leaf_owner() == 0))
         line = {
             "metric": "DSMGP LML+gradient evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
@@ -276,7 +284,8 @@ def main():
             "cholesky_gflops": potrf_tf * 1e3,
             "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
-                         "frac": ach / FP64_DGEMM_TFLOPS, "traffic": None,
+                         "frac": ach / FP64_DGEMM_TFLOPS, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                         "algorithmic": "flops per launch = sum over local experts of n^3/3 + n^2/2 + n/6 (SURVEY 8d), one launch per evaluation",
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (tools/fp64_peaks.cu, profiles/); "
                                         "MEASURED_PEAKS.json has no FP64 entry; DMMA issue roof 37.2",
                          "potrf_tflops": potrf_tf, "inverse_tflops": inv_tf, "gram_gbs": gram_gbs,
