@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdsmgp.so")
+# DSMGP_LIB_PATH: development override for A/B runs of kernel variants (still a CUDA build of this library)
+LIB_PATH = os.environ.get("DSMGP_LIB_PATH") or os.path.join(_HERE, "libdsmgp.so")
 
 OK, ERR_ARG, ERR_CUDA, ERR_COMM, ERR_OOM, ERR_NOT_PD, ERR_STATE = range(7)
 ISO_SE, ARD_SE, ISO_LINEAR, ARD_LINEAR = 0, 1, 2, 3

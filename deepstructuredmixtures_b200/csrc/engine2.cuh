@@ -100,19 +100,22 @@ __device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2],
 
 // Producer top-up: warp 0 issues every chunk the generator can deliver while the ring has room.
 template <class Gen>
-__device__ __forceinline__ void topup(Pipe& p, Gen& gen) {
+__device__ __forceinline__ void topup(Pipe& p, Gen& gen, uint32_t need) {
   ChunkDesc d;
-  while (p.can_issue() && gen.next(d)) p.issue(d);
+  while (p.can_issue() && p.slot_free(need) && gen.next(d)) p.issue(d);
 }
 
 // Triangular epilogue  OUT <- scale * OUT * M^T  (M lower triangular, 32*NP x 32*NP) in registers.
-// M arrives as NE = 2*NP/... epilogue stages: stage e carries M's k-tiles 2e (A part) and 2e+1 (B part); all of them
-// stay resident while the passes run (descending column groups, so the update is in place).
+// M arrives as NP epilogue stages in DESCENDING k order: stage e carries M's k-tiles 2(NP-1-e) (A part) and
+// 2(NP-1-e)+1 (B part).  The passes run over descending column groups (so the update is in place) and pass P reads
+// k-tiles 0 .. 2P+1 only: the stage with the highest k-tiles is dead after the first pass, the next one after the
+// second, ... -- they are released in ring (FIFO) order as the passes retire, so the producer can refill the ring with
+// the next task's chunks while the remaining passes still run.
 template <int P, int J>
 struct TriPass {
-  __device__ static __forceinline__ void run(const Pipe& p, uint32_t q0, const Acc2& acc, double (&o)[2][4][2]) {
-    TriPass<P, J - 1>::run(p, q0, acc, o);
-    const int st = (q0 + (J >> 1)) % NS2;
+  __device__ static __forceinline__ void run(const Pipe& p, uint32_t qlast, const Acc2& acc, double (&o)[2][4][2]) {
+    TriPass<P, J - 1>::run(p, qlast, acc, o);
+    const int st = (qlast - (J >> 1)) % NS2;
     tri_chunk<P, J>(acc, o, (J & 1) ? p.B(st) : p.A(st));
   }
 };
@@ -122,13 +125,13 @@ struct TriPass<P, -1> {
 };
 
 template <int P>
-__device__ __forceinline__ void tri_pass(const Pipe& p, uint32_t q0, Acc2& acc, double scale) {
+__device__ __forceinline__ void tri_pass(const Pipe& p, uint32_t qlast, Acc2& acc, double scale) {
   double o[2][4][2];
 #pragma unroll
   for (int m = 0; m < 2; m++)
 #pragma unroll
     for (int n = 0; n < 4; n++) { o[m][n][0] = 0.0; o[m][n][1] = 0.0; }
-  TriPass<P, 2 * P + 1>::run(p, q0, acc, o);
+  TriPass<P, 2 * P + 1>::run(p, qlast, acc, o);
 #pragma unroll
   for (int m = 0; m < 2; m++)
 #pragma unroll
@@ -140,24 +143,43 @@ __host__ __device__ __forceinline__ int tri_epilogue_nstages(int npass) { return
 template <class Pump>
 __device__ __forceinline__ void tri_epilogue(Pipe& p, Pump&& pump, Acc2& acc, int npass, bool active, double scale) {
   const uint32_t q0 = p.q_cons;
-  for (int e = 0; e < npass; e++) {                 // wait for every epilogue stage (they stay resident)
-    if ((threadIdx.x >> 5) == 0) pump();
+  const uint32_t qlast = q0 + npass - 1;            // chunk that carries k-tiles 0 and 1
+  for (int e = 0; e < npass; e++) {                 // pass NP-1 needs every stage
     const uint32_t q = q0 + e;
+    if ((threadIdx.x >> 5) == 0) pump(q);
     p.wait_bar(&p.full[q % NS2], (q / NS2) & 1, 4);
   }
+  const bool producer = (threadIdx.x >> 5) == 0;
+#if DSM_EPI_EARLY
+  if (npass == 4) {
+    if (active) tri_pass<3>(p, qlast, acc, scale);
+    p.release();
+    if (producer) pump(p.q_cons);
+    if (active) tri_pass<2>(p, qlast, acc, scale);
+    p.release();
+    if (producer) pump(p.q_cons);
+  }
+  if (active) tri_pass<1>(p, qlast, acc, scale);
+  p.release();
+  if (producer) pump(p.q_cons);
+  if (active) tri_pass<0>(p, qlast, acc, scale);
+  p.release();
+#else
   if (active) {
-    if (npass == 4) { tri_pass<3>(p, q0, acc, scale); tri_pass<2>(p, q0, acc, scale); }
-    tri_pass<1>(p, q0, acc, scale);
-    tri_pass<0>(p, q0, acc, scale);
+    if (npass == 4) { tri_pass<3>(p, qlast, acc, scale); tri_pass<2>(p, qlast, acc, scale); }
+    tri_pass<1>(p, qlast, acc, scale);
+    tri_pass<0>(p, qlast, acc, scale);
   }
   for (int e = 0; e < npass; e++) p.release();
+#endif
 }
 
-// Descriptor of epilogue stage `e` for a tiled W block (k-tiles 2e and 2e+1).
-__device__ __forceinline__ ChunkDesc tri_epilogue_chunk(const double* Wblk, int e, const int* flag) {
+// Descriptor of epilogue stage `e` of `npass` for a tiled W block (k-tiles 2(npass-1-e) and 2(npass-1-e)+1).
+__device__ __forceinline__ ChunkDesc tri_epilogue_chunk(const double* Wblk, int e, int npass, const int* flag) {
   ChunkDesc d;
-  d.a = Wblk + (2 * e) * TILE_D; d.abytes = TILE_BYTES;
-  d.b = Wblk + (2 * e + 1) * TILE_D; d.bbytes = TILE_BYTES;
+  const int kt = 2 * (npass - 1 - e);
+  d.a = Wblk + kt * TILE_D; d.abytes = TILE_BYTES;
+  d.b = Wblk + (kt + 1) * TILE_D; d.bbytes = TILE_BYTES;
   d.flag0 = (e == 0) ? flag : nullptr; d.flag1 = nullptr;
   return d;
 }

@@ -16,6 +16,12 @@
 
 namespace dsm {
 
+#ifndef DSM_NONBLOCK
+#define DSM_NONBLOCK 1
+#endif
+#ifndef DSM_EPI_EARLY
+#define DSM_EPI_EARLY 1
+#endif
 constexpr int NS2 = 6;                                   // ring stages (6 x 33,792 B = 202,752 B)
 constexpr int STAGE_DOUBLES = 2 * CHUNK;                 // A chunk then B chunk, each [KC][LDS]
 constexpr int PIPE_SMEM_BYTES = NS2 * STAGE_DOUBLES * 8 + 256;   // + barriers / control words
@@ -36,6 +42,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// truly non-blocking phase test (try_wait may suspend the thread for a system-dependent time)
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
@@ -153,6 +167,15 @@ struct Pipe {
     q_cons++;
   }
   __device__ __forceinline__ bool can_issue() const { return q_issue - q_cons < (uint32_t)NS2; }
+  // Non-blocking producer test: the stage of the next chunk has been released by every warp.  The producer warp is
+  // also a consumer, so it must never SPIN on a slow warp while it has chunks of its own to multiply; it only blocks
+  // (inside issue) when the chunk it needs next has not been issued yet (q_issue <= need).
+  // `need`: the chunk the caller is about to wait for (q_cons, or q_cons + e inside a multi-stage epilogue).
+  __device__ __forceinline__ bool slot_free(uint32_t need) {
+    const uint32_t q = q_issue;
+    if (!DSM_NONBLOCK || q < (uint32_t)NS2 || q <= need) return true;
+    return mbar_test_wait(&empty[q % NS2], ((q / NS2) - 1) & 1);
+  }
 };
 
 }  // namespace dsm

@@ -87,7 +87,7 @@ struct PotrfGen {
       const int e = c - nc - nmain;
       const int* f = (e == 0) ? flags + tile_flag_index(J, J) : nullptr;
       if (f != nullptr && !block && !flag_is_set(f)) { stalled = true; return false; }
-      d = tri_epilogue_chunk(Wj, e, block ? f : nullptr);
+      d = tri_epilogue_chunk(Wj, e, nepi, block ? f : nullptr);
     }
     c++;
     return true;
@@ -107,10 +107,16 @@ struct PotrfSched {
     nxt.load(a, nxt_ti);
     have_next = true;
   }
-  __device__ __forceinline__ void pump(Pipe& p, const Potrf2Args& a) {
+  __device__ __forceinline__ void pump(Pipe& p, const Potrf2Args& a, uint32_t need) {
     ChunkDesc d;
-    while (p.can_issue()) {
-      if (cur.next(d, true)) { p.issue(d); continue; }
+    while (p.can_issue() && p.slot_free(need)) {
+      if (cur.c < cur.total()) {
+        // blocking dependency waits only when warp 0 has nothing of its own left to multiply
+        cur.stalled = false;
+        if (!cur.next(d, !DSM_NONBLOCK || p.q_issue <= need)) break;
+        p.issue(d);
+        continue;
+      }
       if (cur.diag) break;        // a diagonal tile reuses the ring as scratch: nothing may be in flight behind it
       if (!have_next) claim(a);
       if (!nxt.next(d, false)) break;
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       if (e < n_c) {
-        if (warp == 0) sch.pump(p, a);
+        if (warp == 0) sch.pump(p, a, p.q_cons);
         const int st = p.wait();
         if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
         p.release();
@@ -173,14 +179,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
       // ---------------- panel tile ----------------
       if (!trivial) {
         for (int c = 0; c < n_main; c++) {
-          if (warp == 0) sch.pump(p, a);
+          if (warp == 0) sch.pump(p, a, p.q_cons);
           const int st = p.wait();
           if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
           p.release();
         }
         if (trc) trc[2] = clock64();
         // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
-        tri_epilogue(p, [&]() { sch.pump(p, a); }, acc, wj / 32, active, -1.0);
+        tri_epilogue(p, [&](uint32_t need) { sch.pump(p, a, need); }, acc, wj / 32, active, -1.0);
         if (trc) trc[3] = clock64();
         acc2_store(acc, F, nkc, i0, j0, wi, wj);
       }
@@ -190,7 +196,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     {
       const int ng = min(wj / 32, warp / 2 + 1);        // lower triangle only: columns <= 16*warp + 15
       for (int c = 0; c < n_main; c++) {
-        if (warp == 0) sch.pump(p, a);
+        if (warp == 0) sch.pump(p, a, p.q_cons);
         const int st = p.wait();
         if (active) {
           const double* sA = p.A(st);

@@ -35,7 +35,7 @@ struct TrtriGen {
       d.b = F + tile_off(I, kc, nkc); d.bbytes = TILE_BYTES;
       d.flag0 = nullptr; d.flag1 = nullptr;
     } else {
-      d = tri_epilogue_chunk(W + (int64_t)I * WBLK_D, c - n1 - n2, nullptr);
+      d = tri_epilogue_chunk(W + (int64_t)I * WBLK_D, c - n1 - n2, n3, nullptr);
     }
     if (++c == n1 + n2 + n3) { c = 0; I++; }
     return true;
@@ -81,12 +81,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) trtri2_kernel(Trtri2Args a) {
         __syncwarp();
       }
       for (int c = 0; c < nmain; c++) {
-        if (warp == 0) topup(p, gen);
+        if (warp == 0) topup(p, gen, p.q_cons);
         const int st = p.wait();
         if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
         p.release();
       }
-      tri_epilogue(p, [&]() { topup(p, gen); }, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
+      tri_epilogue(p, [&](uint32_t need) { topup(p, gen, need); }, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
       acc2_store(acc, F, m.nkc, j0, i0, BLK, wi);
       // fused reductions: ||X_IJ||_F^2 over real rows/cols, alpha_J += X_IJ^T z_I
       double p0 = 0.0, p1 = 0.0;
