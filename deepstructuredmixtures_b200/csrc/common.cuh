@@ -107,4 +107,22 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return t;
 }
 
+constexpr int NCONS = NTHREADS;     // consumer (MMA) threads of the producer-warp kernels; the producer warp follows them
+
+// block barrier of the 8 consumer warps only (the producer warp never joins it)
+__device__ __forceinline__ void csync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// Block-wide sum over the consumer threads; result valid in every consumer thread.  `red` >= 8 doubles of smem.
+__device__ __forceinline__ double block_sum_c(double v, double* red) {
+  v = warp_sum(v);
+  csync();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  csync();
+  double t = 0;
+#pragma unroll
+  for (int i = 0; i < NCONS / 32; i++) t += red[i];
+  csync();
+  return t;
+}
+
 }  // namespace dsm

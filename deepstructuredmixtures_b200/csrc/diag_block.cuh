@@ -116,7 +116,7 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
   double* Tw = aux + (BLK / PW) * DBLK + warp * DBLK;       // this warp's 16 x 16 scratch
   const int np = m / PW;
   if (tid == 0) *s_info = 0;
-  __syncthreads();
+  csync();
   double* rdiag = aux + (BLK / PW) * DBLK + (NTHREADS / 32) * DBLK;     // 1 / l_cc of the tile
   for (int P = 0; P < np && factor; P++) {
     const int c0 = P * PW, r1 = c0 + PW, nrem = m - r1;
@@ -124,7 +124,7 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
       const int info = warp_potrf16(S, c0, rdiag);
       if (lane == 0 && info != 0 && *s_info == 0) *s_info = c0 + info;
     }
-    __syncthreads();
+    csync();
     if (nrem == 0) continue;
     // ---- panel TRSM: X = A21 * L11^-T by forward substitution, one thread per row (needs L11 only, not its inverse)
     if (tid < nrem) {
@@ -141,7 +141,7 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
 #pragma unroll
       for (int c = 0; c < PW; c++) S[(c0 + c) * LDS + rr] = x[c];
     }
-    __syncthreads();
+    csync();
     // ---- trailing update: A22 -= X X^T  (lower 8 x 8 tiles)
     {
       const int nt = nrem / 8, ntiles = nt * (nt + 1) / 2;
@@ -161,11 +161,11 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
         cp[0] = c0v; cp[LDS] = c1v;
       }
     }
-    __syncthreads();
+    csync();
   }
   // ---- inverses of the diagonal blocks: eight independent 16 x 16 problems, one warp each
   for (int P = warp; P < np; P += NTHREADS / 32) warp_inv16(S, P * PW, DI + P * DBLK);
-  __syncthreads();
+  csync();
   // ---- W = L^-1: warp j owns block column j; row blocks P = j+1 .. np-1 in sequence, no block barrier
   for (int j = warp; j < np; j += NTHREADS / 32) {
     for (int P = j + 1; P < np; P++) {
@@ -216,7 +216,7 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
       __syncwarp();
     }
   }
-  __syncthreads();
+  csync();
   return *s_info;
 }
 

@@ -98,13 +98,6 @@ __device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2],
   }
 }
 
-// Producer top-up: warp 0 issues every chunk the generator can deliver while the ring has room.
-template <class Gen>
-__device__ __forceinline__ void topup(Pipe& p, Gen& gen, uint32_t need) {
-  ChunkDesc d;
-  while (p.can_issue() && p.slot_free(need) && gen.next(d)) p.issue(d);
-}
-
 // Triangular epilogue  OUT <- scale * OUT * M^T  (M lower triangular, 32*NP x 32*NP) in registers.
 // M arrives as NP epilogue stages in DESCENDING k order: stage e carries M's k-tiles 2(NP-1-e) (A part) and
 // 2(NP-1-e)+1 (B part).  The passes run over descending column groups (so the update is in place) and pass P reads
@@ -140,28 +133,22 @@ __device__ __forceinline__ void tri_pass(const Pipe& p, uint32_t qlast, Acc2& ac
 
 __host__ __device__ __forceinline__ int tri_epilogue_nstages(int npass) { return npass; }   // 8 (4) k-tiles, 2 per stage
 
-template <class Pump>
-__device__ __forceinline__ void tri_epilogue(Pipe& p, Pump&& pump, Acc2& acc, int npass, bool active, double scale) {
+__device__ __forceinline__ void tri_epilogue(Pipe& p, Acc2& acc, int npass, bool active, double scale) {
   const uint32_t q0 = p.q_cons;
   const uint32_t qlast = q0 + npass - 1;            // chunk that carries k-tiles 0 and 1
   for (int e = 0; e < npass; e++) {                 // pass NP-1 needs every stage
     const uint32_t q = q0 + e;
-    if ((threadIdx.x >> 5) == 0) pump(q);
     p.wait_bar(&p.full[q % NS2], (q / NS2) & 1, 4);
   }
-  const bool producer = (threadIdx.x >> 5) == 0;
 #if DSM_EPI_EARLY
   if (npass == 4) {
     if (active) tri_pass<3>(p, qlast, acc, scale);
     p.release();
-    if (producer) pump(p.q_cons);
     if (active) tri_pass<2>(p, qlast, acc, scale);
     p.release();
-    if (producer) pump(p.q_cons);
   }
   if (active) tri_pass<1>(p, qlast, acc, scale);
   p.release();
-  if (producer) pump(p.q_cons);
   if (active) tri_pass<0>(p, qlast, acc, scale);
   p.release();
 #else

@@ -6,6 +6,6 @@ cudaError_t init_v2_kernels() {
   if ((e = cudaFuncSetAttribute(potrf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES))) return e;
   return cudaFuncSetAttribute(trtri2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
 }
-void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st) { potrf2_kernel<<<nctas, NTHREADS, PIPE_SMEM_BYTES, st>>>(a); }
-void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st) { trtri2_kernel<<<nctas, NTHREADS, PIPE_SMEM_BYTES, st>>>(a); }
+void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st) { potrf2_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
+void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st) { trtri2_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
 }  // namespace dsm

@@ -4,7 +4,10 @@
 // through mbarriers, so the 8 MMA warps never meet at a block-wide barrier inside a contraction:
 //   full[s]   (count 1 + tx bytes)  producer arrives with expect_tx, the copies complete the transaction
 //   empty[s]  (count 8)             each warp arrives after its last shared-memory read of the stage
-// Warp 0 is producer AND consumer: before consuming chunk q it tops the ring up to q + NS - 1.  Operands are stored in
+// A DEDICATED PRODUCER WARP (warp 8 of a 288-thread CTA) claims tasks, polls dependency flags and issues the copies; the
+// eight MMA warps only wait / multiply / release, so none of the scheduler's latency (atomics, flag polls, descriptor
+// loads) sits on the MMA critical path.  The first chunk of every task carries a TASK HEADER (hdr[stage]) that tells the
+// consumers what the following chunks are; a header with kind < 0 ends the kernel.  Operands are stored in
 // HBM as 16-column tiles that are the exact image of a stage (common.cuh), so a chunk is TWO bulk copies of 16,896 B.  Chunks are numbered monotonically per CTA
 // (stage = q % NS, parity = (q / NS) & 1), so the ring keeps running across segments, epilogues and task iterations.
 //
@@ -16,15 +19,20 @@
 
 namespace dsm {
 
-#ifndef DSM_NONBLOCK
-#define DSM_NONBLOCK 1
-#endif
 #ifndef DSM_EPI_EARLY
 #define DSM_EPI_EARLY 1
 #endif
 constexpr int NS2 = 6;                                   // ring stages (6 x 33,792 B = 202,752 B)
 constexpr int STAGE_DOUBLES = 2 * CHUNK;                 // A chunk then B chunk, each [KC][LDS]
-constexpr int PIPE_SMEM_BYTES = NS2 * STAGE_DOUBLES * 8 + 256;   // + barriers / control words
+constexpr int PIPE_SMEM_BYTES = NS2 * STAGE_DOUBLES * 8 + 512;   // + barriers / control words / task headers
+constexpr int NTHREADS_PW = NTHREADS + 128;              // block size of the producer-warp kernels: 2 MMA warpgroups + 1 producer warpgroup
+// Register re-allocation between the warpgroups (setmaxnreg works per warpgroup of 4 warps): the kernel is compiled for
+// 384 threads (168 registers each); the producer group drops to 40 and the two MMA groups grow to 232.
+constexpr int REGS_PRODUCER = 40, REGS_CONSUMER = 232;
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
+struct TaskHdr { int kind, ti, slot, I, J, wi, wj, n_c, n_main, pad0, pad1, pad2; };   // 48 bytes
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s at 1.97 GHz
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -42,14 +50,6 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// truly non-blocking phase test (try_wait may suspend the thread for a system-dependent time)
-__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n .reg .pred p;\n mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
@@ -78,7 +78,9 @@ struct Pipe {
   double* base;          // NS2 stages
   uint64_t* full;        // [NS2]
   uint64_t* empty;       // [NS2]
+  uint64_t* aux;         // [2] auxiliary consumer -> producer barriers (scratch free / block stored)
   volatile int* abort;   // shared: set on timeout
+  TaskHdr* hdr;          // [NS2] task header of the chunk in each stage (valid for the first chunk of a task)
   int* gerr;             // global error word
   uint32_t q_issue, q_cons;
 
@@ -90,11 +92,14 @@ struct Pipe {
     base = smem;
     full = reinterpret_cast<uint64_t*>(smem + NS2 * STAGE_DOUBLES);
     empty = full + NS2;
-    abort = reinterpret_cast<volatile int*>(empty + NS2);
+    aux = empty + NS2;
+    abort = reinterpret_cast<volatile int*>(aux + 2);
+    hdr = reinterpret_cast<TaskHdr*>(aux + 4);
     gerr = global_err;
     q_issue = 0; q_cons = 0;
     if (threadIdx.x == 0) {
-      for (int s = 0; s < NS2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NTHREADS / 32); }
+      for (int s = 0; s < NS2; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCONS / 32); }
+      mbar_init(&aux[0], 1); mbar_init(&aux[1], 1);
       *abort = 0;
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -134,7 +139,7 @@ struct Pipe {
   }
 
   // Producer side (warp 0): issue one chunk into the ring.  UBLKCP is a warp-uniform instruction: lane 0 issues.
-  __device__ __forceinline__ void issue(const ChunkDesc& d) {
+  __device__ __forceinline__ void issue(const ChunkDesc& d, const TaskHdr* h = nullptr) {
     const uint32_t q = q_issue;
     const int st = q % NS2;
     if (q >= NS2) wait_bar(&empty[st], ((q / NS2) - 1) & 1, 3);
@@ -144,6 +149,7 @@ struct Pipe {
       fence_proxy_async();
     }
     if ((threadIdx.x & 31) == 0) {
+      if (h != nullptr) hdr[st] = *h;               // ordered before the consumers' reads by the barrier's release/acquire
       mbar_expect_tx(&full[st], d.abytes + d.bbytes);
       if (d.abytes) bulk_g2s(A(st), d.a, d.abytes, &full[st]);
       if (d.bbytes) bulk_g2s(B(st), d.b, d.bbytes, &full[st]);
@@ -167,15 +173,6 @@ struct Pipe {
     q_cons++;
   }
   __device__ __forceinline__ bool can_issue() const { return q_issue - q_cons < (uint32_t)NS2; }
-  // Non-blocking producer test: the stage of the next chunk has been released by every warp.  The producer warp is
-  // also a consumer, so it must never SPIN on a slow warp while it has chunks of its own to multiply; it only blocks
-  // (inside issue) when the chunk it needs next has not been issued yet (q_issue <= need).
-  // `need`: the chunk the caller is about to wait for (q_cons, or q_cons + e inside a multi-stage epilogue).
-  __device__ __forceinline__ bool slot_free(uint32_t need) {
-    const uint32_t q = q_issue;
-    if (!DSM_NONBLOCK || q < (uint32_t)NS2 || q <= need) return true;
-    return mbar_test_wait(&empty[q % NS2], ((q / NS2) - 1) & 1);
-  }
 };
 
 }  // namespace dsm

@@ -4,7 +4,7 @@
 // experts in ONE launch.  Left-looking by 128-wide block columns; a task is one 128x128 tile:
 //   diag (J,J):   C = F_JJ - sum_{K<J} L_JK L_JK^T ; L_JJ = chol(C) ; W_J = L_JJ^-1 ; z_J = W_J (y_J - sum_K L_JK z_K)
 //   panel (I,J):  L_IJ = (F_IJ - sum_{K<J} L_IK L_JK^T) W_J^T
-// CTAs (one per SM) claim tasks IN ORDER from a global counter.  The host writes the task list in a topological
+// CTAs (one per SM; 8 MMA warps + 1 producer warp) claim tasks IN ORDER from a global counter.  The host writes the task list in a topological
 // order with look-ahead (the diag tile of column J+1 is scheduled right behind the first panel tile of column J)
 // and with every expert's columns shifted so that all experts finish together.  A task only ever waits on tasks
 // that precede it in the list, and those have been claimed by resident CTAs, so the spin waits cannot deadlock.
@@ -27,37 +27,36 @@ __device__ __forceinline__ bool flag_is_set(const int* f) {
   return __shfl_sync(0xffffffffu, v, 0) != 0;
 }
 
-// Chunk generator of one tile task.  Stage order: the tile F_IJ itself (2 column tiles per stage, no dependency), the
-// contraction chunks (k-block Kb needs tiles (I,Kb) and (J,Kb)), then W_J for the TRSM epilogue (panel tiles only).
+// Chunk generator of one tile task (producer warp).  Stage order: the tile F_IJ itself (2 column tiles per stage, no
+// dependency), the contraction chunks (k-block Kb needs tiles (I,Kb) and (J,Kb)), then W_J for the TRSM epilogue
+// (panel tiles only).  Dependencies are attached to the descriptor; Pipe::issue waits for them.
 struct PotrfGen {
   const double* F; const double* z; const double* Wj; const int* flags;
   int nkc, I, J;
   int nc, nmain, nepi, c;
   bool diag, allready;       // allready: every k-block is known to be complete (tile (.,J-1) done implies all before it)
-  bool stalled;              // a non-blocking dependency test failed: do not poll again until the task is current
+  TaskHdr h;
   __device__ __forceinline__ int total() const { return nc + nmain + nepi; }
 
   __device__ __forceinline__ void load(const Potrf2Args& a, int ti) {
-    c = 0; nc = nmain = nepi = 0; diag = false; allready = false; stalled = false;
-    if (ti >= a.ntasks) return;
+    c = 0; nc = nmain = nepi = 0; diag = false; allready = false;
     const int4 tk = a.tasks[ti];
     const LeafMeta m = a.meta[tk.x];
     I = tk.y; J = tk.z; diag = (I == J);
+    flags = a.flags + a.flag_off[tk.x];
+    h.kind = diag ? 1 : 0; h.ti = ti; h.slot = tk.x; h.I = I; h.J = J;
+    h.wi = blk_width(m.np, I); h.wj = blk_width(m.np, J); h.n_c = 0; h.n_main = 0;
     if (!diag && I < a.jstart) return;                    // tile already final (chol_continue)
     nkc = m.nkc;
     F = a.F + m.foff; z = a.z + m.voff; Wj = a.W + m.woff + (int64_t)J * WBLK_D;
-    flags = a.flags + a.flag_off[tk.x];
-    const int wj = blk_width(m.np, J);
-    nc = wj / 32;
+    nc = h.wj / 32;
     nmain = (diag && J < a.jstart) ? 0 : (J * BLK) / KC;
-    nepi = diag ? 0 : tri_epilogue_nstages(wj / 32);
+    nepi = diag ? 0 : tri_epilogue_nstages(h.wj / 32);
+    h.n_c = nc; h.n_main = nmain;
   }
 
-  // block = true: dependencies are attached to the descriptor and Pipe::issue waits for them;
-  // block = false (prefetch of the NEXT task): a chunk whose dependency is not yet complete is not delivered.
-  __device__ __forceinline__ bool next(ChunkDesc& d, bool block) {
+  __device__ __forceinline__ bool next(ChunkDesc& d) {
     if (c >= nc + nmain + nepi) return false;
-    if (!block && stalled) return false;
     d.flag0 = nullptr; d.flag1 = nullptr;
     if (c < nc) {
       d.a = F + tile_off(I, J * 8 + 2 * c, nkc); d.abytes = TILE_BYTES;
@@ -72,12 +71,11 @@ struct PotrfGen {
             if (!diag) v1 = ld_acquire(flags + tile_flag_index(J, J - 1));
           }
           allready = __shfl_sync(0xffffffffu, (v0 != 0) && (v1 != 0) ? 1 : 0, 0) != 0;
+          if (allready) fence_proxy_async();
         }
         if (!allready) {
-          const int* f0 = flags + tile_flag_index(I, Kb);
-          const int* f1 = diag ? nullptr : flags + tile_flag_index(J, Kb);
-          if (block) { d.flag0 = f0; d.flag1 = f1; }
-          else if (!flag_is_set(f0) || (f1 != nullptr && !flag_is_set(f1))) { stalled = true; return false; }
+          d.flag0 = flags + tile_flag_index(I, Kb);
+          d.flag1 = diag ? nullptr : flags + tile_flag_index(J, Kb);
         }
       }
       d.a = F + tile_off(I, cc, nkc); d.abytes = TILE_BYTES;
@@ -85,49 +83,42 @@ struct PotrfGen {
       else { d.b = F + tile_off(J, cc, nkc); d.bbytes = TILE_BYTES; }
     } else {
       const int e = c - nc - nmain;
-      const int* f = (e == 0) ? flags + tile_flag_index(J, J) : nullptr;
-      if (f != nullptr && !block && !flag_is_set(f)) { stalled = true; return false; }
-      d = tri_epilogue_chunk(Wj, e, nepi, block ? f : nullptr);
+      d = tri_epilogue_chunk(Wj, e, nepi, (e == 0) ? flags + tile_flag_index(J, J) : nullptr);
     }
     c++;
     return true;
   }
 };
 
-// Warp-0 scheduler state: the generator of the running task and of the NEXT task, which is claimed as soon as the
-// running task has issued its last chunk so that its first stages are already in flight at the task boundary.
-struct PotrfSched {
-  PotrfGen cur, nxt;
-  int nxt_ti;
-  bool have_next;
-  __device__ __forceinline__ void claim(const Potrf2Args& a) {
+// Producer warp: claims tasks in list order and streams their chunks into the ring, running ahead of the MMA warps by
+// up to NS2 stages ACROSS task boundaries.  A diagonal tile reuses the ring as scratch for its factorisation, so after
+// the last chunk of a diagonal task the producer waits until the consumers hand the ring back (aux[0]).
+__device__ __forceinline__ void potrf2_producer(Pipe& p, const Potrf2Args& a) {
+  PotrfGen gen;
+  uint32_t scratch_phase = 0;
+  for (;;) {
     int t = 0;
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
-    nxt_ti = __shfl_sync(0xffffffffu, t, 0);
-    nxt.load(a, nxt_ti);
-    have_next = true;
-  }
-  __device__ __forceinline__ void pump(Pipe& p, const Potrf2Args& a, uint32_t need) {
-    ChunkDesc d;
-    while (p.can_issue() && p.slot_free(need)) {
-      if (cur.c < cur.total()) {
-        // blocking dependency waits only when warp 0 has nothing of its own left to multiply
-        cur.stalled = false;
-        if (!cur.next(d, !DSM_NONBLOCK || p.q_issue <= need)) break;
-        p.issue(d);
-        continue;
-      }
-      if (cur.diag) break;        // a diagonal tile reuses the ring as scratch: nothing may be in flight behind it
-      if (!have_next) claim(a);
-      if (!nxt.next(d, false)) break;
-      p.issue(d);
+    const int ti = __shfl_sync(0xffffffffu, t, 0);
+    if (ti >= a.ntasks) break;
+    gen.load(a, ti);
+    if (gen.total() == 0) {                               // already final: publish and move on
+      if ((threadIdx.x & 31) == 0) st_release(const_cast<int*>(gen.flags) + tile_flag_index(gen.I, gen.J), 1);
+      continue;
     }
+    ChunkDesc d;
+    bool first = true;
+    while (gen.next(d)) { p.issue(d, first ? &gen.h : nullptr); first = false; }
+    if (gen.diag) { p.wait_bar(&p.aux[0], scratch_phase & 1, 5); scratch_phase++; }
+    if (*p.abort) break;
   }
-};
+  TaskHdr h; h.kind = -1;
+  ChunkDesc d; d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
+  p.issue(d, &h);
+}
 
-__global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
+__global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
   extern __shared__ __align__(16) double smem[];
-  __shared__ int s_task;
   __shared__ double s_red[16];
   __shared__ double s_v[BLK];
   __shared__ int s_info;
@@ -135,30 +126,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
   const int r0 = 16 * warp;
   Pipe p;
   p.init(smem, a.gerr);
-  PotrfSched sch;
-  sch.have_next = false; sch.nxt_ti = 0;
-  if (tid == 0) s_task = atomicAdd(a.counter, 1);
-  __syncthreads();
-  int ti = s_task;
-  if (warp == 0) sch.cur.load(a, ti);
+  if (warp >= NCONS / 32) {                          // producer warpgroup: one working warp, three that only donate registers
+    setmaxnreg_dec<REGS_PRODUCER>();
+    if (warp == NCONS / 32) potrf2_producer(p, a);
+    return;
+  }
+  setmaxnreg_inc<REGS_CONSUMER>();
   for (;;) {
-    if (ti >= a.ntasks) return;
-    const int4 tk = a.tasks[ti];
-    const LeafMeta m = a.meta[tk.x];
-    const int I = tk.y, J = tk.z;
+    // the first chunk of a task carries its header
+    int st = p.wait();
+    const TaskHdr hd = p.hdr[st];
+    if (hd.kind < 0 || *p.abort) return;
+    const LeafMeta m = a.meta[hd.slot];
+    const int I = hd.I, J = hd.J;
     const int i0 = I * BLK, j0 = J * BLK;
-    const int wi = blk_width(m.np, I), wj = blk_width(m.np, J);
+    const int wi = hd.wi, wj = hd.wj;
     double* F = a.F + m.foff;
-    int* flags = a.flags + a.flag_off[tk.x];
+    int* flags = a.flags + a.flag_off[hd.slot];
     double* Wj = a.W + m.woff + (int64_t)J * WBLK_D;
     const int nkc = m.nkc;
-    const bool diag = (I == J);
+    const bool diag = (hd.kind == 1);
     const bool active = r0 < wi;
     const bool prefactored = (J < a.jstart);     // chol_continue: column already final, diag only rebuilds W
-    const bool trivial = (!diag && I < a.jstart); // tile already final
-    const int n_c = trivial ? 0 : wj / 32;
-    const int n_main = (trivial || (diag && prefactored)) ? 0 : j0 / KC;
-    long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)ti * 8 : nullptr;
+    const int n_c = hd.n_c, n_main = hd.n_main;
+    long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)hd.ti * 8 : nullptr;
     if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = sm; trc[6] = I; trc[7] = J; }
 
     // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
@@ -167,8 +158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
 #pragma unroll
     for (int e = 0; e < 4; e++) {
       if (e < n_c) {
-        if (warp == 0) sch.pump(p, a, p.q_cons);
-        const int st = p.wait();
+        if (e > 0) st = p.wait();
         if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
         p.release();
       }
@@ -177,27 +167,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     if (trc) trc[1] = clock64();
     if (!diag) {
       // ---------------- panel tile ----------------
-      if (!trivial) {
-        for (int c = 0; c < n_main; c++) {
-          if (warp == 0) sch.pump(p, a, p.q_cons);
-          const int st = p.wait();
-          if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
-          p.release();
-        }
-        if (trc) trc[2] = clock64();
-        // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
-        tri_epilogue(p, [&](uint32_t need) { sch.pump(p, a, need); }, acc, wj / 32, active, -1.0);
-        if (trc) trc[3] = clock64();
-        acc2_store(acc, F, nkc, i0, j0, wi, wj);
+      for (int c = 0; c < n_main; c++) {
+        st = p.wait();
+        if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
+        p.release();
       }
+      if (trc) trc[2] = clock64();
+      // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
+      tri_epilogue(p, acc, wj / 32, active, -1.0);
+      if (trc) trc[3] = clock64();
+      acc2_store(acc, F, nkc, i0, j0, wi, wj);
     } else {
     // ---------------- diagonal tile ----------------
     double gemv = 0.0;                                  // row r0 + (lane & 15), k-half lane >> 4
     {
       const int ng = min(wj / 32, warp / 2 + 1);        // lower triangle only: columns <= 16*warp + 15
       for (int c = 0; c < n_main; c++) {
-        if (warp == 0) sch.pump(p, a, p.q_cons);
-        const int st = p.wait();
+        st = p.wait();
         if (active) {
           const double* sA = p.A(st);
           switch (ng) {
@@ -216,7 +202,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
     }
     if (trc) trc[2] = clock64();
     gemv += __shfl_xor_sync(0xffffffffu, gemv, 16);
-    __syncthreads();                                     // every warp is done with the ring: stages become scratch
+    csync();                                             // every warp is done with the ring: stages become scratch
     double* S = smem;                                    // resident tile [c][LDS] (stages 0..3)
     double* aux = smem + 4 * STAGE_DOUBLES;              // stage 4: scratch
     if (active) {
@@ -229,44 +215,44 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
         }
       if (lane < 16) s_v[r0 + lane] = gemv;
     }
-    __syncthreads();
+    csync();
     {
       const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info);
-      if (tid == 0 && info != 0) atomicCAS(&a.scal[tk.x].info, 0, j0 + info);
+      if (tid == 0 && info != 0) atomicCAS(&a.scal[hd.slot].info, 0, j0 + info);
     }
     if (trc) trc[3] = clock64();
     const double* DI = aux;
     if (!prefactored) {
-      for (int c = warp; c < wj; c += NTHREADS / 32) {
+      for (int c = warp; c < wj; c += NCONS / 32) {
         double* dst = F + tidx(j0, j0 + c, nkc);
         for (int r = lane; r < wj; r += 32)
           if (r >= c) dst[r] = S[c * LDS + r];
       }
     }
     double ld = 0.0;
-    for (int r = tid; r < wj; r += NTHREADS)
+    for (int r = tid; r < wj; r += NCONS)
       if (j0 + r < m.n) ld += log(S[r * LDS + r]);
-    ld = block_sum(ld, s_red);
+    ld = block_sum_c(ld, s_red);
     // W_J, W_J^T (zero filled, tiled) and the diagonal-block partial of tr(F^-1)
     double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;
     double tr = 0.0;
-    for (int c = warp; c < BLK; c += NTHREADS / 32)
+    for (int c = warp; c < BLK; c += NCONS / 32)
       for (int r = lane; r < BLK; r += 32) {
         double v = 0.0;
         if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
         Wj[widx(r, c)] = v;
         if (j0 + r < m.n && j0 + c < m.n) tr += v * v;
       }
-    for (int r = warp; r < BLK; r += NTHREADS / 32)
+    for (int r = warp; r < BLK; r += NCONS / 32)
       for (int c = lane; c < BLK; c += 32) {
         double v = 0.0;
         if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
         WTj[widx(c, r)] = v;
       }
-    tr = block_sum(tr, s_red);
+    tr = block_sum_c(tr, s_red);
     // forward solve block: z_J = W_J (y_J - sum_K L_JK z_K)
     if (tid < BLK) s_v[tid] = (tid < wj) ? a.y[m.voff + j0 + tid] - s_v[tid] : 0.0;
-    __syncthreads();
+    csync();
     double zz = 0.0;
     {
       const int r = tid >> 1, h = tid & 1;              // 2 threads per row
@@ -279,26 +265,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) potrf2_kernel(Potrf2Args a) {
         if (j0 + r < m.n) zz = s * s;
       }
     }
-    zz = block_sum(zz, s_red);
+    zz = block_sum_c(zz, s_red);
     if (tid == 0) {
-      const int64_t po = a.trpart_off[tk.x];
+      const int64_t po = a.trpart_off[hd.slot];
       a.trpart[po + J] = tr;
       a.ldpart[po / 2 + J] = 2.0 * ld;
       a.zzpart[po / 2 + J] = zz;
     }
     fence_proxy_async();                                 // generic writes to the stages precede the next bulk copies
     }   // diagonal tile
-    // ---------------- task boundary: publish the tile, hand over to the (possibly already prefetched) next task
-    __syncthreads();
-    if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
-    if (warp == 0) {
-      if (!sch.have_next) sch.claim(a);
-      sch.cur = sch.nxt; sch.have_next = false;
-      if (lane == 0) s_task = sch.nxt_ti;
+    // ---------------- task boundary: publish the tile (and hand the ring back to the producer after a diagonal tile)
+    csync();
+    if (tid == 0) {
+      __threadfence();
+      st_release(flags + tile_flag_index(I, J), 1);
+      if (diag) mbar_arrive(&p.aux[0]);
     }
-    __syncthreads();
     if (trc) trc[4] = clock64();
-    ti = s_task;
   }
 }
 
