@@ -36,6 +36,7 @@ struct Batch {
   int2* d_trtri_tasks = nullptr; int n_trtri = 0;
   int4* d_lauum_tasks = nullptr; int n_lauum = 0;
   int4* d_potrf2_tasks = nullptr; int n_potrf2 = 0;     // engine v2: tile tasks in look-ahead order
+  int4* d_trtri3_tasks = nullptr; int n_trtri3 = 0;     // inverse: tile tasks by anti-diagonal
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
 };
@@ -92,6 +93,7 @@ struct dsmgp_handle {
   DevBuf<int> d_counter;
   DevBuf<int> d_flags;
   DevBuf<double> d_ldpart, d_zzpart;
+  DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
   double* pin_rows = nullptr;
   LeafScal* pin_scal = nullptr;
   std::string err;
@@ -99,10 +101,10 @@ struct dsmgp_handle {
   ~dsmgp_handle() {
     for (auto& b : batches) {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
-      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_flag_off);
+      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_flag_off);
     }
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
-    d_flags.free(); d_ldpart.free(); d_zzpart.free();
+    d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
     d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
     if (pin_rows) cudaFreeHost(pin_rows);
     if (pin_scal) cudaFreeHost(pin_scal);
@@ -318,6 +320,24 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       std::vector<int4> pt(tk.size());
       for (size_t i = 0; i < tk.size(); i++) pt[i] = make_int4(tk[i].slot, tk[i].I, tk[i].J, 0);
       b.n_potrf2 = (int)pt.size(); b.flag_ints = fo;
+      // inverse tile tasks (I > J): anti-diagonal order (a tile depends on the tiles above it in its column, all on
+      // smaller anti-diagonals), experts shifted so that they end together, long tiles first inside a level
+      std::vector<TK> iv;
+      for (int s = b.s0; s < b.s1; s++) {
+        const LeafMeta& m = h->meta[s];
+        const int sl = s - b.s0, shift = b.max_nb - m.nb;
+        for (int J = 0; J < m.nb; J++)
+          for (int I = J + 1; I < m.nb; I++) iv.push_back({I - J + shift, -(I - J), sl, I, J});
+      }
+      std::stable_sort(iv.begin(), iv.end(), [](const TK& a, const TK& c) {
+        if (a.s != c.s) return a.s < c.s;
+        if (a.grp != c.grp) return a.grp < c.grp;
+        if (a.slot != c.slot) return a.slot < c.slot;
+        return a.J < c.J; });
+      std::vector<int4> it(iv.size());
+      for (size_t i = 0; i < iv.size(); i++) it[i] = make_int4(iv[i].slot, iv[i].I, iv[i].J, 0);
+      b.n_trtri3 = (int)it.size();
+      CUDA_TRY(h, upload(&b.d_trtri3_tasks, it));
       CUDA_TRY(h, upload(&b.d_potrf2_tasks, pt));
       CUDA_TRY(h, upload(&b.d_flag_off, foff));
       maxFlags = std::max(maxFlags, fo);
@@ -350,6 +370,8 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   CUDA_TRY(h, h->d_flags.alloc(std::max<int64_t>(maxFlags, 1)));
   CUDA_TRY(h, h->d_ldpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
   CUDA_TRY(h, h->d_zzpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
+  CUDA_TRY(h, h->d_apart.alloc(std::max<int64_t>(maxFlags, 1) * BLK));
+  CUDA_TRY(h, h->d_tpart.alloc(std::max<int64_t>(maxFlags, 1)));
   CUDA_TRY(h, h->d_leaf_mean.alloc(L));
   CUDA_TRY(h, cudaMemcpy(h->d_leaf_mean.p, h->leaf_mean.data(), L * sizeof(double), cudaMemcpyHostToDevice));
   CUDA_TRY(h, cudaMemset(h->d_rows.p, 0, (size_t)L * h->row_width * sizeof(double)));
@@ -559,11 +581,19 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
         h->tm.launches++;
       }
       cudaEventRecord(ev[4], st);
-      if (with_grad) {
+      static const bool column_tasks = getenv("DSMGP_TRTRI_COLUMNS") != nullptr;    // development A/B: one CTA per block column
+      if (with_grad && column_tasks) {
         Trtri2Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
                       b.d_trtri_tasks, b.n_trtri, h->d_counter.p, h->d_counter.p + 8};
         launch_trtri2(ta, std::min(sms, b.n_trtri), st);
         h->tm.launches++;
+      } else if (with_grad) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
+        Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
+                      h->d_flags.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, b.d_trtri3_tasks, b.n_trtri3,
+                      h->d_counter.p, h->d_counter.p + 8};
+        launch_trtri3(ta, std::max(1, std::min(sms, b.n_trtri3)), b.d_trtri_tasks, b.n_trtri, st);
+        h->tm.launches += 2;
       }
     }
     cudaEventRecord(ev[5], st);

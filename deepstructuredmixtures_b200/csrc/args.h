@@ -117,9 +117,11 @@ void launch_gram_rect(const GramRectArgs& a, cudaStream_t st);
 void launch_gather(const GatherArgs& a, int maxnp, int nleaves, cudaStream_t st);
 struct Potrf2Args;
 struct Trtri2Args;
+struct Trtri3Args;
 cudaError_t init_v2_kernels();
 void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st);
 void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st);
+void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, cudaStream_t st);
 void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st);
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
 

@@ -28,7 +28,13 @@ constexpr int PIPE_SMEM_BYTES = NS2 * STAGE_DOUBLES * 8 + 512;   // + barriers /
 constexpr int NTHREADS_PW = NTHREADS + 128;              // block size of the producer-warp kernels: 2 MMA warpgroups + 1 producer warpgroup
 // Register re-allocation between the warpgroups (setmaxnreg works per warpgroup of 4 warps): the kernel is compiled for
 // 384 threads (168 registers each); the producer group drops to 40 and the two MMA groups grow to 232.
-constexpr int REGS_PRODUCER = 40, REGS_CONSUMER = 232;
+#ifndef DSM_REGS_P
+#define DSM_REGS_P 40
+#endif
+#ifndef DSM_REGS_C
+#define DSM_REGS_C 232
+#endif
+constexpr int REGS_PRODUCER = DSM_REGS_P, REGS_CONSUMER = DSM_REGS_C;
 template <int N> __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N> __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 

@@ -25,4 +25,16 @@ struct Trtri2Args {
   int* counter; int* gerr;
 };
 
+// tile-pipelined inverse (trtri3): tasks (slot, I, J, unused), I > J, ordered by anti-diagonal
+struct Trtri3Args {
+  const LeafMeta* meta;
+  double* F; const double* W; const double* WT;
+  const double* z; double* alpha;
+  double* trpart; const int64_t* trpart_off;    // second half [nb + J], written by alpha_reduce_kernel
+  int* flags; const int64_t* flag_off;          // per leaf nb(nb+1)/2 tile flags / partial slots
+  double* apart; double* tpart;                 // per-tile partials: [tile][BLK], [tile]
+  const int4* tasks; int ntasks;
+  int* counter; int* gerr;
+};
+
 }  // namespace dsm
