@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 # FP64 roofs measured on this pool's B200 with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json)
 FP64_DGEMM_TFLOPS = 35.9     # cuBLAS DGEMM 8192^3 (burst == sustained: FP64 is not power capped)
 FP64_DMMA_TFLOPS = 37.2      # DMMA.8x8x4 issue roof
-NCU_TRAFFIC_GB = {("cfg3", 1, "potrf2_kernel"): 53.85, ("cfg3", 1, "trtri2_kernel"): 78.47}
+NCU_TRAFFIC_GB = {("cfg3", 1, "potrf2_kernel"): 51.86, ("cfg3", 1, "trtri3_kernel"): 78.65}   # profiles/ncu_full_*_r01f.txt
 
 WORKLOADS = {
     # name: (N, D, kernel, V, K, M, depth, eps, seed)   SURVEY §8(d)
@@ -265,8 +265,10 @@ def main():
         potrf_tf = potrf_fl * args.steps / (phase["potrf_ms"] * 1e-3) * 1e-12 if phase["potrf_ms"] > 0 else 0.0
         inv_tf = inv_fl * args.steps / (phase["inverse_ms"] * 1e-3) * 1e-12 if phase["inverse_ms"] > 0 else 0.0
         gram_gbs = tm["gram_bytes"] * args.steps / (phase["gram_ms"] * 1e-3) * 1e-9 if phase["gram_ms"] > 0 else 0.0
-        dom = "trtri2_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf2_kernel"
-        ach = inv_tf if dom == "trtri2_kernel" else potrf_tf
+        # roofline numbers are PER GPU (the aggregate flops of all ranks / world / the slowest rank's phase time)
+        potrf_tf /= world; inv_tf /= world; gram_gbs /= world
+        dom = "trtri3_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf2_kernel"
+        ach = inv_tf if dom == "trtri3_kernel" else potrf_tf
         # DRAM bytes per launch from `ncu --set full` (profiles/ncu_full_*_r01e.csv); only known for the profiled config
         traffic = NCU_TRAFFIC_GB.get((args.workload, world, dom))
         ns_local = int(np.sum(H.leaf_owner() == 0))
@@ -281,11 +283,11 @@ def main():
                     "h2d_bytes_per_step": int(ns_local * (4 + w["D"]) * 8),
                     "d2h_bytes_per_step": int(L * H.row_width * 8 + ns_local * 48)},
             "gpu_launches": launches,
-            "cholesky_gflops": potrf_tf * 1e3,
+            "cholesky_gflops": potrf_tf * 1e3 * world,
             "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
             "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
                          "frac": ach / FP64_DGEMM_TFLOPS, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
-                         "algorithmic": "flops per launch = sum over local experts of n^3/3 + n^2/2 + n/6 (SURVEY 8d), one launch per evaluation",
+                         "algorithmic": "flops per launch = sum over local experts of n^3/3 + n^2/2 + n/6 (SURVEY 8d), one launch per evaluation; per-GPU figures",
                          "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (tools/fp64_peaks.cu, profiles/); "
                                         "MEASURED_PEAKS.json has no FP64 entry; DMMA issue roof 37.2",
                          "potrf_tflops": potrf_tf, "inverse_tflops": inv_tf, "gram_gbs": gram_gbs,
@@ -293,6 +295,23 @@ def main():
             "clocks": clocks_summary(samples),
             "host": {"tree_build_s": t_tree, "create_upload_s": t_create},
         }
+        if world == 1 and args.workload != "cfg5":
+            # cold end-to-end: the whole model from HOST arrays every step -- dsmgp_create (upload of x, y and the
+            # leaves' index lists, device gather) + one evaluation + read-back + destroy.
+            reps = 3
+            t0 = time.perf_counter()
+            for i in range(reps):
+                m2 = mdl.DSMGP(root, x, y, [k.copy() for k in klist], -1.0, rank=0, world=1, device=local,
+                               keep_factors=keep, as_written_grads=not args.mathematical)
+                m2.handle.eval(ths[i % len(ths)])
+                m2.close()
+            t_cold = (time.perf_counter() - t0) / reps
+            nidx = int(sizes.sum())
+            line["e2e_cold"] = {"value": 1.0 / t_cold, "unit": "evals/s",
+                                "h2d_bytes_per_step": int(x.nbytes + nidx * 16 + L * 8 + ns_local * (4 + w["D"]) * 8),
+                                "d2h_bytes_per_step": int(L * H.row_width * 8 + ns_local * 48),
+                                "what": "model construction from host arrays (dsmgp_create: x, centred y, 1-based leaf rows) "
+                                        "+ one dsmgp_eval + dsmgp_destroy per step"}
         if not args.no_cpu_baseline and world == 1:
             line["cpu_baseline"] = cpu_baseline(w, x, y, root, args.cpu_budget)
         print(json.dumps(line), flush=True)
