@@ -42,6 +42,7 @@ WORKLOADS = {
     "cfg1": dict(N=100, D=1, kernel="isose", V=3, K=4, M=10, depth=2, eps=0.5, seed=1),
     "cfg2": dict(N=10_000, D=1, kernel="isose", V=3, K=4, M=100, depth=2, eps=0.5, seed=2),
     "cfg3": dict(N=40_000, D=8, kernel="ardse", V=3, K=4, M=500, depth=2, eps=0.5, seed=3),
+    "cfg3iso": dict(N=40_000, D=8, kernel="isose", V=3, K=4, M=500, depth=2, eps=0.5, seed=3),   # HBM-bound Gram build
     "cfg3b": dict(N=40_000, D=8, kernel="ardse", V=3, K=4, M=500, depth=2, eps=0.0, seed=3),
     "cfg4": dict(N=45_730, D=9, kernel="isose+isolinear", V=4, K=4, M=1000, depth=2, eps=0.5, seed=4),
     "cfg5": dict(N=1_000_000, D=8, kernel="ardse", V=3, K=4, M=2000, depth=4, eps=0.1, seed=5),
@@ -179,6 +180,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--mathematical", action="store_true", help="true gradients instead of as-written")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
@@ -295,6 +297,26 @@ def main():
             "clocks": clocks_summary(samples),
             "host": {"tree_build_s": t_tree, "create_upload_s": t_create},
         }
+        if world == 1 and keep and not args.no_predict:
+            # update! + predict (common.jl:323-334, 294-307) on T fresh test points: every point is routed to one leaf
+            # per sum-node branch; device time of predict_kernel and wall time of the public call (routing, H2D of the
+            # routed points, kernel, D2H, log-space mixing on the host).
+            prng = np.random.default_rng(77)
+            T = min(w["N"], 40_000)
+            xt = prng.random((T, w["D"]))
+            mdl.update_(model)
+            mdl.predict(model, xt[:256])
+            t0 = time.perf_counter()
+            mu, var = mdl.predict(model, xt)
+            t_pred = time.perf_counter() - t0
+            tp = H.timings()
+            line["predict"] = {"T": T, "wall_ms": t_pred * 1e3, "points_per_s": T / t_pred,
+                               "kernel_ms": tp["predict_ms"],
+                               "kernel_tflops": tp["predict_flops"] / (tp["predict_ms"] * 1e-3) * 1e-12 if tp["predict_ms"] > 0 else None,
+                               "kernel_gbs": tp["predict_bytes"] / (tp["predict_ms"] * 1e-3) * 1e-9 if tp["predict_ms"] > 0 else None,
+                               "finite": bool(np.isfinite(mu).all() and np.isfinite(var).all()),
+                               "algorithmic": "sum over leaves of n^2 T_l + 2 n T_l flop (SURVEY 8d); bytes = L read once per "
+                                              "128-point block + inputs + outputs"}
         if world == 1 and args.workload != "cfg5":
             # cold end-to-end: the whole model from HOST arrays every step -- dsmgp_create (upload of x, y and the
             # leaves' index lists, device gather) + one evaluation + read-back + destroy.

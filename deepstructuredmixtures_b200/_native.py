@@ -52,7 +52,8 @@ class Opts(C.Structure):
 
 class Timings(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("gram_ms", "potrf_ms", "solve_ms", "inverse_ms", "grad_ms", "tree_ms",
-                                          "total_ms", "potrf_flops", "inverse_flops", "gram_bytes")] + [("launches", C.c_int64)]
+                                          "total_ms", "potrf_flops", "inverse_flops", "gram_bytes")] + [("launches", C.c_int64)] + \
+               [(n, C.c_double) for n in ("predict_ms", "predict_flops", "predict_bytes")]
 
 
 # every symbol include/dsmgp.h declares (tests/test_abi.py checks the list against the header)

@@ -286,7 +286,8 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       gp[s - b.s0] = go; go += (int64_t)(m.nb * (m.nb + 1) / 2) * m.nl;
       for (int J = 0; J < m.nb; J++) tt.push_back(make_int2(s - b.s0, J));
       int idx = 0;
-      for (int I = 0; I < m.nb; I++) for (int J = 0; J <= I; J++) lt.push_back(make_int4(s - b.s0, I, J, idx++));
+      const bool leaf_lauum = m.ktype == DSMGP_ISO_SE || m.ktype == DSMGP_ARD_LINEAR || (m.ktype == DSMGP_ARD_SE && !h->opts.as_written_grads);
+      for (int I = 0; I < m.nb; I++) for (int J = 0; J <= I; J++, idx++) if (leaf_lauum) lt.push_back(make_int4(s - b.s0, I, J, idx));
       const double n = m.n;
       b.potrf_flops += n * n * n / 3.0 + n * n / 2.0 + n / 6.0;
       b.gram_bytes += 8.0 * (n * (n + 1) / 2.0) + 8.0 * n * h->D;
@@ -599,8 +600,10 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     cudaEventRecord(ev[5], st);
     if (lau) {
       LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
-                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D};
-      launch_lauum(la, std::min(sms, b.n_lauum), st);
+                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + 8};
+      static const bool lauum_v1 = getenv("DSMGP_LAUUM_V1") != nullptr;     // development A/B
+      if (lauum_v1) launch_lauum(la, std::min(sms, b.n_lauum), st);
+      else launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
       h->tm.launches++;
     }
     cudaEventRecord(ev[6], st);
@@ -992,7 +995,9 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
   PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
               h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D};
+  cudaEventRecord(h->ev[0], h->stream);
   launch_predict(pa, std::min(num_sms(h->device), (int)tasks.size()), h->stream);
+  cudaEventRecord(h->ev[1], h->stream);
   h->tm.launches++;
   PTRY(cudaGetLastError());
   std::vector<double> hmu(oo), hvar(oo);
@@ -1000,6 +1005,13 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   PTRY(cudaMemcpyAsync(hvar.data(), d_var.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
   PTRY(cudaStreamSynchronize(h->stream));
 #undef PTRY
+  h->tm.predict_ms = ev_ms(h->ev[0], h->ev[1]);
+  h->tm.predict_flops = 0.0; h->tm.predict_bytes = 0.0;
+  for (size_t i = 0; i < pls.size(); i++) {      // TRSM n^2 T_l + 2 n T_l flop; L read once per block of 128 points
+    const double n = h->meta[pls[i].slot].n, Tl = pls[i].T;
+    h->tm.predict_flops += n * n * Tl + 2.0 * n * Tl;
+    h->tm.predict_bytes += 8.0 * (n * (n + 1) / 2.0) * (pls[i].Tp / BLK) + 8.0 * (n + Tl) * (double)D + 16.0 * Tl;
+  }
   for (size_t i = 0; i < pls.size(); i++) {
     const int64_t l = pl_leaf[i];
     mu[l].assign(hmu.begin() + pls[i].ooff, hmu.begin() + pls[i].ooff + pls[i].T);

@@ -61,6 +61,7 @@ struct LauumArgs {
   double* gpart;            // [gpart_off[slot] + task_in_leaf * nl + h]
   const int64_t* gpart_off;
   int D;
+  int* gerr;
 };
 
 struct RowsArgs {
@@ -110,6 +111,7 @@ cudaError_t init_lauum_kernels();
 cudaError_t init_predict_kernels();
 void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
 void launch_lauum(const LauumArgs& a, int nctas, cudaStream_t st);
+void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
 void launch_predict(const PredArgs& a, int nctas, cudaStream_t st);
 void launch_gram_fit(const GramArgs& a, int64_t ntiles, cudaStream_t st);

@@ -189,6 +189,8 @@ typedef struct {
   double gram_ms, potrf_ms, solve_ms, inverse_ms, grad_ms, tree_ms, total_ms;
   double potrf_flops, inverse_flops, gram_bytes;   /* algorithmic work of the last eval (local leaves) */
   int64_t launches;                                 /* kernels launched by the last call */
+  double predict_ms, predict_flops, predict_bytes;  /* last dsmgp_predict / dsmgp_leaf_predict: device time of predict_kernel,
+                                                       sum_l (n_l^2 T_l + 2 n_l T_l) flop, bytes of L + x + xt read */
 } dsmgp_timings;
 int32_t dsmgp_get_timings(const dsmgp_handle* h, dsmgp_timings* t);
 int32_t dsmgp_set_profiling(dsmgp_handle* h, int32_t on); /* per-phase CUDA events (adds syncs) */
