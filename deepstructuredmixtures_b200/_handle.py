@@ -107,6 +107,16 @@ class Handle:
                                       nat.p_d(g), nat.p_d(nodes)))
         return (lml.value, g, nodes) if want_nodes else (lml.value, g)
 
+    def finetune_eval(self, anchors, thetas, overlap):
+        """dsmgp_finetune_eval: (leaf_lml[G], grads[G, H], root_lml[G]) for the anchor experts under their own theta."""
+        an = np.ascontiguousarray(anchors, dtype=np.int64)
+        th = np.ascontiguousarray(thetas, dtype=np.float64).reshape(an.size, self.nparams)
+        ov = nat.colmajor(np.asarray(overlap, dtype=np.float64))
+        ll = np.zeros(an.size); gr = np.zeros((an.size, self.nparams)); rl = np.zeros(an.size)
+        self._ck(self._lib.dsmgp_finetune_eval(self._h, an.size, nat.p_i64(an), nat.p_d(th), nat.p_d(ov), nat.p_d(ll),
+                                               nat.p_d(gr), nat.p_d(rl)))
+        return ll, gr, rl
+
     def eval_local_dev(self, theta=None) -> int:
         th = None if theta is None else nat.f64(theta)
         ptr = C.c_void_p()

@@ -50,6 +50,11 @@ struct DevBuf {
     if (count == 0) return cudaSuccess;
     return cudaMalloc(&p, count * sizeof(T));
   }
+  // grow-only scratch: keeps the allocation across calls (cudaMalloc / cudaFree of GBs cost 10-100 ms per call)
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p != nullptr) return cudaSuccess;
+    return alloc(count + count / 8);
+  }
   void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
 };
 
@@ -94,6 +99,9 @@ struct dsmgp_handle {
   DevBuf<int> d_flags;
   DevBuf<double> d_ldpart, d_zzpart;
   DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
+  DevBuf<double> p_xt, p_VT, p_mu, p_var; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
+  DevBuf<int> d_mask; std::vector<int> h_mask; bool use_mask = false;   // per-slot gradient mask (finetune: zero-overlap experts)
+  double* pin_multi = nullptr; size_t pin_multi_doubles = 0;             // rows of a multi-theta call [G][L][row_width]
   double* pin_rows = nullptr;
   LeafScal* pin_scal = nullptr;
   std::string err;
@@ -105,7 +113,10 @@ struct dsmgp_handle {
     }
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
     d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
+    p_xt.free(); p_VT.free(); p_mu.free(); p_var.free(); p_pl.free(); p_tasks.free();
     d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
+    d_mask.free();
+    if (pin_multi) cudaFreeHost(pin_multi);
     if (pin_rows) cudaFreeHost(pin_rows);
     if (pin_scal) cudaFreeHost(pin_scal);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -367,6 +378,8 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   CUDA_TRY(h, h->d_gpart.alloc(std::max<int64_t>(maxG, 1)));
   CUDA_TRY(h, h->d_rows.alloc((size_t)L * h->row_width));
   CUDA_TRY(h, h->d_scal.alloc(ns));
+  CUDA_TRY(h, h->d_mask.alloc(std::max(ns, 1)));
+  h->h_mask.assign(std::max(ns, 1), 1);
   CUDA_TRY(h, h->d_counter.alloc(16));
   CUDA_TRY(h, h->d_flags.alloc(std::max<int64_t>(maxFlags, 1)));
   CUDA_TRY(h, h->d_ldpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
@@ -534,11 +547,13 @@ static bool needs_lauum(const dsmgp_handle* h) {
 static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 // gram -> potrf -> solves (-> inverse -> lauum) -> rows, batch by batch
-static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
+static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad);
+static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = false) {
   cudaStream_t st = h->stream;
   const int sms = num_sms(h->device);
   const bool lau = with_grad && needs_lauum(h);
   h->tm = dsmgp_timings{};
+  const int* mask_all = (with_grad && h->use_mask) ? h->d_mask.p : nullptr;
   if (h->batches.empty()) {   // a rank that owns no leaf
     h->fitted = true; h->have_rows = true; h->have_grad = with_grad; h->rows_complete = (h->opts.world == 1);
     return DSMGP_OK;
@@ -592,7 +607,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
                       h->d_flags.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, b.d_trtri3_tasks, b.n_trtri3,
-                      h->d_counter.p, h->d_counter.p + 8};
+                      h->d_counter.p, h->d_counter.p + 8, mask_all ? mask_all + b.s0 : nullptr};
         launch_trtri3(ta, std::max(1, std::min(sms, b.n_trtri3)), b.d_trtri_tasks, b.n_trtri, st);
         h->tm.launches += 2;
       }
@@ -600,7 +615,8 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     cudaEventRecord(ev[5], st);
     if (lau) {
       LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
-                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + 8};
+                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + 8,
+                   mask_all ? mask_all + b.s0 : nullptr};
       static const bool lauum_v1 = getenv("DSMGP_LAUUM_V1") != nullptr;     // development A/B
       if (lauum_v1) launch_lauum(la, std::min(sms, b.n_lauum), st);
       else launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
@@ -609,7 +625,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     cudaEventRecord(ev[6], st);
     RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,
                 h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0,
-                h->d_ldpart.p, h->d_zzpart.p, h->d_alpha.p};
+                h->d_ldpart.p, h->d_zzpart.p, h->d_alpha.p, mask_all ? mask_all + b.s0 : nullptr};
     launch_rows(ra, nsl, st);
     h->tm.launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -618,6 +634,12 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad) {
     h->tm.inverse_flops += with_grad ? b.potrf_flops * (lau ? 2.0 : 1.0) : 0.0;
     h->tm.gram_bytes += b.gram_bytes;
   }
+  if (defer_sync) return DSMGP_OK;
+  return finish_pipeline(h, with_grad);
+}
+
+static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad) {
+  cudaStream_t st = h->stream;
   const int ns = (int)h->slot_leaf.size();
   if (ns) CUDA_TRY(h, cudaMemcpyAsync(h->pin_scal, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, st));
   int gerr = 0;
@@ -687,6 +709,18 @@ static void tree_grad(dsmgp_handle* h, const double* leaf_scale, double* grad) {
   down_pass(c, h->tree.root, 0.0, 0.0, 0);
 }
 
+// Per-slot gradient mask from a leaf weight vector (NULL: every expert contributes).
+static void set_grad_mask(dsmgp_handle* h, const double* leaf_scale) {
+  h->use_mask = false;
+  if (!leaf_scale) return;
+  const int ns = (int)h->slot_leaf.size();
+  bool any_zero = false;
+  for (int s = 0; s < ns; s++) { h->h_mask[s] = leaf_scale[h->slot_leaf[s]] != 0.0 ? 1 : 0; any_zero |= !h->h_mask[s]; }
+  if (!any_zero || ns == 0) return;
+  cudaMemcpyAsync(h->d_mask.p, h->h_mask.data(), ns * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+  h->use_mask = true;
+}
+
 extern "C" int32_t dsmgp_fit(dsmgp_handle* h, int32_t* info, double* seconds) {
   if (!h) return DSMGP_ERR_ARG;
   cudaSetDevice(h->device);
@@ -727,7 +761,10 @@ extern "C" int32_t dsmgp_eval(dsmgp_handle* h, const double* theta, int64_t n, c
   int32_t rc;
   if (theta && (rc = dsmgp_set_params(h, theta, n))) return rc;
   cudaSetDevice(h->device);
-  if ((rc = run_pipeline(h, grad != nullptr))) return rc;
+  set_grad_mask(h, grad != nullptr ? leaf_scale : nullptr);   // finetune: experts with zero overlap weight skip the gradient kernels
+  rc = run_pipeline(h, grad != nullptr);
+  h->use_mask = false;
+  if (rc) return rc;
   if ((rc = fetch_rows(h))) return rc;
   if (!h->rows_complete) { h->err = "eval: world > 1 needs eval_local_dev + all-reduce + eval_finish_dev"; return DSMGP_ERR_STATE; }
   up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
@@ -735,6 +772,67 @@ extern "C" int32_t dsmgp_eval(dsmgp_handle* h, const double* theta, int64_t n, c
   if (node_lml) std::copy(h->node_lml.begin(), h->node_lml.end(), node_lml);
   if (grad) tree_grad(h, leaf_scale, grad);
   return check_pd(h);
+}
+
+// finetune!'s inner loop (finetuning.jl:36-58) for G anchor experts in ONE call: the G evaluations of an iteration are
+// independent (theta_g is only updated from its own gradient), so they are enqueued back to back on the stream with
+// no host synchronisation in between; experts with D[g, l] == 0 skip the inverse / LAUUM kernels.
+extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t* anchors, const double* thetas,
+                                       const double* overlap, double* leaf_lml, double* grads, double* root_lml) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (G <= 0 || !anchors || !thetas || !overlap || !leaf_lml || !grads) { h->err = "finetune_eval: bad argument"; return DSMGP_ERR_ARG; }
+  if (h->opts.world != 1) { h->err = "finetune_eval: single-process handles only"; return DSMGP_ERR_STATE; }
+  const int64_t L = h->L, H = h->H, rw = h->row_width;
+  for (int64_t g = 0; g < G; g++) if (anchors[g] < 0 || anchors[g] >= L) { h->err = "finetune_eval: anchor out of range"; return DSMGP_ERR_ARG; }
+  cudaSetDevice(h->device);
+  const size_t need = (size_t)G * L * rw;
+  if (need > h->pin_multi_doubles) {
+    if (h->pin_multi) cudaFreeHost(h->pin_multi);
+    h->pin_multi = nullptr; h->pin_multi_doubles = 0;
+    CUDA_TRY(h, cudaMallocHost(&h->pin_multi, need * sizeof(double)));
+    h->pin_multi_doubles = need;
+  }
+  std::vector<double> scale(L);
+  std::vector<int32_t> info((size_t)G * L, 0);
+  const int ns = (int)h->slot_leaf.size();
+  std::vector<LeafScal> scal_g((size_t)G * std::max(ns, 1));
+  LeafScal* pin_scal_multi = nullptr;
+  CUDA_TRY(h, cudaMallocHost(&pin_scal_multi, scal_g.size() * sizeof(LeafScal)));
+  int32_t rc = DSMGP_OK;
+  for (int64_t g = 0; g < G && rc == DSMGP_OK; g++) {
+    if ((rc = dsmgp_set_params(h, thetas + g * H, H))) break;              // setparams!(spn, hyp_)  finetuning.jl:41
+    for (int64_t l = 0; l < L; l++) scale[l] = overlap[anchors[g] + l * L];   // view(D, g, :)  finetuning.jl:53
+    set_grad_mask(h, scale.data());
+    rc = run_pipeline(h, true, true);
+    h->use_mask = false;
+    if (rc) break;
+    cudaMemcpyAsync(h->pin_multi + (size_t)g * L * rw, h->d_rows.p, (size_t)L * rw * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+    if (ns) cudaMemcpyAsync(pin_scal_multi + (size_t)g * ns, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, h->stream);
+  }
+  if (rc == DSMGP_OK) rc = finish_pipeline(h, true);        // one synchronisation for all G evaluations
+  if (rc) { cudaFreeHost(pin_scal_multi); return rc; }
+  std::vector<int64_t> node_of_leaf(L, -1);
+  for (int64_t i = 0; i < h->tree.n_nodes; i++) if (h->tree.type[i] == DSMGP_NODE_LEAF) node_of_leaf[h->tree.leaf_of_node[i]] = i;
+  for (int64_t g = 0; g < G; g++) {
+    const double* rows = h->pin_multi + (size_t)g * L * rw;
+    std::copy(rows, rows + (size_t)L * rw, h->h_rows.begin());
+    for (int s = 0; s < ns; s++) {           // a non-PD expert poisons its own LML like the reference's log of a bad pivot
+      const int inf = pin_scal_multi[(size_t)g * ns + s].info;
+      if (inf != 0 && inf <= h->meta[s].n && h->opts.strict_pd) {
+        h->err = "PosDefException: leaf " + std::to_string(h->slot_leaf[s]) + " (finetune anchor " + std::to_string(anchors[g]) + ")";
+        cudaFreeHost(pin_scal_multi);
+        return DSMGP_ERR_NOT_PD;
+      }
+    }
+    up_pass(h->tree, h->h_rows.data(), rw, h->node_lml.data());             // mll!(spn, L)  finetuning.jl:47-48
+    leaf_lml[g] = h->node_lml[node_of_leaf[anchors[g]]];                     // L[gp.id]      finetuning.jl:51
+    if (root_lml) root_lml[g] = h->node_lml[h->tree.root];
+    for (int64_t l = 0; l < L; l++) scale[l] = overlap[anchors[g] + l * L];
+    tree_grad(h, scale.data(), grads + g * H);                               // finetuning.jl:53
+  }
+  cudaFreeHost(pin_scal_multi);
+  h->rows_complete = true;
+  return DSMGP_OK;
 }
 
 extern "C" int32_t dsmgp_eval_local_dev(dsmgp_handle* h, const double* theta, int64_t n, double** rows_dev) {
@@ -983,12 +1081,13 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
     for (int64_t d = 0; d < D; d++)
       for (size_t q = 0; q < pv.size(); q++) xt[pls[i].xtoff + d * pls[i].Tp + q] = xtest[d * T + pv[q]];
   }
-  DevBuf<double> d_xt, d_VT, d_mu, d_var; DevBuf<PredLeaf> d_pl; DevBuf<int2> d_tasks;
-  auto cleanup = [&]() { d_xt.free(); d_VT.free(); d_mu.free(); d_var.free(); d_pl.free(); d_tasks.free(); };
+  DevBuf<double>&d_xt = h->p_xt, &d_VT = h->p_VT, &d_mu = h->p_mu, &d_var = h->p_var;
+  DevBuf<PredLeaf>& d_pl = h->p_pl; DevBuf<int2>& d_tasks = h->p_tasks;
+  auto cleanup = [&]() { if (d_VT.n * sizeof(double) > (size_t(16) << 30)) d_VT.free(); };   // keep the scratch unless it is huge
 #define PTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { h->err = std::string(#expr) + ": " + cudaGetErrorString(e_); cleanup(); \
     return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA; } } while (0)
-  PTRY(d_xt.alloc(xto)); PTRY(d_VT.alloc(vto)); PTRY(d_mu.alloc(oo)); PTRY(d_var.alloc(oo));
-  PTRY(d_pl.alloc(pls.size())); PTRY(d_tasks.alloc(tasks.size()));
+  PTRY(d_xt.ensure(xto)); PTRY(d_VT.ensure(vto)); PTRY(d_mu.ensure(oo)); PTRY(d_var.ensure(oo));
+  PTRY(d_pl.ensure(pls.size())); PTRY(d_tasks.ensure(tasks.size()));
   PTRY(cudaMemcpyAsync(d_xt.p, xt.data(), xto * 8, cudaMemcpyHostToDevice, h->stream));
   PTRY(cudaMemcpyAsync(d_pl.p, pls.data(), pls.size() * sizeof(PredLeaf), cudaMemcpyHostToDevice, h->stream));
   PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));

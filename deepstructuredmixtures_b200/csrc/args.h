@@ -62,6 +62,7 @@ struct LauumArgs {
   const int64_t* gpart_off;
   int D;
   int* gerr;
+  const int* mask;          // per slot: 0 = skip this expert, or null
 };
 
 struct RowsArgs {
@@ -75,6 +76,7 @@ struct RowsArgs {
   int as_written; int with_grad; int lauum_ran;
   const double* ldpart; const double* zzpart;   // engine v2: per block-column partials of logdet and z'z (else null)
   const double* alpha;                          // alpha'alpha is reduced here
+  const int* mask;                              // per slot: 0 = gradient entries are written as 0 (expert skipped)
 };
 
 struct PredLeaf {     // per leaf with routed points

@@ -133,15 +133,18 @@ __global__ void rows_kernel(RowsArgs a) {
     sc.logdet = block_sum(l, red);
     sc.zz = block_sum(zq, red);
   }
-  if (a.alpha != nullptr && a.with_grad) {
+  if (a.alpha != nullptr && a.with_grad && !(a.mask != nullptr && a.mask[slot] == 0)) {
     double q = 0.0;
     for (int i = tid; i < m.n; i += blockDim.x) { const double v = a.alpha[m.voff + i]; q = fma(v, v, q); }
     sc.aa = block_sum(q, red);
   }
   double lml = -(sc.zz + sc.logdet + 1.8378770664093453 * n) / 2.0;   // log(2 pi)
   if (sc.info != 0) lml = nan("");
-  if (!a.with_grad) {
-    if (tid == 0) row[0] = lml;
+  if (!a.with_grad || (a.mask != nullptr && a.mask[slot] == 0)) {
+    if (tid == 0) {
+      row[0] = lml;
+      if (a.with_grad) for (int h = 1; h < a.row_width; h++) row[h] = 0.0;      // skipped expert: weight 0 in the down-pass
+    }
     return;
   }
   // tr(F^-1): ordered sum of the per-block partials

@@ -52,6 +52,7 @@ __device__ __forceinline__ void lauum3_producer(Pipe& p, const LauumArgs& a) {
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
     const int ti = __shfl_sync(0xffffffffu, t, 0);
     if (ti >= a.ntasks) break;
+    if (a.mask != nullptr && a.mask[a.tasks[ti].x] == 0) continue;      // expert without a gradient request
     gen.load(a, ti);
     ChunkDesc d;
     bool first = true;

@@ -35,6 +35,7 @@ struct Trtri3Args {
   double* apart; double* tpart;                 // per-tile partials: [tile][BLK], [tile]
   const int4* tasks; int ntasks;
   int* counter; int* gerr;
+  const int* mask;                              // per slot: 0 = skip this expert (no gradient wanted), or null
 };
 
 }  // namespace dsm

@@ -79,6 +79,7 @@ __device__ __forceinline__ void trtri3_producer(Pipe& p, const Trtri3Args& a) {
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
     const int ti = __shfl_sync(0xffffffffu, t, 0);
     if (ti >= a.ntasks) break;
+    if (a.mask != nullptr && a.mask[a.tasks[ti].x] == 0) continue;      // expert without a gradient request
     gen.load(a, ti);
     ChunkDesc d;
     bool first = true;
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) trtri3_kernel(Trtri3Args a) {
 // grid = block columns of the batch (the old column-task list), block = BLK threads.
 __global__ void __launch_bounds__(BLK) alpha_reduce_kernel(Trtri3Args a, const int2* cols, int ncols) {
   const int2 ck = cols[blockIdx.x];
+  if (a.mask != nullptr && a.mask[ck.x] == 0) return;
   const LeafMeta m = a.meta[ck.x];
   const int J = ck.y, j0 = J * BLK, wj = blk_width(m.np, J), tid = threadIdx.x;
   const double* z = a.z + m.voff;

@@ -139,11 +139,14 @@ def train_gp_(gp: LeafGP, *, optim=None, iterations: int = 10_000, lam: float = 
     return gp, ell
 
 
-def finetune_(model: Model, optim=None, *, iterations: int = 1000, lam: float = 0.5):
+def finetune_(model: Model, optim=None, *, iterations: int = 1000, lam: float = 0.5, batch: int = 256):
     """finetune!(model, optim; iterations, λ) finetuning.jl:3-88: per-leaf hyper-parameters.  For every leaf g the
     WHOLE model is evaluated under θ_g and the leaf gradients are weighted by the overlap row D[g,:]
     (optimize.jl:92-102; the diagonal of D is 0, so a leaf's own gradient has weight 0).
-    Kernel mixtures raise, as in the reference (App. B Q10)."""
+    Kernel mixtures raise, as in the reference (App. B Q10).
+
+    The L evaluations of one iteration are independent (hyp[g] is only updated from its own gradient), so they go to the
+    device as ONE `dsmgp_finetune_eval` call; `batch` bounds how many anchors share a call."""
     optim = ADAM() if optim is None else optim
     if len(model.kernels) != 1:
         raise IndexError("finetune! with a kernel vector is a BoundsError in the reference (finetuning.jl:41)")
@@ -152,14 +155,16 @@ def finetune_(model: Model, optim=None, *, iterations: int = 1000, lam: float = 
     hyp = [model.handle.get_leaf_params(g).copy() for g in range(L)]         # :24
     ell = np.zeros(iterations)
     c = 0
-    node_of_leaf = [lf.id for lf in model.leaves]
     for it in range(iterations):
         l = 0.0
-        for g in range(L):
-            lml, grad, nodes = model.handle.eval(hyp[g], leaf_scale=D[g, :], want_nodes=True)   # :41-54
-            l += nodes[node_of_leaf[g]]                                      # :51
-            optim.apply_(hyp[g], grad)
-            hyp[g] = hyp[g] + grad
+        for g0 in range(0, L, batch):
+            gs = list(range(g0, min(L, g0 + batch)))
+            leaf_lml, grads, _ = model.handle.finetune_eval(gs, np.stack([hyp[g] for g in gs]), D)   # :41-54
+            for i, g in enumerate(gs):
+                l += leaf_lml[i]                                             # :51
+                grad = grads[i].copy()
+                optim.apply_(hyp[g], grad)
+                hyp[g] = hyp[g] + grad
         ell[it] = l
         delta = abs(ell[it] - np.mean(ell[it - 9:it])) if it >= 10 else np.inf
         c = c + 1 if delta < lam else 0

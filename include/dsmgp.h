@@ -132,6 +132,17 @@ int32_t dsmgp_grad(dsmgp_handle* h, const double* leaf_scale, double* grad);
 int32_t dsmgp_eval(dsmgp_handle* h, const double* theta, int64_t n, const double* leaf_scale,
                    double* lml, double* grad, double* node_lml);
 
+/* finetune!'s inner loop (finetuning.jl:36-58) for G anchor experts in one call.  For every g: setparams!(spn, theta_g)
+ * (ALL experts get theta_g), fit!, mll!, updategradients!, and the finetune down-pass optimize.jl:92-150 with the
+ * weights D[anchor_g, :] (`overlap` = the L x L matrix of getOverlap, fit.jl:12-39, column-major).  Outputs per g:
+ * leaf_lml[g] = L[gp.id] (finetuning.jl:51), grads[g*H .. ] (finetuning.jl:53), root_lml[g] (may be NULL).
+ * The G evaluations are independent (theta_g is only updated from its own gradient), so they run back to back on the
+ * device without host synchronisation; experts whose weight D[anchor_g, l] is 0 skip the inverse / LAUUM kernels
+ * (dsmgp_eval does the same whenever `leaf_scale` has zeros).  On return the handle holds theta of the last anchor. */
+int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t* anchors, const double* thetas /* G x H row-major */,
+                            const double* overlap /* L x L col-major */, double* leaf_lml /* G */,
+                            double* grads /* G x H row-major */, double* root_lml /* G or NULL */);
+
 /* Per-leaf rows of the last eval: rows[l*(1+Hmax) + 0] = mll(gp_l), [1..] = nabla-mll(gp_l)
  * (gaussianprocess.jl:185-217).  Hmax = max nparams over kernels.  Also the multi-GPU exchange unit:
  * a rank fills only its own leaves, rows of other ranks are 0, so a SUM all-reduce assembles them. */

@@ -39,6 +39,9 @@ def check_eval(model, theta, mathematical=False, leaf_scale=None):
         gp = [lf for lf in orc.getLeaves(root) if lf.leaf_index == l][0].gp
         scale = max(float(gp.alpha @ gp.alpha), float(gp.N)) * max(1.0, gp.noise())
         g = rows[l, 1:1 + orow.size - 1]
+        if leaf_scale is not None and leaf_scale[l] == 0.0:
+            assert np.all(g == 0.0)          # zero-weight experts skip the gradient kernels (include/dsmgp.h: dsmgp_finetune_eval)
+            continue
         assert np.all(np.abs(g - orow[1:]) <= GRAD_TOL * np.maximum(np.abs(orow[1:]), scale)), (l, g, orow[1:])
     gs = np.maximum(np.abs(o_grad), 1e-6 * np.max(np.abs(o_grad)) + 1e-300)
     assert np.all(np.abs(grad - o_grad) <= 1e-8 * np.maximum(gs, 1.0)), (grad, o_grad)
@@ -134,6 +137,29 @@ def test_finetune_leaf_scale():
     assert np.array_equal(D, oD)
     th = np.array([-0.5, 0.1, -1.1])
     check_eval(model, th, leaf_scale=D[1, :])
+
+
+def test_finetune_eval_batched():
+    """dsmgp_finetune_eval (one call for all anchors) == finetuning.jl:36-58 evaluated anchor by anchor by the oracle."""
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(700, 2, 6)
+    model = dsm.buildDSMGP(x, y, 2, 3, M=40, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, rng=6)
+    D = model.D
+    L = len(model.leaves)
+    rng = np.random.default_rng(3)
+    thetas = np.array([-0.4, 0.1, -1.0]) + 0.2 * rng.standard_normal((L, 3))
+    leaf_lml, grads, root_lml = model.handle.finetune_eval(np.arange(L), thetas, D)
+    root = oracle_tree(model)
+    node_of_leaf = {lf.leaf_index: lf.id for lf in orc.getLeaves(root)}
+    for g in range(L):
+        o_lml, o_grad, o_ell, _ = orc.evaluate(root, thetas[g], Drow=D[g, :])
+        assert abs(root_lml[g] - o_lml) <= LML_TOL * abs(o_lml)
+        assert abs(leaf_lml[g] - o_ell[node_of_leaf[g]]) <= LML_TOL * abs(o_ell[node_of_leaf[g]])
+        gs = np.maximum(np.abs(o_grad), 1e-6 * np.max(np.abs(o_grad)) + 1e-300)
+        assert np.all(np.abs(grads[g] - o_grad) <= 1e-8 * np.maximum(gs, 1.0)), (g, grads[g], o_grad)
+    # and the driver: two finetune_ iterations run and keep per-leaf parameters
+    m2, ell = dsm.finetune_(model, dsm.ADAM(), iterations=2)
+    assert np.all(np.isfinite(ell))
 
 
 @pytest.mark.parametrize("mode", ["poe", "gpoe", "rbcm"])
