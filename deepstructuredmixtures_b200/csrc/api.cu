@@ -1321,6 +1321,64 @@ done:
 
 // potrf / chol_continue on one host matrix.  k = number of leading rows/cols that already hold a valid factor.
 // Runs the same persistent tile scheduler as the batched path (potrf2_kernel) on a one-expert batch.
+// getOverlap(spn, D, gpmap) fit.jl:12-39 on the device.
+extern "C" int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
+                                 const int32_t* leaf_kernel_id, const dsmgp_tree* tree, double* D) {
+  if (N <= 0 || L <= 0 || !leaf_ptr || !leaf_obs || !leaf_kernel_id || !tree || !D) { g_create_error = "overlap: bad argument"; return DSMGP_ERR_ARG; }
+  HostTree t; std::string err;
+  if (!t.load(tree, L, err)) { g_create_error = err; return DSMGP_ERR_ARG; }
+  const int64_t total = leaf_ptr[L];
+  for (int64_t i = 0; i < total; i++) if (leaf_obs[i] < 1 || leaf_obs[i] > N) { g_create_error = "overlap: leaf_obs must be 1-based rows in 1..N"; return DSMGP_ERR_ARG; }
+  { int32_t rc = standalone_device_check(g_create_error); if (rc) return rc; }
+  // ancestor chains (root first) from the child lists
+  std::vector<int64_t> parent(t.n_nodes, -1);
+  for (int64_t i = 0; i < t.n_nodes; i++) for (int64_t k = 0; k < t.nchild(i); k++) parent[t.child(i, k)] = i;
+  std::vector<std::vector<int>> chain(L);
+  int AD = 1;
+  for (int64_t i = 0; i < t.n_nodes; i++) {
+    if (t.type[i] != DSMGP_NODE_LEAF) continue;
+    std::vector<int> c;
+    for (int64_t u = parent[i]; u >= 0; u = parent[u]) c.push_back((int)u);
+    std::reverse(c.begin(), c.end());
+    AD = std::max<int>(AD, (int)c.size());
+    chain[t.leaf_of_node[i]] = c;
+  }
+  std::vector<int> anc((size_t)L * AD, -1);
+  for (int64_t l = 0; l < L; l++) std::copy(chain[l].begin(), chain[l].end(), anc.begin() + (size_t)l * AD);
+  std::vector<int> ntype(t.type.begin(), t.type.end()), kid(leaf_kernel_id, leaf_kernel_id + L);
+  int64_t* d_obs = nullptr; int64_t* d_lp = nullptr; int64_t* d_poff = nullptr;
+  int *d_cnt = nullptr, *d_plist = nullptr, *d_inter = nullptr, *d_kid = nullptr, *d_anc = nullptr, *d_nt = nullptr;
+  double* d_D = nullptr;
+  auto cleanup = [&]() { cudaFree(d_obs); cudaFree(d_lp); cudaFree(d_poff); cudaFree(d_cnt); cudaFree(d_plist); cudaFree(d_inter);
+                         cudaFree(d_kid); cudaFree(d_anc); cudaFree(d_nt); cudaFree(d_D); };
+#define OTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_create_error = std::string(#expr) + ": " + cudaGetErrorString(e_); cleanup(); \
+    return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA; } } while (0)
+  OTRY(cudaMalloc(&d_obs, total * 8)); OTRY(cudaMemcpy(d_obs, leaf_obs, total * 8, cudaMemcpyHostToDevice));
+  OTRY(cudaMalloc(&d_lp, (L + 1) * 8)); OTRY(cudaMemcpy(d_lp, leaf_ptr, (L + 1) * 8, cudaMemcpyHostToDevice));
+  OTRY(cudaMalloc(&d_cnt, N * 4)); OTRY(cudaMemset(d_cnt, 0, N * 4));
+  launch_ov_count(d_obs, total, d_cnt, nullptr);
+  std::vector<int> cnt(N);
+  OTRY(cudaMemcpy(cnt.data(), d_cnt, N * 4, cudaMemcpyDeviceToHost));
+  std::vector<int64_t> poff(N + 1, 0);
+  for (int64_t p = 0; p < N; p++) poff[p + 1] = poff[p] + cnt[p];
+  OTRY(cudaMalloc(&d_poff, (N + 1) * 8)); OTRY(cudaMemcpy(d_poff, poff.data(), (N + 1) * 8, cudaMemcpyHostToDevice));
+  OTRY(cudaMalloc(&d_plist, std::max<int64_t>(total, 1) * 4));
+  OTRY(cudaMemset(d_cnt, 0, N * 4));
+  launch_ov_fill(d_obs, d_lp, (int)L, d_poff, d_cnt, d_plist, nullptr);
+  OTRY(cudaMalloc(&d_inter, (size_t)L * L * 4)); OTRY(cudaMemset(d_inter, 0, (size_t)L * L * 4));
+  launch_ov_pairs(d_poff, d_plist, N, L, d_inter, nullptr);
+  OTRY(cudaMalloc(&d_kid, L * 4)); OTRY(cudaMemcpy(d_kid, kid.data(), L * 4, cudaMemcpyHostToDevice));
+  OTRY(cudaMalloc(&d_anc, anc.size() * 4)); OTRY(cudaMemcpy(d_anc, anc.data(), anc.size() * 4, cudaMemcpyHostToDevice));
+  OTRY(cudaMalloc(&d_nt, ntype.size() * 4)); OTRY(cudaMemcpy(d_nt, ntype.data(), ntype.size() * 4, cudaMemcpyHostToDevice));
+  OTRY(cudaMalloc(&d_D, (size_t)L * L * 8));
+  launch_ov_finish(d_inter, d_lp, d_kid, d_anc, AD, d_nt, L, d_D, nullptr);
+  OTRY(cudaGetLastError());
+  OTRY(cudaMemcpy(D, d_D, (size_t)L * L * 8, cudaMemcpyDeviceToHost));
+#undef OTRY
+  cleanup();
+  return DSMGP_OK;
+}
+
 static int32_t chol_host_matrix(double* A, int64_t n, int64_t k, int32_t* info) {
   int32_t rc = standalone_device_check(g_create_error);
   if (rc) return rc;

@@ -127,6 +127,11 @@ void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st);
 void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st);
 void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, cudaStream_t st);
 void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st);
+void launch_ov_count(const int64_t* obs, int64_t total, int* cntp, cudaStream_t st);
+void launch_ov_fill(const int64_t* obs, const int64_t* leaf_ptr, int L, const int64_t* poff, int* fill, int* plist, cudaStream_t st);
+void launch_ov_pairs(const int64_t* poff, const int* plist, int64_t N, int64_t L, int* inter, cudaStream_t st);
+void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
+                      int64_t L, double* D, cudaStream_t st);
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
 
 }  // namespace dsm

@@ -38,4 +38,73 @@ void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t s
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st) {
   delete_rows_kernel<<<1, NTHREADS, 0, st>>>(Lf, n, rows, nrows, v);
 }
+
+// ---- overlap matrix of getOverlap (fit.jl:12-39) -------------------------------------------------------------
+// D[n,m] = 1 - |obs_n \ obs_m| / |obs_n| = f(|obs_n ^ obs_m|) for experts whose lowest common ancestor is a sum node.
+// The reference xors N-bit sets for every pair (O(L^2 N)); here every POINT enumerates the pairs of experts that
+// contain it (it belongs to one expert per sum-node branch), so the work is sum_p k_p^2 integer atomics.
+__global__ void ov_count_kernel(const int64_t* obs, int64_t total, int* cntp) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(cntp + (obs[i] - 1), 1);
+}
+__global__ void ov_fill_kernel(const int64_t* obs, const int64_t* leaf_ptr, int L, const int64_t* poff, int* fill, int* plist) {
+  const int l = blockIdx.x;
+  for (int64_t i = leaf_ptr[l] + threadIdx.x; i < leaf_ptr[l + 1]; i += blockDim.x) {
+    const int64_t p = obs[i] - 1;
+    plist[poff[p] + atomicAdd(fill + p, 1)] = l;
+  }
+  (void)L;
+}
+// one warp per point: every unordered pair of its experts gets one count (both orientations)
+__global__ void ov_pairs_kernel(const int64_t* poff, const int* plist, int64_t N, int64_t L, int* inter) {
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t p = warp; p < N; p += nw) {
+    const int64_t o = poff[p];
+    const int k = (int)(poff[p + 1] - o);
+    const int npairs = k * (k - 1) / 2;
+    for (int q = lane; q < npairs; q += 32) {
+      int i = (int)((sqrtf(8.0f * q + 1.0f) + 1.0f) * 0.5f);      // q = i(i-1)/2 + j, j < i
+      while (i * (i - 1) / 2 > q) i--;
+      while ((i + 1) * i / 2 <= q) i++;
+      const int j = q - i * (i - 1) / 2;
+      const int64_t a = plist[o + i], b = plist[o + j];
+      atomicAdd(inter + a + b * L, 1);
+      atomicAdd(inter + b + a * L, 1);
+    }
+  }
+}
+// anc: [L][AD] node ids from the root down to the expert (-1 padded).  D is L x L column-major.
+__global__ void ov_finish_kernel(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD,
+                                 const int* node_type, int64_t L, double* D) {
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < L * L; e += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = e % L, m = e / L;
+    double v = 0.0;
+    if (n != m) {
+      int lca = -1;
+      for (int d = 0; d < AD; d++) {
+        const int an = anc[n * AD + d], am = anc[m * AD + d];
+        if (an < 0 || an != am) break;
+        lca = an;
+      }
+      if (lca >= 0 && node_type[lca] >= 2) {                       // DSMGP_NODE_SUM / DSMGP_NODE_KSUM
+        const int64_t cn = leaf_ptr[n + 1] - leaf_ptr[n];
+        const int64_t dn = (kid[n] == kid[m]) ? cn - (int64_t)inter[e] : 0;      // sum(xor & obs_n) * (kernelid equal)
+        v = 1.0 - (double)dn / (double)cn;                         // fit.jl:31
+      }
+    }
+    D[e] = v;
+  }
+}
+void launch_ov_count(const int64_t* obs, int64_t total, int* cntp, cudaStream_t st) { ov_count_kernel<<<1184, 256, 0, st>>>(obs, total, cntp); }
+void launch_ov_fill(const int64_t* obs, const int64_t* leaf_ptr, int L, const int64_t* poff, int* fill, int* plist, cudaStream_t st) {
+  ov_fill_kernel<<<L, 256, 0, st>>>(obs, leaf_ptr, L, poff, fill, plist);
+}
+void launch_ov_pairs(const int64_t* poff, const int* plist, int64_t N, int64_t L, int* inter, cudaStream_t st) {
+  ov_pairs_kernel<<<1184, 256, 0, st>>>(poff, plist, N, L, inter);
+}
+void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
+                      int64_t L, double* D, cudaStream_t st) {
+  ov_finish_kernel<<<1184, 256, 0, st>>>(inter, leaf_ptr, kid, anc, AD, node_type, L, D);
+}
 }  // namespace dsm

@@ -34,3 +34,16 @@ def chol_delete_rows(Lf: np.ndarray, rows: Sequence[int]) -> np.ndarray:
     out = np.zeros((n - rows.size, n - rows.size), order="F")
     nat.check(nat.lib().dsmgp_chol_delete_rows(nat.p_d(Lf), n, nat.p_i64(rows), rows.size, nat.p_d(out)))
     return out
+
+
+def overlap_matrix(N: int, leaf_obs: Sequence[np.ndarray], leaf_kernel_id: Sequence[int], tree: "nat.FlatTree") -> np.ndarray:
+    """getOverlap(spn, D, gpmap) fit.jl:12-39 on the device (`dsmgp_overlap`): the L x L overlap matrix D."""
+    L = len(leaf_obs)
+    leaf_ptr = np.zeros(L + 1, dtype=np.int64)
+    leaf_ptr[1:] = np.cumsum([len(o) for o in leaf_obs])
+    obs = np.ascontiguousarray(np.concatenate(leaf_obs), dtype=np.int64)
+    kid = np.ascontiguousarray(leaf_kernel_id, dtype=np.int32)
+    D = np.zeros((L, L), order="F")
+    nat.check(nat.lib().dsmgp_overlap(int(N), L, nat.p_i64(leaf_ptr), nat.p_i64(obs), nat.p_i32(kid),
+                                      C.byref(tree.struct), nat.p_d(D)))
+    return D

@@ -112,9 +112,12 @@ class Model:
 
     @property
     def D(self) -> np.ndarray:
-        """Overlap matrix (getOverlap fit.jl:12-39, built at treeStructure.jl:428-431); computed lazily on the host."""
+        """Overlap matrix (getOverlap fit.jl:12-39, built at treeStructure.jl:428-431); computed lazily, on the device
+        (`dsmgp_overlap`; `structure.getOverlap` is the host restatement of the reference's bit-set loop)."""
         if self._D is None:
-            self._D = getOverlap(self.root, self.x.shape[0])
+            from .linalg import overlap_matrix
+            self._D = overlap_matrix(self.x.shape[0], [lf.obs for lf in self.leaves],
+                                     [lf.kernelid - 1 for lf in self.leaves], self.flat)
         return self._D
 
     @property

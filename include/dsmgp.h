@@ -176,6 +176,12 @@ int32_t dsmgp_leaf_info(const dsmgp_handle* h, int32_t* info /* L */);
  * x1: n1 x D, x2: n2 x D, K: n1 x n2, all column-major. */
 int32_t dsmgp_kernelmatrix(int32_t kernel_type, const double* theta, int64_t D,
                            const double* x1, int64_t n1, const double* x2, int64_t n2, double* K);
+/* getOverlap(spn, D, gpmap) fit.jl:12-39 (called once by build, treeStructure.jl:428-431):  D[n,m] = 1 - card(obs_n \ obs_m)
+ * / card(obs_n) for experts whose lowest common ancestor is a sum node (1 when their kernel ids differ), else 0.
+ * D is L x L column-major (D[n,m] at n + m*L), bit-identical to the reference's formula; computed on the device by
+ * letting every point enumerate the pairs of experts that contain it. */
+int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
+                      const int32_t* leaf_kernel_id, const dsmgp_tree* tree, double* D);
 /* AdvancedCholesky.chol_continue!(A, ki) AdvancedCholeskey.jl:152-174 (ki 1-based): A n x n column-major in/out. */
 int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t* info);
 /* Row/column deletion from a lower Cholesky factor: the operation fit.jl:179-195 composes from

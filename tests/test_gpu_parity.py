@@ -139,6 +139,20 @@ def test_finetune_leaf_scale():
     check_eval(model, th, leaf_scale=D[1, :])
 
 
+@pytest.mark.parametrize("kernel", ["isose", "mixture"])
+def test_overlap_matrix_device_bit_exact(kernel):
+    """dsmgp_overlap == getOverlap (fit.jl:12-39) bit for bit: oracle restatement and the host restatement."""
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import structure as st
+    x, y = synth(1500, 3, 8)
+    k = dsm.IsoSE(0.0, 0.0) if kernel == "isose" else [dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)]
+    model = dsm.buildDSMGP(x, y, 3, 3, M=60, kernel=k, logNoise=-1.0, rng=8)
+    D = model.D
+    assert np.array_equal(D, orc.getOverlap(oracle_tree(model), x.shape[0]))
+    assert np.array_equal(D, st.getOverlap(model.root, x.shape[0]))
+    assert D.max() <= 1.0 and D.min() >= 0.0 and np.all(np.diag(D) == 0.0) and np.count_nonzero(D) > 0
+
+
 def test_finetune_eval_batched():
     """dsmgp_finetune_eval (one call for all anchors) == finetuning.jl:36-58 evaluated anchor by anchor by the oracle."""
     import deepstructuredmixtures_b200 as dsm
