@@ -150,6 +150,20 @@ function update!(h::Handle, spn)
     return z[]
 end
 
+"""
+The inner loop of finetune! (finetuning.jl:36-58) for all anchor experts of one iteration in ONE call.
+`anchors`: 0-based leaf numbers (gpmap order), `thetas`: H x G (one column per anchor), `D`: the L x L overlap matrix.
+Returns (leaf_lml[G], grads H x G, root_lml[G]); the caller applies Flux.Optimise.apply! per anchor as before.
+"""
+function finetune_eval(h::Handle, anchors::Vector{Int64}, thetas::Matrix{Float64}, D::Matrix{Float64})
+    G = length(anchors); H = size(thetas, 1)
+    ll = zeros(G); gr = zeros(H, G); rl = zeros(G)       # column-major H x G == row-major G x H of the C side
+    check(ccall((:dsmgp_finetune_eval, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                h.ptr, G, anchors, thetas, D, ll, gr, rl), h.ptr)
+    return ll, gr, rl
+end
+
 predictmode(::DSMGP) = Int32(0); predictmode(::PoE) = Int32(1); predictmode(::gPoE) = Int32(2); predictmode(::rBCM) = Int32(3)
 function predict(h::Handle, model, x::Matrix{Float64})
     T = size(x, 1); μ = zeros(T); σ² = zeros(T)
