@@ -131,7 +131,6 @@ static bool g_attr_done = false;
 static cudaError_t engine_attrs() {
   if (g_attr_done) return cudaSuccess;
   cudaError_t e;
-  if ((e = init_lauum_kernels())) return e;
   if ((e = init_predict_kernels())) return e;
   if ((e = init_v2_kernels())) return e;
   g_attr_done = true;
@@ -597,13 +596,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
         h->tm.launches++;
       }
       cudaEventRecord(ev[4], st);
-      static const bool column_tasks = getenv("DSMGP_TRTRI_COLUMNS") != nullptr;    // development A/B: one CTA per block column
-      if (with_grad && column_tasks) {
-        Trtri2Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
-                      b.d_trtri_tasks, b.n_trtri, h->d_counter.p, h->d_counter.p + 8};
-        launch_trtri2(ta, std::min(sms, b.n_trtri), st);
-        h->tm.launches++;
-      } else if (with_grad) {
+      if (with_grad) {
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
                       h->d_flags.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, b.d_trtri3_tasks, b.n_trtri3,
@@ -617,9 +610,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
       LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
                    h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + 8,
                    mask_all ? mask_all + b.s0 : nullptr};
-      static const bool lauum_v1 = getenv("DSMGP_LAUUM_V1") != nullptr;     // development A/B
-      if (lauum_v1) launch_lauum(la, std::min(sms, b.n_lauum), st);
-      else launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
+      launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
       h->tm.launches++;
     }
     cudaEventRecord(ev[6], st);

@@ -109,10 +109,8 @@ struct PredArgs {
 };
 
 // ---- launchers (defined next to their kernels) ------------------------------------------------
-cudaError_t init_lauum_kernels();
 cudaError_t init_predict_kernels();
 void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
-void launch_lauum(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
 void launch_predict(const PredArgs& a, int nctas, cudaStream_t st);
@@ -120,11 +118,9 @@ void launch_gram_fit(const GramArgs& a, int64_t ntiles, cudaStream_t st);
 void launch_gram_rect(const GramRectArgs& a, cudaStream_t st);
 void launch_gather(const GatherArgs& a, int maxnp, int nleaves, cudaStream_t st);
 struct Potrf2Args;
-struct Trtri2Args;
 struct Trtri3Args;
 cudaError_t init_v2_kernels();
 void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st);
-void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st);
 void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, cudaStream_t st);
 void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st);
 void launch_ov_count(const int64_t* obs, int64_t total, int* cntp, cudaStream_t st);

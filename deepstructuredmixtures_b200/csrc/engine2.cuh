@@ -8,7 +8,7 @@
 // barrier.  (v1 staged OUT through a 135 KB shared tile and synchronised the block twice per tile.)
 //
 // Accumulator element (mb, nb, e) of thread (g = lane/4, t = lane%4) in warp w -- INTERLEAVED mapping:
-//     row = 16 w + 2 g + mb                      (the two m-tiles own the even / odd rows of the slab)
+//     row = 16 slab(w) + 2 g + mb                (the two m-tiles own the even / odd rows of the slab)
 //     col = 16 (nb/2) + 2 (2 t + e) + (nb % 2)   (tiles 2m, 2m+1 own the even / odd columns of a 16-column group)
 // so that the fragments of a tile PAIR are adjacent in shared memory and one LDS.128 feeds two DMMAs' operands:
 // 9 shared loads per k-step (1 for A, 8 for B) instead of 18.  Any consistent permutation of rows / columns is
@@ -20,7 +20,12 @@ namespace dsm {
 
 typedef double Acc2[2][16][2];
 
-__device__ __forceinline__ int acc_row(int mb) { return 16 * (threadIdx.x >> 5) + 2 * ((threadIdx.x & 31) >> 2) + mb; }
+// Row slab of an MMA warp.  Warps w and w + 4 share an SM sub-partition (and its DMMA pipe); slabs are dealt so that the
+// two warps of a sub-partition own slabs s and 7 - s: whenever work is triangular in the slab index (the lower triangle
+// of a diagonal tile, the structurally-zero part of a triangular operand) every sub-partition gets the same share.
+//   warp 0 1 2 3 4 5 6 7  ->  slab 0 2 4 6 7 5 3 1
+__device__ __forceinline__ int warp_slab() { const int w = threadIdx.x >> 5; return w < 4 ? 2 * w : 15 - 2 * w; }
+__device__ __forceinline__ int acc_row(int mb) { return 16 * warp_slab() + 2 * ((threadIdx.x & 31) >> 2) + mb; }
 __device__ __forceinline__ int acc_col(int nb, int e) { return 16 * (nb >> 1) + 2 * (2 * (threadIdx.x & 3) + e) + (nb & 1); }
 
 __device__ __forceinline__ void acc2_zero(Acc2& acc) {
@@ -79,6 +84,7 @@ __device__ __forceinline__ double acc_to_afrag(const Acc2& acc, int mb, int ks) 
 }
 
 // One epilogue k-tile: pass P (output columns [32P, 32P+32)), k-tile J (k in [16J, 16J+16)):  sM[k][c] = M[c][16J + k].
+// (the last k-tile of a pass, J = 2P+1, holds k in [32P+16, 32P+32): M[c][k] = 0 for the first 16 output columns)
 template <int P, int J>
 __device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2], const double* __restrict__ sM) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -88,7 +94,7 @@ __device__ __forceinline__ void tri_chunk(const Acc2& acc, double (&o)[2][4][2],
     const double a0 = acc_to_afrag<J>(acc, 0, ks);
     const double a1 = acc_to_afrag<J>(acc, 1, ks);
 #pragma unroll
-    for (int m2 = 0; m2 < 2; m2++) {
+    for (int m2 = (J == 2 * P + 1) ? 1 : 0; m2 < 2; m2++) {
       const double2 b = *reinterpret_cast<const double2*>(pb + ks * 4 * LDS + 16 * m2);
       dmma884(o[0][2 * m2][0], o[0][2 * m2][1], a0, b.x);
       dmma884(o[1][2 * m2][0], o[1][2 * m2][1], a1, b.x);
@@ -173,7 +179,7 @@ __device__ __forceinline__ ChunkDesc tri_epilogue_chunk(const double* Wblk, int 
 
 // Store OUT (rows r < mrows, cols c < ncols) into the tiled matrix at (row0 + r, col0 + c).
 __device__ __forceinline__ void acc2_store(const Acc2& acc, double* Fm, int nkc, int row0, int col0, int mrows, int ncols) {
-  const int r0 = 16 * (threadIdx.x >> 5);
+  const int r0 = 16 * warp_slab();
   if (r0 >= mrows) return;
 #pragma unroll
   for (int n = 0; n < 16; n++) {

@@ -1,5 +1,4 @@
 #include "potrf2.cuh"
-#include "trtri2.cuh"
 #include "trtri3.cuh"
 #include "lauum3.cuh"
 namespace dsm {
@@ -8,10 +7,9 @@ cudaError_t init_v2_kernels() {
   if ((e = cudaFuncSetAttribute(potrf2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES))) return e;
   if ((e = cudaFuncSetAttribute(lauum3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES))) return e;
   if ((e = cudaFuncSetAttribute(trtri3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES))) return e;
-  return cudaFuncSetAttribute(trtri2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM_BYTES);
+  return cudaSuccess;
 }
 void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st) { potrf2_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
-void launch_trtri2(const Trtri2Args& a, int nctas, cudaStream_t st) { trtri2_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
 void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st) { lauum3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
 void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, cudaStream_t st) {
   trtri3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a);

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
   __shared__ double s_red[16];
   __shared__ __align__(16) double s_stage[2 * LAUUM_DSTAGE * BLK + 2 * BLK + LAUUM_DSTAGE];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = 16 * warp;
+  const int slab = warp_slab(), r0 = 16 * slab;
   Pipe p;
   p.init(smem, a.gerr);
   if (warp >= NCONS / 32) {
@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
     acc2_zero(acc);
     for (int c = 0; c < hd.n_main; c++) {
       if (c > 0) st = p.wait();
-      if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
+      // K = I block: the A operand is W_I^T (zero for k < row): chunk c is all zero for slabs > c
+      if (active && (c >= wi / KC || c >= slab)) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
       p.release();
     }
     // ---- fused epilogue -------------------------------------------------------------------

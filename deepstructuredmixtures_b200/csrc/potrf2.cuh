@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
   __shared__ double s_v[BLK];
   __shared__ int s_info;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = 16 * warp;
+  const int slab = warp_slab(), r0 = 16 * slab;
   Pipe p;
   p.init(smem, a.gerr);
   if (warp >= NCONS / 32) {                          // producer warpgroup: one working warp, three that only donate registers
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     // ---------------- diagonal tile ----------------
     double gemv = 0.0;                                  // row r0 + (lane & 15), k-half lane >> 4
     {
-      const int ng = min(wj / 32, warp / 2 + 1);        // lower triangle only: columns <= 16*warp + 15
+      const int ng = min(wj / 32, slab / 2 + 1);        // lower triangle only: columns <= 16*slab + 15
       for (int c = 0; c < n_main; c++) {
         st = p.wait();
         if (active) {

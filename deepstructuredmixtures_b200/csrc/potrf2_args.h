@@ -16,15 +16,6 @@ struct Potrf2Args {
   long long* trace;                                // optional [ntasks][8] clock stamps (DSMGP_TRACE_FILE), else null
 };
 
-struct Trtri2Args {
-  const LeafMeta* meta;
-  double* F; const double* W; const double* WT;
-  const double* z; double* alpha;
-  double* trpart; const int64_t* trpart_off;    // second half [nb + J]
-  const int2* tasks; int ntasks;
-  int* counter; int* gerr;
-};
-
 // tile-pipelined inverse (trtri3): tasks (slot, I, J, unused), I > J, ordered by anti-diagonal
 struct Trtri3Args {
   const LeafMeta* meta;

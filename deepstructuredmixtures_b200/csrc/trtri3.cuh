@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) trtri3_kernel(Trtri3Args a) {
   __shared__ double s_red[16];
   __shared__ __align__(32) double s_z[NCONS / 32][BLK];     // per-warp copy of z_I
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int r0 = 16 * warp;
+  const int slab = warp_slab(), r0 = 16 * slab;
   Pipe p;
   p.init(smem, a.gerr);
   if (warp >= NCONS / 32) {                          // producer warpgroup: one working warp, three that only donate registers
@@ -123,7 +123,10 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) trtri3_kernel(Trtri3Args a) {
     }
     for (int c = 0; c < hd.n_main; c++) {
       if (c > 0) st = p.wait();
-      if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
+      // K = J block: the A operand is W_J^T (A[row][k] = W_J[k][row] = 0 for k < row): chunk c is all zero for slabs > c
+      if (c >= BLK / KC || c >= slab) {
+        if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
+      }
       p.release();
     }
     tri_epilogue(p, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
