@@ -131,7 +131,6 @@ static bool g_attr_done = false;
 static cudaError_t engine_attrs() {
   if (g_attr_done) return cudaSuccess;
   cudaError_t e;
-  if ((e = init_predict_kernels())) return e;
   if ((e = init_v2_kernels())) return e;
   g_attr_done = true;
   return cudaSuccess;
@@ -1058,7 +1057,7 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
     if (slot < 0) { h->err = "predict: leaf owned by another rank"; return DSMGP_ERR_STATE; }
     PredLeaf p; p.slot = slot; p.T = (int32_t)pts[l].size(); p.Tp = (p.T + BLK - 1) / BLK * BLK; p.pad_ = 0;
     p.xtoff = xto; xto += (int64_t)p.Tp * D;
-    p.vtoff = vto; vto += (int64_t)p.Tp * h->meta[slot].np;
+    p.vtoff = vto; vto += (int64_t)(p.Tp / BLK) * h->meta[slot].nkc * TILE_D;
     p.ooff = oo; oo += p.Tp;
     for (int q = 0; q < p.Tp / BLK; q++) tasks.push_back(make_int2((int)pls.size(), q));
     pls.push_back(p); pl_leaf.push_back(l);
@@ -1084,16 +1083,19 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
   PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
   PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
-              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D};
+              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + 8};
   cudaEventRecord(h->ev[0], h->stream);
-  launch_predict(pa, std::min(num_sms(h->device), (int)tasks.size()), h->stream);
+  launch_predict3(pa, std::min(num_sms(h->device), (int)tasks.size()), h->stream);
   cudaEventRecord(h->ev[1], h->stream);
   h->tm.launches++;
   PTRY(cudaGetLastError());
   std::vector<double> hmu(oo), hvar(oo);
   PTRY(cudaMemcpyAsync(hmu.data(), d_mu.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
   PTRY(cudaMemcpyAsync(hvar.data(), d_var.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
+  int gerr = 0;
+  PTRY(cudaMemcpyAsync(&gerr, h->d_counter.p + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   PTRY(cudaStreamSynchronize(h->stream));
+  if (gerr != 0) { h->err = "predict: device scheduler timeout (code " + std::to_string(gerr) + ")"; cleanup(); return DSMGP_ERR_STATE; }
 #undef PTRY
   h->tm.predict_ms = ev_ms(h->ev[0], h->ev[1]);
   h->tm.predict_flops = 0.0; h->tm.predict_bytes = 0.0;

@@ -85,7 +85,7 @@ struct PredLeaf {     // per leaf with routed points
   int32_t Tp;         // padded to BLK
   int32_t pad_;
   int64_t xtoff;      // xt: D columns of length Tp
-  int64_t vtoff;      // VT scratch: Tp x np (ld = Tp)
+  int64_t vtoff;      // V^T scratch: Tp/128 row blocks of nkc tiles (factor tile layout)
   int64_t ooff;       // output offset (mu / var), length Tp
 };
 
@@ -106,14 +106,14 @@ struct PredArgs {
   double* mu;
   double* var;
   int D;
+  int* gerr;
 };
 
 // ---- launchers (defined next to their kernels) ------------------------------------------------
-cudaError_t init_predict_kernels();
 void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
 void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
-void launch_predict(const PredArgs& a, int nctas, cudaStream_t st);
+void launch_predict3(const PredArgs& a, int nctas, cudaStream_t st);
 void launch_gram_fit(const GramArgs& a, int64_t ntiles, cudaStream_t st);
 void launch_gram_rect(const GramRectArgs& a, cudaStream_t st);
 void launch_gather(const GatherArgs& a, int maxnp, int nleaves, cudaStream_t st);

@@ -1,7 +1,7 @@
 // Block back-substitution alpha = L^{-T} z for the fit-only path (gaussianprocess.jl:105); the forward solve is
 // fused into the diagonal tiles of potrf2.cuh and, on the gradient path, alpha comes out of trtri3.cuh.
 #pragma once
-#include "engine.cuh"
+#include "common.cuh"
 #include "args.h"
 
 namespace dsm {

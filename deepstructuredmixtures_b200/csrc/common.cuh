@@ -13,13 +13,8 @@ constexpr int PAD = 64;
 constexpr int BLK = 128;
 constexpr int KC = 16;             // k-chunk staged per pipeline stage
 constexpr int LDS = 132;           // smem row stride in doubles (132 % 16 == 4 -> conflict-free DMMA fragment loads)
-constexpr int NST = 4;             // cp.async pipeline stages
 constexpr int CHUNK = KC * LDS;    // doubles per operand per stage
-constexpr int REGION0 = NST * 2 * CHUNK;   // both operands streamed; aliases a resident BLK x LDS tile
-constexpr int REGION1 = NST * CHUNK;       // one streamed operand while REGION0 holds a resident tile
-constexpr int ENGINE_SMEM_BYTES = (REGION0 + REGION1) * 8;   // 202,752 B
-constexpr int NTHREADS = 256;
-static_assert(BLK * LDS == REGION0, "resident tile must alias the two-operand pipeline exactly");
+constexpr int NTHREADS = 256;      // MMA (consumer) threads of the engine kernels; block size of the small kernels
 
 enum KernelType : int { ISO_SE = 0, ARD_SE = 1, ISO_LINEAR = 2, ARD_LINEAR = 3 };
 

@@ -10,6 +10,7 @@
 //   ArdLinear K = sum_d xi_d xj_d / l_d^2                       SURVEY App. A.2 (reference non-functional)
 #pragma once
 #include "common.cuh"
+#include "fastexp.cuh"
 #include "args.h"
 
 namespace dsm {
@@ -20,7 +21,7 @@ namespace dsm {
 __device__ __forceinline__ void gram_tile(int ktype, int D, const double* __restrict__ prm,
                                           const double* __restrict__ xa, int64_t sa, int ra0, int na,
                                           const double* __restrict__ xb, int64_t sb, int rb0, int nb,
-                                          double (&out)[4][4], double* sxa, double* sxb, double* scoef) {
+                                          double (&out)[4][4], double* sxa, double* sxb, double* scoef, const double* sT) {
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   double acc[4][4];
 #pragma unroll
@@ -54,7 +55,7 @@ __device__ __forceinline__ void gram_tile(int ktype, int D, const double* __rest
 #pragma unroll
         for (int i = 0; i < 4; i++)
 #pragma unroll
-          for (int j = 0; j < 4; j++) { const double t = a[i] - b[j]; acc[i][j] += exp(cf * (t * t)); }
+          for (int j = 0; j < 4; j++) { const double t = a[i] - b[j]; acc[i][j] += exp_neg(cf * (t * t), sT); }
       } else if (ktype == ISO_LINEAR) {
 #pragma unroll
         for (int i = 0; i < 4; i++)
@@ -74,7 +75,7 @@ __device__ __forceinline__ void gram_tile(int ktype, int D, const double* __rest
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       double k;
-      if (ktype == ISO_SE) k = v * exp(c0 * acc[i][j]);
+      if (ktype == ISO_SE) k = v * exp_neg(c0 * acc[i][j], sT);
       else if (ktype == ARD_SE) k = v * acc[i][j];
       else if (ktype == ISO_LINEAR) k = c0 * acc[i][j];
       else k = acc[i][j];
@@ -85,7 +86,8 @@ __device__ __forceinline__ void gram_tile(int ktype, int D, const double* __rest
 
 // F = K + (eta + 1e-8) I on the lower triangle (diagonal tiles written in full), identity on the padding.
 __global__ void __launch_bounds__(NTHREADS) gram_fit_kernel(GramArgs a) {
-  __shared__ double sxa[GDC * GT], sxb[GDC * GT], scoef[GDC];
+  __shared__ double sxa[GDC * GT], sxb[GDC * GT], scoef[GDC], sT[EXPTAB_N];
+  exptab_load(sT);                 // visible after the first barrier inside gram_tile
   // leaf of this tile: binary search in tile_off
   const int64_t g = blockIdx.x;
   int lo = 0, hi = a.nleaves;
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(NTHREADS) gram_fit_kernel(GramArgs a) {
   const double* x = a.xg + m.xoff;
   const double* prm = a.prm + m.poff;
   double out[4][4];
-  gram_tile(m.ktype, a.D, prm, x, m.np, ti * GT, m.n, x, m.np, tj * GT, m.n, out, sxa, sxb, scoef);
+  gram_tile(m.ktype, a.D, prm, x, m.np, ti * GT, m.n, x, m.np, tj * GT, m.n, out, sxa, sxb, scoef, sT);
   const double cnoise = prm[PRM_C];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   double* F = a.F + m.foff;
@@ -124,10 +126,11 @@ __global__ void __launch_bounds__(NTHREADS) gram_fit_kernel(GramArgs a) {
 
 // Rectangular Gram K(xa, xb) -> out (na x nb column-major, ld = ldo).  grid = (ceil(na/GT), ceil(nb/GT)).
 __global__ void __launch_bounds__(NTHREADS) gram_rect_kernel(GramRectArgs a) {
-  __shared__ double sxa[GDC * GT], sxb[GDC * GT], scoef[GDC];
+  __shared__ double sxa[GDC * GT], sxb[GDC * GT], scoef[GDC], sT[EXPTAB_N];
+  exptab_load(sT);
   double out[4][4];
   const int ra0 = blockIdx.x * GT, rb0 = blockIdx.y * GT;
-  gram_tile(a.ktype, a.D, a.prm, a.xa, a.sa, ra0, a.na, a.xb, a.sb, rb0, a.nb, out, sxa, sxb, scoef);
+  gram_tile(a.ktype, a.D, a.prm, a.xa, a.sa, ra0, a.na, a.xb, a.sb, rb0, a.nb, out, sxa, sxb, scoef, sT);
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
 #pragma unroll
   for (int j = 0; j < 4; j++) {

@@ -9,6 +9,7 @@
 // next task during the epilogue); for larger D the epilogue borrows the ring as scratch and the producer waits (aux[0]).
 #pragma once
 #include "engine2.cuh"
+#include "fastexp.cuh"
 #include "args.h"
 
 namespace dsm {
@@ -69,8 +70,10 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double s_red[16];
   __shared__ __align__(16) double s_stage[2 * LAUUM_DSTAGE * BLK + 2 * BLK + LAUUM_DSTAGE];
+  __shared__ double sT[EXPTAB_N];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slab = warp_slab(), r0 = 16 * slab;
+  exptab_load(sT);                                  // visible after the barrier inside Pipe::init
   Pipe p;
   p.init(smem, a.gerr);
   if (warp >= NCONS / 32) {
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
                 for (int k = 0; k < 4; k++) {
                   if (ktype == ISO_SE) {
                     const double u = scf[0] * r2[mm][k];                      // -0.5 r2 / l^2
-                    g[0] = fma(mij[mm][k], v * exp(u) * (-2.0 * u), g[0]);     // K * r2 / l^2
+                    g[0] = fma(mij[mm][k], v * exp_neg(u, sT) * (-2.0 * u), g[0]);     // K * r2 / l^2
                   } else {
                     g[0] = fma(mij[mm][k], -2.0 * scf[0] * r2[mm][k], g[0]);
                   }
@@ -189,7 +192,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
                     if (ktype == ARD_SE) {
                       const double tt = xiv[mm] - xjv[k];
                       const double u = cf * (tt * tt);
-                      gs = fma(mij[mm][k], v * exp(u) * (-2.0 * u), gs);
+                      gs = fma(mij[mm][k], v * exp_neg(u, sT) * (-2.0 * u), gs);
                     } else {
                       gs = fma(mij[mm][k], -2.0 * cf * xiv[mm] * xjv[k], gs);
                     }

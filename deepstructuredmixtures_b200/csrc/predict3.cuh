@@ -1,0 +1,255 @@
+// Batched predictive mean / variance of the leaf experts on engine v2 (producer warp + bulk-copy ring).
+//
+// Replaces prediction(gp, xtest) gaussianprocess.jl:110-137:  mu = m + Knt' alpha ;  V = L \ Knt ;
+// Sigma = Ktt - V'V ; diag += exp(2 logNoise).  Only diag(Sigma) is consumed (common.jl:136,147), so the
+// T x T matrices Ktt and V'V are never formed:  var_t = k(x_t,x_t) - sum_k V_kt^2 + eta.
+//
+// Task = (leaf, block Q of 128 routed test points).  Block forward substitution, TRANSPOSED so that a warp owns
+// complete rows (= test points) and the multiplication by W_I = L_II^-1 runs in registers:
+//   for I = 0..nb-1:   OUT[c][r] = sum_{K<I} V_KQ^T[c][.] L_IK^T[.][r]          (A = V^T tiles, B = L tiles)
+//                      V_IQ^T    = (Knt_IQ^T - OUT) W_I^T                        (Knt recomputed from the point tiles)
+// V^T of the task lives in a scratch row block with the factor's tile layout, so the next iterations read it back
+// with one bulk copy per k-chunk; the consumers signal every stored block to the producer through aux[1].
+// The mean and the column sums of squares are accumulated in registers (quad reductions), no shared round trips.
+#pragma once
+#include "engine2.cuh"
+#include "fastexp.cuh"
+#include "args.h"
+
+namespace dsm {
+
+constexpr int PRED_DSTAGE = 8;      // dimensions of the point tiles held in static shared memory (else: ring borrowed)
+
+struct Pred3Gen {
+  const double* F; const double* W; const double* VT;
+  int np, nb, nkc, I, c;
+  __device__ __forceinline__ int kneed() const {       // k-block read by the next chunk from V^T, or -1
+    if (I >= nb) return -1;
+    const int nmain = I * (BLK / KC);
+    return c < nmain ? c / (BLK / KC) : -1;
+  }
+  __device__ __forceinline__ bool next(ChunkDesc& d) {
+    if (I >= nb) return false;
+    const int wi = blk_width(np, I);
+    const int nmain = I * (BLK / KC), nepi = tri_epilogue_nstages(wi / 32);
+    d.flag0 = nullptr; d.flag1 = nullptr;
+    if (c < nmain) {
+      d.a = VT + (int64_t)c * TILE_D; d.abytes = TILE_BYTES;
+      d.b = F + tile_off(I, c, nkc); d.bbytes = TILE_BYTES;
+    } else {
+      d = tri_epilogue_chunk(W + (int64_t)I * WBLK_D, c - nmain, nepi, nullptr);
+    }
+    if (++c == nmain + nepi) { c = 0; I++; }
+    return true;
+  }
+};
+
+__device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
+  uint32_t stored_phase = 0, scratch_phase = 0;
+  const bool borrow = a.D > PRED_DSTAGE;
+  for (;;) {
+    int t = 0;
+    if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
+    const int ti = __shfl_sync(0xffffffffu, t, 0);
+    if (ti >= a.ntasks) break;
+    const int2 tk = a.tasks[ti];
+    const PredLeaf pl = a.pl[tk.x];
+    const LeafMeta m = a.meta[pl.slot];
+    Pred3Gen gen;
+    gen.F = a.F + m.foff; gen.W = a.W + m.woff; gen.np = m.np; gen.nb = m.nb; gen.nkc = m.nkc;
+    gen.VT = a.VT + pl.vtoff + (int64_t)tk.y * m.nkc * TILE_D;
+    gen.I = 0; gen.c = 0;
+    TaskHdr h; h.kind = 0; h.ti = ti; h.slot = tk.x; h.I = 0; h.J = tk.y; h.wi = 0; h.wj = 0; h.n_c = 0; h.n_main = 0;
+    int stored = 0;                              // blocks of V^T in memory
+    int nsig = m.nb;                             // signals the consumers send for this task (one per iteration)
+    bool first = true;
+    ChunkDesc d;
+    if (borrow) {                                // header-only chunk: the ring must be empty whenever the consumers borrow it
+      d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
+      p.issue(d, &h); first = false;
+    }
+    for (;;) {
+      const int kn = gen.kneed();
+      while (kn >= stored) { p.wait_bar(&p.aux[1], stored_phase & 1, 6); stored_phase++; stored++; nsig--; fence_proxy_async(); if (*p.abort) break; }
+      if (borrow && gen.c == gen.I * (BLK / KC) && gen.I < gen.nb) {
+        // the consumers borrow the ring for the point tiles between the contraction and the epilogue of an iteration
+        p.wait_bar(&p.aux[0], scratch_phase & 1, 5); scratch_phase++;
+      }
+      if (!gen.next(d)) break;
+      p.issue(d, first ? &h : nullptr); first = false;
+      if (*p.abort) break;
+    }
+    while (nsig > 0 && !*p.abort) { p.wait_bar(&p.aux[1], stored_phase & 1, 6); stored_phase++; nsig--; }
+    if (*p.abort) break;
+  }
+  TaskHdr h; h.kind = -1;
+  ChunkDesc d; d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
+  p.issue(d, &h);
+}
+
+__global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ __align__(16) double s_stage[2 * PRED_DSTAGE * BLK + BLK + PRED_DSTAGE];
+  __shared__ double sT[EXPTAB_N];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slab = warp_slab(), r0 = 16 * slab;
+  exptab_load(sT);
+  Pipe p;
+  p.init(smem, a.gerr);
+  if (warp >= NCONS / 32) {
+    setmaxnreg_dec<REGS_PRODUCER>();
+    if (warp == NCONS / 32) predict3_producer(p, a);
+    return;
+  }
+  setmaxnreg_inc<REGS_CONSUMER>();
+  const int D = a.D;
+  const bool borrow = D > PRED_DSTAGE;
+  // D <= PRED_DSTAGE: both point tiles in static shared memory.  Larger D: x_t stays static only if it fits, so both
+  // tiles move into the (idle) ring between the contraction and the epilogue of every iteration.
+  double* stage = borrow ? smem : s_stage;
+  double* sxq = stage;                   // [D][BLK] test points of block Q
+  double* sxi = stage + D * BLK;         // [D][BLK] rows of block I
+  double* sal = stage + 2 * D * BLK;     // [BLK] alpha of block I
+  double* scf = sal + BLK;               // [D]
+  for (;;) {
+    int st = p.wait();
+    const TaskHdr hd = p.hdr[st];
+    if (hd.kind < 0 || *p.abort) return;
+    const PredLeaf pl = a.pl[hd.slot];
+    const LeafMeta m = a.meta[pl.slot];
+    const int Q = hd.J, q0 = Q * BLK;
+    const int64_t lda = m.np, ldv = pl.Tp;
+    const double* x = a.xg + m.xoff;
+    const double* xt = a.xt + pl.xtoff;
+    const double* al = a.alpha + m.voff;
+    const double* prm = a.prm + m.poff;
+    double* VT = a.VT + pl.vtoff + (int64_t)Q * m.nkc * TILE_D;
+    const int ktype = m.ktype;
+    const double v = prm[PRM_V];
+    const bool c0ok = q0 + acc_row(0) < pl.T, c1ok = q0 + acc_row(1) < pl.T;
+    double mu0 = 0.0, mu1 = 0.0, sq0 = 0.0, sq1 = 0.0;
+    if (!borrow) {
+      csync();                                       // previous task's readers are done with the static tiles
+      for (int u = tid; u < D * BLK; u += NCONS) {
+        const int d = u / BLK, q = u % BLK;
+        sxq[u] = (q0 + q < pl.Tp) ? xt[(int64_t)d * ldv + q0 + q] : 0.0;
+      }
+      if (tid < D) scf[tid] = (m.nl > 1) ? prm[PRM_COEF + tid] : prm[PRM_COEF];
+    }
+    if (borrow) p.release();                         // header-only chunk
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const int rb = r0 + 2 * g8;                      // this thread's two test points (rows of OUT)
+    for (int I = 0; I < m.nb; I++) {
+      const int wi = blk_width(m.np, I), i0 = I * BLK;
+      Acc2 acc;
+      acc2_zero(acc);
+      for (int c = 0; c < I * (BLK / KC); c++) {     // (I == 0 has no contraction: the header chunk is its first epilogue stage)
+        st = p.wait();
+        if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
+        p.release();
+      }
+      // stage the point tiles of block I (and, when borrowing the ring, of the test block too)
+      csync();
+      if (borrow) {
+        for (int u = tid; u < D * BLK; u += NCONS) {
+          const int d = u / BLK, q = u % BLK;
+          sxq[u] = (q0 + q < pl.Tp) ? xt[(int64_t)d * ldv + q0 + q] : 0.0;
+        }
+        if (tid < D) scf[tid] = (m.nl > 1) ? prm[PRM_COEF + tid] : prm[PRM_COEF];
+      }
+      for (int u = tid; u < D * BLK; u += NCONS) {
+        const int d = u / BLK, q = u % BLK;
+        sxi[u] = (q < wi) ? x[(int64_t)d * lda + i0 + q] : 0.0;
+      }
+      if (tid < BLK) sal[tid] = (tid < wi && i0 + tid < m.n) ? al[i0 + tid] : 0.0;
+      csync();
+      // OUT = Knt_IQ^T - OUT ; mean partial sum_r Knt[r][c] alpha[r].  8 groups of 2 test points x 4 consecutive rows r.
+#pragma unroll
+      for (int nbp = 0; nbp < 8; nbp++) {
+        if (16 * nbp < wi) {
+          const int cb = 16 * nbp + 4 * t4;
+          double kk[2][4];
+#pragma unroll
+          for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) kk[mm][k] = 0.0;
+#pragma unroll 2
+          for (int d = 0; d < D; d++) {
+            const double2 xq = *reinterpret_cast<const double2*>(sxq + d * BLK + rb);
+            const double2 xi0 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb), xi1 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb + 2);
+            const double xqv[2] = {xq.x, xq.y}, xiv[4] = {xi0.x, xi0.y, xi1.x, xi1.y};
+            const double cf = scf[d];
+#pragma unroll
+            for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                if (ktype == ISO_SE) { const double t = xqv[mm] - xiv[k]; kk[mm][k] = fma(t, t, kk[mm][k]); }
+                else if (ktype == ARD_SE) { const double t = xqv[mm] - xiv[k]; kk[mm][k] += exp_neg(cf * (t * t), sT); }
+                else if (ktype == ISO_LINEAR) kk[mm][k] = fma(xqv[mm], xiv[k], kk[mm][k]);
+                else kk[mm][k] = fma(cf * xqv[mm], xiv[k], kk[mm][k]);
+              }
+          }
+          const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
+          const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
+          const double cf0 = scf[0];
+#pragma unroll
+          for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              double kv = kk[mm][k];
+              if (ktype == ISO_SE) kv = v * exp_neg(cf0 * kv, sT);
+              else if (ktype == ARD_SE) kv = v * kv;
+              else if (ktype == ISO_LINEAR) kv = cf0 * kv;
+              if (!((mm ? c1ok : c0ok) && i0 + cb + k < m.n)) kv = 0.0;
+              if (mm) mu1 = fma(kv, alv[k], mu1); else mu0 = fma(kv, alv[k], mu0);
+              acc[mm][2 * nbp + (k & 1)][k >> 1] = kv - acc[mm][2 * nbp + (k & 1)][k >> 1];
+            }
+        }
+      }
+      if (borrow) {                                    // hand the ring back before the epilogue stages arrive
+        fence_proxy_async();
+        csync();
+        if (tid == 0) mbar_arrive(&p.aux[0]);
+      }
+      tri_epilogue(p, acc, wi / 32, true, 1.0);       // V_IQ^T = S^T W_I^T
+      acc2_store(acc, VT, m.nkc, 0, i0, BLK, wi);
+      fence_proxy_async();
+      csync();
+      if (tid == 0) mbar_arrive(&p.aux[1]);
+#pragma unroll
+      for (int nb = 0; nb < 16; nb++)
+        if (8 * nb < wi) {
+#pragma unroll
+          for (int e = 0; e < 2; e++) { sq0 = fma(acc[0][nb][e], acc[0][nb][e], sq0); sq1 = fma(acc[1][nb][e], acc[1][nb][e], sq1); }
+        }
+    }
+    // finish: mu = m + Knt' alpha ; var = k(x_t, x_t) - sum V^2 + eta      (gaussianprocess.jl:117-126)
+    mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
+    mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
+    sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
+    sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+    if ((lane & 3) == 0) {
+#pragma unroll
+      for (int mb = 0; mb < 2; mb++) {
+        const int c = acc_row(mb);
+        if (q0 + c < pl.T) {
+          double ktt;
+          if (ktype == ISO_SE) ktt = v;
+          else if (ktype == ARD_SE) ktt = v * (double)D;
+          else {
+            ktt = 0.0;
+            for (int d = 0; d < D; d++) {
+              const double xv = xt[(int64_t)d * ldv + q0 + c];
+              const double cf = (ktype == ISO_LINEAR) ? prm[PRM_COEF] : prm[PRM_COEF + d];
+              ktt = fma(cf * xv, xv, ktt);
+            }
+          }
+          a.mu[pl.ooff + q0 + c] = a.leaf_mean[m.leaf] + (mb ? mu1 : mu0);
+          a.var[pl.ooff + q0 + c] = ktt - (mb ? sq1 : sq0) + prm[PRM_ETA];
+        }
+      }
+    }
+  }
+}
+
+}  // namespace dsm

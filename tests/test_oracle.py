@@ -153,3 +153,38 @@ def test_golden_vectors():
         assert abs(out["lml"] - g["lml"]) <= 1e-11 * abs(g["lml"]), name
         assert np.allclose(out["grad"], g["grad"], rtol=1e-9, atol=1e-9), name
         assert np.allclose(out["mu"], g["mu"], rtol=1e-10) and np.allclose(out["var"], g["var"], rtol=1e-9), name
+
+
+def test_table_exp_restated_accuracy():
+    """csrc/fastexp.cuh (`exp_neg`: 64-entry 2^(j/64) table + degree-5 polynomial) restated in NumPy, against mpmath:
+    the Gram / predict / LAUUM kernels use it instead of the library exp(), so its error budget is part of parity."""
+    import re, os
+    import mpmath as mp
+    mp.mp.dps = 40
+    src = open(os.path.join(os.path.dirname(__file__), "..", "deepstructuredmixtures_b200", "csrc", "fastexp.cuh")).read()
+    body = src[src.index("g_exptab[EXPTAB_N] = {") + len("g_exptab[EXPTAB_N] = {"):src.index("};")]
+    T = np.array([float(v) for v in re.findall(r"[0-9.eE+-]+", body)])
+    assert T.size == 64 and all(T[j] == float(mp.mpf(2) ** (mp.mpf(j) / 64)) for j in range(64))
+    MAGIC = 6755399441055744.0
+
+    def exp_neg(x):
+        t = x * 92.33248261689366 + MAGIC
+        k = (t.view(np.int64) & 0xFFFFFFFF).astype(np.int64)
+        k = np.where(k >= 2 ** 31, k - 2 ** 32, k)
+        kf = t - MAGIC
+        r = x - kf * 0.01083042469326756
+        r = r - kf * 2.9815858269852933e-12
+        p = r * 8.3333333333333332e-03 + 4.1666666666666664e-02
+        p = r * p + 1.6666666666666666e-01
+        p = r * p + 0.5
+        p = r * p + 1.0
+        p = p * r
+        v = T[k & 63] * p + T[k & 63]
+        return np.where(x < -708.0, 0.0, np.ldexp(v, (k >> 6).astype(np.int32)))
+
+    rng = np.random.default_rng(0)
+    x = -np.abs(rng.standard_normal(4000)) * np.array([1e-3, 1.0, 30.0, 200.0])[rng.integers(0, 4, 4000)]
+    x = np.concatenate([x[x > -700.0], [0.0, -1e-300, -707.9]])
+    ref = np.array([float(mp.e ** mp.mpf(float(v))) for v in x])
+    assert np.max(np.abs(exp_neg(x) - ref) / ref) < 4.5e-16
+    assert exp_neg(np.array([-709.0]))[0] == 0.0 and exp_neg(np.array([0.0]))[0] == 1.0
