@@ -222,19 +222,8 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     }
     if (trc) trc[3] = clock64();
     const double* DI = aux;
-    if (!prefactored) {
-      for (int c = warp; c < wj; c += NCONS / 32) {
-        double* dst = F + tidx(j0, j0 + c, nkc);
-        for (int r = lane; r < wj; r += 32)
-          if (r >= c) dst[r] = S[c * LDS + r];
-      }
-    }
-    double ld = 0.0;
-    for (int r = tid; r < wj; r += NCONS)
-      if (j0 + r < m.n) ld += log(S[r * LDS + r]);
-    ld = block_sum_c(ld, s_red);
-    // W_J, W_J^T (zero filled, tiled) and the diagonal-block partial of tr(F^-1)
-    double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;
+    // Critical path first: the panel tiles of this column wait for W_J and the next diagonal tile (transitively) for
+    // z_J, so those two are stored and the tile is PUBLISHED before the factor, W_J^T and the reductions are written.
     double tr = 0.0;
     for (int c = warp; c < BLK; c += NCONS / 32)
       for (int r = lane; r < BLK; r += 32) {
@@ -243,13 +232,6 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
         Wj[widx(r, c)] = v;
         if (j0 + r < m.n && j0 + c < m.n) tr += v * v;
       }
-    for (int r = warp; r < BLK; r += NCONS / 32)
-      for (int c = lane; c < BLK; c += 32) {
-        double v = 0.0;
-        if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
-        WTj[widx(c, r)] = v;
-      }
-    tr = block_sum_c(tr, s_red);
     // forward solve block: z_J = W_J (y_J - sum_K L_JK z_K)
     if (tid < BLK) s_v[tid] = (tid < wj) ? a.y[m.voff + j0 + tid] - s_v[tid] : 0.0;
     csync();
@@ -265,6 +247,28 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
         if (j0 + r < m.n) zz = s * s;
       }
     }
+    csync();
+    if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
+    // off the critical path: L_JJ, W_J^T, log-det and the partial sums
+    if (!prefactored) {
+      for (int c = warp; c < wj; c += NCONS / 32) {
+        double* dst = F + tidx(j0, j0 + c, nkc);
+        for (int r = lane; r < wj; r += 32)
+          if (r >= c) dst[r] = S[c * LDS + r];
+      }
+    }
+    double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;
+    for (int r = warp; r < BLK; r += NCONS / 32)
+      for (int c = lane; c < BLK; c += 32) {
+        double v = 0.0;
+        if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
+        WTj[widx(c, r)] = v;
+      }
+    double ld = 0.0;
+    for (int r = tid; r < wj; r += NCONS)
+      if (j0 + r < m.n) ld += log(S[r * LDS + r]);
+    ld = block_sum_c(ld, s_red);
+    tr = block_sum_c(tr, s_red);
     zz = block_sum_c(zz, s_red);
     if (tid == 0) {
       const int64_t po = a.trpart_off[hd.slot];
@@ -274,12 +278,11 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     }
     fence_proxy_async();                                 // generic writes to the stages precede the next bulk copies
     }   // diagonal tile
-    // ---------------- task boundary: publish the tile (and hand the ring back to the producer after a diagonal tile)
+    // ---------------- task boundary: publish a panel tile / hand the ring back to the producer after a diagonal tile
     csync();
     if (tid == 0) {
-      __threadfence();
-      st_release(flags + tile_flag_index(I, J), 1);
-      if (diag) mbar_arrive(&p.aux[0]);
+      if (!diag) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
+      else mbar_arrive(&p.aux[0]);
     }
     if (trc) trc[4] = clock64();
   }
