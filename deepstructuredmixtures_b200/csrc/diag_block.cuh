@@ -110,7 +110,7 @@ __device__ __forceinline__ void dmma_tile(double& c0, double& c1, double a, doub
 
 // S (m x m) -> L, W as described above.  All NTHREADS threads.  `aux` >= DIAG_AUX_DOUBLES doubles of shared memory.
 // Returns the 1-based pivot index (within the block) of the first non-positive pivot, or 0.
-__device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux, bool factor, int* s_info) {
+__device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux, bool factor, int* s_info, long long* tstamp = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   double* DI = aux;
   double* Tw = aux + (BLK / PW) * DBLK + warp * DBLK;       // this warp's 16 x 16 scratch
@@ -163,9 +163,11 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
     }
     csync();
   }
+  if (tstamp) tstamp[0] = clock64();
   // ---- inverses of the diagonal blocks: eight independent 16 x 16 problems, one warp each
   for (int P = warp; P < np; P += NTHREADS / 32) warp_inv16(S, P * PW, DI + P * DBLK);
   csync();
+  if (tstamp) tstamp[1] = clock64();
   // ---- W = L^-1: warp j owns block column j; row blocks P = j+1 .. np-1 in sequence, no block barrier
   for (int j = warp; j < np; j += NTHREADS / 32) {
     for (int P = j + 1; P < np; P++) {

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     const bool prefactored = (J < a.jstart);     // chol_continue: column already final, diag only rebuilds W
     const int n_c = hd.n_c, n_main = hd.n_main;
     long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)hd.ti * 8 : nullptr;
-    if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = sm; trc[6] = I; trc[7] = J; }
+    if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = (long long)sm | ((long long)I << 16) | ((long long)J << 32); }
 
     // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
     Acc2 acc;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     }
     csync();
     {
-      const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info);
+      const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info, trc ? trc + 6 : nullptr);
       if (tid == 0 && info != 0) atomicCAS(&a.scal[hd.slot].info, 0, j0 + info);
     }
     if (trc) trc[3] = clock64();

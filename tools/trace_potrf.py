@@ -1,26 +1,30 @@
-"""Analyse a DSMGP_TRACE_FILE dump of potrf2 (per-task clock stamps)."""
-import sys, numpy as np
+"""Analyse a DSMGP_TRACE_FILE dump of potrf2 (per-task clock stamps; clock64 is per SM, so only same-SM differences
+are meaningful).  Record = 8 int64: start, after C-stage, after contraction, after epilogue/factor, end,
+sm | I<<16 | J<<32, and for diagonal tasks: end of the panel loop, end of the 16x16 inverses."""
+import sys
+import numpy as np
+
 t = np.fromfile(sys.argv[1], dtype=np.int64).reshape(-1, 8)
 t = t[t[:, 0] > 0]
-start, c1, c2, c3, end, sm, I, J = t.T
-diag = I == J
 clk = 1.965e3  # cycles per us
-print("tasks", len(t), "diag", diag.sum())
-for name, sel in (("panel", ~diag), ("diag", diag)):
-    s = t[sel]
-    tot = (s[:, 4] - s[:, 0]) / clk
-    print(f"{name}: n={len(s)} mean total {tot.mean():.1f} us; C-stage wait {((s[:,1]-s[:,0])/clk).mean():.2f}; main {((s[:,2]-s[:,1])/clk).mean():.1f}; "
-          f"epi/factor {((s[:,3]-s[:,2])/clk).mean():.2f}; tail {((s[:,4]-s[:,3])/clk).mean():.2f}")
-    Jm = np.maximum(s[:, 7], 1)
-    print(f"   main per k-block: {(((s[:,2]-s[:,1])/clk)[s[:,7]>0] / s[:,7][s[:,7]>0]).mean():.2f} us (ideal 16.7 @peak)")
-# per-SM busy fraction and gaps between consecutive tasks on the same SM
-span = (end.max() - start.min()) / clk
-busy = 0
-gaps = []
+start, c1, c2, c3, end, pk, ta, tb = t.T
+sm, I, J = pk & 0xFFFF, (pk >> 16) & 0xFFFF, (pk >> 32) & 0xFFFF
+diag = I == J
+tot = (end - start).sum() / clk / 1e3
+print(f"tasks {len(t)} (diag {diag.sum()}); total task time {tot:.1f} SM-ms = {tot / 148:.2f} ms x 148 SMs")
+for nm, a, b in (("first-chunk wait", start, c1), ("contraction", c1, c2), ("epilogue / factor", c2, c3), ("tail", c3, end)):
+    print(f"  {nm:18s} panel {((b - a)[~diag]).sum() / clk / 1e3:8.1f}   diag {((b - a)[diag]).sum() / clk / 1e3:8.1f}  SM-ms")
+print(f"  ideal contraction at the DMMA roof (16.68 us per 128-k block): panel {(J[~diag] * 16.68).sum() / 1e3:.1f}, "
+      f"diag (lower triangle, 5/8) {(J[diag] * 16.68 * 0.625).sum() / 1e3:.1f} SM-ms")
+sel = (~diag) & (J > 0)
+per = ((c2 - c1) / clk)[sel] / J[sel]
+print(f"  panel contraction per k-block: median {np.median(per):.2f} p10 {np.percentile(per, 10):.2f} p90 {np.percentile(per, 90):.2f} us")
+d = t[diag]
+print("  diagonal task (us, mean): contraction %.1f | panel loop %.1f | 16x16 inverses %.1f | W %.1f | tail %.1f" % (
+    ((d[:, 2] - d[:, 1]) / clk).mean(), ((d[:, 6] - d[:, 2]) / clk).mean(), ((d[:, 7] - d[:, 6]) / clk).mean(),
+    ((d[:, 3] - d[:, 7]) / clk).mean(), ((d[:, 4] - d[:, 3]) / clk).mean()))
+gaps = 0
 for s_ in np.unique(sm):
     q = t[sm == s_]; q = q[np.argsort(q[:, 0])]
-    busy += ((q[:, 4] - q[:, 0]) / clk).sum()
-    gaps.extend(((q[1:, 0] - q[:-1, 4]) / clk).tolist())
-print(f"kernel span {span/1e3:.2f} ms; mean SM busy {busy/len(np.unique(sm))/span*100:.1f}%; mean gap between tasks {np.mean(gaps):.2f} us")
-last = np.array([t[sm == s_][:, 4].max() for s_ in np.unique(sm)])
-print(f"SM finish spread: min {(last.min()-start.min())/clk/1e3:.2f} ms, max {(last.max()-start.min())/clk/1e3:.2f} ms")
+    gaps += (q[1:, 0] - q[:-1, 4]).sum()
+print(f"  gaps between tasks {gaps / clk / 1e3:.1f} SM-ms")
