@@ -153,6 +153,28 @@ def test_overlap_matrix_device_bit_exact(kernel):
     assert D.max() <= 1.0 and D.min() >= 0.0 and np.all(np.diag(D) == 0.0) and np.count_nonzero(D) > 0
 
 
+@pytest.mark.parametrize("ktype,mathematical", [("isose", False), ("ardse", True), ("ardlin", False)])
+def test_wide_inputs_borrowed_ring(ktype, mathematical):
+    """D = 12 > 8: the LAUUM epilogue and the predict kernel stage their point tiles in the (borrowed) pipeline ring
+    instead of the static shared buffer; multi-block experts so that the producer hand-shake is exercised."""
+    import deepstructuredmixtures_b200 as dsm
+    D = 12
+    x, y = synth(900, D, 21)
+    k = {"isose": dsm.IsoSE(0.3, 0.1), "ardse": dsm.ArdSE(np.linspace(0.2, 0.5, D), 0.1),
+         "ardlin": dsm.ArdLinear(np.linspace(0.1, 0.4, D))}[ktype]
+    model = dsm.buildDSMGP(x, y, 2, 2, M=150, kernel=k, logNoise=-1.0, rng=21, as_written_grads=not mathematical)
+    th = model.handle.get_leaf_params(0).copy()
+    check_eval(model, th, mathematical=mathematical)
+    dsm.fit_(model)
+    dsm.update_(model)
+    xt = np.random.default_rng(9).random((300, D))
+    mu, var = dsm.predict(model, xt)
+    root = oracle_tree(model)
+    orc.setparams(root, th); orc.fit(root); orc.update_weights(root)
+    omu, ovar = orc.predict_dsmgp(root, xt)
+    assert pred_close(mu, omu, var, ovar, float(np.std(y)))
+
+
 def test_finetune_eval_batched():
     """dsmgp_finetune_eval (one call for all anchors) == finetuning.jl:36-58 evaluated anchor by anchor by the oracle."""
     import deepstructuredmixtures_b200 as dsm
