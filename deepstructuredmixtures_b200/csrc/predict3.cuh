@@ -127,6 +127,9 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     const int ktype = m.ktype;
     const double v = prm[PRM_V];
     const bool c0ok = q0 + acc_row(0) < pl.T, c1ok = q0 + acc_row(1) < pl.T;
+    // slabs without a real test point skip all arithmetic: with a handful of points per expert the task is then bound by
+    // the bulk copies of L (HBM), not by 128-wide DMMA tiles that are mostly padding
+    const bool active = q0 + r0 < pl.T;
     double mu0 = 0.0, mu1 = 0.0, sq0 = 0.0, sq1 = 0.0;
     if (!borrow) {
       csync();                                       // previous task's readers are done with the static tiles
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       acc2_zero(acc);
       for (int c = 0; c < I * (BLK / KC); c++) {     // (I == 0 has no contraction: the header chunk is its first epilogue stage)
         st = p.wait();
-        if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
+        if (active) { if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
         p.release();
       }
       // stage the point tiles of block I (and, when borrowing the ring, of the test block too)
@@ -166,7 +169,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       // OUT = Knt_IQ^T - OUT ; mean partial sum_r Knt[r][c] alpha[r].  8 groups of 2 test points x 4 consecutive rows r.
 #pragma unroll
       for (int nbp = 0; nbp < 8; nbp++) {
-        if (16 * nbp < wi) {
+        if (active && 16 * nbp < wi) {
           const int cb = 16 * nbp + 4 * t4;
           double kk[2][4];
 #pragma unroll
@@ -211,8 +214,8 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
         csync();
         if (tid == 0) mbar_arrive(&p.aux[0]);
       }
-      tri_epilogue(p, acc, wi / 32, true, 1.0);       // V_IQ^T = S^T W_I^T
-      acc2_store(acc, VT, m.nkc, 0, i0, BLK, wi);
+      tri_epilogue(p, acc, wi / 32, active, 1.0);     // V_IQ^T = S^T W_I^T
+      if (active) acc2_store(acc, VT, m.nkc, 0, i0, BLK, wi);
       fence_proxy_async();
       csync();
       if (tid == 0) mbar_arrive(&p.aux[1]);

@@ -14,8 +14,8 @@ th = bench.thetas([k.nparams for k in klist], w["seed"])[0]
 H.eval(th)
 mdl.update_(model)
 rng = np.random.default_rng(77)
-for T in (256, 40000, 40000, 40000):
+for T in (1, 1, 16, 256, 256, 40000, 40000):
     xt = rng.random((T, w["D"]))
     t0 = time.perf_counter(); mu, var = mdl.predict(model, xt); dt = time.perf_counter() - t0
     tm = H.timings()
-    print(wl, "T", T, "wall ms %.1f kernel ms %.1f" % (dt * 1e3, tm["predict_ms"]), flush=True)
+    print(wl, "T", T, "wall ms %.2f kernel ms %.3f  kernel GB/s %.0f TF %.2f" % (dt * 1e3, tm["predict_ms"], tm["predict_bytes"] / tm["predict_ms"] * 1e-6, tm["predict_flops"] / tm["predict_ms"] * 1e-9), flush=True)
