@@ -63,7 +63,7 @@ EXPORTS = [
     "dsmgp_leaf_size", "dsmgp_fit", "dsmgp_lml", "dsmgp_grad", "dsmgp_eval", "dsmgp_row_width",
     "dsmgp_finetune_eval", "dsmgp_eval_local_dev", "dsmgp_eval_finish_dev", "dsmgp_leaf_rows", "dsmgp_leaf_owner",
     "dsmgp_update_weights", "dsmgp_predict", "dsmgp_leaf_predict", "dsmgp_leaf_alpha", "dsmgp_leaf_factor",
-    "dsmgp_leaf_info", "dsmgp_kernelmatrix", "dsmgp_overlap", "dsmgp_chol_continue", "dsmgp_chol_delete_rows", "dsmgp_potrf",
+    "dsmgp_leaf_info", "dsmgp_kernelmatrix", "dsmgp_overlap", "dsmgp_release_cache", "dsmgp_chol_continue", "dsmgp_chol_delete_rows", "dsmgp_potrf",
     "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling",
 ]
 
@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "dsmgp_eval": (I32, [P, pd, I64, pd, pd, pd, pd]),
         "dsmgp_finetune_eval": (I32, [P, I64, pi64, pd, pd, pd, pd, pd]),
         "dsmgp_overlap": (I32, [I64, I64, pi64, pi64, pi32, C.POINTER(Tree), pd]),
+        "dsmgp_release_cache": (None, []),
         "dsmgp_row_width": (I64, [P]),
         "dsmgp_eval_local_dev": (I32, [P, pd, I64, C.POINTER(C.c_void_p)]),
         "dsmgp_eval_finish_dev": (I32, [P, pd, pd, pd, pd]),

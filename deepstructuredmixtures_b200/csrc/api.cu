@@ -3,6 +3,7 @@
 #include <cmath>
 #include <cstring>
 #include <numeric>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -41,21 +42,80 @@ struct Batch {
   double potrf_flops = 0, gram_bytes = 0;
 };
 
+// Process-wide cache of large device buffers.  cudaMalloc / cudaFree of multi-GB arenas cost 10 ms ... 3 s each
+// (measured: tools/cold_probe.py), which would dominate building a model from host arrays; freed buffers >= 32 MiB are
+// kept and handed to the next handle that asks for a similar size on the same device.  dsmgp_release_cache() returns
+// them to the driver.
+struct BufCache {
+  struct Ent { void* p; size_t bytes; int dev; };
+  std::vector<Ent> ents;
+  std::mutex mu;
+  static constexpr size_t MIN_BYTES = size_t(32) << 20;
+  size_t cached_bytes(int dev) {
+    std::lock_guard<std::mutex> g(mu);
+    size_t t = 0;
+    for (auto& e : ents) if (e.dev == dev) t += e.bytes;
+    return t;
+  }
+  void* take(size_t bytes, int dev, size_t* got) {
+    std::lock_guard<std::mutex> g(mu);
+    int best = -1;
+    for (int i = 0; i < (int)ents.size(); i++)
+      if (ents[i].dev == dev && ents[i].bytes >= bytes && ents[i].bytes <= bytes + bytes / 4 + (size_t(64) << 20) &&
+          (best < 0 || ents[i].bytes < ents[best].bytes)) best = i;
+    if (best < 0) return nullptr;
+    void* p = ents[best].p;
+    *got = ents[best].bytes;
+    ents.erase(ents.begin() + best);
+    return p;
+  }
+  bool give(void* p, size_t bytes, int dev) {
+    if (bytes < MIN_BYTES) return false;
+    std::lock_guard<std::mutex> g(mu);
+    if (ents.size() >= 64) return false;
+    ents.push_back({p, bytes, dev});
+    return true;
+  }
+  void release_all() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& e : ents) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(e.dev); cudaFree(e.p); cudaSetDevice(cur); }
+    ents.clear();
+  }
+};
+static BufCache g_cache;
+
 template <typename T>
 struct DevBuf {
-  T* p = nullptr; size_t n = 0;
+  T* p = nullptr; size_t n = 0; size_t cap_bytes = 0; int dev = 0;
   cudaError_t alloc(size_t count) {
     free();
     n = count;
     if (count == 0) return cudaSuccess;
-    return cudaMalloc(&p, count * sizeof(T));
+    const size_t bytes = count * sizeof(T);
+    cudaGetDevice(&dev);
+    if (bytes >= BufCache::MIN_BYTES) {
+      if (void* q = g_cache.take(bytes, dev, &cap_bytes)) { p = static_cast<T*>(q); return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // make room: drop the cache and retry once
+      cudaGetLastError();
+      g_cache.release_all();
+      e = cudaMalloc(&p, bytes);
+    }
+    cap_bytes = bytes;
+    return e;
   }
   // grow-only scratch: keeps the allocation across calls (cudaMalloc / cudaFree of GBs cost 10-100 ms per call)
   cudaError_t ensure(size_t count) {
     if (count <= n && p != nullptr) return cudaSuccess;
     return alloc(count + count / 8);
   }
-  void free() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  void free() {
+    if (p) {
+      if (!g_cache.give(p, cap_bytes, dev)) cudaFree(p);
+    }
+    p = nullptr; n = 0; cap_bytes = 0;
+  }
 };
 
 }  // namespace
@@ -204,6 +264,8 @@ extern "C" void dsmgp_default_opts(dsmgp_opts* o) {
   o->arena_bytes = 0;
 }
 
+extern "C" void dsmgp_release_cache(void) { g_cache.release_all(); }
+
 extern "C" const char* dsmgp_last_error(const dsmgp_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 extern "C" void dsmgp_destroy(dsmgp_handle* h) {
@@ -246,6 +308,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   // arena budget
   size_t free_b = 0, total_b = 0;
   CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+  free_b += g_cache.cached_bytes(h->device);      // cached buffers are reusable (and released on demand)
   const int64_t fixed = (voff * 4 + xoff) * 8 + (64ll << 20);
   int64_t budget = h->opts.arena_bytes > 0 ? h->opts.arena_bytes : (int64_t)(free_b * 0.85) - fixed;
   // per leaf bytes in a batch: factor np^2 + W/WT 2*nb*BLK^2

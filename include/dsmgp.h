@@ -93,6 +93,9 @@ int32_t dsmgp_create(const double* x, int64_t N, int64_t D,
                      const dsmgp_tree* tree, const dsmgp_opts* opts,
                      dsmgp_handle** out);
 void dsmgp_destroy(dsmgp_handle* h);
+/* Device buffers >= 32 MiB of destroyed handles are kept in a process-wide cache (cudaMalloc / cudaFree of multi-GB
+ * arenas cost 10 ms ... 3 s) and reused by later handles; this returns them to the driver. */
+void dsmgp_release_cache(void);
 const char* dsmgp_last_error(const dsmgp_handle* h); /* h may be NULL: last create error */
 
 /* ---- parameters ----------------------------------------------------------------------------
