@@ -159,7 +159,8 @@ struct dsmgp_handle {
   DevBuf<int> d_flags;
   DevBuf<double> d_ldpart, d_zzpart;
   DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
-  DevBuf<double> p_xt, p_VT, p_mu, p_var; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
+  DevBuf<double> p_xt, p_VT, p_mu, p_var, p_part; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
+  DevBuf<int4> p_wtasks, p_wcols; DevBuf<int> p_flags;
   DevBuf<int> d_mask; std::vector<int> h_mask; bool use_mask = false;   // per-slot gradient mask (finetune: zero-overlap experts)
   double* pin_multi = nullptr; size_t pin_multi_doubles = 0;             // rows of a multi-theta call [G][L][row_width]
   double* pin_rows = nullptr;
@@ -174,6 +175,7 @@ struct dsmgp_handle {
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
     d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
     p_xt.free(); p_VT.free(); p_mu.free(); p_var.free(); p_pl.free(); p_tasks.free();
+    p_part.free(); p_wtasks.free(); p_wcols.free(); p_flags.free();
     d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
     d_mask.free();
     if (pin_multi) cudaFreeHost(pin_multi);
@@ -1146,9 +1148,41 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
   PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
   PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
-              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + 8};
+              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + 8,
+              0, nullptr, nullptr, nullptr, nullptr, 0};
+  const int sms = num_sms(h->device);
+  const char* force_wave = getenv("DSMGP_PREDICT_WAVE");       // tests: "0" / "1" force the task granularity
+  const bool use_wave = force_wave ? (force_wave[0] == '1') : ((int)tasks.size() < 3 * sms);
+  if (use_wave) {
+    // WAVE mode: too few (leaf, Q) tasks to fill the GPU -> one task per (leaf, Q, row block), ordered by row block
+    // (a block depends only on the blocks above it) with the experts shifted so that they end together
+    std::vector<int4> wt, wc;
+    int base = 0, max_nb = 0;
+    for (auto& p : pls) max_nb = std::max(max_nb, (int)h->meta[p.slot].nb);
+    struct WK { int key, np, pl, Q, I, base; };
+    std::vector<WK> wk;
+    for (size_t i = 0; i < pls.size(); i++) {
+      const LeafMeta& m = h->meta[pls[i].slot];
+      for (int q = 0; q < pls[i].Tp / BLK; q++) {
+        wc.push_back(make_int4((int)i, q, base, m.nb));
+        for (int I = 0; I < m.nb; I++) wk.push_back({I + max_nb - m.nb, m.np, (int)i, q, I, base});
+        base += m.nb;
+      }
+    }
+    std::stable_sort(wk.begin(), wk.end(), [](const WK& a, const WK& b) { return a.key != b.key ? a.key < b.key : a.np > b.np; });
+    for (auto& k : wk) wt.push_back(make_int4(k.pl, k.Q, k.I, k.base));
+    PTRY(h->p_wtasks.ensure(wt.size())); PTRY(h->p_wcols.ensure(wc.size())); PTRY(h->p_flags.ensure(base));
+    PTRY(h->p_part.ensure((size_t)base * 2 * BLK));
+    PTRY(cudaMemcpyAsync(h->p_wtasks.p, wt.data(), wt.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    PTRY(cudaMemcpyAsync(h->p_wcols.p, wc.data(), wc.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    PTRY(cudaMemsetAsync(h->p_flags.p, 0, (size_t)base * sizeof(int), h->stream));
+    PTRY(cudaStreamSynchronize(h->stream));       // wt / wc are locals
+    pa.wave = 1; pa.wtasks = h->p_wtasks.p; pa.ntasks = (int)wt.size(); pa.flags = h->p_flags.p; pa.part = h->p_part.p;
+    pa.wcols = h->p_wcols.p; pa.nwcols = (int)wc.size();
+  }
   cudaEventRecord(h->ev[0], h->stream);
-  launch_predict3(pa, std::min(num_sms(h->device), (int)tasks.size()), h->stream);
+  launch_predict3(pa, std::max(1, std::min(sms, pa.ntasks)), h->stream);
+  if (pa.wave) launch_predict_reduce(pa, h->stream);
   cudaEventRecord(h->ev[1], h->stream);
   h->tm.launches++;
   PTRY(cudaGetLastError());

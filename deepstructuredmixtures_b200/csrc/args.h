@@ -107,6 +107,13 @@ struct PredArgs {
   double* var;
   int D;
   int* gerr;
+  // wave mode (few test points): one task per (pred leaf, Q, I), cross-CTA order by flags, per-task partials
+  int wave;
+  const int4* wtasks;      // (pred leaf index, Q, I, base): flag / partial slot of (pl, Q, K) = base + K
+  int* flags;
+  double* part;            // [slot][2][BLK]: mean partial, sum-of-squares partial
+  const int4* wcols;       // (pred leaf index, Q, base, nb) per (pl, Q), for the final reduction
+  int nwcols;
 };
 
 // ---- launchers (defined next to their kernels) ------------------------------------------------
@@ -114,6 +121,7 @@ void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
 void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
 void launch_predict3(const PredArgs& a, int nctas, cudaStream_t st);
+void launch_predict_reduce(const PredArgs& a, cudaStream_t st);
 void launch_gram_fit(const GramArgs& a, int64_t ntiles, cudaStream_t st);
 void launch_gram_rect(const GramRectArgs& a, cudaStream_t st);
 void launch_gather(const GatherArgs& a, int maxnp, int nleaves, cudaStream_t st);

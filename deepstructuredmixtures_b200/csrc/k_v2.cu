@@ -13,6 +13,7 @@ cudaError_t init_v2_kernels() {
 }
 void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st) { potrf2_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
 void launch_predict3(const PredArgs& a, int nctas, cudaStream_t st) { predict3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
+void launch_predict_reduce(const PredArgs& a, cudaStream_t st) { if (a.nwcols > 0) predict_reduce_kernel<<<a.nwcols, BLK, 0, st>>>(a); }
 void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st) { lauum3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
 void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, cudaStream_t st) {
   trtri3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a);

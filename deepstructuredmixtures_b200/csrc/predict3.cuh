@@ -4,7 +4,10 @@
 // Sigma = Ktt - V'V ; diag += exp(2 logNoise).  Only diag(Sigma) is consumed (common.jl:136,147), so the
 // T x T matrices Ktt and V'V are never formed:  var_t = k(x_t,x_t) - sum_k V_kt^2 + eta.
 //
-// Task = (leaf, block Q of 128 routed test points).  Block forward substitution, TRANSPOSED so that a warp owns
+// Task = (leaf, block Q of 128 routed test points) -- or, in WAVE mode (few test points, so few such tasks), one task
+// per (leaf, Q, row block I) with per-block flags: the row blocks of one forward substitution then stream L from HBM on
+// many SMs at once (a wavefront: only the last k-block of a task waits for the block above it) instead of one CTA
+// walking the whole factor.  Block forward substitution, TRANSPOSED so that a warp owns
 // complete rows (= test points) and the multiplication by W_I = L_II^-1 runs in registers:
 //   for I = 0..nb-1:   OUT[c][r] = sum_{K<I} V_KQ^T[c][.] L_IK^T[.][r]          (A = V^T tiles, B = L tiles)
 //                      V_IQ^T    = (Knt_IQ^T - OUT) W_I^T                        (Knt recomputed from the point tiles)
@@ -52,17 +55,19 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
     const int ti = __shfl_sync(0xffffffffu, t, 0);
     if (ti >= a.ntasks) break;
-    const int2 tk = a.tasks[ti];
+    int4 wt = make_int4(0, 0, 0, 0);
+    if (a.wave) wt = a.wtasks[ti];
+    const int2 tk = a.wave ? make_int2(wt.x, wt.y) : a.tasks[ti];
     const PredLeaf pl = a.pl[tk.x];
     const LeafMeta m = a.meta[pl.slot];
     Pred3Gen gen;
-    gen.F = a.F + m.foff; gen.W = a.W + m.woff; gen.np = m.np; gen.nb = m.nb; gen.nkc = m.nkc;
+    gen.F = a.F + m.foff; gen.W = a.W + m.woff; gen.np = m.np; gen.nb = a.wave ? wt.z + 1 : m.nb; gen.nkc = m.nkc;
     gen.VT = a.VT + pl.vtoff + (int64_t)tk.y * m.nkc * TILE_D;
-    gen.I = 0; gen.c = 0;
-    TaskHdr h; h.kind = 0; h.ti = ti; h.slot = tk.x; h.I = 0; h.J = tk.y; h.wi = 0; h.wj = 0; h.n_c = 0; h.n_main = 0;
-    int stored = 0;                              // blocks of V^T in memory
-    int nsig = m.nb;                             // signals the consumers send for this task (one per iteration)
-    bool first = true;
+    gen.I = a.wave ? wt.z : 0; gen.c = 0;
+    TaskHdr h; h.kind = 0; h.ti = ti; h.slot = tk.x; h.I = gen.I; h.J = tk.y; h.wi = 0; h.wj = 0; h.n_c = 0; h.n_main = 0; h.pad0 = wt.w;
+    int stored = a.wave ? gen.I : 0;             // blocks of V^T in memory (wave mode: ordered by the flags below instead)
+    int nsig = a.wave ? 0 : m.nb;                // signals the consumers send for this task (one per iteration)
+    bool first = true, allready = false;
     ChunkDesc d;
     if (borrow) {                                // header-only chunk: the ring must be empty whenever the consumers borrow it
       d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
@@ -75,7 +80,19 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
         // the consumers borrow the ring for the point tiles between the contraction and the epilogue of an iteration
         p.wait_bar(&p.aux[0], scratch_phase & 1, 5); scratch_phase++;
       }
+      const int cnext = gen.c, Inext = gen.I;
       if (!gen.next(d)) break;
+      if (a.wave && cnext < Inext * (BLK / KC) && (cnext & (BLK / KC - 1)) == 0 && !allready) {
+        // block K = cnext / 8 of V^T is written by another CTA: acquire its flag (the last block's flag implies all)
+        const int* fl = a.flags + wt.w;
+        if (cnext == 0 && Inext > 1) {
+          int v = 1;
+          if ((threadIdx.x & 31) == 0) v = ld_acquire(fl + Inext - 1);
+          allready = __shfl_sync(0xffffffffu, v, 0) != 0;
+          if (allready) fence_proxy_async();
+        }
+        if (!allready) d.flag0 = fl + cnext / (BLK / KC);
+      }
       p.issue(d, first ? &h : nullptr); first = false;
       if (*p.abort) break;
     }
@@ -142,12 +159,13 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     if (borrow) p.release();                         // header-only chunk
     const int g8 = lane >> 2, t4 = lane & 3;
     const int rb = r0 + 2 * g8;                      // this thread's two test points (rows of OUT)
-    for (int I = 0; I < m.nb; I++) {
+    const int I_begin = a.wave ? hd.I : 0, I_end = a.wave ? hd.I + 1 : m.nb;
+    for (int I = I_begin; I < I_end; I++) {
       const int wi = blk_width(m.np, I), i0 = I * BLK;
       Acc2 acc;
       acc2_zero(acc);
       for (int c = 0; c < I * (BLK / KC); c++) {     // (I == 0 has no contraction: the header chunk is its first epilogue stage)
-        st = p.wait();
+        st = p.wait();                                 // (idempotent for the header chunk, which is still unreleased)
         if (active) { if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
         p.release();
       }
@@ -218,7 +236,10 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       if (active) acc2_store(acc, VT, m.nkc, 0, i0, BLK, wi);
       fence_proxy_async();
       csync();
-      if (tid == 0) mbar_arrive(&p.aux[1]);
+      if (tid == 0) {
+        if (a.wave) { __threadfence(); st_release(a.flags + hd.pad0 + I, 1); }     // other CTAs read this block of V^T
+        else mbar_arrive(&p.aux[1]);
+      }
 #pragma unroll
       for (int nb = 0; nb < 16; nb++)
         if (8 * nb < wi) {
@@ -231,6 +252,14 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
     sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
     sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+    if (a.wave) {                                    // per-task partials; predict_reduce_kernel finishes
+      if ((lane & 3) == 0 && active) {
+        double* pp = a.part + (int64_t)(hd.pad0 + hd.I) * 2 * BLK;
+        *reinterpret_cast<double2*>(pp + acc_row(0)) = make_double2(mu0, mu1);
+        *reinterpret_cast<double2*>(pp + BLK + acc_row(0)) = make_double2(sq0, sq1);
+      }
+      continue;
+    }
     if ((lane & 3) == 0) {
 #pragma unroll
       for (int mb = 0; mb < 2; mb++) {
@@ -253,6 +282,36 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       }
     }
   }
+}
+
+// Wave mode: mu = m + sum_I partial ; var = k(x_t, x_t) - sum_I partial + eta, summed in block order (deterministic).
+__global__ void __launch_bounds__(BLK) predict_reduce_kernel(PredArgs a) {
+  const int4 wc = a.wcols[blockIdx.x];
+  const PredLeaf pl = a.pl[wc.x];
+  const LeafMeta m = a.meta[pl.slot];
+  const int q0 = wc.y * BLK, c = threadIdx.x;
+  if (q0 + c >= pl.T) return;
+  double mu = 0.0, sq = 0.0;
+  for (int I = 0; I < wc.w; I++) {
+    const double* pp = a.part + (int64_t)(wc.z + I) * 2 * BLK;
+    mu += pp[c]; sq += pp[BLK + c];
+  }
+  const double* prm = a.prm + m.poff;
+  const double* xt = a.xt + pl.xtoff;
+  const double v = prm[PRM_V];
+  double ktt;
+  if (m.ktype == ISO_SE) ktt = v;
+  else if (m.ktype == ARD_SE) ktt = v * (double)a.D;
+  else {
+    ktt = 0.0;
+    for (int d = 0; d < a.D; d++) {
+      const double xv = xt[(int64_t)d * pl.Tp + q0 + c];
+      const double cf = (m.ktype == ISO_LINEAR) ? prm[PRM_COEF] : prm[PRM_COEF + d];
+      ktt = fma(cf * xv, xv, ktt);
+    }
+  }
+  a.mu[pl.ooff + q0 + c] = a.leaf_mean[m.leaf] + mu;
+  a.var[pl.ooff + q0 + c] = ktt - sq + prm[PRM_ETA];
 }
 
 }  // namespace dsm

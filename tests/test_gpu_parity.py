@@ -175,6 +175,29 @@ def test_wide_inputs_borrowed_ring(ktype, mathematical):
     assert pred_close(mu, omu, var, ovar, float(np.std(y)))
 
 
+def test_predict_task_granularities_agree(monkeypatch):
+    """predict3 runs one task per (expert, 128 test points) when there are many test points and one task per
+    (expert, 128 test points, row block) with cross-CTA flags when there are few: both against the oracle."""
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(2500, 3, 31)
+    model = dsm.buildDSMGP(x, y, 2, 2, M=300, kernel=dsm.ArdSE(np.zeros(3), 0.0), logNoise=-1.0, rng=31)
+    th = np.array([0.1, -0.1, 0.2, 0.1, -1.0])
+    model.handle.eval(th)
+    dsm.update_(model)
+    xt = np.random.default_rng(4).random((700, 3))
+    root = oracle_tree(model, th)
+    orc.fit(root); orc.update_weights(root)
+    omu, ovar = orc.predict_dsmgp(root, xt)
+    out = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("DSMGP_PREDICT_WAVE", mode)
+        mu, var = dsm.predict(model, xt)
+        assert pred_close(mu, omu, var, ovar, float(np.std(y))), mode
+        out[mode] = (mu, var)
+    assert np.max(np.abs(out["0"][0] - out["1"][0])) <= 1e-10 * np.max(np.abs(omu))
+    assert np.max(np.abs(out["0"][1] - out["1"][1]) / np.abs(ovar)) <= 1e-10
+
+
 def test_finetune_eval_batched():
     """dsmgp_finetune_eval (one call for all anchors) == finetuning.jl:36-58 evaluated anchor by anchor by the oracle."""
     import deepstructuredmixtures_b200 as dsm
