@@ -163,6 +163,7 @@ struct dsmgp_handle {
   DevBuf<int4> p_wtasks, p_wcols; DevBuf<int> p_flags;
   DevBuf<int> d_mask; std::vector<int> h_mask; bool use_mask = false;   // per-slot gradient mask (finetune: zero-overlap experts)
   double* pin_multi = nullptr; size_t pin_multi_doubles = 0;             // rows of a multi-theta call [G][L][row_width]
+  LeafScal* pin_scal_multi = nullptr; size_t pin_scal_multi_n = 0;       // per-slot scalars of a multi-theta call [G][slots]
   double* pin_rows = nullptr;
   LeafScal* pin_scal = nullptr;
   std::string err;
@@ -179,6 +180,7 @@ struct dsmgp_handle {
     d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
     d_mask.free();
     if (pin_multi) cudaFreeHost(pin_multi);
+    if (pin_scal_multi) cudaFreeHost(pin_scal_multi);
     if (pin_rows) cudaFreeHost(pin_rows);
     if (pin_scal) cudaFreeHost(pin_scal);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
@@ -850,9 +852,14 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
   std::vector<double> scale(L);
   std::vector<int32_t> info((size_t)G * L, 0);
   const int ns = (int)h->slot_leaf.size();
-  std::vector<LeafScal> scal_g((size_t)G * std::max(ns, 1));
-  LeafScal* pin_scal_multi = nullptr;
-  CUDA_TRY(h, cudaMallocHost(&pin_scal_multi, scal_g.size() * sizeof(LeafScal)));
+  const size_t need_scal = (size_t)G * std::max(ns, 1);
+  if (need_scal > h->pin_scal_multi_n) {
+    if (h->pin_scal_multi) cudaFreeHost(h->pin_scal_multi);
+    h->pin_scal_multi = nullptr; h->pin_scal_multi_n = 0;
+    CUDA_TRY(h, cudaMallocHost(&h->pin_scal_multi, need_scal * sizeof(LeafScal)));
+    h->pin_scal_multi_n = need_scal;
+  }
+  LeafScal* pin_scal_multi = h->pin_scal_multi;
   int32_t rc = DSMGP_OK;
   for (int64_t g = 0; g < G && rc == DSMGP_OK; g++) {
     if ((rc = dsmgp_set_params(h, thetas + g * H, H))) break;              // setparams!(spn, hyp_)  finetuning.jl:41
@@ -865,7 +872,7 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
     if (ns) cudaMemcpyAsync(pin_scal_multi + (size_t)g * ns, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, h->stream);
   }
   if (rc == DSMGP_OK) rc = finish_pipeline(h, true);        // one synchronisation for all G evaluations
-  if (rc) { cudaFreeHost(pin_scal_multi); return rc; }
+  if (rc) return rc;
   std::vector<int64_t> node_of_leaf(L, -1);
   for (int64_t i = 0; i < h->tree.n_nodes; i++) if (h->tree.type[i] == DSMGP_NODE_LEAF) node_of_leaf[h->tree.leaf_of_node[i]] = i;
   for (int64_t g = 0; g < G; g++) {
@@ -875,7 +882,6 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
       const int inf = pin_scal_multi[(size_t)g * ns + s].info;
       if (inf != 0 && inf <= h->meta[s].n && h->opts.strict_pd) {
         h->err = "PosDefException: leaf " + std::to_string(h->slot_leaf[s]) + " (finetune anchor " + std::to_string(anchors[g]) + ")";
-        cudaFreeHost(pin_scal_multi);
         return DSMGP_ERR_NOT_PD;
       }
     }
@@ -885,7 +891,6 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
     for (int64_t l = 0; l < L; l++) scale[l] = overlap[anchors[g] + l * L];
     tree_grad(h, scale.data(), grads + g * H);                               // finetuning.jl:53
   }
-  cudaFreeHost(pin_scal_multi);
   h->rows_complete = true;
   return DSMGP_OK;
 }
