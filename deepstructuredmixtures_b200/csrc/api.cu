@@ -345,6 +345,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     }
   }
   int64_t maxF = 0, maxW = 0, maxTr = 0, maxG = 0, maxFlags = 0;
+  const int sms_plan = num_sms(h->device);
   for (auto& b : h->batches) {
     const int nb_s = b.s1 - b.s0;
     b.max_nb = 0;
@@ -373,7 +374,9 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
     std::stable_sort(lt.begin(), lt.end(), [&](const int4& a, const int4& c) {
       const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
-    {   // engine v2 tile tasks: topological order with look-ahead, columns shifted so that all experts end together
+    const char* ord_env = getenv("DSMGP_ORDER");           // development A/B: 0 = end together, 1 = stretch
+    const bool stretch = ord_env ? (ord_env[0] == '1') : (nb_s * 4 < sms_plan);
+    {   // engine v2 tile tasks: topological order with look-ahead
       struct TK { int s, grp, slot, I, J; };
       std::vector<TK> tk;
       std::vector<int64_t> foff(nb_s, 0);
@@ -382,11 +385,15 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         const LeafMeta& m = h->meta[s];
         const int sl = s - b.s0, shift = b.max_nb - m.nb;
         foff[sl] = fo; fo += (int64_t)m.nb * (m.nb + 1) / 2;
-        tk.push_back({shift - 1, 1, sl, 0, 0});
+        // level of block column J in the global order.  "end together" (shift) keeps the tail of a throughput-bound
+        // batch parallel; "stretch" lets every expert progress proportionally through the whole launch, which spreads the
+        // other experts' work evenly along the critical path of the largest one (small shards: multi-GPU strong scaling)
+        auto level = [&](int J) { return stretch ? (int)(((int64_t)J * 1024 * b.max_nb) / m.nb) : (J + shift) * 1024; };
+        tk.push_back({level(0) - 1, 1, sl, 0, 0});
         for (int J = 0; J + 1 < m.nb; J++) {
-          tk.push_back({J + shift, 0, sl, J + 1, J});
-          tk.push_back({J + shift, 1, sl, J + 1, J + 1});
-          for (int I = J + 2; I < m.nb; I++) tk.push_back({J + shift, 2, sl, I, J});
+          tk.push_back({level(J), 0, sl, J + 1, J});
+          tk.push_back({level(J), 1, sl, J + 1, J + 1});
+          for (int I = J + 2; I < m.nb; I++) tk.push_back({level(J), 2, sl, I, J});
         }
       }
       std::stable_sort(tk.begin(), tk.end(), [](const TK& a, const TK& c) {
@@ -404,7 +411,8 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         const LeafMeta& m = h->meta[s];
         const int sl = s - b.s0, shift = b.max_nb - m.nb;
         for (int J = 0; J < m.nb; J++)
-          for (int I = J + 1; I < m.nb; I++) iv.push_back({I - J + shift, -(I - J), sl, I, J});
+          for (int I = J + 1; I < m.nb; I++)
+            iv.push_back({stretch ? (int)(((int64_t)(I - J) * 1024 * b.max_nb) / m.nb) : (I - J + shift) * 1024, -(I - J), sl, I, J});
       }
       std::stable_sort(iv.begin(), iv.end(), [](const TK& a, const TK& c) {
         if (a.s != c.s) return a.s < c.s;
