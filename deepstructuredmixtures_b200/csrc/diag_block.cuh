@@ -118,13 +118,15 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
   if (tid == 0) *s_info = 0;
   csync();
   double* rdiag = aux + (BLK / PW) * DBLK + (NTHREADS / 32) * DBLK;     // 1 / l_cc of the tile
+  // Look-ahead: the 16 x 16 pivot block of panel P+1 is updated first and factored by warp 0 WHILE the other warps
+  // finish the trailing update of panel P, so the serial register Cholesky leaves the critical path of the tile.
+  if (factor && warp == 0) {
+    const int info = warp_potrf16(S, 0, rdiag);
+    if (lane == 0 && info != 0 && *s_info == 0) *s_info = info;
+  }
+  csync();
   for (int P = 0; P < np && factor; P++) {
     const int c0 = P * PW, r1 = c0 + PW, nrem = m - r1;
-    if (warp == 0) {
-      const int info = warp_potrf16(S, c0, rdiag);
-      if (lane == 0 && info != 0 && *s_info == 0) *s_info = c0 + info;
-    }
-    csync();
     if (nrem == 0) continue;
     // ---- panel TRSM: X = A21 * L11^-T by forward substitution, one thread per row (needs L11 only, not its inverse)
     if (tid < nrem) {
@@ -142,10 +144,13 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
       for (int c = 0; c < PW; c++) S[(c0 + c) * LDS + rr] = x[c];
     }
     csync();
-    // ---- trailing update: A22 -= X X^T  (lower 8 x 8 tiles)
+    // ---- trailing update: A22 -= X X^T  (lower 8 x 8 tiles).  Tiles 0..2 are the next pivot block: warp 0 takes them,
+    // then factors that block; warps 1..7 share the rest.
     {
       const int nt = nrem / 8, ntiles = nt * (nt + 1) / 2;
-      for (int q = warp; q < ntiles; q += NTHREADS / 32) {
+      const int qbeg = (warp == 0) ? 0 : 3 + (warp - 1), qend = (warp == 0) ? min(3, ntiles) : ntiles;
+      const int qstep = (warp == 0) ? 1 : (NCONS / 32 - 1);
+      for (int q = qbeg; q < qend; q += qstep) {
         int ti = (int)((sqrtf(8.0f * q + 1.0f) - 1.0f) * 0.5f);
         while ((ti + 1) * (ti + 2) / 2 <= q) ti++;
         while (ti * (ti + 1) / 2 > q) ti--;
@@ -159,6 +164,11 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
           dmma_tile(c0v, c1v, av, bv);
         }
         cp[0] = c0v; cp[LDS] = c1v;
+      }
+      if (warp == 0) {
+        __syncwarp();
+        const int info = warp_potrf16(S, r1, rdiag);
+        if (lane == 0 && info != 0 && *s_info == 0) *s_info = r1 + info;
       }
     }
     csync();
