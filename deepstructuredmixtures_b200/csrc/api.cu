@@ -376,6 +376,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
     const char* ord_env = getenv("DSMGP_ORDER");           // development A/B: 0 = end together, 1 = stretch
     const bool stretch = ord_env ? (ord_env[0] == '1') : (nb_s * 4 < sms_plan);
+    const bool start_together = ord_env && ord_env[0] == '2';     // experiment: no shift at all
     {   // engine v2 tile tasks: topological order with look-ahead
       struct TK { int s, grp, slot, I, J; };
       std::vector<TK> tk;
@@ -388,7 +389,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         // level of block column J in the global order.  "end together" (shift) keeps the tail of a throughput-bound
         // batch parallel; "stretch" lets every expert progress proportionally through the whole launch, which spreads the
         // other experts' work evenly along the critical path of the largest one (small shards: multi-GPU strong scaling)
-        auto level = [&](int J) { return stretch ? (int)(((int64_t)J * 1024 * b.max_nb) / m.nb) : (J + shift) * 1024; };
+        auto level = [&](int J) { return start_together ? J * 1024 : stretch ? (int)(((int64_t)J * 1024 * b.max_nb) / m.nb) : (J + shift) * 1024; };
         tk.push_back({level(0) - 1, 1, sl, 0, 0});
         for (int J = 0; J + 1 < m.nb; J++) {
           tk.push_back({level(J), 0, sl, J + 1, J});
@@ -412,7 +413,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         const int sl = s - b.s0, shift = b.max_nb - m.nb;
         for (int J = 0; J < m.nb; J++)
           for (int I = J + 1; I < m.nb; I++)
-            iv.push_back({stretch ? (int)(((int64_t)(I - J) * 1024 * b.max_nb) / m.nb) : (I - J + shift) * 1024, -(I - J), sl, I, J});
+            iv.push_back({start_together ? (I - J) * 1024 : stretch ? (int)(((int64_t)(I - J) * 1024 * b.max_nb) / m.nb) : (I - J + shift) * 1024, -(I - J), sl, I, J});
       }
       std::stable_sort(iv.begin(), iv.end(), [](const TK& a, const TK& c) {
         if (a.s != c.s) return a.s < c.s;
