@@ -104,10 +104,64 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
   p.issue(d, &h);
 }
 
+// Kernel values of one group of 2 test points (rows rb, rb+1 of the test tile) x 4 consecutive training rows (cb .. cb+3).
+__device__ __forceinline__ void kernel_group(int ktype, int D, const double* sxq, const double* sxi, const double* scf,
+                                             const double* sT, double v, int rb, int cb, double (&kv)[2][4]) {
+#pragma unroll
+  for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) kv[mm][k] = 0.0;
+#pragma unroll 2
+  for (int d = 0; d < D; d++) {
+    const double2 xq = *reinterpret_cast<const double2*>(sxq + d * BLK + rb);
+    const double2 xi0 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb), xi1 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb + 2);
+    const double xqv[2] = {xq.x, xq.y}, xiv[4] = {xi0.x, xi0.y, xi1.x, xi1.y};
+    const double cf = scf[d];
+#pragma unroll
+    for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (ktype == ISO_SE) { const double t = xqv[mm] - xiv[k]; kv[mm][k] = fma(t, t, kv[mm][k]); }
+        else if (ktype == ARD_SE) { const double t = xqv[mm] - xiv[k]; kv[mm][k] += exp_neg(cf * (t * t), sT); }
+        else if (ktype == ISO_LINEAR) kv[mm][k] = fma(xqv[mm], xiv[k], kv[mm][k]);
+        else kv[mm][k] = fma(cf * xqv[mm], xiv[k], kv[mm][k]);
+      }
+  }
+  const double cf0 = scf[0];
+#pragma unroll
+  for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (ktype == ISO_SE) kv[mm][k] = v * exp_neg(cf0 * kv[mm][k], sT);
+      else if (ktype == ARD_SE) kv[mm][k] = v * kv[mm][k];
+      else if (ktype == ISO_LINEAR) kv[mm][k] = cf0 * kv[mm][k];
+    }
+}
+
+// STRIP mode (at most 16 real test points in the block, i.e. only slab 0 is live): the 128 columns of the 16-row strip are
+// split over the eight warps -- warp w contracts columns [16w, 16w+16) -- so that a task streams L at the bulk-copy
+// rate instead of being bound by ONE warp issuing 128 DMMAs per chunk.  sacc[mb][n][e]: row 2g+mb, col 16w + 2(2t+e) + n.
+__device__ __forceinline__ void strip_chunk(double (&sacc)[2][2][2], const double* __restrict__ sA, const double* __restrict__ sB, int col0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double* pa = sA + t * LDS + 2 * g;
+  const double* pb = sB + t * LDS + 2 * g + col0;
+#pragma unroll
+  for (int ks = 0; ks < KC / 4; ks++) {
+    const double2 av = *reinterpret_cast<const double2*>(pa + ks * 4 * LDS);
+    const double2 bv = *reinterpret_cast<const double2*>(pb + ks * 4 * LDS);
+    dmma884(sacc[0][0][0], sacc[0][0][1], av.x, bv.x);
+    dmma884(sacc[1][0][0], sacc[1][0][1], av.y, bv.x);
+    dmma884(sacc[0][1][0], sacc[0][1][1], av.x, bv.y);
+    dmma884(sacc[1][1][0], sacc[1][1][1], av.y, bv.y);
+  }
+}
+
 __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ __align__(16) double s_stage[2 * PRED_DSTAGE * BLK + BLK + PRED_DSTAGE];
   __shared__ double sT[EXPTAB_N];
+  __shared__ double s_xch[4][8][32];               // strip mode: exchange of the column-split strip (two rounds of 4 warps)
+  __shared__ double s_musum[NCONS / 32][16];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slab = warp_slab(), r0 = 16 * slab;
   exptab_load(sT);
@@ -147,6 +201,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     // slabs without a real test point skip all arithmetic: with a handful of points per expert the task is then bound by
     // the bulk copies of L (HBM), not by 128-wide DMMA tiles that are mostly padding
     const bool active = q0 + r0 < pl.T;
+    const bool strip = pl.T - q0 <= 16;              // only slab 0 (= warp 0) holds real test points
     double mu0 = 0.0, mu1 = 0.0, sq0 = 0.0, sq1 = 0.0;
     if (!borrow) {
       csync();                                       // previous task's readers are done with the static tiles
@@ -164,9 +219,14 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       const int wi = blk_width(m.np, I), i0 = I * BLK;
       Acc2 acc;
       acc2_zero(acc);
+      double sacc[2][2][2];
+#pragma unroll
+      for (int mm = 0; mm < 2; mm++) { sacc[mm][0][0] = 0.0; sacc[mm][0][1] = 0.0; sacc[mm][1][0] = 0.0; sacc[mm][1][1] = 0.0; }
+      const bool wact = strip && 16 * warp < wi;     // strip mode: this warp's 16 columns exist in block I
       for (int c = 0; c < I * (BLK / KC); c++) {     // (I == 0 has no contraction: the header chunk is its first epilogue stage)
         st = p.wait();                                 // (idempotent for the header chunk, which is still unreleased)
-        if (active) { if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
+        if (strip) { if (wact) strip_chunk(sacc, p.A(st), p.B(st), 16 * warp); }
+        else if (active) { if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
         p.release();
       }
       // stage the point tiles of block I (and, when borrowing the ring, of the test block too)
@@ -184,48 +244,68 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       }
       if (tid < BLK) sal[tid] = (tid < wi && i0 + tid < m.n) ? al[i0 + tid] : 0.0;
       csync();
-      // OUT = Knt_IQ^T - OUT ; mean partial sum_r Knt[r][c] alpha[r].  8 groups of 2 test points x 4 consecutive rows r.
-#pragma unroll
-      for (int nbp = 0; nbp < 8; nbp++) {
-        if (active && 16 * nbp < wi) {
-          const int cb = 16 * nbp + 4 * t4;
-          double kk[2][4];
-#pragma unroll
-          for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) kk[mm][k] = 0.0;
-#pragma unroll 2
-          for (int d = 0; d < D; d++) {
-            const double2 xq = *reinterpret_cast<const double2*>(sxq + d * BLK + rb);
-            const double2 xi0 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb), xi1 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb + 2);
-            const double xqv[2] = {xq.x, xq.y}, xiv[4] = {xi0.x, xi0.y, xi1.x, xi1.y};
-            const double cf = scf[d];
-#pragma unroll
-            for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                if (ktype == ISO_SE) { const double t = xqv[mm] - xiv[k]; kk[mm][k] = fma(t, t, kk[mm][k]); }
-                else if (ktype == ARD_SE) { const double t = xqv[mm] - xiv[k]; kk[mm][k] += exp_neg(cf * (t * t), sT); }
-                else if (ktype == ISO_LINEAR) kk[mm][k] = fma(xqv[mm], xiv[k], kk[mm][k]);
-                else kk[mm][k] = fma(cf * xqv[mm], xiv[k], kk[mm][k]);
-              }
-          }
+      // OUT = Knt_IQ^T - OUT ; mean partial sum_r Knt[r][c] alpha[r].  Groups of 2 test points x 4 consecutive rows r.
+      if (strip) {
+        if (wact) {
+          const int rbs = 2 * g8, cb = 16 * warp + 4 * t4;
+          double kv[2][4];
+          kernel_group(ktype, D, sxq, sxi, scf, sT, v, rbs, cb, kv);
           const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
           const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
-          const double cf0 = scf[0];
 #pragma unroll
           for (int mm = 0; mm < 2; mm++)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              double kv = kk[mm][k];
-              if (ktype == ISO_SE) kv = v * exp_neg(cf0 * kv, sT);
-              else if (ktype == ARD_SE) kv = v * kv;
-              else if (ktype == ISO_LINEAR) kv = cf0 * kv;
-              if (!((mm ? c1ok : c0ok) && i0 + cb + k < m.n)) kv = 0.0;
-              if (mm) mu1 = fma(kv, alv[k], mu1); else mu0 = fma(kv, alv[k], mu0);
-              acc[mm][2 * nbp + (k & 1)][k >> 1] = kv - acc[mm][2 * nbp + (k & 1)][k >> 1];
+              double kk = kv[mm][k];
+              if (!(q0 + rbs + mm < pl.T && i0 + cb + k < m.n)) kk = 0.0;
+              if (mm) mu1 = fma(kk, alv[k], mu1); else mu0 = fma(kk, alv[k], mu0);
+              sacc[mm][k & 1][k >> 1] = kk - sacc[mm][k & 1][k >> 1];
             }
         }
+        // gather the strip in warp 0's accumulator fragments: same lane, tiles 2 cg + n of the interleaved mapping
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+          if ((warp >> 2) == hh) {
+#pragma unroll
+            for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+              for (int n = 0; n < 2; n++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) s_xch[warp & 3][mm * 4 + n * 2 + e][lane] = sacc[mm][n][e];
+          }
+          csync();
+          if (warp == 0) {
+#pragma unroll
+            for (int cg = 0; cg < 4; cg++)
+#pragma unroll
+              for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+                for (int n = 0; n < 2; n++)
+#pragma unroll
+                  for (int e = 0; e < 2; e++) acc[mm][2 * (4 * hh + cg) + n][e] = s_xch[cg][mm * 4 + n * 2 + e][lane];
+          }
+          csync();
+        }
+      } else {
+#pragma unroll
+      for (int nbp = 0; nbp < 8; nbp++) {
+        if (active && 16 * nbp < wi) {
+          const int cb = 16 * nbp + 4 * t4;
+          double kv[2][4];
+          kernel_group(ktype, D, sxq, sxi, scf, sT, v, rb, cb, kv);
+          const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
+          const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
+#pragma unroll
+          for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              double kk = kv[mm][k];
+              if (!((mm ? c1ok : c0ok) && i0 + cb + k < m.n)) kk = 0.0;
+              if (mm) mu1 = fma(kk, alv[k], mu1); else mu0 = fma(kk, alv[k], mu0);
+              acc[mm][2 * nbp + (k & 1)][k >> 1] = kk - acc[mm][2 * nbp + (k & 1)][k >> 1];
+            }
+        }
+      }
       }
       if (borrow) {                                    // hand the ring back before the epilogue stages arrive
         fence_proxy_async();
@@ -252,6 +332,16 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
     sq0 += __shfl_xor_sync(0xffffffffu, sq0, 1); sq0 += __shfl_xor_sync(0xffffffffu, sq0, 2);
     sq1 += __shfl_xor_sync(0xffffffffu, sq1, 1); sq1 += __shfl_xor_sync(0xffffffffu, sq1, 2);
+    if (strip) {                                     // the mean partials of the strip live in all eight warps
+      if ((lane & 3) == 0) { s_musum[warp][2 * g8] = mu0; s_musum[warp][2 * g8 + 1] = mu1; }
+      csync();
+      if (warp == 0) {
+        mu0 = 0.0; mu1 = 0.0;
+#pragma unroll
+        for (int w8 = 0; w8 < NCONS / 32; w8++) { mu0 += s_musum[w8][2 * g8]; mu1 += s_musum[w8][2 * g8 + 1]; }
+      }
+      csync();
+    }
     if (a.wave) {                                    // per-task partials; predict_reduce_kernel finishes
       if ((lane & 3) == 0 && active) {
         double* pp = a.part + (int64_t)(hd.pad0 + hd.I) * 2 * BLK;

@@ -14,7 +14,7 @@ th = bench.thetas([k.nparams for k in klist], w["seed"])[0]
 H.eval(th)
 mdl.update_(model)
 rng = np.random.default_rng(77)
-for T in (1, 1, 16, 256, 256, 40000, 40000):
+for T in (1, 1, 1, 1, 16, 16, 256, 256, 40000, 40000, 1, 1):
     xt = rng.random((T, w["D"]))
     t0 = time.perf_counter(); mu, var = mdl.predict(model, xt); dt = time.perf_counter() - t0
     tm = H.timings()
