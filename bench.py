@@ -305,7 +305,7 @@ def main():
             T = min(w["N"], 40_000)
             xt = prng.random((T, w["D"]))
             mdl.update_(model)
-            mdl.predict(model, xt[:256])
+            mdl.predict(model, xt)          # warm-up at full size: the routed-point scratch (GBs) is allocated once
             t0 = time.perf_counter()
             mu, var = mdl.predict(model, xt)
             t_pred = time.perf_counter() - t0
