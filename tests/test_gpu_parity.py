@@ -368,3 +368,106 @@ def test_streaming_batches_match_resident():
     with pytest.raises(dsm.DsmgpError):
         dsm.predict(mb, x[:10])
     mb.close()
+
+
+def test_full_size_cfg3_properties():
+    """BASELINE.json config 3 at FULL size (40,000 x 8 ArdSE, V=3 K=4 M=500: 144 experts of 918..5008 points), where the
+    oracle would need minutes: size-independent properties instead of an oracle comparison.
+      * the factor of a sampled expert reproduces its Gram matrix:  ||L L^T - (K + c I)|| / ||K + c I|| < 1e-13
+      * alpha solves the system:                                     ||(K + c I) alpha - y|| / ||y|| < 1e-9
+      * mathematical gradients agree with a central finite difference of the LML along a random direction -- up to the
+        factor V^2 = 9 of the reference's down-pass, whose sum nodes cancel the -log K prior (optimize.jl:64-74, SURVEY
+        App. B Q4): every expert sits below two sum nodes with V = 3 children
+      * a second evaluation is bit-identical (deterministic reductions)
+      * the root LML is the up-pass of the per-expert LMLs (host restatement of optimize.jl:27-39)
+    """
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import model as mdl
+    w = bench.WORKLOADS["cfg3"]
+    x, y, root, kern = bench.build_structure(w)
+    model = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, as_written_grads=False)
+    H = model.handle
+    th = bench.thetas([kern.nparams], w["seed"])[1]
+    lml, grad, nodes = H.eval(th, want_nodes=True)
+    rows = H.leaf_rows()
+    assert np.isfinite(lml) and np.all(np.isfinite(grad)) and np.all(H.leaf_info() == 0)
+    lml2, grad2 = H.eval(th)
+    assert lml2 == lml and np.array_equal(grad, grad2)
+    # up-pass of the per-expert LMLs through the oracle's tree walk
+    o_root = oracle_tree(model)
+    ell = {}
+    leaf_lml = {lf.id: rows[lf.leaf_index, 0] for lf in orc.getLeaves(o_root)}
+
+    def up(node):
+        if node.type == orc.NODE_LEAF:
+            ell[node.id] = leaf_lml[node.id]
+        elif node.type == orc.NODE_SPLIT:
+            ell[node.id] = sum(up(c) for c in node.children)
+        else:
+            K = len(node.children)
+            ell[node.id] = orc.logsumexp([-math.log(K) + up(c) for c in node.children])
+        return ell[node.id]
+
+    assert abs(up(o_root) - lml) <= 1e-12 * abs(lml)
+    # finite difference along a random direction (central, step 1e-4: truncation ~1e-8 relative)
+    rng = np.random.default_rng(0)
+    d = rng.standard_normal(th.size); d /= np.linalg.norm(d)
+    hstep = 1e-4
+    lp, _ = H.eval(th + hstep * d, want_grad=False)
+    lm, _ = H.eval(th - hstep * d, want_grad=False)
+    fd = (lp - lm) / (2 * hstep)
+    gd = (grad @ d) / w["V"] ** 2
+    assert abs(fd - gd) <= 1e-6 * max(abs(fd), np.linalg.norm(grad) / w["V"] ** 2), (fd, gd)
+    # factor / alpha of the smallest expert against its Gram matrix (dsmgp_kernelmatrix)
+    H.eval(th, want_grad=False)
+    sizes = np.diff(H.leaf_ptr)
+    l = int(np.argmin(sizes))
+    lf = model.leaves[l]
+    xl = x[lf.obs - 1]
+    k = kern.copy(); k.logl[:] = th[:8]; k.logs = float(th[8])
+    F = dsm.kernelmatrix(k, xl, xl)
+    # (a corner of the Gram matrix against the formula itself: additive ARD, kernels.jl:31-49)
+    sub = xl[:60]
+    ell2 = np.exp(th[:8]) ** 2
+    Kref = math.exp(2 * th[8]) * np.sum(np.exp(-0.5 * (sub[:, None, :] - sub[None, :, :]) ** 2 / ell2), axis=2)
+    assert np.max(np.abs(F[:60, :60] - Kref)) <= 1e-13 * np.max(np.abs(Kref))
+    F[np.diag_indices(F.shape[0])] += math.exp(2 * th[9]) + 1e-8
+    Lf = H.leaf_factor(l)
+    assert np.linalg.norm(Lf @ Lf.T - F) <= 1e-13 * np.linalg.norm(F)
+    al = H.leaf_alpha(l)
+    yc = y[lf.obs - 1] - lf.mean
+    assert np.linalg.norm(F @ al - yc) <= 1e-9 * np.linalg.norm(yc)
+    model.close()
+
+
+def test_full_size_cfg2_properties():
+    """BASELINE.json config 2 at full size (10,000 x 1 IsoSE, V=3 K=4 M=100, 144 experts; LAUUM path): finite difference of
+    the LML, and the as-written quirk ratio at scale -- kernel gradients carry an extra factor exp(log sigma)
+    (kernels.jl:90), the noise gradient does not."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from deepstructuredmixtures_b200 import model as mdl
+    w = bench.WORKLOADS["cfg2"]
+    x, y, root, kern = bench.build_structure(w)
+    th = np.array([-1.2, 0.35, -1.1])
+    grads = {}
+    for aw in (False, True):
+        model = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, as_written_grads=aw)
+        lml, grads[aw] = model.handle.eval(th)
+        if not aw:
+            rng = np.random.default_rng(1)
+            d = rng.standard_normal(3); d /= np.linalg.norm(d)
+            hstep = 1e-5
+            lp, _ = model.handle.eval(th + hstep * d, want_grad=False)
+            lm, _ = model.handle.eval(th - hstep * d, want_grad=False)
+            fd = (lp - lm) / (2 * hstep)
+            gd = (grads[aw] @ d) / w["V"] ** 2
+            assert abs(fd - gd) <= 1e-6 * max(abs(fd), np.linalg.norm(grads[aw]) / w["V"] ** 2), (fd, gd)
+        model.close()
+    s = math.exp(th[1])
+    assert np.all(np.abs(grads[True][:2] - s * grads[False][:2]) <= 1e-10 * np.abs(grads[True][:2]))
+    assert abs(grads[True][2] - grads[False][2]) <= 1e-12 * abs(grads[False][2])
