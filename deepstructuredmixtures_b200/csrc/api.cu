@@ -38,6 +38,7 @@ struct Batch {
   int4* d_lauum_tasks = nullptr; int n_lauum = 0;
   int4* d_potrf2_tasks = nullptr; int n_potrf2 = 0;     // engine v2: tile tasks in look-ahead order
   int4* d_trtri3_tasks = nullptr; int n_trtri3 = 0;     // inverse: tile tasks by anti-diagonal
+  int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
 };
@@ -171,7 +172,7 @@ struct dsmgp_handle {
   ~dsmgp_handle() {
     for (auto& b : batches) {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
-      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_flag_off);
+      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
     }
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
     d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
@@ -424,6 +425,17 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       for (size_t i = 0; i < iv.size(); i++) it[i] = make_int4(iv[i].slot, iv[i].I, iv[i].J, 0);
       b.n_trtri3 = (int)it.size();
       CUDA_TRY(h, upload(&b.d_trtri3_tasks, it));
+      // back-substitution tasks (slot, J): level = distance from the bottom (a task depends on the tasks below it)
+      std::vector<TK> sv;
+      for (int s = b.s0; s < b.s1; s++) {
+        const LeafMeta& m = h->meta[s];
+        for (int J = 0; J < m.nb; J++) sv.push_back({m.nb - 1 - J, 0, s - b.s0, J, J});
+      }
+      std::stable_sort(sv.begin(), sv.end(), [](const TK& a, const TK& c) { return a.s != c.s ? a.s < c.s : a.slot < c.slot; });
+      std::vector<int2> st2(sv.size());
+      for (size_t i = 0; i < sv.size(); i++) st2[i] = make_int2(sv[i].slot, sv[i].J);
+      b.n_solve = (int)st2.size();
+      CUDA_TRY(h, upload(&b.d_solve_tasks, st2));
       CUDA_TRY(h, upload(&b.d_potrf2_tasks, pt));
       CUDA_TRY(h, upload(&b.d_flag_off, foff));
       maxFlags = std::max(maxFlags, fo);
@@ -666,8 +678,10 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
       h->tm.launches++;
       cudaEventRecord(ev[3], st);
       if (!with_grad) {       // fit only: alpha by block back-substitution (the forward solve was fused above)
-        SolveArgs sa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, scal, 1};
-        launch_solve(sa, nsl, st);
+        CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
+        SolveArgs sa{meta, h->d_F.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_flags.p, b.d_flag_off, b.d_solve_tasks, b.n_solve,
+                     h->d_counter.p + 3, h->d_counter.p + 8};
+        launch_solve(sa, std::max(1, std::min(solve_max_ctas(sms), b.n_solve)), st);
         h->tm.launches++;
       }
       cudaEventRecord(ev[4], st);
@@ -740,8 +754,11 @@ static int32_t refine_alpha(dsmgp_handle* h) {
   Batch& b = h->batches[0];
   const int nsl = b.s1 - b.s0;
   if (nsl > 0) {
-    SolveArgs sa{h->d_meta.p, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, h->d_alpha.p, h->d_scal.p, 1};
-    launch_solve(sa, nsl, h->stream);
+    CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p + 3, 0, sizeof(int), h->stream));
+    SolveArgs sa{h->d_meta.p, h->d_F.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_flags.p, b.d_flag_off, b.d_solve_tasks, b.n_solve,
+                 h->d_counter.p + 3, h->d_counter.p + 8};
+    launch_solve(sa, std::max(1, std::min(solve_max_ctas(num_sms(h->device)), b.n_solve)), h->stream);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
   }

@@ -13,13 +13,12 @@ constexpr int GDC = 16;      // dimensions staged per pass
 struct SolveArgs {
   const LeafMeta* meta;
   const double* F;
-  const double* W;
   const double* WT;
-  const double* y;
-  double* z;
+  const double* z;
   double* alpha;
-  LeafScal* scal;
-  int skip_forward;      // 1: z (and z'z) already produced by the fused forward solve of potrf2
+  int* flags; const int64_t* flag_off;    // flag J of an expert: alpha_J stored
+  const int2* tasks; int ntasks;          // (slot, J), descending J inside an expert
+  int* counter; int* gerr;
 };
 
 struct GramArgs {
@@ -117,7 +116,8 @@ struct PredArgs {
 };
 
 // ---- launchers (defined next to their kernels) ------------------------------------------------
-void launch_solve(const SolveArgs& a, int nleaves, cudaStream_t st);
+void launch_solve(const SolveArgs& a, int nctas, cudaStream_t st);
+int solve_max_ctas(int sms);
 void launch_lauum3(const LauumArgs& a, int nctas, cudaStream_t st);
 void launch_rows(const RowsArgs& a, int nleaves, cudaStream_t st);
 void launch_predict3(const PredArgs& a, int nctas, cudaStream_t st);
