@@ -117,6 +117,16 @@ class Handle:
                                                nat.p_d(gr), nat.p_d(rl)))
         return ll, gr, rl
 
+    def train(self, theta, optimiser: int, eta: float, beta1: float, beta2: float, state_by_identity: bool,
+              iterations: int, lam: float, earlystop: int):
+        """dsmgp_train: the whole train! loop inside the library -> (final theta, LML trace)."""
+        th = np.array(theta, dtype=np.float64)
+        ell = np.zeros(iterations)
+        nd = C.c_int64(0)
+        self._ck(self._lib.dsmgp_train(self._h, optimiser, eta, beta1, beta2, 1 if state_by_identity else 0, iterations,
+                                       lam, earlystop, nat.p_d(th), nat.p_d(ell), C.byref(nd)))
+        return th, ell[:nd.value]
+
     def eval_local_dev(self, theta=None) -> int:
         th = None if theta is None else nat.f64(theta)
         ptr = C.c_void_p()

@@ -2,6 +2,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <limits>
 #include <numeric>
 #include <mutex>
 #include <string>
@@ -918,6 +919,56 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
     tree_grad(h, scale.data(), grads + g * H);                               // finetuning.jl:53
   }
   h->rows_complete = true;
+  return DSMGP_OK;
+}
+
+// train!(spn, D, gpmap, optim; iterations, lambda, earlystop) optimisers.jl:40-83 as ONE call: the loop stays inside the
+// library (no per-iteration host round trip through the binding).  Optimisers = Flux.Optimise Descent / ADAM / RMSProp;
+// `state_by_identity` reproduces the reference's `hyp += grad` rebinding, which gives apply! a fresh state every iteration
+// (SURVEY App. B Q9).  The update is gradient ASCENT.  Returns the number of iterations executed in *n_done.
+extern "C" int32_t dsmgp_train(dsmgp_handle* h, int32_t optimiser, double eta, double beta1, double beta2,
+                               int32_t state_by_identity, int64_t iterations, double lambda, int64_t earlystop,
+                               double* theta, double* ell, int64_t* n_done) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!theta || !ell || iterations <= 0 || optimiser < 0 || optimiser > 2) { h->err = "train: bad argument"; return DSMGP_ERR_ARG; }
+  if (h->opts.world != 1) { h->err = "train: single-process handles only"; return DSMGP_ERR_STATE; }
+  const int64_t H = h->H;
+  std::vector<double> hyp(theta, theta + H), grad(H), mt(H, 0.0), vt(H, 0.0), acc(H, 0.0);
+  double bp1 = beta1, bp2 = beta2;
+  int64_t c = 0, it = 0;
+  if (n_done) *n_done = 0;
+  for (it = 0; it < iterations; it++) {
+    double lml = 0.0;
+    int32_t rc = dsmgp_eval(h, hyp.data(), H, nullptr, &lml, grad.data(), nullptr);     // :43-49, 68-77
+    if (rc) return rc;
+    ell[it] = lml;
+    double delta = std::numeric_limits<double>::infinity();
+    if (it >= 10) { double mean = 0.0; for (int64_t k = it - 9; k < it; k++) mean += ell[k]; delta = std::fabs(ell[it] - mean / 9.0); }   // :53
+    c = (delta < lambda) ? c + 1 : 0;                                                    // :57-61
+    if (c >= earlystop) { it++; break; }                                                 // :63-66 (returns before the update)
+    if (state_by_identity) { std::fill(mt.begin(), mt.end(), 0.0); std::fill(vt.begin(), vt.end(), 0.0); std::fill(acc.begin(), acc.end(), 0.0); bp1 = beta1; bp2 = beta2; }
+    for (int64_t k = 0; k < H; k++) {                                                    // Flux.Optimise.apply!  :78
+      double d = grad[k];
+      if (optimiser == 0) d *= eta;
+      else if (optimiser == 1) {
+        mt[k] = beta1 * mt[k] + (1.0 - beta1) * d;
+        vt[k] = beta2 * vt[k] + (1.0 - beta2) * d * d;
+        d = mt[k] / (1.0 - bp1) / (std::sqrt(vt[k] / (1.0 - bp2)) + 1e-8) * eta;
+      } else {
+        acc[k] = beta1 * acc[k] + (1.0 - beta1) * d * d;                                 // RMSProp: beta1 = rho
+        d = d * (eta / (std::sqrt(acc[k]) + 1e-8));
+      }
+      hyp[k] = hyp[k] + d;                                                               // :79
+    }
+    if (optimiser == 1) { bp1 *= beta1; bp2 *= beta2; }
+  }
+  std::copy(hyp.begin(), hyp.end(), theta);
+  if (n_done) *n_done = it;
+  if (it >= iterations) {                                                                // :82-83 final setparams! + fit!
+    int32_t rc = dsmgp_set_params(h, hyp.data(), H);
+    if (rc) return rc;
+    return dsmgp_fit(h, nullptr, nullptr);
+  }
   return DSMGP_OK;
 }
 

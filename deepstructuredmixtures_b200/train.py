@@ -93,6 +93,13 @@ def train_(model, optim=None, *, iterations: int = 10_000, lam: float = 0.05, ra
     rng = np.random.default_rng() if rng is None else (np.random.default_rng(rng) if isinstance(rng, int) else rng)
     n = model.nparams
     hyp = rng.standard_normal(n) if randinit else _current_hyp(model)      # :18
+    if callback is None and type(optim) in (Descent, ADAM, RMSProp):
+        # the loop itself runs inside the library (dsmgp_train): no per-iteration round trip
+        kind = {Descent: 0, ADAM: 1, RMSProp: 2}[type(optim)]
+        b1, b2 = (optim.beta if kind == 1 else ((optim.rho, 0.0) if kind == 2 else (0.0, 0.0)))
+        hyp, ell = model.handle.train(hyp, kind, optim.eta, b1, b2, optim.state_by_identity, iterations, lam, earlystop)
+        model._mirror_params(hyp)
+        return model, ell
     ell = np.zeros(iterations)
     c = 0
     delta = np.inf

@@ -146,6 +146,16 @@ int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t* anchors, 
                             const double* overlap /* L x L col-major */, double* leaf_lml /* G */,
                             double* grads /* G x H row-major */, double* root_lml /* G or NULL */);
 
+/* train!(spn, D, gpmap, optim; iterations, lambda, earlystop) optimisers.jl:40-83 in one call: every
+ * iteration is a dsmgp_eval followed by the Flux.Optimise step (optimiser 0 Descent(eta), 1 ADAM(eta, (beta1, beta2)),
+ * 2 RMSProp(eta, rho = beta1); epsilon 1e-8) and `hyp += grad` (gradient ASCENT).  state_by_identity = 1 reproduces the
+ * reference, whose rebinding of `hyp` hands apply! a fresh optimiser state every iteration.
+ * theta[H]: start values in, final values out; ell[iterations]: LML trace; *n_done: iterations executed (early stopping:
+ * |ell_t - mean(ell_{t-9..t-1})| < lambda for `earlystop` consecutive iterations returns BEFORE the update, as :63-66).
+ * When the loop runs to the end the handle is left fitted at the final theta (:82-83). */
+int32_t dsmgp_train(dsmgp_handle* h, int32_t optimiser, double eta, double beta1, double beta2, int32_t state_by_identity,
+                    int64_t iterations, double lambda, int64_t earlystop, double* theta, double* ell, int64_t* n_done);
+
 /* Per-leaf rows of the last eval: rows[l*(1+Hmax) + 0] = mll(gp_l), [1..] = nabla-mll(gp_l)
  * (gaussianprocess.jl:185-217).  Hmax = max nparams over kernels.  Also the multi-GPU exchange unit:
  * a rank fills only its own leaves, rows of other ranks are 0, so a SUM all-reduce assembles them. */

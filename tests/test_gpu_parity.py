@@ -471,3 +471,32 @@ def test_full_size_cfg2_properties():
     s = math.exp(th[1])
     assert np.all(np.abs(grads[True][:2] - s * grads[False][:2]) <= 1e-10 * np.abs(grads[True][:2]))
     assert abs(grads[True][2] - grads[False][2]) <= 1e-12 * abs(grads[False][2])
+
+
+@pytest.mark.parametrize("opt", ["adam", "rmsprop", "descent"])
+def test_train_loop_in_library_matches_host_loop(opt):
+    """dsmgp_train (optimisers.jl:40-83 inside the library) == the host loop that calls dsmgp_eval per iteration
+    (forced here by passing a callback), for the Flux optimisers incl. the identity-keyed state quirk (App. B Q9)."""
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(600, 2, 41)
+
+    def make():
+        return dsm.buildDSMGP(x, y, 2, 2, M=60, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, rng=41)
+
+    def optimiser(identity):
+        return {"adam": dsm.ADAM(0.05, state_by_identity=identity), "rmsprop": dsm.RMSProp(0.05, state_by_identity=identity),
+                "descent": dsm.Descent(1e-4, state_by_identity=identity)}[opt]
+
+    for identity in (True, False):
+        m1, m2 = make(), make()
+        _, ell_lib = dsm.train_(m1, optimiser(identity), iterations=14, randinit=False, lam=1e-12)
+        _, ell_host = dsm.train_(m2, optimiser(identity), iterations=14, randinit=False, lam=1e-12, callback=lambda *a: None)
+        assert ell_lib.size == ell_host.size == 14
+        assert np.max(np.abs(ell_lib - ell_host)) <= 1e-10 * np.max(np.abs(ell_host)), (opt, identity)
+        th1 = m1.handle.get_leaf_params(0); th2 = m2.handle.get_leaf_params(0)
+        assert np.max(np.abs(th1 - th2)) <= 1e-10
+    # early stopping returns the trace up to the stopping iteration in both implementations
+    m1, m2 = make(), make()
+    _, e1 = dsm.train_(m1, dsm.Descent(1e-9), iterations=40, randinit=False, lam=1e3, earlystop=3)
+    _, e2 = dsm.train_(m2, dsm.Descent(1e-9), iterations=40, randinit=False, lam=1e3, earlystop=3, callback=lambda *a: None)
+    assert e1.size == e2.size == 13
