@@ -45,8 +45,8 @@ kerneltype(::IsoSE) = Int32(0); kerneltype(::ArdSE) = Int32(1)
 kerneltype(::IsoLinear) = Int32(2); kerneltype(::ArdLinear) = Int32(3)
 nkparams(k::KernelFunction) = Int32(length(k.logℓ) + 2)
 
-"Flatten the region graph (post order) and create the device handle.  x is the GLOBAL N×D input matrix."
-function create(spn, x::Matrix{Float64}; as_written=true, keep_factors=true)
+"Flatten the region graph (post order: children before parents) into the arrays of `dsmgp_tree` + the leaf tables."
+function flatten(spn)
     nodes = Any[]; index = Dict{Symbol,Int}()
     function rec(n)
         n isa GPNode || foreach(rec, children(n))
@@ -74,9 +74,32 @@ function create(spn, x::Matrix{Float64}; as_written=true, keep_factors=true)
     isempty(child_idx) && push!(child_idx, 0); isempty(split_val) && push!(split_val, 0.0)
     leaf_ptr = vcat(0, cumsum([l.nobs for l in leaves]))
     leaf_obs = reduce(vcat, [Int64.(l.obs) for l in leaves])
+    leaf_kid = Int32[l.kernelid - 1 for l in leaves]
+    return (; nodes, index, leaves, nn, node_type, child_ptr, child_idx, leaf_of_node, split_dim, split_ptr, split_val,
+            leaf_ptr, leaf_obs, leaf_kid, root = index[spn.id])
+end
+
+"getOverlap(spn, D, gpmap) fit.jl:12-39 on the device: the L×L overlap matrix (treeStructure.jl:428-431)."
+function overlap(spn, N::Integer)
+    f = flatten(spn); L = length(f.leaves); D = zeros(L, L)
+    (; node_type, child_ptr, child_idx, leaf_of_node, split_dim, split_ptr, split_val) = f
+    GC.@preserve node_type child_ptr child_idx leaf_of_node split_dim split_ptr split_val begin
+        tree = Tree(f.nn, pointer(node_type), pointer(child_ptr), pointer(child_idx), pointer(leaf_of_node),
+                    pointer(split_dim), pointer(split_ptr), pointer(split_val), f.root)
+        check(ccall((:dsmgp_overlap, LIB), Int32,
+                    (Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}, Ref{Tree}, Ptr{Float64}),
+                    N, L, f.leaf_ptr, f.leaf_obs, f.leaf_kid, tree, D))
+    end
+    return D
+end
+
+"Create the device handle.  x is the GLOBAL N×D input matrix."
+function create(spn, x::Matrix{Float64}; as_written=true, keep_factors=true)
+    f = flatten(spn)
+    (; index, leaves, nn, node_type, child_ptr, child_idx, leaf_of_node, split_dim, split_ptr, split_val,
+       leaf_ptr, leaf_obs, leaf_kid) = f
     y_centered = reduce(vcat, [l.dist.y for l in leaves])              # already mean-subtracted (gaussianprocess.jl:72-74)
     leaf_mean = [l.dist.mean.m for l in leaves]
-    leaf_kid = Int32[l.kernelid - 1 for l in leaves]
     nk = maximum(l.kernelid for l in leaves)
     kerns = [first(l for l in leaves if l.kernelid == k).dist.kernel for k in 1:nk]
     kd = [KernelDesc(kerneltype(k), nkparams(k)) for k in kerns]
@@ -148,6 +171,20 @@ function update!(h::Handle, spn)
         off += k
     end
     return z[]
+end
+
+"""
+train!(spn, D, gpmap, optim; iterations, λ, earlystop) optimisers.jl:40-83 as one call.  `optimiser`: 0 Descent(η), 1 ADAM(η, (β1, β2)),
+2 RMSProp(η, ρ = β1); the reference's `hyp += grad` rebinding gives Flux a fresh state every iteration (state_by_identity).
+Returns (final hyp, ℓ trace).
+"""
+function train!(h::Handle, hyp::Vector{Float64}; optimiser=1, η=0.001, β1=0.9, β2=0.999, state_by_identity=true,
+                iterations=10_000, λ=0.05, earlystop=10)
+    ℓ = zeros(iterations); nd = Ref{Int64}(0)
+    check(ccall((:dsmgp_train, LIB), Int32,
+                (Ptr{Cvoid}, Int32, Float64, Float64, Float64, Int32, Int64, Float64, Int64, Ptr{Float64}, Ptr{Float64}, Ref{Int64}),
+                h.ptr, optimiser, η, β1, β2, state_by_identity ? 1 : 0, iterations, λ, earlystop, hyp, ℓ, nd), h.ptr)
+    return hyp, ℓ[1:nd[]]
 end
 
 """
