@@ -365,6 +365,10 @@ def test_streaming_batches_match_resident():
     mb = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, keep_factors=False, arena_bytes=24 << 20)
     lml_b, g_b = mb.handle.eval(th)
     assert lml_a == lml_b and np.array_equal(g_a, g_b)
+    # the fit-only path (potrf + back-substitution, no inverse) streams the same way and gives the same LML table
+    info, _ = mb.handle.fit()
+    assert np.all(info == 0)
+    assert mb.handle.lml()[mb.handle.tree.root] == lml_a
     with pytest.raises(dsm.DsmgpError):
         dsm.predict(mb, x[:10])
     mb.close()
