@@ -379,6 +379,11 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     const char* ord_env = getenv("DSMGP_ORDER");           // development A/B: 0 = end together, 1 = stretch
     const bool stretch = ord_env ? (ord_env[0] == '1') : (nb_s * 4 < sms_plan);
     const bool start_together = ord_env && ord_env[0] == '2';     // experiment: no shift at all
+    // position of the next diagonal tile inside a level: right behind the first panel tile (1: shortest critical path) or
+    // behind all panel tiles of the level (3: in a large batch the first panel tile has then finished and the diagonal
+    // task does not sit on an SM waiting for it)
+    const char* dg_env = getenv("DSMGP_DIAG_LATE");
+    const int diag_grp = (dg_env ? dg_env[0] == '1' : false) ? 3 : 1;
     {   // engine v2 tile tasks: topological order with look-ahead
       struct TK { int s, grp, slot, I, J; };
       std::vector<TK> tk;
@@ -395,7 +400,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         tk.push_back({level(0) - 1, 1, sl, 0, 0});
         for (int J = 0; J + 1 < m.nb; J++) {
           tk.push_back({level(J), 0, sl, J + 1, J});
-          tk.push_back({level(J), 1, sl, J + 1, J + 1});
+          tk.push_back({level(J), diag_grp, sl, J + 1, J + 1});
           for (int I = J + 2; I < m.nb; I++) tk.push_back({level(J), 2, sl, I, J});
         }
       }
