@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 # FP64 roofs measured on this pool's B200 with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json)
 FP64_DGEMM_TFLOPS = 35.9     # cuBLAS DGEMM 8192^3 (burst == sustained: FP64 is not power capped)
 FP64_DMMA_TFLOPS = 37.2      # DMMA.8x8x4 issue roof
-NCU_TRAFFIC_GB = {("cfg3", 1, "potrf2_kernel"): 51.78, ("cfg3", 1, "trtri3_kernel"): 78.65}   # profiles/ncu_full_*_r01g.txt
+NCU_TRAFFIC_GB = {("cfg3", 1, "potrf2_kernel"): 51.87, ("cfg3", 1, "trtri3_kernel"): 78.64}   # profiles/ncu_full_*_r01h.txt
 
 WORKLOADS = {
     # name: (N, D, kernel, V, K, M, depth, eps, seed)   SURVEY §8(d)
