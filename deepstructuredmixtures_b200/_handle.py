@@ -168,6 +168,23 @@ class Handle:
         self._ck(self._lib.dsmgp_predict(self._h, nat.p_d(xt), T, mode, nat.p_d(mu), nat.p_d(var)))
         return mu, var
 
+    def predict_local(self, xtest, mode: int = nat.PREDICT_DSMGP) -> np.ndarray:
+        """dsmgp_predict_local: [mu | var] of the local experts in (leaf, routing order) layout, 0 elsewhere."""
+        xt = nat.colmajor(np.asarray(xtest, dtype=np.float64).reshape(len(xtest), -1))
+        tot = C.c_int64(0)
+        self._ck(self._lib.dsmgp_predict_local(self._h, nat.p_d(xt), xt.shape[0], mode, None, C.byref(tot)))
+        buf = np.zeros(2 * tot.value)
+        self._ck(self._lib.dsmgp_predict_local(self._h, nat.p_d(xt), xt.shape[0], mode, nat.p_d(buf), C.byref(tot)))
+        return buf
+
+    def predict_finish(self, xtest, buf: np.ndarray, mode: int = nat.PREDICT_DSMGP):
+        xt = nat.colmajor(np.asarray(xtest, dtype=np.float64).reshape(len(xtest), -1))
+        T = xt.shape[0]
+        mu = np.zeros(T); var = np.zeros(T)
+        b = nat.f64(buf)
+        self._ck(self._lib.dsmgp_predict_finish(self._h, nat.p_d(xt), T, mode, nat.p_d(b), nat.p_d(mu), nat.p_d(var)))
+        return mu, var
+
     def leaf_predict(self, leaf: int, xtest):
         xt = nat.colmajor(np.asarray(xtest, dtype=np.float64).reshape(len(xtest), -1))
         T = xt.shape[0]

@@ -62,7 +62,7 @@ EXPORTS = [
     "dsmgp_set_leaf_params", "dsmgp_get_leaf_params", "dsmgp_nparams", "dsmgp_n_leaves", "dsmgp_n_nodes",
     "dsmgp_leaf_size", "dsmgp_fit", "dsmgp_lml", "dsmgp_grad", "dsmgp_eval", "dsmgp_row_width",
     "dsmgp_finetune_eval", "dsmgp_train", "dsmgp_eval_local_dev", "dsmgp_eval_finish_dev", "dsmgp_leaf_rows", "dsmgp_leaf_owner",
-    "dsmgp_update_weights", "dsmgp_predict", "dsmgp_leaf_predict", "dsmgp_leaf_alpha", "dsmgp_leaf_factor",
+    "dsmgp_update_weights", "dsmgp_predict", "dsmgp_predict_local", "dsmgp_predict_finish", "dsmgp_leaf_predict", "dsmgp_leaf_alpha", "dsmgp_leaf_factor",
     "dsmgp_leaf_info", "dsmgp_kernelmatrix", "dsmgp_overlap", "dsmgp_release_cache", "dsmgp_chol_continue", "dsmgp_chol_delete_rows", "dsmgp_potrf",
     "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling",
 ]
@@ -97,6 +97,8 @@ def lib() -> C.CDLL:
         "dsmgp_grad": (I32, [P, pd, pd]),
         "dsmgp_eval": (I32, [P, pd, I64, pd, pd, pd, pd]),
         "dsmgp_finetune_eval": (I32, [P, I64, pi64, pd, pd, pd, pd, pd]),
+        "dsmgp_predict_local": (I32, [P, pd, I64, I32, pd, pi64]),
+        "dsmgp_predict_finish": (I32, [P, pd, I64, I32, pd, pd, pd]),
         "dsmgp_train": (I32, [P, I32, D, D, D, I32, I64, D, I64, pd, pd, pi64]),
         "dsmgp_overlap": (I32, [I64, I64, pi64, pi64, pi32, C.POINTER(Tree), pd]),
         "dsmgp_release_cache": (None, []),

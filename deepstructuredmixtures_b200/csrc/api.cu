@@ -1195,7 +1195,8 @@ struct Mixer {
 
 // Device prediction of every leaf on its routed points.  pts[l] = test rows routed to leaf l.
 static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, const std::vector<std::vector<int64_t>>& pts,
-                              std::vector<std::vector<double>>& mu, std::vector<std::vector<double>>& var) {
+                              std::vector<std::vector<double>>& mu, std::vector<std::vector<double>>& var,
+                              bool local_only = false) {
   if (!h->fitted) { h->err = "predict: call fit first"; return DSMGP_ERR_STATE; }
   if (!h->opts.keep_factors || h->batches.size() != 1) { h->err = "predict needs keep_factors=1"; return DSMGP_ERR_STATE; }
   { int32_t rr = refine_alpha(h); if (rr) return rr; }
@@ -1206,7 +1207,11 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   for (int64_t l = 0; l < L; l++) {
     if (pts[l].empty()) continue;
     const int slot = h->leaf_slot[l];
-    if (slot < 0) { h->err = "predict: leaf owned by another rank"; return DSMGP_ERR_STATE; }
+    if (slot < 0) {
+      if (local_only) continue;               // predicted by its owner (dsmgp_predict_local / _finish)
+      h->err = "predict: leaf owned by another rank (use dsmgp_predict_local + all-reduce + dsmgp_predict_finish)";
+      return DSMGP_ERR_STATE;
+    }
     PredLeaf p; p.slot = slot; p.T = (int32_t)pts[l].size(); p.Tp = (p.T + BLK - 1) / BLK * BLK; p.pad_ = 0;
     p.xtoff = xto; xto += (int64_t)p.Tp * D;
     p.vtoff = vto; vto += (int64_t)(p.Tp / BLK) * h->meta[slot].nkc * TILE_D;
@@ -1311,9 +1316,9 @@ extern "C" int32_t dsmgp_leaf_predict(dsmgp_handle* h, int64_t leaf, const doubl
   return DSMGP_OK;
 }
 
-extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
-  if (!h) return DSMGP_ERR_ARG;
-  if (!xtest || T <= 0 || !mu || !var || mode < 0 || mode > 3) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
+// argument checks + routing shared by the predict entry points
+static int32_t predict_route(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, std::vector<std::vector<int64_t>>& pts) {
+  if (!xtest || T <= 0 || mode < 0 || mode > 3) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
   for (int64_t i = 0; i < T * h->D; i++) if (!std::isfinite(xtest[i])) { h->err = "predict: non-finite input"; return DSMGP_ERR_ARG; }
   cudaSetDevice(h->device);
   const HostTree& t = h->tree;
@@ -1330,9 +1335,77 @@ extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T
   Router r(t, xtest, T, h->L);
   r.route(t.root, all, poe);
   if (r.bad) { h->err = "predict: a test point lies outside every split interval"; return DSMGP_ERR_ARG; }
-  std::vector<std::vector<double>> lmu, lvar;
-  int32_t rc = predict_leaves(h, xtest, T, r.pts, lmu, lvar);
+  pts.swap(r.pts);
+  return DSMGP_OK;
+}
+
+static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode,
+                           const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
+                           double* mu, double* var);
+
+extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!mu || !var) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<int64_t>> pts;
+  int32_t rc = predict_route(h, xtest, T, mode, pts);
   if (rc) return rc;
+  std::vector<std::vector<double>> lmu, lvar;
+  if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar))) return rc;
+  return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
+}
+
+// Leaf-sharded prediction (one process per GPU): every rank predicts its own experts on the points routed to them and
+// writes them into a buffer in (leaf, routing order) layout -- entries of other ranks' experts stay 0, so a SUM all-reduce
+// assembles the buffer -- then every rank mixes (common.jl:134-307) redundantly, like the tree passes of an evaluation.
+extern "C" int32_t dsmgp_predict_local(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* buf, int64_t* total) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!total) { h->err = "predict_local: bad argument"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<int64_t>> pts;
+  int32_t rc = predict_route(h, xtest, T, mode, pts);
+  if (rc) return rc;
+  int64_t tot = 0;
+  for (auto& v : pts) tot += (int64_t)v.size();
+  *total = tot;
+  if (!buf) return DSMGP_OK;                   // size query
+  std::vector<std::vector<double>> lmu, lvar;
+  if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar, true))) return rc;
+  std::fill(buf, buf + 2 * tot, 0.0);
+  int64_t off = 0;
+  for (int64_t l = 0; l < h->L; l++) {
+    if (!lmu.empty() && !lmu[l].empty()) {
+      std::copy(lmu[l].begin(), lmu[l].end(), buf + off);
+      std::copy(lvar[l].begin(), lvar[l].end(), buf + tot + off);
+    }
+    off += (int64_t)pts[l].size();
+  }
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_predict_finish(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, const double* buf,
+                                        double* mu, double* var) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!buf || !mu || !var) { h->err = "predict_finish: bad argument"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<int64_t>> pts;
+  int32_t rc = predict_route(h, xtest, T, mode, pts);
+  if (rc) return rc;
+  int64_t tot = 0;
+  for (auto& v : pts) tot += (int64_t)v.size();
+  std::vector<std::vector<double>> lmu(h->L), lvar(h->L);
+  int64_t off = 0;
+  for (int64_t l = 0; l < h->L; l++) {
+    lmu[l].assign(buf + off, buf + off + pts[l].size());
+    lvar[l].assign(buf + tot + off, buf + tot + off + pts[l].size());
+    off += (int64_t)pts[l].size();
+  }
+  return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
+}
+
+static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode,
+                           const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
+                           double* mu, double* var) {
+  const HostTree& t = h->tree;
+  std::vector<int64_t> all(T);
+  std::iota(all.begin(), all.end(), 0);
   Mixer mx(t, xtest, T, lmu, lvar, h->sum_logw);
   if (mode == DSMGP_PREDICT_DSMGP) {
     // predict(node) common.jl:175-179 (leaf), :243-254 (split root), :294-302 (sum root)

@@ -64,3 +64,28 @@ def evaluate_distributed(model, theta, leaf_scale=None) -> Tuple[float, np.ndarr
     allreduce_rows_(rows)
     torch.cuda.synchronize()
     return H.eval_finish_dev(leaf_scale)
+
+
+def update_distributed(model) -> float:
+    """update!(model) on a sharded model: the row table is complete on every rank after `evaluate_distributed`."""
+    from .model import update_
+    return update_(model)
+
+
+def predict_distributed(model, xtest) -> Tuple[np.ndarray, np.ndarray]:
+    """predict(model, x) of a model whose experts are sharded over the ranks of the default process group: every rank
+    predicts its own experts (`dsmgp_predict_local`), ONE SUM all-reduce assembles the per-(expert, point) table, every
+    rank mixes (`dsmgp_predict_finish`).  Call after `evaluate_distributed` (or `fit_`) and `update_distributed`."""
+    import torch
+    import torch.distributed as dist
+    H = model.handle
+    buf = H.predict_local(xtest, model.predict_mode)
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.from_numpy(buf)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            buf = t.cpu().numpy()
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return H.predict_finish(xtest, buf, model.predict_mode)

@@ -176,6 +176,14 @@ enum { DSMGP_PREDICT_DSMGP = 0, DSMGP_PREDICT_POE = 1, DSMGP_PREDICT_GPOE = 2, D
  * the DSMGP mode, like the reference). */
 int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var);
 
+/* Leaf-sharded prediction (rank/world in dsmgp_opts, one process per GPU).  dsmgp_predict_local routes the test points,
+ * predicts the LOCAL experts and writes mu into buf[0 .. total) and var into buf[total .. 2 total) in (leaf, routing order)
+ * layout, 0 for experts of other ranks (buf == NULL: only *total is returned).  After a SUM all-reduce of buf over the
+ * ranks, dsmgp_predict_finish mixes (common.jl:134-307) on every rank.  Needs a preceding fit/eval (+ update_weights). */
+int32_t dsmgp_predict_local(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* buf, int64_t* total);
+int32_t dsmgp_predict_finish(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, const double* buf,
+                             double* mu, double* var);
+
 /* prediction(gp, xtest) of ONE leaf: mu[T] and diag(Sigma)[T] (gaussianprocess.jl:110-137) */
 int32_t dsmgp_leaf_predict(dsmgp_handle* h, int64_t leaf, const double* xtest, int64_t T, double* mu, double* var);
 

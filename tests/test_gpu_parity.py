@@ -504,3 +504,46 @@ def test_train_loop_in_library_matches_host_loop(opt):
     _, e1 = dsm.train_(m1, dsm.Descent(1e-9), iterations=40, randinit=False, lam=1e3, earlystop=3)
     _, e2 = dsm.train_(m2, dsm.Descent(1e-9), iterations=40, randinit=False, lam=1e3, earlystop=3, callback=lambda *a: None)
     assert e1.size == e2.size == 13
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_predict_matches_single_handle(world):
+    """Leaf-sharded prediction: `world` handles (rank r of world, here all on one GPU) each predict their own experts;
+    the SUM of their buffers (what the all-reduce produces) mixed by any rank equals the single-handle prediction."""
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import model as mdl, structure as st
+    x, y = synth(3000, 4, 51)
+    kern = dsm.ArdSE(np.zeros(4), 0.0)
+    cfg = st.DSMGPConfig(None, kern, -1.0, 150, 3, 3, 2, 0.5, True)
+    th = np.array([0.1, -0.2, 0.0, 0.2, 0.1, -1.0])
+    xt = np.random.default_rng(3).random((900, 4))
+    root = st.buildTree(x, y, cfg, np.random.default_rng(51))
+    single = mdl.DSMGP(root, x, y, [kern.copy()], -1.0)
+    lml0, g0 = single.handle.eval(th); dsm.update_(single)
+    mu0, var0 = dsm.predict(single, xt)
+    ranks = [mdl.DSMGP(root, x, y, [kern.copy()], -1.0, rank=r, world=world) for r in range(world)]
+    # evaluation: every rank fills its rows on the device; their SUM (the all-reduce) goes back into every rank's table
+    import torch
+    from deepstructuredmixtures_b200.distributed import _DevPtr
+    n = single.handle.L * single.handle.row_width
+    tens = [torch.as_tensor(_DevPtr(m.handle.eval_local_dev(th), n), device="cuda:0") for m in ranks]
+    tot = torch.stack(tens).sum(0)
+    for t in tens:
+        t.copy_(tot)
+    torch.cuda.synchronize()
+    bufs = []
+    for m in ranks:
+        lml, g = m.handle.eval_finish_dev()
+        assert lml == lml0 and np.array_equal(g, g0)
+        dsm.update_(m)
+        bufs.append(m.handle.predict_local(xt))
+    total = np.sum(bufs, axis=0)
+    nz = [np.count_nonzero(b) for b in bufs]
+    assert all(n > 0 for n in nz) and sum(nz) == np.count_nonzero(total)       # disjoint supports
+    for m in ranks:
+        mu, var = m.handle.predict_finish(xt, total)
+        assert np.allclose(mu, mu0, rtol=1e-12, atol=1e-12 * np.max(np.abs(mu0))) and np.allclose(var, var0, rtol=1e-12, atol=0)
+        with pytest.raises(dsm.DsmgpError):
+            dsm.predict(m, xt)                          # the single-handle call refuses experts of other ranks
+    for m in ranks + [single]:
+        m.close()
