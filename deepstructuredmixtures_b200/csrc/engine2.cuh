@@ -35,6 +35,26 @@ __device__ __forceinline__ void acc2_zero(Acc2& acc) {
     for (int n = 0; n < 16; n++) { acc[m][n][0] = 0.0; acc[m][n][1] = 0.0; }
 }
 
+// One 16-k chunk of the contraction; N16 = number of live 16-column groups (cols < 16*N16).
+template <int N16>
+__device__ __forceinline__ void mma_chunk16(Acc2& acc, const double* __restrict__ sA, const double* __restrict__ sB, int r0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const double* pa = sA + t * LDS + r0 + 2 * g;
+  const double* pb = sB + t * LDS + 2 * g;
+#pragma unroll
+  for (int ks = 0; ks < KC / 4; ks++) {
+    const double2 a = *reinterpret_cast<const double2*>(pa + ks * 4 * LDS);
+#pragma unroll
+    for (int m2 = 0; m2 < N16; m2++) {
+      const double2 b = *reinterpret_cast<const double2*>(pb + ks * 4 * LDS + 16 * m2);
+      dmma884(acc[0][2 * m2][0], acc[0][2 * m2][1], a.x, b.x);
+      dmma884(acc[1][2 * m2][0], acc[1][2 * m2][1], a.y, b.x);
+      dmma884(acc[0][2 * m2 + 1][0], acc[0][2 * m2 + 1][1], a.x, b.y);
+      dmma884(acc[1][2 * m2 + 1][0], acc[1][2 * m2 + 1][1], a.y, b.y);
+    }
+  }
+}
+
 // One 16-k chunk of the contraction; NG = number of 4-tile column groups that are live (cols < 32*NG).
 template <int NG>
 __device__ __forceinline__ void mma_chunk(Acc2& acc, const double* __restrict__ sA, const double* __restrict__ sB, int r0) {

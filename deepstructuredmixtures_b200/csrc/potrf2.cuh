@@ -181,16 +181,20 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     // ---------------- diagonal tile ----------------
     double gemv = 0.0;                                  // row r0 + (lane & 15), k-half lane >> 4
     {
-      const int ng = min(wj / 32, slab / 2 + 1);        // lower triangle only: columns <= 16*slab + 15
+      const int ng = min(wj / 16, slab + 1);            // lower triangle only: 16-column groups 0 .. slab
       for (int c = 0; c < n_main; c++) {
         st = p.wait();
         if (active) {
           const double* sA = p.A(st);
           switch (ng) {
-            case 1: mma_chunk<1>(acc, sA, sA, r0); break;
-            case 2: mma_chunk<2>(acc, sA, sA, r0); break;
-            case 3: mma_chunk<3>(acc, sA, sA, r0); break;
-            default: mma_chunk<4>(acc, sA, sA, r0); break;
+            case 1: mma_chunk16<1>(acc, sA, sA, r0); break;
+            case 2: mma_chunk16<2>(acc, sA, sA, r0); break;
+            case 3: mma_chunk16<3>(acc, sA, sA, r0); break;
+            case 4: mma_chunk16<4>(acc, sA, sA, r0); break;
+            case 5: mma_chunk16<5>(acc, sA, sA, r0); break;
+            case 6: mma_chunk16<6>(acc, sA, sA, r0); break;
+            case 7: mma_chunk16<7>(acc, sA, sA, r0); break;
+            default: mma_chunk16<8>(acc, sA, sA, r0); break;
           }
           const double* zs = p.B(st);
           const double* ar = sA + r0 + (lane & 15) + (lane >> 4) * 8 * LDS;
