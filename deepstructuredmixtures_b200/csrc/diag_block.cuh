@@ -32,12 +32,13 @@ __device__ __forceinline__ double diag_W(const double* S, const double* DI, int 
 // complete unrolling that keeps a[] in registers (register arrays cannot be indexed dynamically).
 template <int J>
 struct PotrfStep {
-  __device__ static __forceinline__ void run(double (&a)[PW], int r, int& info) {
-    PotrfStep<J - 1>::run(a, r, info);
+  __device__ static __forceinline__ void run(double (&a)[PW], int r, int& info, double& myinv) {
+    PotrfStep<J - 1>::run(a, r, info, myinv);
     const double d = __shfl_sync(0xffffffffu, a[J], J);
     if (!(d > 0.0) && info == 0) info = J + 1;
     const double inv = rsqrt(d);                 // one long-latency op on the pivot chain instead of sqrt + divide
     const double piv = d * inv;
+    if (r == J) myinv = inv;                     // 1 / l_JJ for the panel TRSM and the block inverse: no division anywhere
     a[J] = (r == J) ? piv : a[J] * inv;
 #pragma unroll
     for (int c = J + 1; c < PW; c++) {
@@ -48,7 +49,7 @@ struct PotrfStep {
 };
 template <>
 struct PotrfStep<-1> {
-  __device__ static __forceinline__ void run(double (&)[PW], int, int&) {}
+  __device__ static __forceinline__ void run(double (&)[PW], int, int&, double&) {}
 };
 
 // Row q of W = L^-1 for every column at once (lane r builds column r: w[k] = W[k][r], zero for k < r).
@@ -80,17 +81,18 @@ __device__ __forceinline__ int warp_potrf16(double* S, int c0, double* rdiag) {
 #pragma unroll
   for (int c = 0; c < PW; c++) a[c] = S[(c0 + c) * LDS + c0 + r];      // row r (entries c > r are never used)
   int info = 0;
-  PotrfStep<PW - 1>::run(a, r, info);
+  double myinv = 1.0;
+  PotrfStep<PW - 1>::run(a, r, info, myinv);
 #pragma unroll
-  for (int c = 0; c < PW; c++) {
+  for (int c = 0; c < PW; c++)
     if (writer && r >= c) S[(c0 + c) * LDS + c0 + r] = a[c];
-    if (writer && r == c) rdiag[c0 + c] = 1.0 / a[c];
-  }
+  if (writer) rdiag[c0 + r] = myinv;
   return info;
 }
 
 // Warp-level inverse of the lower-triangular PW x PW block at (c0, c0) into the scratch block DIp.
-__device__ __forceinline__ void warp_inv16(const double* S, int c0, double* DIp) {
+// rdiag: reciprocals of the diagonal from the factorisation, or null (a block that was not factored here).
+__device__ __forceinline__ void warp_inv16(const double* S, int c0, double* DIp, const double* rdiag) {
   const int r = threadIdx.x & (PW - 1);
   const bool writer = (threadIdx.x & 31) < PW;
   double a[PW];
@@ -99,7 +101,12 @@ __device__ __forceinline__ void warp_inv16(const double* S, int c0, double* DIp)
   double w[PW];
   double rinv = 1.0;
 #pragma unroll
-  for (int k = 0; k < PW; k++) { w[k] = 0.0; if (k == r) rinv = 1.0 / a[k]; }     // 1 / l_rr without dynamic indexing
+  for (int k = 0; k < PW; k++) w[k] = 0.0;
+  if (rdiag != nullptr) rinv = rdiag[c0 + r];
+  else {
+#pragma unroll
+    for (int k = 0; k < PW; k++) if (k == r) rinv = 1.0 / a[k];                    // 1 / l_rr without dynamic indexing
+  }
   InvStep<PW - 1>::run(a, w, r, rinv);
 #pragma unroll
   for (int k = 0; k < PW; k++)
@@ -175,7 +182,7 @@ __device__ __forceinline__ int diag_factor_invert(double* S, int m, double* aux,
   }
   if (tstamp) tstamp[0] = clock64();
   // ---- inverses of the diagonal blocks: eight independent 16 x 16 problems, one warp each
-  for (int P = warp; P < np; P += NTHREADS / 32) warp_inv16(S, P * PW, DI + P * DBLK);
+  for (int P = warp; P < np; P += NTHREADS / 32) warp_inv16(S, P * PW, DI + P * DBLK, factor ? rdiag : nullptr);
   csync();
   if (tstamp) tstamp[1] = clock64();
   // ---- W = L^-1: warp j owns block column j; row blocks P = j+1 .. np-1 in sequence, no block barrier
