@@ -1,223 +1,40 @@
-// libdsmgp.so : C ABI implementation (include/dsmgp.h).  sm_100a only, no CPU fallback.
-#include <algorithm>
-#include <cmath>
-#include <cstring>
-#include <limits>
-#include <numeric>
-#include <mutex>
-#include <string>
-#include <vector>
-
-#include "../../include/dsmgp.h"
-#include "args.h"
-#include "potrf2_args.h"
-#include "tree_host.h"
+// libdsmgp.so : C ABI implementation (include/dsmgp.h), core: lifetime, parameters, the fit / evaluation pipeline.
+// sm_100a only, no CPU fallback.  Prediction lives in api_predict.cu, the stand-alone operators in api_ops.cu.
+#include "handle.h"
 
 using namespace dsm;
 
-static thread_local std::string g_create_error;
-
-#define CUDA_TRY(h, expr)                                                                       \
-  do {                                                                                          \
-    cudaError_t e_ = (expr);                                                                    \
-    if (e_ != cudaSuccess) {                                                                    \
-      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                            \
-      return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA;                  \
-    }                                                                                           \
-  } while (0)
-
-namespace {
-
-struct Batch {
-  int s0 = 0, s1 = 0, max_nb = 0;
-  std::vector<int> cnt;                  // cnt[J]: slots of the batch that own block column J (slots sorted by size)
-  int64_t f_doubles = 0, w_doubles = 0, ntiles = 0, trpart_doubles = 0, gpart_doubles = 0;
-  int64_t* d_tile_off = nullptr;
-  int64_t* d_trpart_off = nullptr;
-  int64_t* d_gpart_off = nullptr;
-  int2* d_trtri_tasks = nullptr; int n_trtri = 0;
-  int4* d_lauum_tasks = nullptr; int n_lauum = 0;
-  int4* d_potrf2_tasks = nullptr; int n_potrf2 = 0;     // engine v2: tile tasks in look-ahead order
-  int4* d_trtri3_tasks = nullptr; int n_trtri3 = 0;     // inverse: tile tasks by anti-diagonal
-  int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
-  int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
-  double potrf_flops = 0, gram_bytes = 0;
-};
-
-// Process-wide cache of large device buffers.  cudaMalloc / cudaFree of multi-GB arenas cost 10 ms ... 3 s each
-// (measured: tools/cold_probe.py), which would dominate building a model from host arrays; freed buffers >= 32 MiB are
-// kept and handed to the next handle that asks for a similar size on the same device.  dsmgp_release_cache() returns
-// them to the driver.
-struct BufCache {
-  struct Ent { void* p; size_t bytes; int dev; };
-  std::vector<Ent> ents;
-  std::mutex mu;
-  static constexpr size_t MIN_BYTES = size_t(32) << 20;
-  size_t cached_bytes(int dev) {
-    std::lock_guard<std::mutex> g(mu);
-    size_t t = 0;
-    for (auto& e : ents) if (e.dev == dev) t += e.bytes;
-    return t;
-  }
-  void* take(size_t bytes, int dev, size_t* got) {
-    std::lock_guard<std::mutex> g(mu);
-    int best = -1;
-    for (int i = 0; i < (int)ents.size(); i++)
-      if (ents[i].dev == dev && ents[i].bytes >= bytes && ents[i].bytes <= bytes + bytes / 4 + (size_t(64) << 20) &&
-          (best < 0 || ents[i].bytes < ents[best].bytes)) best = i;
-    if (best < 0) return nullptr;
-    void* p = ents[best].p;
-    *got = ents[best].bytes;
-    ents.erase(ents.begin() + best);
-    return p;
-  }
-  bool give(void* p, size_t bytes, int dev) {
-    if (bytes < MIN_BYTES) return false;
-    std::lock_guard<std::mutex> g(mu);
-    if (ents.size() >= 64) return false;
-    ents.push_back({p, bytes, dev});
-    return true;
-  }
-  void release_all() {
-    std::lock_guard<std::mutex> g(mu);
-    for (auto& e : ents) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(e.dev); cudaFree(e.p); cudaSetDevice(cur); }
-    ents.clear();
-  }
-};
-static BufCache g_cache;
-
-template <typename T>
-struct DevBuf {
-  T* p = nullptr; size_t n = 0; size_t cap_bytes = 0; int dev = 0;
-  cudaError_t alloc(size_t count) {
-    free();
-    n = count;
-    if (count == 0) return cudaSuccess;
-    const size_t bytes = count * sizeof(T);
-    cudaGetDevice(&dev);
-    if (bytes >= BufCache::MIN_BYTES) {
-      if (void* q = g_cache.take(bytes, dev, &cap_bytes)) { p = static_cast<T*>(q); return cudaSuccess; }
-    }
-    cudaError_t e = cudaMalloc(&p, bytes);
-    if (e == cudaErrorMemoryAllocation) {          // make room: drop the cache and retry once
-      cudaGetLastError();
-      g_cache.release_all();
-      e = cudaMalloc(&p, bytes);
-    }
-    cap_bytes = bytes;
-    return e;
-  }
-  // grow-only scratch: keeps the allocation across calls (cudaMalloc / cudaFree of GBs cost 10-100 ms per call)
-  cudaError_t ensure(size_t count) {
-    if (count <= n && p != nullptr) return cudaSuccess;
-    return alloc(count + count / 8);
-  }
-  void free() {
-    if (p) {
-      if (!g_cache.give(p, cap_bytes, dev)) cudaFree(p);
-    }
-    p = nullptr; n = 0; cap_bytes = 0;
-  }
-};
-
-}  // namespace
-
-struct dsmgp_handle {
-  int64_t N = 0, D = 0, L = 0;
-  int nk = 0;
-  std::vector<dsmgp_kernel_desc> kernels;
-  std::vector<int64_t> koff;      // theta offset per kernel
-  std::vector<int32_t> knp;       // nparams per kernel
-  int64_t H = 0; int Hmax = 0; int row_width = 0; int pstride = 0;
-  std::vector<int64_t> leaf_ptr;
-  std::vector<int32_t> leaf_kid;
-  std::vector<double> leaf_mean;
-  HostTree tree;
-  dsmgp_opts opts;
-  std::vector<int32_t> owner;
-  std::vector<int> slot_leaf;     // slot -> global leaf
-  std::vector<int> leaf_slot;     // global leaf -> slot or -1
-  std::vector<LeafMeta> meta;     // per slot
-  std::vector<Batch> batches;
-  std::vector<double> theta_leaf; // L x Hmax
-  std::vector<double> h_prm;      // nslots x pstride
-  std::vector<double> h_rows;     // L x row_width
-  std::vector<double> node_lml;
-  std::vector<int32_t> h_info;    // L
-  std::vector<double> sum_logw;   // CSR by child_ptr (update!)
-  bool have_weights = false;
-  bool fitted = false, have_rows = false, have_grad = false, rows_complete = false;
-  bool alpha_exact = false;       // alpha from back-substitution (fit path); the gradient path leaves X^T z
-  int device = 0;
-  cudaStream_t stream = nullptr;
-  std::vector<cudaEvent_t> ev;     // 8 per batch: phase boundaries, always recorded (no extra syncs)
-  bool profiling = false;
-  dsmgp_timings tm = {};
-  // device
-  DevBuf<LeafMeta> d_meta;
-  DevBuf<double> d_xg, d_y, d_z, d_alpha, d_F, d_W, d_WT, d_prm, d_trpart, d_gpart, d_rows, d_leaf_mean;
-  DevBuf<LeafScal> d_scal;
-  DevBuf<int> d_counter;
-  DevBuf<int> d_flags;
-  DevBuf<double> d_ldpart, d_zzpart;
-  DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
-  DevBuf<double> p_xt, p_VT, p_mu, p_var, p_part; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
-  DevBuf<int4> p_wtasks, p_wcols; DevBuf<int> p_flags;
-  DevBuf<int> d_mask; std::vector<int> h_mask; bool use_mask = false;   // per-slot gradient mask (finetune: zero-overlap experts)
-  double* pin_multi = nullptr; size_t pin_multi_doubles = 0;             // rows of a multi-theta call [G][L][row_width]
-  LeafScal* pin_scal_multi = nullptr; size_t pin_scal_multi_n = 0;       // per-slot scalars of a multi-theta call [G][slots]
-  double* pin_rows = nullptr;
-  LeafScal* pin_scal = nullptr;
-  std::string err;
-
-  ~dsmgp_handle() {
-    for (auto& b : batches) {
-      cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
-      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
-    }
-    d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
-    d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
-    p_xt.free(); p_VT.free(); p_mu.free(); p_var.free(); p_pl.free(); p_tasks.free();
-    p_part.free(); p_wtasks.free(); p_wcols.free(); p_flags.free();
-    d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
-    d_mask.free();
-    if (pin_multi) cudaFreeHost(pin_multi);
-    if (pin_scal_multi) cudaFreeHost(pin_scal_multi);
-    if (pin_rows) cudaFreeHost(pin_rows);
-    if (pin_scal) cudaFreeHost(pin_scal);
-    for (auto& e : ev) if (e) cudaEventDestroy(e);
-    if (stream) cudaStreamDestroy(stream);
-  }
-};
+namespace dsm {
+std::string& create_error() { static thread_local std::string e; return e; }
+BufCache g_cache;
+}
+#define g_create_error (dsm::create_error())
 
 // ------------------------------------------------------------------------------------------
 // helpers
 // ------------------------------------------------------------------------------------------
-static bool g_attr_done = false;
-static cudaError_t engine_attrs() {
-  if (g_attr_done) return cudaSuccess;
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies to the CURRENT device only: track the opt-in per device
+// (handles may live on several GPUs of one process; create may be called from several threads).
+static std::mutex g_attr_mu;
+static uint64_t g_attr_done[4] = {0, 0, 0, 0};      // bitset indexed by device ordinal (< 256)
+cudaError_t dsm::engine_attrs() {
+  int dev = 0;
   cudaError_t e;
+  if ((e = cudaGetDevice(&dev))) return e;
+  std::lock_guard<std::mutex> g(g_attr_mu);
+  if (dev >= 0 && dev < 256 && ((g_attr_done[dev >> 6] >> (dev & 63)) & 1)) return cudaSuccess;
   if ((e = init_v2_kernels())) return e;
-  g_attr_done = true;
+  if (dev >= 0 && dev < 256) g_attr_done[dev >> 6] |= (uint64_t(1) << (dev & 63));
   return cudaSuccess;
 }
 
-static int num_sms(int device) {
+int dsm::num_sms(int device) {
   int n = 148;
   cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device);
   return n;
 }
 
-template <typename T>
-static cudaError_t upload(T** dptr, const std::vector<T>& v) {
-  *dptr = nullptr;
-  if (v.empty()) return cudaSuccess;
-  cudaError_t e = cudaMalloc(dptr, v.size() * sizeof(T));
-  if (e) return e;
-  return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
-}
-
-static void shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* owner) {
+void dsm::shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* owner) {
   std::vector<int64_t> order(L);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
@@ -233,7 +50,7 @@ static void shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* ow
   }
 }
 
-static void derive_params(const dsmgp_handle* h, int kid, const double* th, double* prm) {
+void dsm::derive_params(const dsmgp_handle* h, int kid, const double* th, double* prm) {
   const int type = h->kernels[kid].type, np = h->kernels[kid].nparams, nl = np - 2;
   const bool se = (type == DSMGP_ISO_SE || type == DSMGP_ARD_SE);
   const double logs = th[nl], logn = th[nl + 1];
@@ -636,7 +453,6 @@ static bool needs_lauum(const dsmgp_handle* h) {
   return false;
 }
 
-static float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 
 // gram -> potrf -> solves (-> inverse -> lauum) -> rows, batch by batch
 static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad);
@@ -755,7 +571,7 @@ static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad) {
 // alpha = L^-T z by block back-substitution (gaussianprocess.jl:105).  The gradient path leaves alpha = X^T z, which is
 // what tr(W) needs but carries the rounding of the explicit inverse; consumers of alpha itself (predict, accessors)
 // get the back-substituted vector, exactly like the reference.
-static int32_t refine_alpha(dsmgp_handle* h) {
+int32_t dsm::refine_alpha(dsmgp_handle* h) {
   if (h->alpha_exact || !h->fitted || h->batches.size() != 1) return DSMGP_OK;
   Batch& b = h->batches[0];
   const int nsl = b.s1 - b.s0;
@@ -1068,421 +884,6 @@ extern "C" int32_t dsmgp_leaf_factor(const dsmgp_handle* h, int64_t leaf, double
 }
 
 // ------------------------------------------------------------------------------------------
-// prediction
-// ------------------------------------------------------------------------------------------
-namespace {
-struct Router {
-  const HostTree& t; const double* x; int64_t T;
-  std::vector<std::vector<int64_t>> pts;   // per leaf
-  bool bad = false;
-  Router(const HostTree& tt, const double* xx, int64_t TT, int64_t L) : t(tt), x(xx), T(TT), pts(L) {}
-  void route(int64_t node, const std::vector<int64_t>& idx, bool poe) {
-    const int ty = t.type[node];
-    if (ty == DSMGP_NODE_LEAF) { auto& v = pts[t.leaf_of_node[node]]; v.insert(v.end(), idx.begin(), idx.end()); return; }
-    if (ty == DSMGP_NODE_SPLIT && !poe) {
-      std::vector<std::vector<int64_t>> sub(t.nchild(node));
-      for (int64_t p : idx) { const int64_t k = getchild(t, node, x, T, p); if (k < 0) { bad = true; return; } sub[k].push_back(p); }
-      for (int64_t k = 0; k < t.nchild(node); k++) if (!sub[k].empty()) route(t.child(node, k), sub[k], poe);
-      return;
-    }
-    for (int64_t k = 0; k < t.nchild(node); k++) route(t.child(node, k), idx, poe);
-  }
-};
-
-// common.jl mixing on the host.  Leaf predictions are stored per leaf in routing order; `cursor` replays it.
-struct Mixer {
-  const HostTree& t; const double* x; int64_t T;
-  const std::vector<std::vector<double>>& mu; const std::vector<std::vector<double>>& var;
-  const std::vector<double>& logw;
-  std::vector<size_t> cursor;
-  Mixer(const HostTree& tt, const double* xx, int64_t TT, const std::vector<std::vector<double>>& m,
-        const std::vector<std::vector<double>>& v, const std::vector<double>& lw)
-      : t(tt), x(xx), T(TT), mu(m), var(v), logw(lw), cursor(m.size(), 0) {}
-  void reset() { std::fill(cursor.begin(), cursor.end(), 0); }
-
-  // _minpredict common.jl:151-173
-  void minpredict(int64_t node, const std::vector<int64_t>& idx, std::vector<double>& out) {
-    const int ty = t.type[node];
-    out.assign(idx.size(), 0.0);
-    if (ty == DSMGP_NODE_LEAF) {
-      const int64_t l = t.leaf_of_node[node];
-      for (size_t i = 0; i < idx.size(); i++) out[i] = mu[l][cursor[l] + i];
-      cursor[l] += idx.size();
-    } else if (ty == DSMGP_NODE_SPLIT) {
-      std::vector<std::vector<int64_t>> sub(t.nchild(node)); std::vector<std::vector<size_t>> pos(t.nchild(node));
-      for (size_t i = 0; i < idx.size(); i++) { const int64_t k = getchild(t, node, x, T, idx[i]); sub[k].push_back(idx[i]); pos[k].push_back(i); }
-      std::vector<double> o;
-      for (int64_t k = 0; k < t.nchild(node); k++) {
-        if (sub[k].empty()) continue;
-        minpredict(t.child(node, k), sub[k], o);
-        for (size_t i = 0; i < o.size(); i++) out[pos[k][i]] = o[i];
-      }
-    } else {
-      std::fill(out.begin(), out.end(), std::numeric_limits<double>::infinity());
-      std::vector<double> o;
-      for (int64_t k = 0; k < t.nchild(node); k++) {
-        minpredict(t.child(node, k), idx, o);
-        for (size_t i = 0; i < o.size(); i++) out[i] = std::min(out[i], o[i]);
-      }
-    }
-  }
-  // _predict common.jl:134-143,181-196,275-292 : log(mu - mumin), log(mu^2), log(sigma^2)
-  void predict(int64_t node, const std::vector<int64_t>& idx, const std::vector<double>& mumin,
-               std::vector<double>& lm, std::vector<double>& lm2, std::vector<double>& ls) {
-    const int ty = t.type[node];
-    const size_t n = idx.size();
-    lm.assign(n, 0.0); lm2.assign(n, 0.0); ls.assign(n, 0.0);
-    if (ty == DSMGP_NODE_LEAF) {
-      const int64_t l = t.leaf_of_node[node];
-      for (size_t i = 0; i < n; i++) {
-        const double m = mu[l][cursor[l] + i];
-        double s2 = var[l][cursor[l] + i];
-        if (s2 <= 0) s2 = 1e-8;                                  // common.jl:137
-        lm[i] = std::log(m - mumin[i]); lm2[i] = std::log(m * m); ls[i] = std::log(s2);
-      }
-      cursor[l] += n;
-    } else if (ty == DSMGP_NODE_SPLIT) {
-      std::vector<std::vector<int64_t>> sub(t.nchild(node)); std::vector<std::vector<size_t>> pos(t.nchild(node));
-      std::vector<std::vector<double>> mm(t.nchild(node));
-      for (size_t i = 0; i < n; i++) {
-        const int64_t k = getchild(t, node, x, T, idx[i]);
-        sub[k].push_back(idx[i]); pos[k].push_back(i); mm[k].push_back(mumin[i]);
-      }
-      std::vector<double> a, b, c;
-      for (int64_t k = 0; k < t.nchild(node); k++) {
-        if (sub[k].empty()) continue;
-        predict(t.child(node, k), sub[k], mm[k], a, b, c);
-        for (size_t i = 0; i < a.size(); i++) { lm[pos[k][i]] = a[i]; lm2[pos[k][i]] = b[i]; ls[pos[k][i]] = c[i]; }
-      }
-    } else {
-      const int64_t K = t.nchild(node);
-      std::vector<std::vector<double>> A(K), B(K), C(K);
-      for (int64_t k = 0; k < K; k++) predict(t.child(node, k), idx, mumin, A[k], B[k], C[k]);
-      const double* lw = logw.data() + t.child_ptr[node];
-      auto lse = [&](std::vector<std::vector<double>>& M, size_t i) {   // common.jl:309-313
-        double m = -std::numeric_limits<double>::infinity();
-        for (int64_t k = 0; k < K; k++) m = std::max(m, M[k][i] + lw[k]);
-        double s = 0.0;
-        for (int64_t k = 0; k < K; k++) s += std::exp((M[k][i] + lw[k]) - m);
-        return std::log(s) + m;
-      };
-      for (size_t i = 0; i < n; i++) { lm[i] = lse(A, i); lm2[i] = lse(B, i); ls[i] = lse(C, i); }
-    }
-  }
-  // _predictPoE common.jl:145-149,198-208 : (mu, precision)
-  bool poe(int64_t node, const std::vector<int64_t>& idx, std::vector<double>& m, std::vector<double>& tau) {
-    const int ty = t.type[node];
-    const size_t n = idx.size();
-    if (ty == DSMGP_NODE_LEAF) {
-      const int64_t l = t.leaf_of_node[node];
-      m.resize(n); tau.resize(n);
-      for (size_t i = 0; i < n; i++) { m[i] = mu[l][cursor[l] + i]; tau[i] = 1.0 / var[l][cursor[l] + i]; }
-      cursor[l] += n;
-      return true;
-    }
-    if (ty != DSMGP_NODE_SPLIT) return false;    // MethodError in the reference
-    m.assign(n, 0.0); tau.assign(n, 0.0);
-    std::vector<double> m_, t_;
-    for (int64_t k = 0; k < t.nchild(node); k++) {
-      if (!poe(t.child(node, k), idx, m_, t_)) return false;
-      for (size_t i = 0; i < n; i++) { tau[i] += t_[i]; m[i] += t_[i] * m_[i]; }
-    }
-    for (size_t i = 0; i < n; i++) m[i] = m[i] / tau[i];
-    return true;
-  }
-};
-}  // namespace
-
-// Device prediction of every leaf on its routed points.  pts[l] = test rows routed to leaf l.
-static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, const std::vector<std::vector<int64_t>>& pts,
-                              std::vector<std::vector<double>>& mu, std::vector<std::vector<double>>& var,
-                              bool local_only = false) {
-  if (!h->fitted) { h->err = "predict: call fit first"; return DSMGP_ERR_STATE; }
-  if (!h->opts.keep_factors || h->batches.size() != 1) { h->err = "predict needs keep_factors=1"; return DSMGP_ERR_STATE; }
-  { int32_t rr = refine_alpha(h); if (rr) return rr; }
-  const int64_t L = h->L, D = h->D;
-  mu.assign(L, {}); var.assign(L, {});
-  std::vector<PredLeaf> pls; std::vector<int2> tasks; std::vector<int64_t> pl_leaf;
-  int64_t xto = 0, vto = 0, oo = 0;
-  for (int64_t l = 0; l < L; l++) {
-    if (pts[l].empty()) continue;
-    const int slot = h->leaf_slot[l];
-    if (slot < 0) {
-      if (local_only) continue;               // predicted by its owner (dsmgp_predict_local / _finish)
-      h->err = "predict: leaf owned by another rank (use dsmgp_predict_local + all-reduce + dsmgp_predict_finish)";
-      return DSMGP_ERR_STATE;
-    }
-    PredLeaf p; p.slot = slot; p.T = (int32_t)pts[l].size(); p.Tp = (p.T + BLK - 1) / BLK * BLK; p.pad_ = 0;
-    p.xtoff = xto; xto += (int64_t)p.Tp * D;
-    p.vtoff = vto; vto += (int64_t)(p.Tp / BLK) * h->meta[slot].nkc * TILE_D;
-    p.ooff = oo; oo += p.Tp;
-    for (int q = 0; q < p.Tp / BLK; q++) tasks.push_back(make_int2((int)pls.size(), q));
-    pls.push_back(p); pl_leaf.push_back(l);
-  }
-  if (pls.empty()) return DSMGP_OK;
-  std::stable_sort(tasks.begin(), tasks.end(), [&](const int2& a, const int2& b) {
-    return h->meta[pls[a.x].slot].np > h->meta[pls[b.x].slot].np; });
-  std::vector<double> xt(xto, 0.0);
-  for (size_t i = 0; i < pls.size(); i++) {
-    const auto& pv = pts[pl_leaf[i]];
-    for (int64_t d = 0; d < D; d++)
-      for (size_t q = 0; q < pv.size(); q++) xt[pls[i].xtoff + d * pls[i].Tp + q] = xtest[d * T + pv[q]];
-  }
-  DevBuf<double>&d_xt = h->p_xt, &d_VT = h->p_VT, &d_mu = h->p_mu, &d_var = h->p_var;
-  DevBuf<PredLeaf>& d_pl = h->p_pl; DevBuf<int2>& d_tasks = h->p_tasks;
-  auto cleanup = [&]() { if (d_VT.n * sizeof(double) > (size_t(16) << 30)) d_VT.free(); };   // keep the scratch unless it is huge
-#define PTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { h->err = std::string(#expr) + ": " + cudaGetErrorString(e_); cleanup(); \
-    return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA; } } while (0)
-  PTRY(d_xt.ensure(xto)); PTRY(d_VT.ensure(vto)); PTRY(d_mu.ensure(oo)); PTRY(d_var.ensure(oo));
-  PTRY(d_pl.ensure(pls.size())); PTRY(d_tasks.ensure(tasks.size()));
-  PTRY(cudaMemcpyAsync(d_xt.p, xt.data(), xto * 8, cudaMemcpyHostToDevice, h->stream));
-  PTRY(cudaMemcpyAsync(d_pl.p, pls.data(), pls.size() * sizeof(PredLeaf), cudaMemcpyHostToDevice, h->stream));
-  PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
-  PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
-  PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
-              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + 8,
-              0, nullptr, nullptr, nullptr, nullptr, 0};
-  const int sms = num_sms(h->device);
-  const char* force_wave = getenv("DSMGP_PREDICT_WAVE");       // tests: "0" / "1" force the task granularity
-  const bool use_wave = force_wave ? (force_wave[0] == '1') : ((int)tasks.size() < 3 * sms);
-  if (use_wave) {
-    // WAVE mode: too few (leaf, Q) tasks to fill the GPU -> one task per (leaf, Q, row block), ordered by row block
-    // (a block depends only on the blocks above it) with the experts shifted so that they end together
-    std::vector<int4> wt, wc;
-    int base = 0, max_nb = 0;
-    for (auto& p : pls) max_nb = std::max(max_nb, (int)h->meta[p.slot].nb);
-    struct WK { int key, np, pl, Q, I, base; };
-    std::vector<WK> wk;
-    for (size_t i = 0; i < pls.size(); i++) {
-      const LeafMeta& m = h->meta[pls[i].slot];
-      for (int q = 0; q < pls[i].Tp / BLK; q++) {
-        wc.push_back(make_int4((int)i, q, base, m.nb));
-        for (int I = 0; I < m.nb; I++) wk.push_back({I + max_nb - m.nb, m.np, (int)i, q, I, base});
-        base += m.nb;
-      }
-    }
-    std::stable_sort(wk.begin(), wk.end(), [](const WK& a, const WK& b) { return a.key != b.key ? a.key < b.key : a.np > b.np; });
-    for (auto& k : wk) wt.push_back(make_int4(k.pl, k.Q, k.I, k.base));
-    PTRY(h->p_wtasks.ensure(wt.size())); PTRY(h->p_wcols.ensure(wc.size())); PTRY(h->p_flags.ensure(base));
-    PTRY(h->p_part.ensure((size_t)base * 2 * BLK));
-    PTRY(cudaMemcpyAsync(h->p_wtasks.p, wt.data(), wt.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-    PTRY(cudaMemcpyAsync(h->p_wcols.p, wc.data(), wc.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
-    PTRY(cudaMemsetAsync(h->p_flags.p, 0, (size_t)base * sizeof(int), h->stream));
-    PTRY(cudaStreamSynchronize(h->stream));       // wt / wc are locals
-    pa.wave = 1; pa.wtasks = h->p_wtasks.p; pa.ntasks = (int)wt.size(); pa.flags = h->p_flags.p; pa.part = h->p_part.p;
-    pa.wcols = h->p_wcols.p; pa.nwcols = (int)wc.size();
-  }
-  cudaEventRecord(h->ev[0], h->stream);
-  launch_predict3(pa, std::max(1, std::min(sms, pa.ntasks)), h->stream);
-  if (pa.wave) launch_predict_reduce(pa, h->stream);
-  cudaEventRecord(h->ev[1], h->stream);
-  h->tm.launches++;
-  PTRY(cudaGetLastError());
-  std::vector<double> hmu(oo), hvar(oo);
-  PTRY(cudaMemcpyAsync(hmu.data(), d_mu.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
-  PTRY(cudaMemcpyAsync(hvar.data(), d_var.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
-  int gerr = 0;
-  PTRY(cudaMemcpyAsync(&gerr, h->d_counter.p + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
-  PTRY(cudaStreamSynchronize(h->stream));
-  if (gerr != 0) { h->err = "predict: device scheduler timeout (code " + std::to_string(gerr) + ")"; cleanup(); return DSMGP_ERR_STATE; }
-#undef PTRY
-  h->tm.predict_ms = ev_ms(h->ev[0], h->ev[1]);
-  h->tm.predict_flops = 0.0; h->tm.predict_bytes = 0.0;
-  for (size_t i = 0; i < pls.size(); i++) {      // TRSM n^2 T_l + 2 n T_l flop; L read once per block of 128 points
-    const double n = h->meta[pls[i].slot].n, Tl = pls[i].T;
-    h->tm.predict_flops += n * n * Tl + 2.0 * n * Tl;
-    h->tm.predict_bytes += 8.0 * (n * (n + 1) / 2.0) * (pls[i].Tp / BLK) + 8.0 * (n + Tl) * (double)D + 16.0 * Tl;
-  }
-  for (size_t i = 0; i < pls.size(); i++) {
-    const int64_t l = pl_leaf[i];
-    mu[l].assign(hmu.begin() + pls[i].ooff, hmu.begin() + pls[i].ooff + pls[i].T);
-    var[l].assign(hvar.begin() + pls[i].ooff, hvar.begin() + pls[i].ooff + pls[i].T);
-  }
-  cleanup();
-  return DSMGP_OK;
-}
-
-extern "C" int32_t dsmgp_leaf_predict(dsmgp_handle* h, int64_t leaf, const double* xtest, int64_t T, double* mu, double* var) {
-  if (!h || leaf < 0 || leaf >= h->L || !xtest || T <= 0 || !mu || !var) return DSMGP_ERR_ARG;
-  cudaSetDevice(h->device);
-  std::vector<std::vector<int64_t>> pts(h->L);
-  pts[leaf].resize(T);
-  std::iota(pts[leaf].begin(), pts[leaf].end(), 0);
-  std::vector<std::vector<double>> m, v;
-  int32_t rc = predict_leaves(h, xtest, T, pts, m, v);
-  if (rc) return rc;
-  std::copy(m[leaf].begin(), m[leaf].end(), mu);
-  std::copy(v[leaf].begin(), v[leaf].end(), var);
-  return DSMGP_OK;
-}
-
-// argument checks + routing shared by the predict entry points
-static int32_t predict_route(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, std::vector<std::vector<int64_t>>& pts) {
-  if (!xtest || T <= 0 || mode < 0 || mode > 3) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
-  for (int64_t i = 0; i < T * h->D; i++) if (!std::isfinite(xtest[i])) { h->err = "predict: non-finite input"; return DSMGP_ERR_ARG; }
-  cudaSetDevice(h->device);
-  const HostTree& t = h->tree;
-  const bool poe = mode != DSMGP_PREDICT_DSMGP;
-  if (poe && t.type[t.root] != DSMGP_NODE_SPLIT) { h->err = "predict: PoE/gPoE/rBCM need a split root (buildPoE/buildBCM model)"; return DSMGP_ERR_ARG; }
-  if (!poe && !h->have_weights) {
-    // the reference predicts with whatever logweights the sum nodes hold (uniform -log K after build)
-    h->sum_logw.assign(t.child_ptr[t.n_nodes], 0.0);
-    for (int64_t i = 0; i < t.n_nodes; i++)
-      if (t.type[i] >= DSMGP_NODE_SUM) for (int64_t c = t.child_ptr[i]; c < t.child_ptr[i + 1]; c++) h->sum_logw[c] = -std::log((double)t.nchild(i));
-  }
-  std::vector<int64_t> all(T);
-  std::iota(all.begin(), all.end(), 0);
-  Router r(t, xtest, T, h->L);
-  r.route(t.root, all, poe);
-  if (r.bad) { h->err = "predict: a test point lies outside every split interval"; return DSMGP_ERR_ARG; }
-  pts.swap(r.pts);
-  return DSMGP_OK;
-}
-
-static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode,
-                           const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
-                           double* mu, double* var);
-
-extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
-  if (!h) return DSMGP_ERR_ARG;
-  if (!mu || !var) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
-  std::vector<std::vector<int64_t>> pts;
-  int32_t rc = predict_route(h, xtest, T, mode, pts);
-  if (rc) return rc;
-  std::vector<std::vector<double>> lmu, lvar;
-  if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar))) return rc;
-  return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
-}
-
-// Leaf-sharded prediction (one process per GPU): every rank predicts its own experts on the points routed to them and
-// writes them into a buffer in (leaf, routing order) layout -- entries of other ranks' experts stay 0, so a SUM all-reduce
-// assembles the buffer -- then every rank mixes (common.jl:134-307) redundantly, like the tree passes of an evaluation.
-extern "C" int32_t dsmgp_predict_local(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* buf, int64_t* total) {
-  if (!h) return DSMGP_ERR_ARG;
-  if (!total) { h->err = "predict_local: bad argument"; return DSMGP_ERR_ARG; }
-  std::vector<std::vector<int64_t>> pts;
-  int32_t rc = predict_route(h, xtest, T, mode, pts);
-  if (rc) return rc;
-  int64_t tot = 0;
-  for (auto& v : pts) tot += (int64_t)v.size();
-  *total = tot;
-  if (!buf) return DSMGP_OK;                   // size query
-  std::vector<std::vector<double>> lmu, lvar;
-  if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar, true))) return rc;
-  std::fill(buf, buf + 2 * tot, 0.0);
-  int64_t off = 0;
-  for (int64_t l = 0; l < h->L; l++) {
-    if (!lmu.empty() && !lmu[l].empty()) {
-      std::copy(lmu[l].begin(), lmu[l].end(), buf + off);
-      std::copy(lvar[l].begin(), lvar[l].end(), buf + tot + off);
-    }
-    off += (int64_t)pts[l].size();
-  }
-  return DSMGP_OK;
-}
-
-extern "C" int32_t dsmgp_predict_finish(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, const double* buf,
-                                        double* mu, double* var) {
-  if (!h) return DSMGP_ERR_ARG;
-  if (!buf || !mu || !var) { h->err = "predict_finish: bad argument"; return DSMGP_ERR_ARG; }
-  std::vector<std::vector<int64_t>> pts;
-  int32_t rc = predict_route(h, xtest, T, mode, pts);
-  if (rc) return rc;
-  int64_t tot = 0;
-  for (auto& v : pts) tot += (int64_t)v.size();
-  std::vector<std::vector<double>> lmu(h->L), lvar(h->L);
-  int64_t off = 0;
-  for (int64_t l = 0; l < h->L; l++) {
-    lmu[l].assign(buf + off, buf + off + pts[l].size());
-    lvar[l].assign(buf + tot + off, buf + tot + off + pts[l].size());
-    off += (int64_t)pts[l].size();
-  }
-  return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
-}
-
-static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode,
-                           const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
-                           double* mu, double* var) {
-  const HostTree& t = h->tree;
-  std::vector<int64_t> all(T);
-  std::iota(all.begin(), all.end(), 0);
-  Mixer mx(t, xtest, T, lmu, lvar, h->sum_logw);
-  if (mode == DSMGP_PREDICT_DSMGP) {
-    // predict(node) common.jl:175-179 (leaf), :243-254 (split root), :294-302 (sum root)
-    struct Rec {
-      Mixer& mx; const HostTree& t; double* mu; double* var; const double* x; int64_t T;
-      void run(int64_t node, const std::vector<int64_t>& idx) {
-        if (t.type[node] == DSMGP_NODE_SPLIT) {
-          std::vector<std::vector<int64_t>> sub(t.nchild(node));
-          for (int64_t p : idx) sub[getchild(t, node, x, T, p)].push_back(p);
-          for (int64_t k = 0; k < t.nchild(node); k++) if (!sub[k].empty()) run(t.child(node, k), sub[k]);
-          return;
-        }
-        // leaf or sum: two traversals of the subtree -> replay cursors must restart for this subtree.
-        std::vector<size_t> save = mx.cursor;
-        std::vector<double> mumin, lm, lm2, ls;
-        mx.minpredict(node, idx, mumin);
-        mx.cursor = save;
-        for (auto& v : mumin) v -= 1.0;
-        mx.predict(node, idx, mumin, lm, lm2, ls);
-        for (size_t i = 0; i < idx.size(); i++) {
-          const double m = std::exp(lm[i]) + mumin[i];
-          mu[idx[i]] = m;
-          var[idx[i]] = (t.type[node] == DSMGP_NODE_LEAF) ? std::exp(ls[i]) : std::exp(ls[i]) + (std::exp(lm2[i]) - m * m);
-        }
-      }
-    } rec{mx, t, mu, var, xtest, T};
-    rec.run(t.root, all);
-    return DSMGP_OK;
-  }
-  const int64_t K = t.nchild(t.root);
-  std::vector<double> m_, t_;
-  if (mode == DSMGP_PREDICT_POE) {
-    if (!mx.poe(t.root, all, m_, t_)) { h->err = "predictPoE: sum node below a split (MethodError in the reference)"; return DSMGP_ERR_ARG; }
-    for (int64_t i = 0; i < T; i++) { mu[i] = m_[i]; var[i] = 1.0 / t_[i]; }
-  } else if (mode == DSMGP_PREDICT_GPOE) {       // common.jl:211-222
-    const double beta = 1.0 / (double)K;
-    std::vector<double> M(T, 0.0), Tt(T, 0.0);
-    for (int64_t k = 0; k < K; k++) {
-      if (!mx.poe(t.child(t.root, k), all, m_, t_)) { h->err = "predictgPoE: sum node below a split"; return DSMGP_ERR_ARG; }
-      for (int64_t i = 0; i < T; i++) { Tt[i] += beta * t_[i]; M[i] += beta * t_[i] * m_[i]; }
-    }
-    for (int64_t i = 0; i < T; i++) { mu[i] = M[i] / Tt[i]; var[i] = 1.0 / Tt[i]; }
-  } else {                                       // rBCM common.jl:224-241
-    int64_t nd = t.root;
-    while (t.type[nd] != DSMGP_NODE_LEAF) nd = t.child(nd, 0);
-    const int64_t l0 = t.leaf_of_node[nd];
-    const int k0 = h->leaf_kid[l0];
-    std::vector<double> prm(h->pstride);
-    derive_params(h, k0, &h->theta_leaf[(size_t)l0 * h->Hmax], prm.data());
-    const int type = h->kernels[k0].type;
-    std::vector<double> s(T), C(T), M(T, 0.0);
-    for (int64_t i = 0; i < T; i++) {
-      double ktt;
-      if (type == DSMGP_ISO_SE) ktt = prm[PRM_V];
-      else if (type == DSMGP_ARD_SE) ktt = prm[PRM_V] * (double)h->D;
-      else {
-        ktt = 0.0;
-        for (int64_t d = 0; d < h->D; d++) { const double xv = xtest[d * T + i]; ktt += (type == DSMGP_ISO_LINEAR ? prm[PRM_COEF] : prm[PRM_COEF + d]) * xv * xv; }
-      }
-      s[i] = ktt + prm[PRM_ETA];
-      C[i] = 1.0 / s[i];
-    }
-    for (int64_t k = 0; k < K; k++) {
-      if (!mx.poe(t.child(t.root, k), all, m_, t_)) { h->err = "predictrBCM: sum node below a split"; return DSMGP_ERR_ARG; }
-      for (int64_t i = 0; i < T; i++) {
-        const double s_ = 1.0 / t_[i];
-        const double beta = 0.5 * (std::log(s[i]) - std::log(s_));
-        C[i] = C[i] + (beta * t_[i]) - (beta / s[i]);
-        M[i] = M[i] + m_[i] * (beta * t_[i]);
-      }
-    }
-    for (int64_t i = 0; i < T; i++) { mu[i] = M[i] / C[i]; var[i] = 1.0 / C[i]; }
-  }
-  return DSMGP_OK;
-}
-
-// ------------------------------------------------------------------------------------------
 // host-only helpers
 // ------------------------------------------------------------------------------------------
 extern "C" int32_t dsmgp_host_shard(int64_t L, const int64_t* leaf_ptr, int32_t world, int32_t* owner) {
@@ -1526,202 +927,4 @@ extern "C" int32_t dsmgp_set_profiling(dsmgp_handle* h, int32_t on) {
   if (!h) return DSMGP_ERR_ARG;
   h->profiling = on != 0;
   return DSMGP_OK;
-}
-
-// ------------------------------------------------------------------------------------------
-// stand-alone operators
-// ------------------------------------------------------------------------------------------
-static int32_t standalone_device_check(std::string& err) {
-  int ndev = 0;
-  cudaError_t ce = cudaGetDeviceCount(&ndev);
-  if (ce != cudaSuccess || ndev == 0) { err = std::string("no CUDA device: libdsmgp has no CPU fallback (") + cudaGetErrorString(ce) + ")"; return DSMGP_ERR_CUDA; }
-  if ((ce = engine_attrs()) != cudaSuccess) { err = cudaGetErrorString(ce); return DSMGP_ERR_CUDA; }
-  return DSMGP_OK;
-}
-#define SA_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_create_error = std::string(#expr) + ": " + cudaGetErrorString(e_); rc = DSMGP_ERR_CUDA; goto done; } } while (0)
-
-extern "C" int32_t dsmgp_kernelmatrix(int32_t kernel_type, const double* theta, int64_t D, const double* x1, int64_t n1,
-                                      const double* x2, int64_t n2, double* K) {
-  if (kernel_type < 0 || kernel_type > 3 || !theta || !x1 || !x2 || !K || D <= 0 || n1 <= 0 || n2 <= 0) return DSMGP_ERR_ARG;
-  int32_t rc = standalone_device_check(g_create_error);
-  if (rc) return rc;
-  const bool iso = (kernel_type == DSMGP_ISO_SE || kernel_type == DSMGP_ISO_LINEAR);
-  const bool se = (kernel_type == DSMGP_ISO_SE || kernel_type == DSMGP_ARD_SE);
-  const int nl = iso ? 1 : (int)D;
-  std::vector<double> prm(PRM_COEF + D, 0.0);
-  prm[PRM_V] = se ? std::exp(2.0 * theta[nl]) : 1.0;
-  prm[PRM_S] = se ? std::exp(theta[nl]) : 1.0;
-  for (int d = 0; d < nl; d++) { const double l = std::exp(theta[d]); prm[PRM_COEF + d] = se ? -0.5 / (l * l) : 1.0 / (l * l); }
-  double *d1 = nullptr, *d2 = nullptr, *dk = nullptr, *dp = nullptr;
-  SA_TRY(cudaMalloc(&d1, n1 * D * 8)); SA_TRY(cudaMalloc(&d2, n2 * D * 8)); SA_TRY(cudaMalloc(&dk, n1 * n2 * 8));
-  SA_TRY(cudaMalloc(&dp, prm.size() * 8));
-  SA_TRY(cudaMemcpy(d1, x1, n1 * D * 8, cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemcpy(d2, x2, n2 * D * 8, cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemcpy(dp, prm.data(), prm.size() * 8, cudaMemcpyHostToDevice));
-  {
-    GramRectArgs ga{kernel_type, (int)D, dp, d1, n1, (int)n1, d2, n2, (int)n2, dk, n1};
-    launch_gram_rect(ga, 0);
-    SA_TRY(cudaGetLastError());
-    SA_TRY(cudaMemcpy(K, dk, n1 * n2 * 8, cudaMemcpyDeviceToHost));
-  }
-done:
-  cudaFree(d1); cudaFree(d2); cudaFree(dk); cudaFree(dp);
-  return rc;
-}
-
-// potrf / chol_continue on one host matrix.  k = number of leading rows/cols that already hold a valid factor.
-// Runs the same persistent tile scheduler as the batched path (potrf2_kernel) on a one-expert batch.
-// getOverlap(spn, D, gpmap) fit.jl:12-39 on the device.
-extern "C" int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
-                                 const int32_t* leaf_kernel_id, const dsmgp_tree* tree, double* D) {
-  if (N <= 0 || L <= 0 || !leaf_ptr || !leaf_obs || !leaf_kernel_id || !tree || !D) { g_create_error = "overlap: bad argument"; return DSMGP_ERR_ARG; }
-  HostTree t; std::string err;
-  if (!t.load(tree, L, err)) { g_create_error = err; return DSMGP_ERR_ARG; }
-  const int64_t total = leaf_ptr[L];
-  for (int64_t i = 0; i < total; i++) if (leaf_obs[i] < 1 || leaf_obs[i] > N) { g_create_error = "overlap: leaf_obs must be 1-based rows in 1..N"; return DSMGP_ERR_ARG; }
-  { int32_t rc = standalone_device_check(g_create_error); if (rc) return rc; }
-  // ancestor chains (root first) from the child lists
-  std::vector<int64_t> parent(t.n_nodes, -1);
-  for (int64_t i = 0; i < t.n_nodes; i++) for (int64_t k = 0; k < t.nchild(i); k++) parent[t.child(i, k)] = i;
-  std::vector<std::vector<int>> chain(L);
-  int AD = 1;
-  for (int64_t i = 0; i < t.n_nodes; i++) {
-    if (t.type[i] != DSMGP_NODE_LEAF) continue;
-    std::vector<int> c;
-    for (int64_t u = parent[i]; u >= 0; u = parent[u]) c.push_back((int)u);
-    std::reverse(c.begin(), c.end());
-    AD = std::max<int>(AD, (int)c.size());
-    chain[t.leaf_of_node[i]] = c;
-  }
-  std::vector<int> anc((size_t)L * AD, -1);
-  for (int64_t l = 0; l < L; l++) std::copy(chain[l].begin(), chain[l].end(), anc.begin() + (size_t)l * AD);
-  std::vector<int> ntype(t.type.begin(), t.type.end()), kid(leaf_kernel_id, leaf_kernel_id + L);
-  int64_t* d_obs = nullptr; int64_t* d_lp = nullptr; int64_t* d_poff = nullptr;
-  int *d_cnt = nullptr, *d_plist = nullptr, *d_inter = nullptr, *d_kid = nullptr, *d_anc = nullptr, *d_nt = nullptr;
-  double* d_D = nullptr;
-  auto cleanup = [&]() { cudaFree(d_obs); cudaFree(d_lp); cudaFree(d_poff); cudaFree(d_cnt); cudaFree(d_plist); cudaFree(d_inter);
-                         cudaFree(d_kid); cudaFree(d_anc); cudaFree(d_nt); cudaFree(d_D); };
-#define OTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { g_create_error = std::string(#expr) + ": " + cudaGetErrorString(e_); cleanup(); \
-    return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA; } } while (0)
-  OTRY(cudaMalloc(&d_obs, total * 8)); OTRY(cudaMemcpy(d_obs, leaf_obs, total * 8, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_lp, (L + 1) * 8)); OTRY(cudaMemcpy(d_lp, leaf_ptr, (L + 1) * 8, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_cnt, N * 4)); OTRY(cudaMemset(d_cnt, 0, N * 4));
-  launch_ov_count(d_obs, total, d_cnt, nullptr);
-  std::vector<int> cnt(N);
-  OTRY(cudaMemcpy(cnt.data(), d_cnt, N * 4, cudaMemcpyDeviceToHost));
-  std::vector<int64_t> poff(N + 1, 0);
-  for (int64_t p = 0; p < N; p++) poff[p + 1] = poff[p] + cnt[p];
-  OTRY(cudaMalloc(&d_poff, (N + 1) * 8)); OTRY(cudaMemcpy(d_poff, poff.data(), (N + 1) * 8, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_plist, std::max<int64_t>(total, 1) * 4));
-  OTRY(cudaMemset(d_cnt, 0, N * 4));
-  launch_ov_fill(d_obs, d_lp, (int)L, d_poff, d_cnt, d_plist, nullptr);
-  OTRY(cudaMalloc(&d_inter, (size_t)L * L * 4)); OTRY(cudaMemset(d_inter, 0, (size_t)L * L * 4));
-  launch_ov_pairs(d_poff, d_plist, N, L, d_inter, nullptr);
-  OTRY(cudaMalloc(&d_kid, L * 4)); OTRY(cudaMemcpy(d_kid, kid.data(), L * 4, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_anc, anc.size() * 4)); OTRY(cudaMemcpy(d_anc, anc.data(), anc.size() * 4, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_nt, ntype.size() * 4)); OTRY(cudaMemcpy(d_nt, ntype.data(), ntype.size() * 4, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_D, (size_t)L * L * 8));
-  launch_ov_finish(d_inter, d_lp, d_kid, d_anc, AD, d_nt, L, d_D, nullptr);
-  OTRY(cudaGetLastError());
-  OTRY(cudaMemcpy(D, d_D, (size_t)L * L * 8, cudaMemcpyDeviceToHost));
-#undef OTRY
-  cleanup();
-  return DSMGP_OK;
-}
-
-static int32_t chol_host_matrix(double* A, int64_t n, int64_t k, int32_t* info) {
-  int32_t rc = standalone_device_check(g_create_error);
-  if (rc) return rc;
-  const int64_t kp = (k + BLK - 1) / BLK * BLK;          // leading part padded to a block boundary
-  const int64_t nn = kp + (n - k);
-  LeafMeta m{};
-  m.n = (int32_t)nn; m.np = (int32_t)((nn + PAD - 1) / PAD * PAD); m.nb = (m.np + BLK - 1) / BLK; m.nkc = m.np / KC;
-  const int np = m.np, nkc = m.nkc;
-  const int64_t fd = tiled_doubles(np);
-  std::vector<double> P((size_t)fd, 0.0);
-  auto map = [&](int64_t i) { return i < k ? i : kp + (i - k); };
-  for (int i = 0; i < np; i++) P[tidx(i, i, nkc)] = 1.0;
-  for (int64_t c = 0; c < n; c++)
-    for (int64_t r = c; r < n; r++) P[tidx((int)map(r), (int)map(c), nkc)] = A[c * n + r];
-  std::vector<int4> tasks;
-  tasks.push_back(make_int4(0, 0, 0, 0));
-  for (int J = 0; J + 1 < m.nb; J++) {
-    tasks.push_back(make_int4(0, J + 1, J, 0));
-    tasks.push_back(make_int4(0, J + 1, J + 1, 0));
-    for (int I = J + 2; I < m.nb; I++) tasks.push_back(make_int4(0, I, J, 0));
-  }
-  const int64_t nflags = (int64_t)m.nb * (m.nb + 1) / 2;
-  double *dF = nullptr, *dW = nullptr, *dWT = nullptr, *dtr = nullptr, *dv = nullptr; LeafMeta* dm = nullptr; LeafScal* ds = nullptr;
-  int64_t* doff = nullptr; int* dflags = nullptr; int* dcnt = nullptr; int4* dtasks = nullptr;
-  LeafScal sc{}; int gerr = 0;
-  const int64_t zero[2] = {0, 0};
-  int sms = 148;
-  SA_TRY(cudaMalloc(&dF, fd * 8)); SA_TRY(cudaMalloc(&dW, (size_t)m.nb * WBLK_D * 8)); SA_TRY(cudaMalloc(&dWT, (size_t)m.nb * WBLK_D * 8));
-  SA_TRY(cudaMalloc(&dtr, 4 * m.nb * 8)); SA_TRY(cudaMalloc(&dv, 2 * (size_t)np * 8)); SA_TRY(cudaMalloc(&dm, sizeof(LeafMeta)));
-  SA_TRY(cudaMalloc(&ds, sizeof(LeafScal))); SA_TRY(cudaMalloc(&doff, 16)); SA_TRY(cudaMalloc(&dflags, nflags * 4));
-  SA_TRY(cudaMalloc(&dcnt, 64)); SA_TRY(cudaMalloc(&dtasks, tasks.size() * sizeof(int4)));
-  SA_TRY(cudaMemcpy(dF, P.data(), fd * 8, cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemcpy(dm, &m, sizeof(m), cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemset(ds, 0, sizeof(LeafScal))); SA_TRY(cudaMemset(dflags, 0, nflags * 4)); SA_TRY(cudaMemset(dcnt, 0, 64));
-  SA_TRY(cudaMemset(dv, 0, 2 * (size_t)np * 8));
-  SA_TRY(cudaMemcpy(doff, zero, 16, cudaMemcpyHostToDevice));
-  SA_TRY(cudaMemcpy(dtasks, tasks.data(), tasks.size() * sizeof(int4), cudaMemcpyHostToDevice));
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
-  {
-    Potrf2Args pa{dm, dF, dW, dWT, dv, dv + np, ds, dtr, doff, dtr + 2 * m.nb, dtr + 3 * m.nb, dflags, doff + 1, dtasks,
-                  (int)tasks.size(), dcnt, dcnt + 8, (int)(kp / BLK), nullptr};
-    launch_potrf2(pa, std::min(sms, (int)tasks.size()), 0);
-    SA_TRY(cudaGetLastError());
-    SA_TRY(cudaMemcpy(P.data(), dF, fd * 8, cudaMemcpyDeviceToHost));
-    SA_TRY(cudaMemcpy(&sc, ds, sizeof(sc), cudaMemcpyDeviceToHost));
-    SA_TRY(cudaMemcpy(&gerr, dcnt + 8, sizeof(int), cudaMemcpyDeviceToHost));
-  }
-  if (gerr != 0) { g_create_error = "device scheduler timeout"; rc = DSMGP_ERR_STATE; goto done; }
-  for (int64_t c = 0; c < n; c++)
-    for (int64_t r = 0; r < n; r++) A[c * n + r] = (r >= c) ? P[tidx((int)map(r), (int)map(c), nkc)] : 0.0;    // tril!
-  if (info) {
-    int64_t i = sc.info;                       // 1-based pivot in padded coordinates
-    if (i > 0) { i = (i - 1 >= kp) ? (i - 1 - kp) + 1 : i; if (i > n - k) i = 0; }
-    *info = (int32_t)i;                        // relative to the trailing block, as LAPACK.potrf!(C) reports it
-  }
-done:
-  cudaFree(dF); cudaFree(dW); cudaFree(dWT); cudaFree(dtr); cudaFree(dv); cudaFree(dm); cudaFree(ds); cudaFree(doff);
-  cudaFree(dflags); cudaFree(dcnt); cudaFree(dtasks);
-  return rc;
-}
-
-extern "C" int32_t dsmgp_potrf(double* A, int64_t n, int32_t* info) {
-  if (!A || n <= 0) return DSMGP_ERR_ARG;
-  return chol_host_matrix(A, n, 0, info);
-}
-
-extern "C" int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t* info) {
-  if (!A || n <= 0 || ki < 1 || ki > n) return DSMGP_ERR_ARG;
-  return chol_host_matrix(A, n, ki - 1, info);
-}
-
-extern "C" int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, int64_t nrows, double* out) {
-  if (!A || n <= 0 || !rows || nrows < 0 || nrows >= n || !out) return DSMGP_ERR_ARG;
-  for (int64_t q = 0; q < nrows; q++)
-    if (rows[q] < 1 || rows[q] > n || (q > 0 && rows[q] <= rows[q - 1])) { g_create_error = "delete_rows: rows must be 1-based ascending"; return DSMGP_ERR_ARG; }
-  int32_t rc = standalone_device_check(g_create_error);
-  if (rc) return rc;
-  double *dL = nullptr, *dv = nullptr; int64_t* dr = nullptr;
-  std::vector<double> P((size_t)n * n);
-  SA_TRY(cudaMalloc(&dL, n * n * 8)); SA_TRY(cudaMalloc(&dv, n * 8)); SA_TRY(cudaMalloc(&dr, std::max<int64_t>(nrows, 1) * 8));
-  SA_TRY(cudaMemcpy(dL, A, n * n * 8, cudaMemcpyHostToDevice));
-  if (nrows) SA_TRY(cudaMemcpy(dr, rows, nrows * 8, cudaMemcpyHostToDevice));
-  launch_delete_rows(dL, (int)n, dr, (int)nrows, dv, 0);
-  SA_TRY(cudaGetLastError());
-  SA_TRY(cudaMemcpy(P.data(), dL, n * n * 8, cudaMemcpyDeviceToHost));
-  {
-    std::vector<int64_t> keep;
-    for (int64_t i = 0, q = 0; i < n; i++) { if (q < nrows && rows[q] - 1 == i) { q++; continue; } keep.push_back(i); }
-    const int64_t m = (int64_t)keep.size();
-    for (int64_t c = 0; c < m; c++)
-      for (int64_t r = 0; r < m; r++) out[c * m + r] = (r >= c) ? P[keep[c] * n + keep[r]] : 0.0;
-  }
-done:
-  cudaFree(dL); cudaFree(dv); cudaFree(dr);
-  return rc;
 }

@@ -1,0 +1,420 @@
+// libdsmgp.so : prediction entry points (common.jl:101-122, 134-313; gaussianprocess.jl:110-137).
+#include "handle.h"
+
+using namespace dsm;
+#define g_create_error (dsm::create_error())
+
+// ------------------------------------------------------------------------------------------
+// prediction
+// ------------------------------------------------------------------------------------------
+namespace {
+struct Router {
+  const HostTree& t; const double* x; int64_t T;
+  std::vector<std::vector<int64_t>> pts;   // per leaf
+  bool bad = false;
+  Router(const HostTree& tt, const double* xx, int64_t TT, int64_t L) : t(tt), x(xx), T(TT), pts(L) {}
+  void route(int64_t node, const std::vector<int64_t>& idx, bool poe) {
+    const int ty = t.type[node];
+    if (ty == DSMGP_NODE_LEAF) { auto& v = pts[t.leaf_of_node[node]]; v.insert(v.end(), idx.begin(), idx.end()); return; }
+    if (ty == DSMGP_NODE_SPLIT && !poe) {
+      std::vector<std::vector<int64_t>> sub(t.nchild(node));
+      for (int64_t p : idx) { const int64_t k = getchild(t, node, x, T, p); if (k < 0) { bad = true; return; } sub[k].push_back(p); }
+      for (int64_t k = 0; k < t.nchild(node); k++) if (!sub[k].empty()) route(t.child(node, k), sub[k], poe);
+      return;
+    }
+    for (int64_t k = 0; k < t.nchild(node); k++) route(t.child(node, k), idx, poe);
+  }
+};
+
+// common.jl mixing on the host.  Leaf predictions are stored per leaf in routing order; `cursor` replays it.
+struct Mixer {
+  const HostTree& t; const double* x; int64_t T;
+  const std::vector<std::vector<double>>& mu; const std::vector<std::vector<double>>& var;
+  const std::vector<double>& logw;
+  std::vector<size_t> cursor;
+  Mixer(const HostTree& tt, const double* xx, int64_t TT, const std::vector<std::vector<double>>& m,
+        const std::vector<std::vector<double>>& v, const std::vector<double>& lw)
+      : t(tt), x(xx), T(TT), mu(m), var(v), logw(lw), cursor(m.size(), 0) {}
+  void reset() { std::fill(cursor.begin(), cursor.end(), 0); }
+
+  // _minpredict common.jl:151-173
+  void minpredict(int64_t node, const std::vector<int64_t>& idx, std::vector<double>& out) {
+    const int ty = t.type[node];
+    out.assign(idx.size(), 0.0);
+    if (ty == DSMGP_NODE_LEAF) {
+      const int64_t l = t.leaf_of_node[node];
+      for (size_t i = 0; i < idx.size(); i++) out[i] = mu[l][cursor[l] + i];
+      cursor[l] += idx.size();
+    } else if (ty == DSMGP_NODE_SPLIT) {
+      std::vector<std::vector<int64_t>> sub(t.nchild(node)); std::vector<std::vector<size_t>> pos(t.nchild(node));
+      for (size_t i = 0; i < idx.size(); i++) { const int64_t k = getchild(t, node, x, T, idx[i]); sub[k].push_back(idx[i]); pos[k].push_back(i); }
+      std::vector<double> o;
+      for (int64_t k = 0; k < t.nchild(node); k++) {
+        if (sub[k].empty()) continue;
+        minpredict(t.child(node, k), sub[k], o);
+        for (size_t i = 0; i < o.size(); i++) out[pos[k][i]] = o[i];
+      }
+    } else {
+      std::fill(out.begin(), out.end(), std::numeric_limits<double>::infinity());
+      std::vector<double> o;
+      for (int64_t k = 0; k < t.nchild(node); k++) {
+        minpredict(t.child(node, k), idx, o);
+        for (size_t i = 0; i < o.size(); i++) out[i] = std::min(out[i], o[i]);
+      }
+    }
+  }
+  // _predict common.jl:134-143,181-196,275-292 : log(mu - mumin), log(mu^2), log(sigma^2)
+  void predict(int64_t node, const std::vector<int64_t>& idx, const std::vector<double>& mumin,
+               std::vector<double>& lm, std::vector<double>& lm2, std::vector<double>& ls) {
+    const int ty = t.type[node];
+    const size_t n = idx.size();
+    lm.assign(n, 0.0); lm2.assign(n, 0.0); ls.assign(n, 0.0);
+    if (ty == DSMGP_NODE_LEAF) {
+      const int64_t l = t.leaf_of_node[node];
+      for (size_t i = 0; i < n; i++) {
+        const double m = mu[l][cursor[l] + i];
+        double s2 = var[l][cursor[l] + i];
+        if (s2 <= 0) s2 = 1e-8;                                  // common.jl:137
+        lm[i] = std::log(m - mumin[i]); lm2[i] = std::log(m * m); ls[i] = std::log(s2);
+      }
+      cursor[l] += n;
+    } else if (ty == DSMGP_NODE_SPLIT) {
+      std::vector<std::vector<int64_t>> sub(t.nchild(node)); std::vector<std::vector<size_t>> pos(t.nchild(node));
+      std::vector<std::vector<double>> mm(t.nchild(node));
+      for (size_t i = 0; i < n; i++) {
+        const int64_t k = getchild(t, node, x, T, idx[i]);
+        sub[k].push_back(idx[i]); pos[k].push_back(i); mm[k].push_back(mumin[i]);
+      }
+      std::vector<double> a, b, c;
+      for (int64_t k = 0; k < t.nchild(node); k++) {
+        if (sub[k].empty()) continue;
+        predict(t.child(node, k), sub[k], mm[k], a, b, c);
+        for (size_t i = 0; i < a.size(); i++) { lm[pos[k][i]] = a[i]; lm2[pos[k][i]] = b[i]; ls[pos[k][i]] = c[i]; }
+      }
+    } else {
+      const int64_t K = t.nchild(node);
+      std::vector<std::vector<double>> A(K), B(K), C(K);
+      for (int64_t k = 0; k < K; k++) predict(t.child(node, k), idx, mumin, A[k], B[k], C[k]);
+      const double* lw = logw.data() + t.child_ptr[node];
+      auto lse = [&](std::vector<std::vector<double>>& M, size_t i) {   // common.jl:309-313
+        double m = -std::numeric_limits<double>::infinity();
+        for (int64_t k = 0; k < K; k++) m = std::max(m, M[k][i] + lw[k]);
+        double s = 0.0;
+        for (int64_t k = 0; k < K; k++) s += std::exp((M[k][i] + lw[k]) - m);
+        return std::log(s) + m;
+      };
+      for (size_t i = 0; i < n; i++) { lm[i] = lse(A, i); lm2[i] = lse(B, i); ls[i] = lse(C, i); }
+    }
+  }
+  // _predictPoE common.jl:145-149,198-208 : (mu, precision)
+  bool poe(int64_t node, const std::vector<int64_t>& idx, std::vector<double>& m, std::vector<double>& tau) {
+    const int ty = t.type[node];
+    const size_t n = idx.size();
+    if (ty == DSMGP_NODE_LEAF) {
+      const int64_t l = t.leaf_of_node[node];
+      m.resize(n); tau.resize(n);
+      for (size_t i = 0; i < n; i++) { m[i] = mu[l][cursor[l] + i]; tau[i] = 1.0 / var[l][cursor[l] + i]; }
+      cursor[l] += n;
+      return true;
+    }
+    if (ty != DSMGP_NODE_SPLIT) return false;    // MethodError in the reference
+    m.assign(n, 0.0); tau.assign(n, 0.0);
+    std::vector<double> m_, t_;
+    for (int64_t k = 0; k < t.nchild(node); k++) {
+      if (!poe(t.child(node, k), idx, m_, t_)) return false;
+      for (size_t i = 0; i < n; i++) { tau[i] += t_[i]; m[i] += t_[i] * m_[i]; }
+    }
+    for (size_t i = 0; i < n; i++) m[i] = m[i] / tau[i];
+    return true;
+  }
+};
+}  // namespace
+
+// Device prediction of every leaf on its routed points.  pts[l] = test rows routed to leaf l.
+static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, const std::vector<std::vector<int64_t>>& pts,
+                              std::vector<std::vector<double>>& mu, std::vector<std::vector<double>>& var,
+                              bool local_only = false) {
+  if (!h->fitted) { h->err = "predict: call fit first"; return DSMGP_ERR_STATE; }
+  if (!h->opts.keep_factors || h->batches.size() != 1) { h->err = "predict needs keep_factors=1"; return DSMGP_ERR_STATE; }
+  { int32_t rr = refine_alpha(h); if (rr) return rr; }
+  const int64_t L = h->L, D = h->D;
+  mu.assign(L, {}); var.assign(L, {});
+  std::vector<PredLeaf> pls; std::vector<int2> tasks; std::vector<int64_t> pl_leaf;
+  int64_t xto = 0, vto = 0, oo = 0;
+  for (int64_t l = 0; l < L; l++) {
+    if (pts[l].empty()) continue;
+    const int slot = h->leaf_slot[l];
+    if (slot < 0) {
+      if (local_only) continue;               // predicted by its owner (dsmgp_predict_local / _finish)
+      h->err = "predict: leaf owned by another rank (use dsmgp_predict_local + all-reduce + dsmgp_predict_finish)";
+      return DSMGP_ERR_STATE;
+    }
+    PredLeaf p; p.slot = slot; p.T = (int32_t)pts[l].size(); p.Tp = (p.T + BLK - 1) / BLK * BLK; p.pad_ = 0;
+    p.xtoff = xto; xto += (int64_t)p.Tp * D;
+    p.vtoff = vto; vto += (int64_t)(p.Tp / BLK) * h->meta[slot].nkc * TILE_D;
+    p.ooff = oo; oo += p.Tp;
+    for (int q = 0; q < p.Tp / BLK; q++) tasks.push_back(make_int2((int)pls.size(), q));
+    pls.push_back(p); pl_leaf.push_back(l);
+  }
+  if (pls.empty()) return DSMGP_OK;
+  std::stable_sort(tasks.begin(), tasks.end(), [&](const int2& a, const int2& b) {
+    return h->meta[pls[a.x].slot].np > h->meta[pls[b.x].slot].np; });
+  std::vector<double> xt(xto, 0.0);
+  for (size_t i = 0; i < pls.size(); i++) {
+    const auto& pv = pts[pl_leaf[i]];
+    for (int64_t d = 0; d < D; d++)
+      for (size_t q = 0; q < pv.size(); q++) xt[pls[i].xtoff + d * pls[i].Tp + q] = xtest[d * T + pv[q]];
+  }
+  DevBuf<double>&d_xt = h->p_xt, &d_VT = h->p_VT, &d_mu = h->p_mu, &d_var = h->p_var;
+  DevBuf<PredLeaf>& d_pl = h->p_pl; DevBuf<int2>& d_tasks = h->p_tasks;
+  auto cleanup = [&]() { if (d_VT.n * sizeof(double) > (size_t(16) << 30)) d_VT.free(); };   // keep the scratch unless it is huge
+#define PTRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { h->err = std::string(#expr) + ": " + cudaGetErrorString(e_); cleanup(); \
+    return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA; } } while (0)
+  PTRY(d_xt.ensure(xto)); PTRY(d_VT.ensure(vto)); PTRY(d_mu.ensure(oo)); PTRY(d_var.ensure(oo));
+  PTRY(d_pl.ensure(pls.size())); PTRY(d_tasks.ensure(tasks.size()));
+  PTRY(cudaMemcpyAsync(d_xt.p, xt.data(), xto * 8, cudaMemcpyHostToDevice, h->stream));
+  PTRY(cudaMemcpyAsync(d_pl.p, pls.data(), pls.size() * sizeof(PredLeaf), cudaMemcpyHostToDevice, h->stream));
+  PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
+  PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
+  PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
+              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + 8,
+              0, nullptr, nullptr, nullptr, nullptr, 0};
+  const int sms = num_sms(h->device);
+  const char* force_wave = getenv("DSMGP_PREDICT_WAVE");       // tests: "0" / "1" force the task granularity
+  const bool use_wave = force_wave ? (force_wave[0] == '1') : ((int)tasks.size() < 3 * sms);
+  if (use_wave) {
+    // WAVE mode: too few (leaf, Q) tasks to fill the GPU -> one task per (leaf, Q, row block), ordered by row block
+    // (a block depends only on the blocks above it) with the experts shifted so that they end together
+    std::vector<int4> wt, wc;
+    int base = 0, max_nb = 0;
+    for (auto& p : pls) max_nb = std::max(max_nb, (int)h->meta[p.slot].nb);
+    struct WK { int key, np, pl, Q, I, base; };
+    std::vector<WK> wk;
+    for (size_t i = 0; i < pls.size(); i++) {
+      const LeafMeta& m = h->meta[pls[i].slot];
+      for (int q = 0; q < pls[i].Tp / BLK; q++) {
+        wc.push_back(make_int4((int)i, q, base, m.nb));
+        for (int I = 0; I < m.nb; I++) wk.push_back({I + max_nb - m.nb, m.np, (int)i, q, I, base});
+        base += m.nb;
+      }
+    }
+    std::stable_sort(wk.begin(), wk.end(), [](const WK& a, const WK& b) { return a.key != b.key ? a.key < b.key : a.np > b.np; });
+    for (auto& k : wk) wt.push_back(make_int4(k.pl, k.Q, k.I, k.base));
+    PTRY(h->p_wtasks.ensure(wt.size())); PTRY(h->p_wcols.ensure(wc.size())); PTRY(h->p_flags.ensure(base));
+    PTRY(h->p_part.ensure((size_t)base * 2 * BLK));
+    PTRY(cudaMemcpyAsync(h->p_wtasks.p, wt.data(), wt.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    PTRY(cudaMemcpyAsync(h->p_wcols.p, wc.data(), wc.size() * sizeof(int4), cudaMemcpyHostToDevice, h->stream));
+    PTRY(cudaMemsetAsync(h->p_flags.p, 0, (size_t)base * sizeof(int), h->stream));
+    PTRY(cudaStreamSynchronize(h->stream));       // wt / wc are locals
+    pa.wave = 1; pa.wtasks = h->p_wtasks.p; pa.ntasks = (int)wt.size(); pa.flags = h->p_flags.p; pa.part = h->p_part.p;
+    pa.wcols = h->p_wcols.p; pa.nwcols = (int)wc.size();
+  }
+  cudaEventRecord(h->ev[0], h->stream);
+  launch_predict3(pa, std::max(1, std::min(sms, pa.ntasks)), h->stream);
+  if (pa.wave) launch_predict_reduce(pa, h->stream);
+  cudaEventRecord(h->ev[1], h->stream);
+  h->tm.launches++;
+  PTRY(cudaGetLastError());
+  std::vector<double> hmu(oo), hvar(oo);
+  PTRY(cudaMemcpyAsync(hmu.data(), d_mu.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
+  PTRY(cudaMemcpyAsync(hvar.data(), d_var.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
+  int gerr = 0;
+  PTRY(cudaMemcpyAsync(&gerr, h->d_counter.p + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PTRY(cudaStreamSynchronize(h->stream));
+  if (gerr != 0) { h->err = "predict: device scheduler timeout (code " + std::to_string(gerr) + ")"; cleanup(); return DSMGP_ERR_STATE; }
+#undef PTRY
+  h->tm.predict_ms = ev_ms(h->ev[0], h->ev[1]);
+  h->tm.predict_flops = 0.0; h->tm.predict_bytes = 0.0;
+  for (size_t i = 0; i < pls.size(); i++) {      // TRSM n^2 T_l + 2 n T_l flop; L read once per block of 128 points
+    const double n = h->meta[pls[i].slot].n, Tl = pls[i].T;
+    h->tm.predict_flops += n * n * Tl + 2.0 * n * Tl;
+    h->tm.predict_bytes += 8.0 * (n * (n + 1) / 2.0) * (pls[i].Tp / BLK) + 8.0 * (n + Tl) * (double)D + 16.0 * Tl;
+  }
+  for (size_t i = 0; i < pls.size(); i++) {
+    const int64_t l = pl_leaf[i];
+    mu[l].assign(hmu.begin() + pls[i].ooff, hmu.begin() + pls[i].ooff + pls[i].T);
+    var[l].assign(hvar.begin() + pls[i].ooff, hvar.begin() + pls[i].ooff + pls[i].T);
+  }
+  cleanup();
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_leaf_predict(dsmgp_handle* h, int64_t leaf, const double* xtest, int64_t T, double* mu, double* var) {
+  if (!h || leaf < 0 || leaf >= h->L || !xtest || T <= 0 || !mu || !var) return DSMGP_ERR_ARG;
+  cudaSetDevice(h->device);
+  std::vector<std::vector<int64_t>> pts(h->L);
+  pts[leaf].resize(T);
+  std::iota(pts[leaf].begin(), pts[leaf].end(), 0);
+  std::vector<std::vector<double>> m, v;
+  int32_t rc = predict_leaves(h, xtest, T, pts, m, v);
+  if (rc) return rc;
+  std::copy(m[leaf].begin(), m[leaf].end(), mu);
+  std::copy(v[leaf].begin(), v[leaf].end(), var);
+  return DSMGP_OK;
+}
+
+// argument checks + routing shared by the predict entry points
+static int32_t predict_route(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, std::vector<std::vector<int64_t>>& pts) {
+  if (!xtest || T <= 0 || mode < 0 || mode > 3) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
+  for (int64_t i = 0; i < T * h->D; i++) if (!std::isfinite(xtest[i])) { h->err = "predict: non-finite input"; return DSMGP_ERR_ARG; }
+  cudaSetDevice(h->device);
+  const HostTree& t = h->tree;
+  const bool poe = mode != DSMGP_PREDICT_DSMGP;
+  if (poe && t.type[t.root] != DSMGP_NODE_SPLIT) { h->err = "predict: PoE/gPoE/rBCM need a split root (buildPoE/buildBCM model)"; return DSMGP_ERR_ARG; }
+  if (!poe && !h->have_weights) {
+    // the reference predicts with whatever logweights the sum nodes hold (uniform -log K after build)
+    h->sum_logw.assign(t.child_ptr[t.n_nodes], 0.0);
+    for (int64_t i = 0; i < t.n_nodes; i++)
+      if (t.type[i] >= DSMGP_NODE_SUM) for (int64_t c = t.child_ptr[i]; c < t.child_ptr[i + 1]; c++) h->sum_logw[c] = -std::log((double)t.nchild(i));
+  }
+  std::vector<int64_t> all(T);
+  std::iota(all.begin(), all.end(), 0);
+  Router r(t, xtest, T, h->L);
+  r.route(t.root, all, poe);
+  if (r.bad) { h->err = "predict: a test point lies outside every split interval"; return DSMGP_ERR_ARG; }
+  pts.swap(r.pts);
+  return DSMGP_OK;
+}
+
+static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode,
+                           const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
+                           double* mu, double* var);
+
+extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!mu || !var) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<int64_t>> pts;
+  int32_t rc = predict_route(h, xtest, T, mode, pts);
+  if (rc) return rc;
+  std::vector<std::vector<double>> lmu, lvar;
+  if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar))) return rc;
+  return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
+}
+
+// Leaf-sharded prediction (one process per GPU): every rank predicts its own experts on the points routed to them and
+// writes them into a buffer in (leaf, routing order) layout -- entries of other ranks' experts stay 0, so a SUM all-reduce
+// assembles the buffer -- then every rank mixes (common.jl:134-307) redundantly, like the tree passes of an evaluation.
+extern "C" int32_t dsmgp_predict_local(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* buf, int64_t* total) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!total) { h->err = "predict_local: bad argument"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<int64_t>> pts;
+  int32_t rc = predict_route(h, xtest, T, mode, pts);
+  if (rc) return rc;
+  int64_t tot = 0;
+  for (auto& v : pts) tot += (int64_t)v.size();
+  *total = tot;
+  if (!buf) return DSMGP_OK;                   // size query
+  std::vector<std::vector<double>> lmu, lvar;
+  if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar, true))) return rc;
+  std::fill(buf, buf + 2 * tot, 0.0);
+  int64_t off = 0;
+  for (int64_t l = 0; l < h->L; l++) {
+    if (!lmu.empty() && !lmu[l].empty()) {
+      std::copy(lmu[l].begin(), lmu[l].end(), buf + off);
+      std::copy(lvar[l].begin(), lvar[l].end(), buf + tot + off);
+    }
+    off += (int64_t)pts[l].size();
+  }
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_predict_finish(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, const double* buf,
+                                        double* mu, double* var) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!buf || !mu || !var) { h->err = "predict_finish: bad argument"; return DSMGP_ERR_ARG; }
+  std::vector<std::vector<int64_t>> pts;
+  int32_t rc = predict_route(h, xtest, T, mode, pts);
+  if (rc) return rc;
+  int64_t tot = 0;
+  for (auto& v : pts) tot += (int64_t)v.size();
+  std::vector<std::vector<double>> lmu(h->L), lvar(h->L);
+  int64_t off = 0;
+  for (int64_t l = 0; l < h->L; l++) {
+    lmu[l].assign(buf + off, buf + off + pts[l].size());
+    lvar[l].assign(buf + tot + off, buf + tot + off + pts[l].size());
+    off += (int64_t)pts[l].size();
+  }
+  return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
+}
+
+static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode,
+                           const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
+                           double* mu, double* var) {
+  const HostTree& t = h->tree;
+  std::vector<int64_t> all(T);
+  std::iota(all.begin(), all.end(), 0);
+  Mixer mx(t, xtest, T, lmu, lvar, h->sum_logw);
+  if (mode == DSMGP_PREDICT_DSMGP) {
+    // predict(node) common.jl:175-179 (leaf), :243-254 (split root), :294-302 (sum root)
+    struct Rec {
+      Mixer& mx; const HostTree& t; double* mu; double* var; const double* x; int64_t T;
+      void run(int64_t node, const std::vector<int64_t>& idx) {
+        if (t.type[node] == DSMGP_NODE_SPLIT) {
+          std::vector<std::vector<int64_t>> sub(t.nchild(node));
+          for (int64_t p : idx) sub[getchild(t, node, x, T, p)].push_back(p);
+          for (int64_t k = 0; k < t.nchild(node); k++) if (!sub[k].empty()) run(t.child(node, k), sub[k]);
+          return;
+        }
+        // leaf or sum: two traversals of the subtree -> replay cursors must restart for this subtree.
+        std::vector<size_t> save = mx.cursor;
+        std::vector<double> mumin, lm, lm2, ls;
+        mx.minpredict(node, idx, mumin);
+        mx.cursor = save;
+        for (auto& v : mumin) v -= 1.0;
+        mx.predict(node, idx, mumin, lm, lm2, ls);
+        for (size_t i = 0; i < idx.size(); i++) {
+          const double m = std::exp(lm[i]) + mumin[i];
+          mu[idx[i]] = m;
+          var[idx[i]] = (t.type[node] == DSMGP_NODE_LEAF) ? std::exp(ls[i]) : std::exp(ls[i]) + (std::exp(lm2[i]) - m * m);
+        }
+      }
+    } rec{mx, t, mu, var, xtest, T};
+    rec.run(t.root, all);
+    return DSMGP_OK;
+  }
+  const int64_t K = t.nchild(t.root);
+  std::vector<double> m_, t_;
+  if (mode == DSMGP_PREDICT_POE) {
+    if (!mx.poe(t.root, all, m_, t_)) { h->err = "predictPoE: sum node below a split (MethodError in the reference)"; return DSMGP_ERR_ARG; }
+    for (int64_t i = 0; i < T; i++) { mu[i] = m_[i]; var[i] = 1.0 / t_[i]; }
+  } else if (mode == DSMGP_PREDICT_GPOE) {       // common.jl:211-222
+    const double beta = 1.0 / (double)K;
+    std::vector<double> M(T, 0.0), Tt(T, 0.0);
+    for (int64_t k = 0; k < K; k++) {
+      if (!mx.poe(t.child(t.root, k), all, m_, t_)) { h->err = "predictgPoE: sum node below a split"; return DSMGP_ERR_ARG; }
+      for (int64_t i = 0; i < T; i++) { Tt[i] += beta * t_[i]; M[i] += beta * t_[i] * m_[i]; }
+    }
+    for (int64_t i = 0; i < T; i++) { mu[i] = M[i] / Tt[i]; var[i] = 1.0 / Tt[i]; }
+  } else {                                       // rBCM common.jl:224-241
+    int64_t nd = t.root;
+    while (t.type[nd] != DSMGP_NODE_LEAF) nd = t.child(nd, 0);
+    const int64_t l0 = t.leaf_of_node[nd];
+    const int k0 = h->leaf_kid[l0];
+    std::vector<double> prm(h->pstride);
+    derive_params(h, k0, &h->theta_leaf[(size_t)l0 * h->Hmax], prm.data());
+    const int type = h->kernels[k0].type;
+    std::vector<double> s(T), C(T), M(T, 0.0);
+    for (int64_t i = 0; i < T; i++) {
+      double ktt;
+      if (type == DSMGP_ISO_SE) ktt = prm[PRM_V];
+      else if (type == DSMGP_ARD_SE) ktt = prm[PRM_V] * (double)h->D;
+      else {
+        ktt = 0.0;
+        for (int64_t d = 0; d < h->D; d++) { const double xv = xtest[d * T + i]; ktt += (type == DSMGP_ISO_LINEAR ? prm[PRM_COEF] : prm[PRM_COEF + d]) * xv * xv; }
+      }
+      s[i] = ktt + prm[PRM_ETA];
+      C[i] = 1.0 / s[i];
+    }
+    for (int64_t k = 0; k < K; k++) {
+      if (!mx.poe(t.child(t.root, k), all, m_, t_)) { h->err = "predictrBCM: sum node below a split"; return DSMGP_ERR_ARG; }
+      for (int64_t i = 0; i < T; i++) {
+        const double s_ = 1.0 / t_[i];
+        const double beta = 0.5 * (std::log(s[i]) - std::log(s_));
+        C[i] = C[i] + (beta * t_[i]) - (beta / s[i]);
+        M[i] = M[i] + m_[i] * (beta * t_[i]);
+      }
+    }
+    for (int64_t i = 0; i < T; i++) { mu[i] = M[i] / C[i]; var[i] = 1.0 / C[i]; }
+  }
+  return DSMGP_OK;
+}

@@ -1,0 +1,212 @@
+// Internal definitions shared by the translation units that implement the C ABI (api*.cu, comm.cu).
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/dsmgp.h"
+#include "args.h"
+#include "potrf2_args.h"
+#include "tree_host.h"
+
+namespace dsm {
+std::string& create_error();                 // thread-local message of the last failed call without a handle
+}
+
+#define CUDA_TRY(h, expr)                                                                       \
+  do {                                                                                          \
+    cudaError_t e_ = (expr);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      (h)->err = std::string(#expr) + ": " + cudaGetErrorString(e_);                            \
+      return e_ == cudaErrorMemoryAllocation ? DSMGP_ERR_OOM : DSMGP_ERR_CUDA;                  \
+    }                                                                                           \
+  } while (0)
+
+namespace dsm {
+
+struct Batch {
+  int s0 = 0, s1 = 0, max_nb = 0;
+  std::vector<int> cnt;                  // cnt[J]: slots of the batch that own block column J (slots sorted by size)
+  int64_t f_doubles = 0, w_doubles = 0, ntiles = 0, trpart_doubles = 0, gpart_doubles = 0;
+  int64_t* d_tile_off = nullptr;
+  int64_t* d_trpart_off = nullptr;
+  int64_t* d_gpart_off = nullptr;
+  int2* d_trtri_tasks = nullptr; int n_trtri = 0;
+  int4* d_lauum_tasks = nullptr; int n_lauum = 0;
+  int4* d_potrf2_tasks = nullptr; int n_potrf2 = 0;     // engine v2: tile tasks in look-ahead order
+  int4* d_trtri3_tasks = nullptr; int n_trtri3 = 0;     // inverse: tile tasks by anti-diagonal
+  int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
+  int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
+  double potrf_flops = 0, gram_bytes = 0;
+};
+
+// Process-wide cache of large device buffers.  cudaMalloc / cudaFree of multi-GB arenas cost 10 ms ... 3 s each
+// (measured: tools/cold_probe.py), which would dominate building a model from host arrays; freed buffers >= 32 MiB are
+// kept and handed to the next handle that asks for a similar size on the same device.  dsmgp_release_cache() returns
+// them to the driver.
+struct BufCache {
+  struct Ent { void* p; size_t bytes; int dev; };
+  std::vector<Ent> ents;
+  std::mutex mu;
+  static constexpr size_t MIN_BYTES = size_t(32) << 20;
+  size_t cached_bytes(int dev) {
+    std::lock_guard<std::mutex> g(mu);
+    size_t t = 0;
+    for (auto& e : ents) if (e.dev == dev) t += e.bytes;
+    return t;
+  }
+  void* take(size_t bytes, int dev, size_t* got) {
+    std::lock_guard<std::mutex> g(mu);
+    int best = -1;
+    for (int i = 0; i < (int)ents.size(); i++)
+      if (ents[i].dev == dev && ents[i].bytes >= bytes && ents[i].bytes <= bytes + bytes / 4 + (size_t(64) << 20) &&
+          (best < 0 || ents[i].bytes < ents[best].bytes)) best = i;
+    if (best < 0) return nullptr;
+    void* p = ents[best].p;
+    *got = ents[best].bytes;
+    ents.erase(ents.begin() + best);
+    return p;
+  }
+  bool give(void* p, size_t bytes, int dev) {
+    if (bytes < MIN_BYTES) return false;
+    std::lock_guard<std::mutex> g(mu);
+    if (ents.size() >= 64) return false;
+    ents.push_back({p, bytes, dev});
+    return true;
+  }
+  void release_all() {
+    std::lock_guard<std::mutex> g(mu);
+    for (auto& e : ents) { int cur = 0; cudaGetDevice(&cur); cudaSetDevice(e.dev); cudaFree(e.p); cudaSetDevice(cur); }
+    ents.clear();
+  }
+};
+extern BufCache g_cache;
+
+template <typename T>
+struct DevBuf {
+  T* p = nullptr; size_t n = 0; size_t cap_bytes = 0; int dev = 0;
+  cudaError_t alloc(size_t count) {
+    free();
+    n = count;
+    if (count == 0) return cudaSuccess;
+    const size_t bytes = count * sizeof(T);
+    cudaGetDevice(&dev);
+    if (bytes >= BufCache::MIN_BYTES) {
+      if (void* q = g_cache.take(bytes, dev, &cap_bytes)) { p = static_cast<T*>(q); return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaErrorMemoryAllocation) {          // make room: drop the cache and retry once
+      cudaGetLastError();
+      g_cache.release_all();
+      e = cudaMalloc(&p, bytes);
+    }
+    cap_bytes = bytes;
+    return e;
+  }
+  // grow-only scratch: keeps the allocation across calls (cudaMalloc / cudaFree of GBs cost 10-100 ms per call)
+  cudaError_t ensure(size_t count) {
+    if (count <= n && p != nullptr) return cudaSuccess;
+    return alloc(count + count / 8);
+  }
+  void free() {
+    if (p) {
+      if (!g_cache.give(p, cap_bytes, dev)) cudaFree(p);
+    }
+    p = nullptr; n = 0; cap_bytes = 0;
+  }
+};
+
+}  // namespace dsm
+
+using namespace dsm;     // internal header: only the ABI translation units include it
+
+struct dsmgp_handle {
+  int64_t N = 0, D = 0, L = 0;
+  int nk = 0;
+  std::vector<dsmgp_kernel_desc> kernels;
+  std::vector<int64_t> koff;      // theta offset per kernel
+  std::vector<int32_t> knp;       // nparams per kernel
+  int64_t H = 0; int Hmax = 0; int row_width = 0; int pstride = 0;
+  std::vector<int64_t> leaf_ptr;
+  std::vector<int32_t> leaf_kid;
+  std::vector<double> leaf_mean;
+  HostTree tree;
+  dsmgp_opts opts;
+  std::vector<int32_t> owner;
+  std::vector<int> slot_leaf;     // slot -> global leaf
+  std::vector<int> leaf_slot;     // global leaf -> slot or -1
+  std::vector<LeafMeta> meta;     // per slot
+  std::vector<Batch> batches;
+  std::vector<double> theta_leaf; // L x Hmax
+  std::vector<double> h_prm;      // nslots x pstride
+  std::vector<double> h_rows;     // L x row_width
+  std::vector<double> node_lml;
+  std::vector<int32_t> h_info;    // L
+  std::vector<double> sum_logw;   // CSR by child_ptr (update!)
+  bool have_weights = false;
+  bool fitted = false, have_rows = false, have_grad = false, rows_complete = false;
+  bool alpha_exact = false;       // alpha from back-substitution (fit path); the gradient path leaves X^T z
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<cudaEvent_t> ev;     // 8 per batch: phase boundaries, always recorded (no extra syncs)
+  bool profiling = false;
+  dsmgp_timings tm = {};
+  // device
+  DevBuf<LeafMeta> d_meta;
+  DevBuf<double> d_xg, d_y, d_z, d_alpha, d_F, d_W, d_WT, d_prm, d_trpart, d_gpart, d_rows, d_leaf_mean;
+  DevBuf<LeafScal> d_scal;
+  DevBuf<int> d_counter;
+  DevBuf<int> d_flags;
+  DevBuf<double> d_ldpart, d_zzpart;
+  DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
+  DevBuf<double> p_xt, p_VT, p_mu, p_var, p_part; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
+  DevBuf<int4> p_wtasks, p_wcols; DevBuf<int> p_flags;
+  DevBuf<int> d_mask; std::vector<int> h_mask; bool use_mask = false;   // per-slot gradient mask (finetune: zero-overlap experts)
+  double* pin_multi = nullptr; size_t pin_multi_doubles = 0;             // rows of a multi-theta call [G][L][row_width]
+  LeafScal* pin_scal_multi = nullptr; size_t pin_scal_multi_n = 0;       // per-slot scalars of a multi-theta call [G][slots]
+  double* pin_rows = nullptr;
+  LeafScal* pin_scal = nullptr;
+  std::string err;
+
+  ~dsmgp_handle() {
+    for (auto& b : batches) {
+      cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
+      cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
+    }
+    d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
+    d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
+    p_xt.free(); p_VT.free(); p_mu.free(); p_var.free(); p_pl.free(); p_tasks.free();
+    p_part.free(); p_wtasks.free(); p_wcols.free(); p_flags.free();
+    d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
+    d_mask.free();
+    if (pin_multi) cudaFreeHost(pin_multi);
+    if (pin_scal_multi) cudaFreeHost(pin_scal_multi);
+    if (pin_rows) cudaFreeHost(pin_rows);
+    if (pin_scal) cudaFreeHost(pin_scal);
+    for (auto& e : ev) if (e) cudaEventDestroy(e);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace dsm {
+cudaError_t engine_attrs();
+int num_sms(int device);
+template <typename T>
+inline cudaError_t upload(T** dptr, const std::vector<T>& v) {
+  *dptr = nullptr;
+  if (v.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc(dptr, v.size() * sizeof(T));
+  if (e) return e;
+  return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+void shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* owner);
+void derive_params(const dsmgp_handle* h, int kid, const double* th, double* prm);
+inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+int32_t refine_alpha(dsmgp_handle* h);
+int32_t standalone_device_check(std::string& err);
+}  // namespace dsm
