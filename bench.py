@@ -32,10 +32,46 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# FP64 roofs measured on this pool's B200 with tools/fp64_peaks.cu (profiles/fp64_peaks_r01.json)
-FP64_DGEMM_TFLOPS = 35.9     # cuBLAS DGEMM 8192^3 (burst == sustained: FP64 is not power capped)
-FP64_DMMA_TFLOPS = 37.2      # DMMA.8x8x4 issue roof
-NCU_TRAFFIC_GB = {("cfg3", 1, "potrf2_kernel"): 51.87, ("cfg3", 1, "trtri3_kernel"): 78.64}   # profiles/ncu_full_*_r01h.txt
+
+
+def fp64_peaks():
+    """FP64 roofs measured on this pool's B200 with tools/fp64_peaks.cu (MEASURED_PEAKS.json has HBM / bf16 only): the newest
+    profiles/fp64_peaks_r*.json.  DGEMM = cuBLAS 8192^3 (burst == sustained: FP64 is not power capped), DMMA = issue roof."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "fp64_peaks_r*.json")))
+    if not files:
+        return {"dgemm": 35.9, "dmma": 37.2, "hbm": 6568.0, "source": "fallback constants (profiles/fp64_peaks_r*.json missing)"}
+    d = json.load(open(files[-1]))
+    return {"dgemm": float(d["dgemm_nt_8192_tflops"]), "dmma": float(d["dmma_tflops_w32"]), "hbm": float(d.get("hbm_copy_gbs", 6568.0)),
+            "source": os.path.relpath(files[-1], ROOT)}
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        return 6458.4, "fallback 6458.4 (MEASURED_PEAKS.json missing)"
+
+
+def ncu_traffic_gb(kernel, workload, world):
+    """dram__bytes_read + dram__bytes_write of one launch from the newest committed `ncu --set full` summary of that kernel
+    (profiles/ncu_full_<kernel>_r*.txt, captured on the cfg3 1-GPU bench); None for any other configuration."""
+    import glob
+    if workload != "cfg3" or world != 1:
+        return None, None
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"ncu_full_{kernel}_r*.txt")))
+    if not files:
+        return None, None
+    rd = wr = None
+    for ln in open(files[-1]):
+        if ln.startswith("dram__bytes_read.sum,Gbyte,"):
+            rd = float(ln.strip().split(",")[2])
+        if ln.startswith("dram__bytes_write.sum,Gbyte,"):
+            wr = float(ln.strip().split(",")[2])
+    if rd is None or wr is None:
+        return None, None
+    return rd + wr, os.path.relpath(files[-1], ROOT)
+
 
 WORKLOADS = {
     # name: (N, D, kernel, V, K, M, depth, eps, seed)   SURVEY §8(d)
@@ -124,44 +160,70 @@ def build_structure(w):
     return x, y, root, kern
 
 
-def cpu_baseline(w, x, y, root, budget_s, optimised=False, threads=None):
+def blas_threads(want=None):
+    """Pin the BLAS pool to `want` threads (default: every host core) regardless of OMP_NUM_THREADS -- torchrun exports
+    OMP_NUM_THREADS=1 to its workers -- and return the number of threads the pool really uses."""
+    from threadpoolctl import threadpool_info, threadpool_limits
+    want = want or os.cpu_count() or 1
+    threadpool_limits(limits=want)
+    got = [int(p.get("num_threads", 1)) for p in threadpool_info() if p.get("user_api") == "blas"]
+    return max(got) if got else 1
+
+
+def cpu_baseline(w, x, y, root, budget_s, optimised=False):
     from deepstructuredmixtures_b200 import structure as st
     from oracle import reference_shape as rs
+    threads = blas_threads()
     leaves = st.getLeaves(root)
     ok = oracle_kernel(w)
     # mixtures: time the first kernel's leaves and the second's separately through their own kernel objects
-    res_total = 0.0
-    used = []
+    res_total, sample_s, used = 0.0, 0.0, []
     for kid, k in enumerate(ok):
         lv = [lf for lf in leaves if lf.kernelid - 1 == kid]
         r = rs.sample_model_time(x, y, [lf.obs - 1 for lf in lv], [lf.mean for lf in lv], k, -1.0,
                                  budget_s=budget_s / len(ok), optimised=optimised)
-        res_total += r["seconds_per_eval"]; used.extend(r["sample_sizes"])
-    return {"value": 1.0 / res_total, "unit": "evals/s", "cores": threads or os.cpu_count(),
-            "kind": "port",
-            "sample": f"oracle port in the reference's algorithmic shape (2x update_cholesky!, potrs(-I)+GEMM traces, "
-                      f"gradients twice; SciPy/OpenBLAS) on leaves of size {used}, extrapolated by sum n^3 to all "
-                      f"{len(leaves)} leaves; seconds/eval={res_total:.1f}"}
+        res_total += r["seconds_per_eval"]; sample_s += r["sample_seconds"]; used.extend(r["sample_sizes"])
+    sum_n3 = float(sum(float(lf.nobs) ** 3 for lf in leaves))
+    what = ("minimal CPU algorithm (1x dpotrf, dpotri, O(n^2) traces" if optimised else
+            "oracle port in the reference's algorithmic shape (2x update_cholesky!, potrs(-I)+GEMM traces, gradients twice")
+    return {"value": 1.0 / res_total, "unit": "evals/s", "cores": threads, "host_cores": os.cpu_count(),
+            "kind": "port", "extrapolated": True, "seconds_per_eval_extrapolated": res_total,
+            "sample_seconds": sample_s, "sample_share_of_sum_n3": float(sum(float(n) ** 3 for n in used)) / sum_n3,
+            "sample": f"{what}; SciPy/OpenBLAS, {threads} BLAS threads) on leaves of size {used} "
+                      f"({sample_s:.1f} s measured), extrapolated by sum n^3 to all {len(leaves)} leaves; "
+                      f"seconds/eval={res_total:.1f}"}
 
 
 def run_reference(args, w):
+    """The reference's CPU path (Julia is not installed: the oracle port in the reference's algorithmic shape) on the box's
+    host cores.  A step = one bounded sample of leaves (timed for real), whose cost is extrapolated to a whole evaluation by
+    sum n^3: `value` is that extrapolated rate, `ms_per_step` the MEASURED wall time of a step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["DSMGP_STRUCTURE_ONLY"] = "1"      # host-side region-graph builder only: libdsmgp.so is not mapped into this arm
     x, y, root, _ = build_structure(w)
-    vals = []
-    for _ in range(max(1, min(args.steps, 3))):
-        vals.append(cpu_baseline(w, x, y, root, budget_s=max(10.0, 60.0 / max(1, min(args.steps, 3)))))
+    nsteps = max(1, min(args.steps, 3))
+    for _ in range(min(args.warmup, 1)):
+        cpu_baseline(w, x, y, root, budget_s=3.0)
+    vals, walls = [], []
+    for _ in range(nsteps):
+        t0 = time.perf_counter()
+        vals.append(cpu_baseline(w, x, y, root, budget_s=max(10.0, 60.0 / nsteps)))
+        walls.append(time.perf_counter() - t0)
     best = max(vals, key=lambda r: r["value"])
     v = float(np.mean([r["value"] for r in vals]))
     line = {"impl": "reference", "metric": "DSMGP LML+gradient evals/sec", "value": v, "unit": "evals/s",
-            "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": 1e3 / v, "higher_is_better": True,
+            "n_gpus": args.gpus, "steps": len(vals), "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * float(np.mean(walls)),
+            "ms_per_eval_extrapolated": 1e3 / v, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.workload, w),
             "cpu_baseline": dict(best, value=v),
             "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "native_library_loaded": any("libdsmgp" in ln for ln in open("/proc/self/maps")),
             "note": "Julia is not installed in this image: the reference arm is the oracle port timed in the "
-                    "reference's algorithmic shape on the host cores"}
+                    "reference's algorithmic shape on the host cores; each step times a bounded stratified sample of leaves "
+                    "(ms_per_step) and extrapolates it to a whole evaluation by sum n^3 (value, ms_per_eval_extrapolated)"}
     print(json.dumps(line), flush=True)
 
 
@@ -182,6 +244,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-predict", action="store_true")
     ap.add_argument("--mathematical", action="store_true", help="true gradients instead of as-written")
+    ap.add_argument("--no-sub-records", action="store_true", help="skip the `mathematical` and `scale_cfg5` sub-records")
+    ap.add_argument("--no-share", action="store_true", help="fit_naive!: do not hand the overlap matrix to the library")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -215,17 +279,23 @@ def main():
     ths = thetas([k.nparams for k in klist], w["seed"])
     L = len(model.leaves)
     sizes = np.array([lf.nobs for lf in model.leaves], dtype=np.float64)
+    if world > 1:
+        # the collective lives INSIDE the library (dsmgp_comm_init): from here on dsmgp_eval is the same call at any world size
+        from deepstructuredmixtures_b200.distributed import init_library_comm
+        init_library_comm(model)
+    sharing = None
+    if not args.no_share and world == 1 and L <= 4096:
+        # train! calls fit!(spn, D, gpmap) every iteration (optimisers.jl:45): the library gets the overlap matrix and shares
+        # what the reference's fit! shares (identical experts once, common leading block rows copied)
+        t0 = time.perf_counter()
+        H.set_sharing(model.D, 0.05)
+        kind, _, blocks = H.get_sharing()
+        sharing = {"identical_experts": int((kind == 1).sum()), "prefix_experts": int((kind == 2).sum()),
+                   "block_rows_copied": int(blocks.sum()), "overlap_and_plan_s": time.perf_counter() - t0}
 
     def step_device(i):
-        """device-resident inputs; returns device ms of this rank"""
-        if world == 1:
-            H.eval(ths[i % len(ths)])
-        else:
-            ptr = H.eval_local_dev(ths[i % len(ths)])
-            rows = torch.as_tensor(_DevPtr(ptr, (L * H.row_width,)), device=f"cuda:{local}")
-            dist.all_reduce(rows)
-            torch.cuda.synchronize()
-            H.eval_finish_dev()
+        """one LML+gradient evaluation through dsmgp_eval (world > 1: the row table is all-reduced inside the library)"""
+        H.eval(ths[i % len(ths)])
         return H.timings()
 
     for i in range(args.warmup):
@@ -260,6 +330,7 @@ def main():
     dev_ms, wall_ms = float(tt[0]), float(tt[1])
     phase["potrf_ms"], phase["inverse_ms"], phase["gram_ms"] = float(tt[2]), float(tt[3]), float(tt[4])
     tm = dict(tm, potrf_flops=float(fl[0]), inverse_flops=float(fl[1]), gram_bytes=float(fl[2]))
+    line = None
     if rank == 0:
         value = args.steps / (dev_ms * 1e-3)
         e2e = args.steps / (wall_ms * 1e-3)
@@ -272,7 +343,9 @@ def main():
         dom = "trtri3_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf2_kernel"
         ach = inv_tf if dom == "trtri3_kernel" else potrf_tf
         # DRAM bytes per launch from `ncu --set full` (profiles/ncu_full_*_r01e.csv); only known for the profiled config
-        traffic = NCU_TRAFFIC_GB.get((args.workload, world, dom))
+        traffic, traffic_src = ncu_traffic_gb(dom, args.workload, world)
+        pk = fp64_peaks()
+        hbm, hbm_src = hbm_peak()
         ns_local = int(np.sum(H.leaf_owner() == 0))
         line = {
             "metric": "DSMGP LML+gradient evals/sec", "value": value, "unit": "evals/s", "n_gpus": world,
@@ -287,13 +360,16 @@ def main():
             "gpu_launches": launches,
             "cholesky_gflops": potrf_tf * 1e3 * world,
             "phases_ms_per_step": {k: v / args.steps for k, v in phase.items()},
-            "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": FP64_DGEMM_TFLOPS, "unit": "TFLOP/s",
-                         "frac": ach / FP64_DGEMM_TFLOPS, "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+            "roofline": {"bound": "tensor", "kernel": dom, "achieved": ach, "peak": pk["dgemm"], "unit": "TFLOP/s",
+                         "frac": ach / pk["dgemm"], "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write)",
+                         "traffic_source": traffic_src, "frac_of_dmma_issue_roof": ach / pk["dmma"],
                          "algorithmic": "flops per launch = sum over local experts of n^3/3 + n^2/2 + n/6 (SURVEY 8d), one launch per evaluation; per-GPU figures",
-                         "peak_source": "cuBLAS DGEMM 8192^3 measured on this pool (tools/fp64_peaks.cu, profiles/); "
-                                        "MEASURED_PEAKS.json has no FP64 entry; DMMA issue roof 37.2",
+                         "peak_source": f"cuBLAS DGEMM 8192^3 measured on this pool (tools/fp64_peaks.cu -> {pk['source']}); "
+                                        f"MEASURED_PEAKS.json has no FP64 entry; DMMA issue roof {pk['dmma']:.1f}",
                          "potrf_tflops": potrf_tf, "inverse_tflops": inv_tf, "gram_gbs": gram_gbs,
-                         "gram_frac_hbm": gram_gbs / 6458.4},
+                         "gram_frac_hbm": gram_gbs / hbm, "hbm_peak_source": hbm_src,
+                         "gram_bound": "FP64 ALU (D exp per element)" if "ard" in w["kernel"] else "HBM write"},
+            "sharing": sharing,
             "clocks": clocks_summary(samples),
             "host": {"tree_build_s": t_tree, "create_upload_s": t_create},
         }
@@ -340,14 +416,86 @@ def main():
             line["cpu_baseline"] = cpu_baseline(w, x, y, root, args.cpu_budget)
             # the algorithmically minimal CPU version (one factorisation, dpotri, O(n^2) traces), so that the GPU/CPU
             # ratio can also be read without the reference's redundant work
-            opt = cpu_baseline(w, x, y, root, max(5.0, args.cpu_budget / 3), optimised=True)
-            line["cpu_baseline_optimised"] = dict(opt, sample=opt["sample"].replace(
-                "oracle port in the reference's algorithmic shape (2x update_cholesky!, potrs(-I)+GEMM traces, gradients twice; SciPy/OpenBLAS)",
-                "minimal CPU algorithm (1x dpotrf, dpotri, O(n^2) traces; SciPy/OpenBLAS)"))
-        print(json.dumps(line), flush=True)
+            line["cpu_baseline_optimised"] = cpu_baseline(w, x, y, root, max(5.0, args.cpu_budget / 3), optimised=True)
     model.close()
+    if not args.no_sub_records:
+        if world == 1 and not args.mathematical and args.workload != "cfg5":
+            # the benchmarked as-written ArdSE gradient needs no LAUUM pass (its length-scale part is identically 0,
+            # kernels.jl:161 / SURVEY App. B Q3): the same evaluation with the TRUE gradients, so that the rate is not only
+            # meaningful through that quirk
+            m3 = mdl.DSMGP(root, x, y, [k.copy() for k in klist], -1.0, device=local, as_written_grads=False)
+            for i in range(2):
+                m3.handle.eval(ths[i % len(ths)])
+            ms, ph = 0.0, {"gram_ms": 0.0, "potrf_ms": 0.0, "inverse_ms": 0.0, "grad_ms": 0.0}
+            nrep = max(3, min(args.steps, 5))
+            for i in range(nrep):
+                m3.handle.eval(ths[i % len(ths)])
+                tmm = m3.handle.timings()
+                ms += tmm["total_ms"]
+                for k in ph:
+                    ph[k] += tmm[k] / nrep
+            line["mathematical"] = {"value": nrep / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms / nrep, "steps": nrep,
+                                    "phases_ms_per_step": ph,
+                                    "what": "same workload with as_written_grads=0: true d LML / d theta (adds the LAUUM pass with the fused dK traces)"}
+            m3.close()
+        if args.workload == "cfg3":
+            rec = scale_record(args, rank, world, local)
+            if rank == 0:
+                line["scale_cfg5"] = rec
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def scale_record(args, rank, world, local):
+    """north_star's scale run as a bounded sub-record: synthetic 1,000,000 x 8 ArdSE DSMGP (depth 4, 20,736 experts), experts
+    sharded over the ranks, factors streamed (factor -> reduce -> discard), ONE all-reduce of the per-leaf rows per evaluation
+    inside the library.  1 warm-up + 2 timed evaluations; device time = max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from deepstructuredmixtures_b200 import model as mdl
+    w = WORKLOADS["cfg5"]
+    t0 = time.perf_counter()
+    x, y, root, kern = build_structure(w)
+    t_tree = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    model = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, rank=rank, world=world, device=local, keep_factors=False)
+    if world > 1:
+        from deepstructuredmixtures_b200.distributed import init_library_comm
+        init_library_comm(model)
+    t_create = time.perf_counter() - t0
+    H = model.handle
+    ths = thetas([kern.nparams], w["seed"])
+    H.eval(ths[0])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    nrep, dev_ms, pot_ms, inv_ms = 2, 0.0, 0.0, 0.0
+    tw = time.perf_counter()
+    for i in range(nrep):
+        H.eval(ths[(1 + i) % len(ths)])
+        tm = H.timings()
+        dev_ms += tm["total_ms"]; pot_ms += tm["potrf_ms"]; inv_ms += tm["inverse_ms"]
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall_ms = (time.perf_counter() - tw) * 1e3
+    tt = torch.tensor([dev_ms, wall_ms, pot_ms, inv_ms], dtype=torch.float64, device=f"cuda:{local}")
+    fl = torch.tensor([tm["potrf_flops"], tm["inverse_flops"]], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
+    L = len(model.leaves)
+    model.close()
+    dev_ms, wall_ms, pot_ms, inv_ms = (float(v) for v in tt)
+    return {"workload": workload_config("cfg5", w)["workload"], "n_gpus": world, "steps": nrep, "warmup": 1,
+            "value": nrep / (dev_ms * 1e-3), "unit": "evals/s", "ms_per_step": dev_ms / nrep,
+            "e2e": {"value": nrep / (wall_ms * 1e-3), "unit": "evals/s"},
+            "potrf_tflops_per_gpu": float(fl[0]) * nrep / (pot_ms * 1e-3) * 1e-12 / world,
+            "inverse_tflops_per_gpu": float(fl[1]) * nrep / (inv_ms * 1e-3) * 1e-12 / world,
+            "leaves": L, "scaling": "strong (same 1M-point model, experts sharded by LPT on n^3)",
+            "host": {"tree_build_s": t_tree, "create_upload_s": t_create}}
 
 
 if __name__ == "__main__":

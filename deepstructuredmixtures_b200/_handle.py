@@ -10,6 +10,13 @@ from . import _native as nat
 from .kernels import KernelFunction
 
 
+def comm_unique_id() -> bytes:
+    """dsmgp_comm_unique_id: NCCL's 128-byte id, created by rank 0 and handed to every rank's `Handle.comm_init`."""
+    buf = C.create_string_buffer(nat.COMM_ID_BYTES)
+    nat.check(nat.lib().dsmgp_comm_unique_id(C.cast(buf, C.c_void_p)))
+    return buf.raw
+
+
 class Handle:
     def __init__(self, x: np.ndarray, leaf_obs: Sequence[np.ndarray], y_centered: Sequence[np.ndarray],
                  leaf_mean: Sequence[float], leaf_kernel_id: Sequence[int], kernels: Sequence[KernelFunction],
@@ -80,11 +87,30 @@ class Handle:
         return th
 
     # ---- compute
-    def fit(self):
+    def fit(self, overlap=None, tau: float = 0.05):
+        """dsmgp_fit(h, tau, overlap, info, seconds): overlap = the L x L matrix of getOverlap (shared Cholesky of fit!),
+        or None for fit_naive!."""
         info = np.zeros(self.L, dtype=np.int32)
         sec = C.c_double(0)
-        self._ck(self._lib.dsmgp_fit(self._h, nat.p_i32(info), C.byref(sec)))
+        ov = None if overlap is None else nat.colmajor(np.asarray(overlap, dtype=np.float64))
+        self._ck(self._lib.dsmgp_fit(self._h, float(tau), nat.p_d(ov), nat.p_i32(info), C.byref(sec)))
         return info, sec.value
+
+    def set_sharing(self, overlap=None, tau: float = 0.05):
+        """Store (or clear, overlap=None) the sharing plan used by every later fit / eval."""
+        ov = None if overlap is None else nat.colmajor(np.asarray(overlap, dtype=np.float64))
+        self._ck(self._lib.dsmgp_set_sharing(self._h, nat.p_d(ov), float(tau)))
+
+    def get_sharing(self):
+        """(kind, source, blocks) per leaf: 0 own factor / 1 identical to source / 2 continues behind copied block rows."""
+        k = np.zeros(self.L, dtype=np.int32); s = np.zeros(self.L, dtype=np.int32); b = np.zeros(self.L, dtype=np.int32)
+        self._ck(self._lib.dsmgp_get_sharing(self._h, nat.p_i32(k), nat.p_i32(s), nat.p_i32(b)))
+        return k, s, b
+
+    def comm_init(self, unique_id: bytes):
+        """dsmgp_comm_init: attach this rank's handle to the NCCL communicator named by `unique_id` (collective call)."""
+        buf = C.create_string_buffer(bytes(unique_id), nat.COMM_ID_BYTES)
+        self._ck(self._lib.dsmgp_comm_init(self._h, C.cast(buf, C.c_void_p)))
 
     def lml(self) -> np.ndarray:
         out = np.zeros(self.n_nodes)
@@ -160,6 +186,17 @@ class Handle:
         z = C.c_double(0)
         self._ck(self._lib.dsmgp_update_weights(self._h, nat.p_d(lw), C.byref(z)))
         return lw, z.value
+
+    def infer(self):
+        lw = np.zeros(max(int(self.tree.child_ptr[-1]), 1))
+        z = C.c_double(0)
+        self._ck(self._lib.dsmgp_infer(self._h, nat.p_d(lw), C.byref(z)))
+        return lw, z.value
+
+    def reset_weights(self):
+        lw = np.zeros(max(int(self.tree.child_ptr[-1]), 1))
+        self._ck(self._lib.dsmgp_reset_weights(self._h, nat.p_d(lw)))
+        return lw
 
     def predict(self, xtest, mode: int = nat.PREDICT_DSMGP):
         xt = nat.colmajor(np.asarray(xtest, dtype=np.float64).reshape(len(xtest), -1))

@@ -65,7 +65,9 @@ EXPORTS = [
     "dsmgp_update_weights", "dsmgp_predict", "dsmgp_predict_local", "dsmgp_predict_finish", "dsmgp_leaf_predict", "dsmgp_leaf_alpha", "dsmgp_leaf_factor",
     "dsmgp_leaf_info", "dsmgp_kernelmatrix", "dsmgp_overlap", "dsmgp_release_cache", "dsmgp_chol_continue", "dsmgp_chol_delete_rows", "dsmgp_potrf",
     "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling",
+    "dsmgp_set_sharing", "dsmgp_get_sharing", "dsmgp_infer", "dsmgp_reset_weights", "dsmgp_comm_unique_id", "dsmgp_comm_init", "dsmgp_host_sharing_plan",
 ]
+COMM_ID_BYTES = 128
 
 _lib: Optional[C.CDLL] = None
 
@@ -92,7 +94,13 @@ def lib() -> C.CDLL:
         "dsmgp_get_leaf_params": (I32, [P, I64, pd, I64]),
         "dsmgp_nparams": (I64, [P]), "dsmgp_n_leaves": (I64, [P]), "dsmgp_n_nodes": (I64, [P]),
         "dsmgp_leaf_size": (I64, [P, I64]),
-        "dsmgp_fit": (I32, [P, pi32, pd]),
+        "dsmgp_fit": (I32, [P, D, pd, pi32, pd]),
+        "dsmgp_set_sharing": (I32, [P, pd, D]),
+        "dsmgp_get_sharing": (I32, [P, pi32, pi32, pi32]),
+        "dsmgp_infer": (I32, [P, pd, pd]),
+        "dsmgp_reset_weights": (I32, [P, pd]),
+        "dsmgp_comm_unique_id": (I32, [C.c_void_p]),
+        "dsmgp_comm_init": (I32, [P, C.c_void_p]),
         "dsmgp_lml": (I32, [P, pd]),
         "dsmgp_grad": (I32, [P, pd, pd]),
         "dsmgp_eval": (I32, [P, pd, I64, pd, pd, pd, pd]),
@@ -119,6 +127,7 @@ def lib() -> C.CDLL:
         "dsmgp_potrf": (I32, [pd, I64, pi32]),
         "dsmgp_host_tree_eval": (I32, [C.POINTER(Tree), I64, pi32, C.POINTER(KernelDesc), I32, pd, I64, pd, pd, pd, pd, pd]),
         "dsmgp_host_shard": (I32, [I64, pi64, I32, pi32]),
+        "dsmgp_host_sharing_plan": (I32, [I64, pi64, pi64, pi32, pd, D, pi32, pi32, pi32]),
         "dsmgp_get_timings": (I32, [P, C.POINTER(Timings)]),
         "dsmgp_set_profiling": (I32, [P, I32]),
     }

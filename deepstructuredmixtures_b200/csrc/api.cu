@@ -77,6 +77,47 @@ static void upload_params(dsmgp_handle* h) {
 // ------------------------------------------------------------------------------------------
 // create / destroy
 // ------------------------------------------------------------------------------------------
+// potrf2 tile tasks of a batch in topological order with look-ahead, restricted to the experts with keep[] != 0.
+std::vector<int4> dsm::build_potrf2_tasks(const dsmgp_handle* h, const Batch& b, const std::vector<char>& keep, int sms) {
+  struct TK { int s, grp, slot, I, J; };
+  const int nb_s = b.s1 - b.s0;
+  int nkeep = 0, max_nb = 0;
+  for (int sl = 0; sl < nb_s; sl++) if (keep[sl]) { nkeep++; max_nb = std::max(max_nb, (int)h->meta[b.s0 + sl].nb); }
+  const char* ord_env = getenv("DSMGP_ORDER");           // development A/B: 0 = end together, 1 = stretch
+  const bool stretch = ord_env ? (ord_env[0] == '1') : (nkeep * 4 < sms);
+  const bool start_together = ord_env && ord_env[0] == '2';     // experiment: no shift at all
+  // position of the next diagonal tile inside a level: right behind the first panel tile (1: shortest critical path) or
+  // behind all panel tiles of the level (3: in a large batch the first panel tile has then finished and the diagonal
+  // task does not sit on an SM waiting for it)
+  const char* dg_env = getenv("DSMGP_DIAG_LATE");
+  const int diag_grp = (dg_env ? dg_env[0] == '1' : false) ? 3 : 1;
+  std::vector<TK> tk;
+  for (int s = b.s0; s < b.s1; s++) {
+    const int sl = s - b.s0;
+    if (!keep[sl]) continue;
+    const LeafMeta& m = h->meta[s];
+    const int shift = max_nb - m.nb;
+    // level of block column J in the global order.  "end together" (shift) keeps the tail of a throughput-bound
+    // batch parallel; "stretch" lets every expert progress proportionally through the whole launch, which spreads the
+    // other experts' work evenly along the critical path of the largest one (small shards: multi-GPU strong scaling)
+    auto level = [&](int J) { return start_together ? J * 1024 : stretch ? (int)(((int64_t)J * 1024 * max_nb) / m.nb) : (J + shift) * 1024; };
+    tk.push_back({level(0) - 1, 1, sl, 0, 0});
+    for (int J = 0; J + 1 < m.nb; J++) {
+      tk.push_back({level(J), 0, sl, J + 1, J});
+      tk.push_back({level(J), diag_grp, sl, J + 1, J + 1});
+      for (int I = J + 2; I < m.nb; I++) tk.push_back({level(J), 2, sl, I, J});
+    }
+  }
+  std::stable_sort(tk.begin(), tk.end(), [](const TK& a, const TK& c) {
+    if (a.s != c.s) return a.s < c.s;
+    if (a.grp != c.grp) return a.grp < c.grp;
+    if (a.slot != c.slot) return a.slot < c.slot;
+    return a.I < c.I; });
+  std::vector<int4> pt(tk.size());
+  for (size_t i = 0; i < tk.size(); i++) pt[i] = make_int4(tk[i].slot, tk[i].I, tk[i].J, 0);
+  return pt;
+}
+
 extern "C" void dsmgp_default_opts(dsmgp_opts* o) {
   memset(o, 0, sizeof(*o));
   o->as_written_grads = 1;
@@ -203,31 +244,10 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     const int diag_grp = (dg_env ? dg_env[0] == '1' : false) ? 3 : 1;
     {   // engine v2 tile tasks: topological order with look-ahead
       struct TK { int s, grp, slot, I, J; };
-      std::vector<TK> tk;
       std::vector<int64_t> foff(nb_s, 0);
       int64_t fo = 0;
-      for (int s = b.s0; s < b.s1; s++) {
-        const LeafMeta& m = h->meta[s];
-        const int sl = s - b.s0, shift = b.max_nb - m.nb;
-        foff[sl] = fo; fo += (int64_t)m.nb * (m.nb + 1) / 2;
-        // level of block column J in the global order.  "end together" (shift) keeps the tail of a throughput-bound
-        // batch parallel; "stretch" lets every expert progress proportionally through the whole launch, which spreads the
-        // other experts' work evenly along the critical path of the largest one (small shards: multi-GPU strong scaling)
-        auto level = [&](int J) { return start_together ? J * 1024 : stretch ? (int)(((int64_t)J * 1024 * b.max_nb) / m.nb) : (J + shift) * 1024; };
-        tk.push_back({level(0) - 1, 1, sl, 0, 0});
-        for (int J = 0; J + 1 < m.nb; J++) {
-          tk.push_back({level(J), 0, sl, J + 1, J});
-          tk.push_back({level(J), diag_grp, sl, J + 1, J + 1});
-          for (int I = J + 2; I < m.nb; I++) tk.push_back({level(J), 2, sl, I, J});
-        }
-      }
-      std::stable_sort(tk.begin(), tk.end(), [](const TK& a, const TK& c) {
-        if (a.s != c.s) return a.s < c.s;
-        if (a.grp != c.grp) return a.grp < c.grp;
-        if (a.slot != c.slot) return a.slot < c.slot;
-        return a.I < c.I; });
-      std::vector<int4> pt(tk.size());
-      for (size_t i = 0; i < tk.size(); i++) pt[i] = make_int4(tk[i].slot, tk[i].I, tk[i].J, 0);
+      for (int s = b.s0; s < b.s1; s++) { foff[s - b.s0] = fo; fo += (int64_t)h->meta[s].nb * (h->meta[s].nb + 1) / 2; }
+      std::vector<int4> pt = build_potrf2_tasks(h, b, std::vector<char>(nb_s, 1), sms_plan);
       b.n_potrf2 = (int)pt.size(); b.flag_ints = fo;
       // inverse tile tasks (I > J): anti-diagonal order (a tile depends on the tiles above it in its column, all on
       // smaller anti-diagonals), experts shifted so that they end together, long tiles first inside a level
@@ -289,7 +309,11 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   CUDA_TRY(h, h->d_scal.alloc(ns));
   CUDA_TRY(h, h->d_mask.alloc(std::max(ns, 1)));
   h->h_mask.assign(std::max(ns, 1), 1);
-  CUDA_TRY(h, h->d_counter.alloc(16));
+  CUDA_TRY(h, h->d_counter.alloc(32));      // [0,16) task counters (cleared per batch), [16] scheduler error word (cleared per call)
+  CUDA_TRY(h, cudaMemset(h->d_counter.p, 0, 32 * sizeof(int)));
+  CUDA_TRY(h, h->d_share.alloc(std::max(ns, 1)));
+  h->share.slot.assign(std::max(ns, 1), make_int4(0, 0, 0, 0));
+  h->exec_slot = h->leaf_slot;
   CUDA_TRY(h, h->d_flags.alloc(std::max<int64_t>(maxFlags, 1)));
   CUDA_TRY(h, h->d_ldpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
   CUDA_TRY(h, h->d_zzpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
@@ -359,6 +383,7 @@ extern "C" int32_t dsmgp_create(const double* x, int64_t N, int64_t D, int64_t L
   h->row_width = 1 + h->Hmax;
   h->leaf_ptr.assign(leaf_ptr, leaf_ptr + L + 1);
   h->leaf_kid.assign(leaf_kernel_id, leaf_kernel_id + L);
+  if (leaf_ptr[L] <= (int64_t(1) << 26) && N < (int64_t(1) << 31)) h->leaf_obs32.assign(leaf_obs, leaf_obs + leaf_ptr[L]);
   h->leaf_mean.assign(leaf_mean, leaf_mean + L);
   if (leaf_ptr[0] != 0) { delete h; return fail(DSMGP_ERR_ARG, "leaf_ptr[0] != 0"); }
   for (int64_t l = 0; l < L; l++) {
@@ -422,6 +447,7 @@ extern "C" int32_t dsmgp_set_params(dsmgp_handle* h, const double* theta, int64_
   cudaSetDevice(h->device);
   upload_params(h);
   h->fitted = false; h->have_rows = false; h->have_grad = false;
+  h->theta_global = true;
   return DSMGP_OK;
 }
 
@@ -430,8 +456,16 @@ extern "C" int32_t dsmgp_set_leaf_params(dsmgp_handle* h, int64_t leaf, const do
   if (leaf < 0 || leaf >= h->L || !theta || n != h->knp[h->leaf_kid[leaf]]) { h->err = "set_leaf_params: bad leaf or length"; return DSMGP_ERR_ARG; }
   std::copy(theta, theta + n, h->theta_leaf.begin() + (size_t)leaf * h->Hmax);
   cudaSetDevice(h->device);
-  upload_params(h);
+  {   // only this expert's parameter block changes
+    const int s = h->leaf_slot[leaf];
+    if (s >= 0) {
+      derive_params(h, h->leaf_kid[leaf], &h->theta_leaf[(size_t)leaf * h->Hmax], &h->h_prm[(size_t)s * h->pstride]);
+      cudaMemcpyAsync(h->d_prm.p + (size_t)s * h->pstride, &h->h_prm[(size_t)s * h->pstride], h->pstride * sizeof(double),
+                      cudaMemcpyHostToDevice, h->stream);
+    }
+  }
   h->fitted = false; h->have_rows = false; h->have_grad = false;
+  h->theta_global = false;                 // per-expert theta: the sharing plan (same theta for source and dependent) is off
   return DSMGP_OK;
 }
 
@@ -454,14 +488,47 @@ static bool needs_lauum(const dsmgp_handle* h) {
 }
 
 
-// gram -> potrf -> solves (-> inverse -> lauum) -> rows, batch by batch
+// Per-slot gradient mask from a leaf weight vector (NULL: every expert contributes); with the sharing plan active an
+// aliased expert is never computed itself (mask 0) and its source is computed whenever either of them is wanted.
+static void prepare_masks(dsmgp_handle* h, const double* leaf_scale, bool with_grad, bool shr) {
+  h->use_mask = false;
+  const int ns = (int)h->slot_leaf.size();
+  if (!with_grad || ns == 0 || (!leaf_scale && !(shr && h->share.n_alias > 0))) return;
+  for (int s = 0; s < ns; s++) h->h_mask[s] = (!leaf_scale || leaf_scale[h->slot_leaf[s]] != 0.0) ? 1 : 0;
+  if (shr) {
+    for (const Batch& b : h->batches)
+      for (int s = b.s0; s < b.s1; s++)
+        if (h->share.slot[s].x == SHARE_ALIAS) { h->h_mask[b.s0 + h->share.slot[s].y] |= h->h_mask[s]; }
+    for (int s = 0; s < ns; s++) if (h->share.slot[s].x == SHARE_ALIAS) h->h_mask[s] = 0;
+  }
+  bool any_zero = false;
+  for (int s = 0; s < ns; s++) any_zero |= !h->h_mask[s];
+  if (!any_zero) return;
+  cudaMemcpyAsync(h->d_mask.p, h->h_mask.data(), ns * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+  h->use_mask = true;
+}
+
+// gram -> potrf -> solves (-> inverse -> lauum) -> rows, batch by batch.
+//   leaf_scale  finetune weights D[g,:] or null: experts with weight 0 skip the gradient kernels
+//   naive       ignore the sharing plan (fit_naive!)
+//   first       first pipeline of an API call: clears the scheduler error word (a later pipeline of the same call must not
+//               erase the error of an earlier one; finish_pipeline reads it once at the end)
 static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad);
-static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = false) {
+static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_scale = nullptr, bool defer_sync = false,
+                            bool naive = false, bool first = true) {
   cudaStream_t st = h->stream;
   const int sms = num_sms(h->device);
   const bool lau = with_grad && needs_lauum(h);
+  const bool shr = !naive && h->share.active && h->theta_global && (h->share.n_alias + h->share.n_prefix) > 0;
   h->tm = dsmgp_timings{};
+  h->share_applied = shr;
+  prepare_masks(h, with_grad ? leaf_scale : nullptr, with_grad, shr);
   const int* mask_all = (with_grad && h->use_mask) ? h->d_mask.p : nullptr;
+  const int4* share_all = shr ? h->d_share.p : nullptr;
+  if (first) CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p + GERR, 0, sizeof(int), st));
+  // multi-rank: the row table is the exchange unit (SUM all-reduce in place), so the rows of the other ranks' experts
+  // must be zero again before every evaluation
+  if (h->opts.world > 1) CUDA_TRY(h, cudaMemsetAsync(h->d_rows.p, 0, (size_t)h->L * h->row_width * sizeof(double), st));
   if (h->batches.empty()) {   // a rank that owns no leaf
     h->fitted = true; h->have_rows = true; h->have_grad = with_grad; h->rows_complete = (h->opts.world == 1);
     return DSMGP_OK;
@@ -474,9 +541,10 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
     if (nsl == 0) { for (int k = 1; k < 8; k++) cudaEventRecord(ev[k], st); continue; }
     const LeafMeta* meta = h->d_meta.p + b.s0;
     LeafScal* scal = h->d_scal.p + b.s0;
+    const int4* share_b = share_all ? share_all + b.s0 : nullptr;
     CUDA_TRY(h, cudaMemsetAsync(scal, 0, nsl * sizeof(LeafScal), st));
     cudaEventRecord(ev[1], st);
-    GramArgs ga{meta, h->d_xg.p, h->d_prm.p, h->d_F.p, b.d_tile_off, nsl, (int)h->D};
+    GramArgs ga{meta, h->d_xg.p, h->d_prm.p, h->d_F.p, b.d_tile_off, nsl, (int)h->D, share_b};
     launch_gram_fit(ga, b.ntiles, st);
     h->tm.launches++;
     cudaEventRecord(ev[2], st);
@@ -485,24 +553,37 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
       CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
       Potrf2Args pa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, scal, h->d_trpart.p, b.d_trpart_off,
                     h->d_ldpart.p, h->d_zzpart.p, h->d_flags.p, b.d_flag_off, b.d_potrf2_tasks, b.n_potrf2,
-                    h->d_counter.p + 4, h->d_counter.p + 8, 0, nullptr};
-      long long* d_trace = nullptr;
-      const char* trace_file = getenv("DSMGP_TRACE_FILE");
-      if (trace_file) { cudaMalloc(&d_trace, (size_t)b.n_potrf2 * 64); cudaMemsetAsync(d_trace, 0, (size_t)b.n_potrf2 * 64, st); pa.trace = d_trace; }
-      launch_potrf2(pa, std::min(sms, b.n_potrf2), st);
-      if (trace_file) {
-        std::vector<long long> tr((size_t)b.n_potrf2 * 8);
-        cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        if (FILE* f = fopen(trace_file, "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
-        cudaFree(d_trace);
+                    h->d_counter.p + 4, h->d_counter.p + GERR, 0, share_b, nullptr};
+      if (shr) {
+        // shared Cholesky (fit.jl:71-122): the experts that are factored on their own first, then the leading block rows
+        // of the SHARE_PREFIX experts are copied from their sources and their factorisation continues behind them
+        pa.tasks = b.d_potrf2_A; pa.ntasks = b.n_potrf2_A;
+        if (pa.ntasks > 0) { launch_potrf2(pa, std::min(sms, pa.ntasks), st); h->tm.launches++; }
+        if (b.n_prefix > 0) {
+          launch_share_copy(meta, share_b, b.d_prefix_slots, b.n_prefix, b.max_jb, h->d_F.p, st);
+          pa.tasks = b.d_potrf2_B; pa.ntasks = b.n_potrf2_B; pa.counter = h->d_counter.p + 5;
+          launch_potrf2(pa, std::min(sms, pa.ntasks), st);
+          h->tm.launches += 2;
+        }
+      } else {
+        long long* d_trace = nullptr;
+        const char* trace_file = getenv("DSMGP_TRACE_FILE");
+        if (trace_file) { cudaMalloc(&d_trace, (size_t)b.n_potrf2 * 64); cudaMemsetAsync(d_trace, 0, (size_t)b.n_potrf2 * 64, st); pa.trace = d_trace; }
+        launch_potrf2(pa, std::min(sms, b.n_potrf2), st);
+        if (trace_file) {
+          std::vector<long long> tr((size_t)b.n_potrf2 * 8);
+          cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
+          cudaStreamSynchronize(st);
+          if (FILE* f = fopen(trace_file, "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+          cudaFree(d_trace);
+        }
+        h->tm.launches++;
       }
-      h->tm.launches++;
       cudaEventRecord(ev[3], st);
       if (!with_grad) {       // fit only: alpha by block back-substitution (the forward solve was fused above)
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         SolveArgs sa{meta, h->d_F.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_flags.p, b.d_flag_off, b.d_solve_tasks, b.n_solve,
-                     h->d_counter.p + 3, h->d_counter.p + 8};
+                     h->d_counter.p + 3, h->d_counter.p + GERR, share_b};
         launch_solve(sa, std::max(1, std::min(solve_max_ctas(sms), b.n_solve)), st);
         h->tm.launches++;
       }
@@ -511,7 +592,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
                       h->d_flags.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, b.d_trtri3_tasks, b.n_trtri3,
-                      h->d_counter.p, h->d_counter.p + 8, mask_all ? mask_all + b.s0 : nullptr};
+                      h->d_counter.p, h->d_counter.p + GERR, mask_all ? mask_all + b.s0 : nullptr};
         launch_trtri3(ta, std::max(1, std::min(sms, b.n_trtri3)), b.d_trtri_tasks, b.n_trtri, st);
         h->tm.launches += 2;
       }
@@ -519,7 +600,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
     cudaEventRecord(ev[5], st);
     if (lau) {
       LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
-                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + 8,
+                   h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + GERR,
                    mask_all ? mask_all + b.s0 : nullptr};
       launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
       h->tm.launches++;
@@ -527,14 +608,24 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, bool defer_sync = f
     cudaEventRecord(ev[6], st);
     RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,
                 h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0,
-                h->d_ldpart.p, h->d_zzpart.p, h->d_alpha.p, mask_all ? mask_all + b.s0 : nullptr};
+                h->d_ldpart.p, h->d_zzpart.p, h->d_alpha.p, mask_all ? mask_all + b.s0 : nullptr, share_b};
     launch_rows(ra, nsl, st);
     h->tm.launches++;
+    if (shr && h->share.n_alias > 0) { launch_rows_alias(meta, share_b, nsl, h->d_rows.p, h->row_width, scal, st); h->tm.launches++; }
     CUDA_TRY(h, cudaGetLastError());
     cudaEventRecord(ev[7], st);
-    h->tm.potrf_flops += b.potrf_flops;
-    h->tm.inverse_flops += with_grad ? b.potrf_flops * (lau ? 2.0 : 1.0) : 0.0;
-    h->tm.gram_bytes += b.gram_bytes;
+    double pf = b.potrf_flops, gb = b.gram_bytes;
+    if (shr) {                 // work that the plan removed is not counted
+      for (int s = b.s0; s < b.s1; s++) {
+        const int4 sh = h->share.slot[s];
+        const double n = h->meta[s].n;
+        if (sh.x == SHARE_ALIAS) { pf -= n * n * n / 3.0 + n * n / 2.0 + n / 6.0; gb -= 8.0 * (n * (n + 1) / 2.0) + 8.0 * n * h->D; }
+        else if (sh.x == SHARE_PREFIX) { const double k = (double)sh.z * BLK; pf -= k * k * k / 3.0; gb -= 8.0 * k * (k + 1) / 2.0; }
+      }
+    }
+    h->tm.potrf_flops += pf;
+    h->tm.inverse_flops += with_grad ? pf * (lau ? 2.0 : 1.0) : 0.0;
+    h->tm.gram_bytes += gb;
   }
   if (defer_sync) return DSMGP_OK;
   return finish_pipeline(h, with_grad);
@@ -545,7 +636,7 @@ static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad) {
   const int ns = (int)h->slot_leaf.size();
   if (ns) CUDA_TRY(h, cudaMemcpyAsync(h->pin_scal, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, st));
   int gerr = 0;
-  CUDA_TRY(h, cudaMemcpyAsync(&gerr, h->d_counter.p + 8, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaMemcpyAsync(&gerr, h->d_counter.p + GERR, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_TRY(h, cudaStreamSynchronize(st));
   if (gerr != 0) { h->err = "device scheduler timeout (code " + std::to_string(gerr) + ")"; return DSMGP_ERR_STATE; }
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
@@ -556,14 +647,21 @@ static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad) {
     h->tm.inverse_ms += ev_ms(ev[4], ev[5]);
     h->tm.grad_ms += ev_ms(ev[5], ev[7]);
   }
-  h->tm.total_ms = ev_ms(h->ev[0], h->ev[8 * (h->batches.size() - 1) + 7]);
+  if (!h->batches.empty()) h->tm.total_ms = ev_ms(h->ev[0], h->ev[8 * (h->batches.size() - 1) + 7]);
   std::fill(h->h_info.begin(), h->h_info.end(), 0);
   for (int s = 0; s < ns; s++) {
     int info = h->pin_scal[s].info;
     if (info > h->meta[s].n) info = 0;     // padding rows are identity
     h->h_info[h->slot_leaf[s]] = info;
   }
-  h->fitted = true; h->have_rows = true; h->have_grad = with_grad; h->rows_complete = (h->opts.world == 1);
+  // where the results of every expert live: its own slot, or its source's slot when it was aliased by the sharing plan
+  h->exec_slot = h->leaf_slot;
+  if (h->share_applied)
+    for (const Batch& b : h->batches)
+      for (int s = b.s0; s < b.s1; s++)
+        if (h->share.slot[s].x == SHARE_ALIAS) h->exec_slot[h->slot_leaf[s]] = b.s0 + h->share.slot[s].y;
+  h->fitted = true; h->have_rows = true; h->rows_complete = (h->opts.world == 1);
+  h->have_grad = with_grad && !h->use_mask;     // a masked evaluation holds zero gradients for the skipped experts
   h->alpha_exact = !with_grad;
   return DSMGP_OK;
 }
@@ -579,7 +677,7 @@ int32_t dsm::refine_alpha(dsmgp_handle* h) {
     CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p + 3, 0, sizeof(int), h->stream));
     SolveArgs sa{h->d_meta.p, h->d_F.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_flags.p, b.d_flag_off, b.d_solve_tasks, b.n_solve,
-                 h->d_counter.p + 3, h->d_counter.p + 8};
+                 h->d_counter.p + 3, h->d_counter.p + GERR, h->share_applied ? h->d_share.p : nullptr};
     launch_solve(sa, std::max(1, std::min(solve_max_ctas(num_sms(h->device)), b.n_solve)), h->stream);
     CUDA_TRY(h, cudaGetLastError());
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -588,11 +686,185 @@ int32_t dsm::refine_alpha(dsmgp_handle* h) {
   return DSMGP_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// the sharing plan of fit! (fit.jl:71-122)
+// ------------------------------------------------------------------------------------------
+// Mirrors the reference's scheduling: every expert j picks the "main" expert i = argmax_i D[i,j] D[j,i] (fit.jl:78-84), the
+// experts are visited by how often they are somebody's main (:86), a main is factored in full (:97-100) and j shares with
+// it according to (D[i,j] == 1, D[j,i] == 1) and tau (:107-116, fitcontained! :124-292).  What "sharing" executes here:
+//   (true, true)    identical experts                       -> SHARE_ALIAS  (the reference copies factors and alpha, :132-143)
+//   (false, true)   j inside main, few rows to delete (tau) -> SHARE_PREFIX (the reference downdates by Givens sweeps, :145-206)
+//   (true, false)   main is a leading part of j             -> SHARE_PREFIX (the reference continues the factor, :208-292)
+// SHARE_PREFIX reuses the factor tiles of the leading 128-row blocks the two experts have in common and re-factors what
+// follows the first differing observation (= chol_continue! from there).  That is the exact factor of update_cholesky!
+// (the reference's own downdate is numerically wrong, SURVEY App. B Q7, and a Givens sweep is a serial chain of n column
+// steps per deleted row -- orders of magnitude slower on this machine than re-factoring the trailing blocks on DMMA).
+static int64_t sorted_diff_count(const int32_t* a, int64_t na, const int32_t* b, int64_t nb) {   // |a \ b|, both ascending
+  int64_t i = 0, j = 0, c = 0;
+  while (i < na) {
+    while (j < nb && b[j] < a[i]) j++;
+    if (j >= nb || b[j] != a[i]) c++;
+    i++;
+  }
+  return c;
+}
+
+// The plan itself (host only): kind / source / copied block rows per leaf.
+static void plan_sharing(int64_t L, const int64_t* leaf_ptr, const int32_t* obs, const int32_t* leaf_kid, const double* overlap,
+                         double tau, int* kind, int* source, int* blocks) {
+  auto lobs = [&](int64_t l) { return obs + leaf_ptr[l]; };
+  auto ln = [&](int64_t l) { return leaf_ptr[l + 1] - leaf_ptr[l]; };
+  std::fill(kind, kind + L, 0); std::fill(source, source + L, -1); std::fill(blocks, blocks + L, 0);
+  // fit.jl:78-84: main of every expert, and how often an expert is a main
+  std::vector<int64_t> S(L), counts(L, 0);
+  for (int64_t j = 0; j < L; j++) {
+    double best = -std::numeric_limits<double>::infinity(); int64_t bi = 0;
+    for (int64_t i = 0; i < L; i++) {
+      const double v = overlap[i + j * L] * overlap[j + i * L];          // D[:,j] .* D[j,:]
+      if (v > best) { best = v; bi = i; }                                 // argmax: first maximum
+    }
+    S[j] = bi; counts[bi]++;
+  }
+  std::vector<int64_t> order(L);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t c) { return counts[a] < counts[c]; });     // :86
+  std::vector<char> processed(L, 0);
+  for (int64_t j : order) {
+    if (processed[j]) continue;                                           // :90
+    const int64_t i = S[j];
+    processed[i] = 1; processed[j] = 1;                                   // :97-103
+    if (i == j) continue;
+    if (leaf_kid[i] != leaf_kid[j]) continue;                             // :107-109
+    const int32_t *oj = lobs(j), *oi = lobs(i);
+    const int64_t nj = ln(j), ni = ln(i);
+    if (oj[0] < oi[0]) continue;                                          // :110-112
+    const bool ione = overlap[i + j * L] == 1.0, jone = overlap[j + i * L] == 1.0;
+    // resolve the source through an alias (the main may itself have been aliased to an earlier main)
+    int64_t src = i;
+    if (kind[src] == SHARE_ALIAS) src = source[src];
+    if (ione && jone) {                                                   // :132-143 copy
+      if (nj == ni && std::equal(oj, oj + nj, oi)) { kind[j] = SHARE_ALIAS; source[j] = (int)src; }
+      continue;
+    }
+    bool share = false;
+    if (!ione && jone) {                                                  // :145-206 j inside main: rows to delete behind tau
+      if (oj[0] >= oi[0] && oj[nj - 1] <= oi[ni - 1]) {
+        const int64_t e = std::upper_bound(oi, oi + ni, oj[nj - 1]) - oi;       // main.obs[1:e]
+        const int64_t ndel = sorted_diff_count(oi, e, oj, nj);
+        share = (double)ndel / (double)nj < tau;
+      }
+    } else if (ione && !jone) {                                           // :208-292 main is (part of) the head of j
+      if (oj[0] >= oi[0] && oj[nj - 1] >= oi[ni - 1]) {
+        const int64_t k1 = std::upper_bound(oj, oj + nj, oi[ni - 1]) - oj;      // s1 = j.obs[1:findfirst(== maxM)]
+        const int64_t s = std::lower_bound(oi, oi + ni, oj[0]) - oi;            // idx = s:e
+        const bool minsame = oj[0] == oi[0];
+        if (!((k1 != ni - s) && minsame)) {                               // :246-248
+          const int64_t ndel = sorted_diff_count(oi, ni, oj, k1);
+          share = (double)ndel / (double)nj < tau;
+        }
+      }
+    }
+    if (!share) continue;
+    if (kind[src] == SHARE_PREFIX) continue;              // the source itself waits for a copy: factor j on its own
+    const int32_t* os = lobs(src);
+    const int64_t nsr = ln(src);
+    int64_t k = 0;
+    while (k < nj && k < nsr && oj[k] == os[k]) k++;
+    const int jb = (int)(k / BLK);
+    if (jb < 1) continue;
+    kind[j] = SHARE_PREFIX; source[j] = (int)src; blocks[j] = jb;
+  }
+}
+
+// HOST-ONLY: the plan for a given structure (what dsmgp_set_sharing stores), for inspection and CPU tests.
+extern "C" int32_t dsmgp_host_sharing_plan(int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs, const int32_t* leaf_kernel_id,
+                                           const double* overlap, double tau, int32_t* kind, int32_t* source, int32_t* blocks) {
+  if (L <= 0 || !leaf_ptr || !leaf_obs || !leaf_kernel_id || !overlap || !kind || !source || !blocks) return DSMGP_ERR_ARG;
+  std::vector<int32_t> obs(leaf_obs, leaf_obs + leaf_ptr[L]);
+  plan_sharing(L, leaf_ptr, obs.data(), leaf_kernel_id, overlap, tau, kind, source, blocks);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_set_sharing(dsmgp_handle* h, const double* overlap, double tau) {
+  if (!h) return DSMGP_ERR_ARG;
+  auto& sp = h->share;
+  const int64_t L = h->L;
+  const int ns = (int)h->slot_leaf.size();
+  sp = dsmgp_handle::Share{};
+  sp.tau = tau;
+  sp.slot.assign(std::max(ns, 1), make_int4(0, 0, 0, 0));
+  sp.leaf_kind.assign(L, 0); sp.leaf_src.assign(L, -1);
+  for (auto& b : h->batches) {
+    cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots);
+    b.d_potrf2_A = b.d_potrf2_B = nullptr; b.d_prefix_slots = nullptr; b.n_potrf2_A = b.n_potrf2_B = b.n_prefix = b.max_jb = 0;
+  }
+  if (!overlap) return DSMGP_OK;                       // fit_naive!: no sharing
+  if (h->leaf_obs32.empty()) { h->err = "set_sharing: observation lists too large to keep (sharing unavailable)"; return DSMGP_ERR_STATE; }
+  cudaSetDevice(h->device);
+  std::vector<int> blocks(L, 0);
+  plan_sharing(L, h->leaf_ptr.data(), h->leaf_obs32.data(), h->leaf_kid.data(), overlap, tau, sp.leaf_kind.data(), sp.leaf_src.data(), blocks.data());
+  // map to local slots: source and dependent must live in the same batch of the same rank
+  std::vector<int> slot_batch(std::max(ns, 1), -1);
+  for (size_t bi = 0; bi < h->batches.size(); bi++) for (int s = h->batches[bi].s0; s < h->batches[bi].s1; s++) slot_batch[s] = (int)bi;
+  for (int64_t l = 0; l < L; l++) {
+    const int s = h->leaf_slot[l];
+    if (sp.leaf_kind[l] == SHARE_NONE) continue;
+    const int ss = h->leaf_slot[sp.leaf_src[l]];
+    if (s < 0 || ss < 0 || slot_batch[s] != slot_batch[ss]) { if (s >= 0 || ss >= 0) { /* not co-located: factor on its own */ } sp.leaf_kind[l] = SHARE_NONE; sp.leaf_src[l] = -1; continue; }
+    const Batch& b = h->batches[slot_batch[s]];
+    sp.slot[s] = make_int4(sp.leaf_kind[l], ss - b.s0, blocks[l], 0);
+    const double n = (double)h->meta[s].n;
+    if (sp.leaf_kind[l] == SHARE_ALIAS) { sp.n_alias++; sp.flops_saved += n * n * n / 3.0; }
+    else { sp.n_prefix++; sp.blocks_copied += blocks[l]; const double k = (double)blocks[l] * BLK; sp.flops_saved += k * k * k / 3.0; }
+  }
+  // an alias whose source was demoted above keeps pointing at a valid local source or was demoted with it; a prefix expert
+  // whose source is an alias was resolved before.  Task lists per batch.
+  const int sms = num_sms(h->device);
+  for (auto& b : h->batches) {
+    const int nb_s = b.s1 - b.s0;
+    std::vector<char> keepA(nb_s, 0), keepB(nb_s, 0);
+    std::vector<int> pslots;
+    for (int s = b.s0; s < b.s1; s++) {
+      const int4 sh = sp.slot[s];
+      if (sh.x == SHARE_NONE) keepA[s - b.s0] = 1;
+      else if (sh.x == SHARE_PREFIX) { keepB[s - b.s0] = 1; pslots.push_back(s - b.s0); b.max_jb = std::max(b.max_jb, sh.z); }
+    }
+    std::vector<int4> ta = build_potrf2_tasks(h, b, keepA, sms), tb = build_potrf2_tasks(h, b, keepB, sms);
+    b.n_potrf2_A = (int)ta.size(); b.n_potrf2_B = (int)tb.size(); b.n_prefix = (int)pslots.size();
+    CUDA_TRY(h, upload(&b.d_potrf2_A, ta));
+    CUDA_TRY(h, upload(&b.d_potrf2_B, tb));
+    CUDA_TRY(h, upload(&b.d_prefix_slots, pslots));
+  }
+  if (ns) CUDA_TRY(h, cudaMemcpy(h->d_share.p, sp.slot.data(), ns * sizeof(int4), cudaMemcpyHostToDevice));
+  sp.active = true;
+  h->fitted = false; h->have_rows = false; h->have_grad = false;
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_get_sharing(const dsmgp_handle* h, int32_t* kind, int32_t* source, int32_t* blocks) {
+  if (!h) return DSMGP_ERR_ARG;
+  for (int64_t l = 0; l < h->L; l++) {
+    const bool on = h->share.active && !h->share.leaf_kind.empty();
+    const int k = on ? h->share.leaf_kind[l] : 0;
+    if (kind) kind[l] = k;
+    if (source) source[l] = (on && k != SHARE_NONE) ? h->share.leaf_src[l] : -1;
+    if (blocks) { const int s = h->leaf_slot[l]; blocks[l] = (on && s >= 0 && k == SHARE_PREFIX) ? h->share.slot[s].z : 0; }
+  }
+  return DSMGP_OK;
+}
+
+// After the pipeline: per-leaf rows on the host.  With a communicator (dsmgp_comm_init) the table is first assembled by a
+// SUM all-reduce on the library's stream (every rank filled only its own experts' rows).
 static int32_t fetch_rows(dsmgp_handle* h) {
-  const size_t bytes = (size_t)h->L * h->row_width * sizeof(double);
-  CUDA_TRY(h, cudaMemcpyAsync(h->pin_rows, h->d_rows.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+  const size_t count = (size_t)h->L * h->row_width;
+  if (h->opts.world > 1 && h->comm != nullptr && !h->rows_complete) {
+    int32_t rc = comm_allreduce_sum(h, h->d_rows.p, count);
+    if (rc) return rc;
+    h->rows_complete = true;
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(h->pin_rows, h->d_rows.p, count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-  memcpy(h->h_rows.data(), h->pin_rows, bytes);
+  memcpy(h->h_rows.data(), h->pin_rows, count * sizeof(double));
   return DSMGP_OK;
 }
 
@@ -614,22 +886,14 @@ static void tree_grad(dsmgp_handle* h, const double* leaf_scale, double* grad) {
   down_pass(c, h->tree.root, 0.0, 0.0, 0);
 }
 
-// Per-slot gradient mask from a leaf weight vector (NULL: every expert contributes).
-static void set_grad_mask(dsmgp_handle* h, const double* leaf_scale) {
-  h->use_mask = false;
-  if (!leaf_scale) return;
-  const int ns = (int)h->slot_leaf.size();
-  bool any_zero = false;
-  for (int s = 0; s < ns; s++) { h->h_mask[s] = leaf_scale[h->slot_leaf[s]] != 0.0 ? 1 : 0; any_zero |= !h->h_mask[s]; }
-  if (!any_zero || ns == 0) return;
-  cudaMemcpyAsync(h->d_mask.p, h->h_mask.data(), ns * sizeof(int), cudaMemcpyHostToDevice, h->stream);
-  h->use_mask = true;
-}
+static const char* kNeedComm = "rows of other ranks missing: call dsmgp_comm_init, or all-reduce the rows yourself (dsmgp_eval_local_dev / dsmgp_eval_finish_dev)";
 
-extern "C" int32_t dsmgp_fit(dsmgp_handle* h, int32_t* info, double* seconds) {
+extern "C" int32_t dsmgp_fit(dsmgp_handle* h, double tau, const double* overlap, int32_t* info, double* seconds) {
   if (!h) return DSMGP_ERR_ARG;
   cudaSetDevice(h->device);
-  int32_t rc = run_pipeline(h, false);
+  int32_t rc;
+  if (overlap && (rc = dsmgp_set_sharing(h, overlap, tau))) return rc;      // fit!(spn, D, gpmap; tau)
+  rc = run_pipeline(h, false, nullptr, false, /*naive=*/overlap == nullptr);  // overlap == NULL: fit_naive!
   if (rc) return rc;
   if ((rc = fetch_rows(h))) return rc;
   if (info) std::copy(h->h_info.begin(), h->h_info.end(), info);
@@ -640,7 +904,7 @@ extern "C" int32_t dsmgp_fit(dsmgp_handle* h, int32_t* info, double* seconds) {
 extern "C" int32_t dsmgp_lml(dsmgp_handle* h, double* node_lml) {
   if (!h) return DSMGP_ERR_ARG;
   if (!h->have_rows) { h->err = "lml: call fit or eval first"; return DSMGP_ERR_STATE; }
-  if (!h->rows_complete) { h->err = "lml: rows of other ranks missing (all-reduce the rows, then eval_finish_dev)"; return DSMGP_ERR_STATE; }
+  if (!h->rows_complete) { h->err = std::string("lml: ") + kNeedComm; return DSMGP_ERR_STATE; }
   up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
   if (node_lml) std::copy(h->node_lml.begin(), h->node_lml.end(), node_lml);
   return DSMGP_OK;
@@ -654,7 +918,7 @@ extern "C" int32_t dsmgp_grad(dsmgp_handle* h, const double* leaf_scale, double*
     if ((rc = run_pipeline(h, true))) return rc;
     if ((rc = fetch_rows(h))) return rc;
   }
-  if (!h->rows_complete) { h->err = "grad: rows of other ranks missing"; return DSMGP_ERR_STATE; }
+  if (!h->rows_complete) { h->err = std::string("grad: ") + kNeedComm; return DSMGP_ERR_STATE; }
   up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
   tree_grad(h, leaf_scale, grad);
   return DSMGP_OK;
@@ -666,12 +930,11 @@ extern "C" int32_t dsmgp_eval(dsmgp_handle* h, const double* theta, int64_t n, c
   int32_t rc;
   if (theta && (rc = dsmgp_set_params(h, theta, n))) return rc;
   cudaSetDevice(h->device);
-  set_grad_mask(h, grad != nullptr ? leaf_scale : nullptr);   // finetune: experts with zero overlap weight skip the gradient kernels
-  rc = run_pipeline(h, grad != nullptr);
-  h->use_mask = false;
+  // finetune: experts with zero overlap weight skip the gradient kernels
+  rc = run_pipeline(h, grad != nullptr, grad != nullptr ? leaf_scale : nullptr);
   if (rc) return rc;
   if ((rc = fetch_rows(h))) return rc;
-  if (!h->rows_complete) { h->err = "eval: world > 1 needs eval_local_dev + all-reduce + eval_finish_dev"; return DSMGP_ERR_STATE; }
+  if (!h->rows_complete) { h->err = std::string("eval: ") + kNeedComm; return DSMGP_ERR_STATE; }
   up_pass(h->tree, h->h_rows.data(), h->row_width, h->node_lml.data());
   if (lml) *lml = h->node_lml[h->tree.root];
   if (node_lml) std::copy(h->node_lml.begin(), h->node_lml.end(), node_lml);
@@ -712,9 +975,7 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
   for (int64_t g = 0; g < G && rc == DSMGP_OK; g++) {
     if ((rc = dsmgp_set_params(h, thetas + g * H, H))) break;              // setparams!(spn, hyp_)  finetuning.jl:41
     for (int64_t l = 0; l < L; l++) scale[l] = overlap[anchors[g] + l * L];   // view(D, g, :)  finetuning.jl:53
-    set_grad_mask(h, scale.data());
-    rc = run_pipeline(h, true, true);
-    h->use_mask = false;
+    rc = run_pipeline(h, true, scale.data(), /*defer_sync=*/true, /*naive=*/false, /*first=*/g == 0);
     if (rc) break;
     cudaMemcpyAsync(h->pin_multi + (size_t)g * L * rw, h->d_rows.p, (size_t)L * rw * sizeof(double), cudaMemcpyDeviceToHost, h->stream);
     if (ns) cudaMemcpyAsync(pin_scal_multi + (size_t)g * ns, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, h->stream);
@@ -788,7 +1049,8 @@ extern "C" int32_t dsmgp_train(dsmgp_handle* h, int32_t optimiser, double eta, d
   if (it >= iterations) {                                                                // :82-83 final setparams! + fit!
     int32_t rc = dsmgp_set_params(h, hyp.data(), H);
     if (rc) return rc;
-    return dsmgp_fit(h, nullptr, nullptr);
+    if ((rc = run_pipeline(h, false))) return rc;
+    return fetch_rows(h);
   }
   return DSMGP_OK;
 }
@@ -846,6 +1108,25 @@ extern "C" int32_t dsmgp_update_weights(dsmgp_handle* h, double* sum_logweights,
   return DSMGP_OK;
 }
 
+extern "C" int32_t dsmgp_infer(dsmgp_handle* h, double* sum_logweights, double* z) {
+  if (!h) return DSMGP_ERR_ARG;
+  if (!h->have_rows || !h->rows_complete) { h->err = "infer: call fit or eval first"; return DSMGP_ERR_STATE; }
+  h->sum_logw.assign(h->tree.child_ptr[h->tree.n_nodes], 0.0);
+  infer_weights(h->tree, h->h_rows.data(), h->row_width, h->sum_logw.data(), z);
+  h->have_weights = true;
+  if (sum_logweights) std::copy(h->sum_logw.begin(), h->sum_logw.end(), sum_logweights);
+  return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_reset_weights(dsmgp_handle* h, double* sum_logweights) {
+  if (!h) return DSMGP_ERR_ARG;
+  h->sum_logw.assign(h->tree.child_ptr[h->tree.n_nodes], 0.0);
+  reset_weights(h->tree, h->sum_logw.data());
+  h->have_weights = true;
+  if (sum_logweights) std::copy(h->sum_logw.begin(), h->sum_logw.end(), sum_logweights);
+  return DSMGP_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // accessors
 // ------------------------------------------------------------------------------------------
@@ -853,7 +1134,7 @@ static int32_t need_resident(const dsmgp_handle* h, int64_t leaf, int* slot) {
   if (!h || leaf < 0 || leaf >= h->L) return DSMGP_ERR_ARG;
   if (!h->fitted) return DSMGP_ERR_STATE;
   if (!h->opts.keep_factors || h->batches.size() != 1) return DSMGP_ERR_STATE;
-  *slot = h->leaf_slot[leaf];
+  *slot = h->exec_slot[leaf];              // an aliased expert reads its source's results (fit.jl:132-143)
   if (*slot < 0) return DSMGP_ERR_STATE;    // owned by another rank
   return DSMGP_OK;
 }

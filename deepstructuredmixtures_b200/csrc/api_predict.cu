@@ -143,7 +143,7 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   int64_t xto = 0, vto = 0, oo = 0;
   for (int64_t l = 0; l < L; l++) {
     if (pts[l].empty()) continue;
-    const int slot = h->leaf_slot[l];
+    const int slot = h->exec_slot[l];       // an aliased expert predicts with its source's factor and alpha
     if (slot < 0) {
       if (local_only) continue;               // predicted by its owner (dsmgp_predict_local / _finish)
       h->err = "predict: leaf owned by another rank (use dsmgp_predict_local + all-reduce + dsmgp_predict_finish)";
@@ -176,8 +176,9 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   PTRY(cudaMemcpyAsync(d_pl.p, pls.data(), pls.size() * sizeof(PredLeaf), cudaMemcpyHostToDevice, h->stream));
   PTRY(cudaMemcpyAsync(d_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, h->stream));
   PTRY(cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), h->stream));
+  PTRY(cudaMemsetAsync(h->d_counter.p + GERR, 0, sizeof(int), h->stream));
   PredArgs pa{h->d_meta.p, d_pl.p, d_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
-              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + 8,
+              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, d_xt.p, d_VT.p, d_mu.p, d_var.p, (int)D, h->d_counter.p + GERR,
               0, nullptr, nullptr, nullptr, nullptr, 0};
   const int sms = num_sms(h->device);
   const char* force_wave = getenv("DSMGP_PREDICT_WAVE");       // tests: "0" / "1" force the task granularity
@@ -219,7 +220,7 @@ static int32_t predict_leaves(dsmgp_handle* h, const double* xtest, int64_t T, c
   PTRY(cudaMemcpyAsync(hmu.data(), d_mu.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
   PTRY(cudaMemcpyAsync(hvar.data(), d_var.p, oo * 8, cudaMemcpyDeviceToHost, h->stream));
   int gerr = 0;
-  PTRY(cudaMemcpyAsync(&gerr, h->d_counter.p + 8, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  PTRY(cudaMemcpyAsync(&gerr, h->d_counter.p + GERR, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   PTRY(cudaStreamSynchronize(h->stream));
   if (gerr != 0) { h->err = "predict: device scheduler timeout (code " + std::to_string(gerr) + ")"; cleanup(); return DSMGP_ERR_STATE; }
 #undef PTRY
@@ -287,6 +288,36 @@ extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T
   int32_t rc = predict_route(h, xtest, T, mode, pts);
   if (rc) return rc;
   std::vector<std::vector<double>> lmu, lvar;
+  if (h->opts.world > 1) {
+    // experts sharded over ranks: predict the local ones, assemble the (expert, point) table with ONE SUM all-reduce on the
+    // library's communicator, mix on every rank
+    if (!h->comm) { h->err = "predict: world > 1 needs dsmgp_comm_init (or dsmgp_predict_local + all-reduce + dsmgp_predict_finish)"; return DSMGP_ERR_STATE; }
+    if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar, true))) return rc;
+    int64_t tot = 0;
+    for (auto& v : pts) tot += (int64_t)v.size();
+    std::vector<double> buf(2 * tot, 0.0);
+    int64_t off = 0;
+    for (int64_t l = 0; l < h->L; l++) {
+      if (!lmu.empty() && !lmu[l].empty()) {
+        std::copy(lmu[l].begin(), lmu[l].end(), buf.begin() + off);
+        std::copy(lvar[l].begin(), lvar[l].end(), buf.begin() + tot + off);
+      }
+      off += (int64_t)pts[l].size();
+    }
+    CUDA_TRY(h, h->d_comm_buf.ensure(2 * tot));
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_comm_buf.p, buf.data(), 2 * tot * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if ((rc = comm_allreduce_sum(h, h->d_comm_buf.p, 2 * tot))) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(buf.data(), h->d_comm_buf.p, 2 * tot * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    lmu.assign(h->L, {}); lvar.assign(h->L, {});
+    off = 0;
+    for (int64_t l = 0; l < h->L; l++) {
+      lmu[l].assign(buf.begin() + off, buf.begin() + off + pts[l].size());
+      lvar[l].assign(buf.begin() + tot + off, buf.begin() + tot + off + pts[l].size());
+      off += (int64_t)pts[l].size();
+    }
+    return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
+  }
   if ((rc = predict_leaves(h, xtest, T, pts, lmu, lvar))) return rc;
   return predict_mix(h, xtest, T, mode, lmu, lvar, mu, var);
 }

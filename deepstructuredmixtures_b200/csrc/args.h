@@ -19,7 +19,17 @@ struct SolveArgs {
   int* flags; const int64_t* flag_off;    // flag J of an expert: alpha_J stored
   const int2* tasks; int ntasks;          // (slot, J), descending J inside an expert
   int* counter; int* gerr;
+  const int4* share;                      // per slot sharing plan (see ShareKind) or null: aliased experts are skipped
 };
+
+// Sharing plan of fit! (fit.jl:71-122), one int4 per slot: x = kind, y = source slot (the "main" expert), z = number of
+// leading 128-row blocks whose factor tiles are copied from the source, w = unused.
+//   SHARE_NONE   the expert is factored on its own (update_cholesky!)
+//   SHARE_ALIAS  fitcontained!(Val(true), Val(true)) fit.jl:132-143: identical observations -> every result of the source is
+//                reused (no Gram, no factorisation, no inverse; rows / alpha / predictions read the source's slot)
+//   SHARE_PREFIX fitcontained! :145-292 (row deletion / chol_continue!): the experts share their first 128*z observations,
+//                the factor tiles of those block rows are copied and the factorisation continues behind them
+enum ShareKind : int { SHARE_NONE = 0, SHARE_ALIAS = 1, SHARE_PREFIX = 2 };
 
 struct GramArgs {
   const LeafMeta* meta;
@@ -29,6 +39,7 @@ struct GramArgs {
   const int64_t* tile_off;   // [nleaves+1] prefix sum of lower-triangular GT tiles per leaf
   int nleaves;
   int D;
+  const int4* share;         // per slot sharing plan or null: aliased experts and copied block rows are not built
 };
 
 struct GramRectArgs {
@@ -76,6 +87,7 @@ struct RowsArgs {
   const double* ldpart; const double* zzpart;   // engine v2: per block-column partials of logdet and z'z (else null)
   const double* alpha;                          // alpha'alpha is reduced here
   const int* mask;                              // per slot: 0 = gradient entries are written as 0 (expert skipped)
+  const int4* share;                            // per slot sharing plan or null: aliased experts get their row copied afterwards
 };
 
 struct PredLeaf {     // per leaf with routed points
@@ -137,5 +149,7 @@ void launch_ov_pairs(const int64_t* poff, const int* plist, int64_t N, int64_t L
 void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
                       int64_t L, double* D, cudaStream_t st);
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
+void launch_share_copy(const LeafMeta* meta, const int4* share, const int* slots, int nslots, int max_jb, double* F, cudaStream_t st);
+void launch_rows_alias(const LeafMeta* meta, const int4* share, int nslots, double* rows, int row_width, LeafScal* scal, cudaStream_t st);
 
 }  // namespace dsm

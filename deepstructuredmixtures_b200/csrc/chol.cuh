@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(NTHREADS) solve3_kernel(SolveArgs a) {
     __syncthreads();
     if (ti >= a.ntasks) return;
     const int2 tk = a.tasks[ti];
+    if (a.share != nullptr && a.share[tk.x].x == SHARE_ALIAS) continue;     // block-uniform: alpha of the source expert is used
     const LeafMeta m = a.meta[tk.x];
     const int J = tk.y, j0 = J * BLK, wj = blk_width(m.np, J);
     const double* F = a.F + m.foff;

@@ -22,6 +22,7 @@ namespace dsm {
 __global__ void rows_kernel(RowsArgs a) {
   __shared__ double red[16];
   const int slot = blockIdx.x, tid = threadIdx.x;
+  if (a.share != nullptr && a.share[slot].x == SHARE_ALIAS) return;       // row copied from the source by rows_alias_kernel
   const LeafMeta m = a.meta[slot];
   LeafScal sc = a.scal[slot];
   const double* prm = a.prm + m.poff;

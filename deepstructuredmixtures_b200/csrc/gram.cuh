@@ -99,6 +99,10 @@ __global__ void __launch_bounds__(NTHREADS) gram_fit_kernel(GramArgs a) {
   while ((ti + 1) * (ti + 2) / 2 <= t) ti++;
   while (ti * (ti + 1) / 2 > t) ti--;
   const int tj = t - ti * (ti + 1) / 2;
+  if (a.share != nullptr) {          // block-uniform: aliased experts are not built, copied block rows neither
+    const int4 sh = a.share[lo];
+    if (sh.x == SHARE_ALIAS || (sh.x == SHARE_PREFIX && (ti + 1) * GT <= sh.z * BLK)) return;
+  }
   const double* x = a.xg + m.xoff;
   const double* prm = a.prm + m.poff;
   double out[4][4];

@@ -39,6 +39,11 @@ struct Batch {
   int2* d_trtri_tasks = nullptr; int n_trtri = 0;
   int4* d_lauum_tasks = nullptr; int n_lauum = 0;
   int4* d_potrf2_tasks = nullptr; int n_potrf2 = 0;     // engine v2: tile tasks in look-ahead order
+  // sharing plan active (dsmgp_set_sharing): A = experts factored on their own, B = SHARE_PREFIX experts (second launch,
+  // after their leading block rows have been copied from the source); aliased experts appear in neither
+  int4* d_potrf2_A = nullptr; int n_potrf2_A = 0;
+  int4* d_potrf2_B = nullptr; int n_potrf2_B = 0;
+  int* d_prefix_slots = nullptr; int n_prefix = 0, max_jb = 0;   // batch-relative slots of the SHARE_PREFIX experts
   int4* d_trtri3_tasks = nullptr; int n_trtri3 = 0;     // inverse: tile tasks by anti-diagonal
   int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
@@ -125,6 +130,12 @@ struct DevBuf {
 
 using namespace dsm;     // internal header: only the ABI translation units include it
 
+namespace dsm {
+// comm.cu: NCCL through dlopen (the library has no link-time dependency on it)
+void comm_destroy(void* comm);
+int32_t comm_allreduce_sum(dsmgp_handle* h, double* dev_buf, size_t count);   // on h->stream; DSMGP_OK / DSMGP_ERR_COMM
+}
+
 struct dsmgp_handle {
   int64_t N = 0, D = 0, L = 0;
   int nk = 0;
@@ -133,6 +144,7 @@ struct dsmgp_handle {
   std::vector<int32_t> knp;       // nparams per kernel
   int64_t H = 0; int Hmax = 0; int row_width = 0; int pstride = 0;
   std::vector<int64_t> leaf_ptr;
+  std::vector<int32_t> leaf_obs32;   // observation lists (1-based), kept for the sharing plan when they fit (<= 2^26 entries)
   std::vector<int32_t> leaf_kid;
   std::vector<double> leaf_mean;
   HostTree tree;
@@ -171,13 +183,30 @@ struct dsmgp_handle {
   LeafScal* pin_scal_multi = nullptr; size_t pin_scal_multi_n = 0;       // per-slot scalars of a multi-theta call [G][slots]
   double* pin_rows = nullptr;
   LeafScal* pin_scal = nullptr;
+  // sharing plan of fit! (fit.jl:71-122), built by dsmgp_set_sharing / dsmgp_fit(tau, overlap)
+  struct Share {
+    bool active = false; double tau = 0.05;
+    std::vector<int4> slot;               // per local slot: (kind, source slot, copied block rows, 0)
+    std::vector<int> leaf_kind, leaf_src; // per global leaf (diagnostics / accessors)
+    int64_t n_alias = 0, n_prefix = 0, blocks_copied = 0;
+    double flops_saved = 0.0;
+  } share;
+  DevBuf<int4> d_share;
+  bool theta_global = true;               // every expert of a kernel holds the same theta (set_params); sharing needs it
+  bool share_applied = false;             // the last pipeline ran with the sharing plan
+  std::vector<int> exec_slot;             // global leaf -> slot that holds its results (the source's slot for an alias)
+  void* comm = nullptr;                   // ncclComm_t (dsmgp_comm_init), or null
+  DevBuf<double> d_comm_buf;              // device staging for the prediction all-reduce
   std::string err;
 
   ~dsmgp_handle() {
     for (auto& b : batches) {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
       cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
+      cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots);
     }
+    d_share.free(); d_comm_buf.free();
+    dsm::comm_destroy(comm);
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
     d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
     p_xt.free(); p_VT.free(); p_mu.free(); p_var.free(); p_pl.free(); p_tasks.free();
@@ -194,6 +223,7 @@ struct dsmgp_handle {
 };
 
 namespace dsm {
+constexpr int GERR = 16;     // index of the scheduler error word inside d_counter ([0,16): task counters, cleared per batch)
 cudaError_t engine_attrs();
 int num_sms(int device);
 template <typename T>
@@ -208,5 +238,7 @@ void shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* owner);
 void derive_params(const dsmgp_handle* h, int kid, const double* th, double* prm);
 inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 int32_t refine_alpha(dsmgp_handle* h);
+// potrf2 task list of one batch in topological look-ahead order, restricted to the slots with keep[slot - b.s0] != 0
+std::vector<int4> build_potrf2_tasks(const dsmgp_handle* h, const Batch& b, const std::vector<char>& keep, int sms);
 int32_t standalone_device_check(std::string& err);
 }  // namespace dsm

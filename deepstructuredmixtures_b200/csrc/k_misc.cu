@@ -39,6 +39,38 @@ void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, doubl
   delete_rows_kernel<<<1, NTHREADS, 0, st>>>(Lf, n, rows, nrows, v);
 }
 
+// ---- shared Cholesky of fit! (fit.jl:132-143, 208-292): block rows I < jb of a SHARE_PREFIX expert are the source expert's
+// tiles (I, 0 .. 8(I+1)-1) verbatim (same observations, same hyper-parameters => bit-identical factor).  grid = (experts, max jb).
+__global__ void __launch_bounds__(NTHREADS) share_copy_kernel(const LeafMeta* meta, const int4* share, const int* slots, double* F) {
+  const int s = slots[blockIdx.x];
+  const int4 sh = share[s];
+  const int I = blockIdx.y;
+  if (sh.x != SHARE_PREFIX || I >= sh.z) return;
+  const LeafMeta md = meta[s], ms = meta[sh.y];
+  const double2* src = reinterpret_cast<const double2*>(F + ms.foff + tile_off(I, 0, ms.nkc));
+  double2* dst = reinterpret_cast<double2*>(F + md.foff + tile_off(I, 0, md.nkc));
+  const int n2 = (I + 1) * (BLK / KC) * TILE_D / 2;
+  for (int i = threadIdx.x; i < n2; i += NTHREADS) dst[i] = src[i];
+}
+void launch_share_copy(const LeafMeta* meta, const int4* share, const int* slots, int nslots, int max_jb, double* F, cudaStream_t st) {
+  if (nslots <= 0 || max_jb <= 0) return;
+  share_copy_kernel<<<dim3(nslots, max_jb), NTHREADS, 0, st>>>(meta, share, slots, F);
+}
+// rows (and the potrf info) of SHARE_ALIAS experts = those of their source (fit.jl:132-143 copies factors and alpha)
+__global__ void rows_alias_kernel(const LeafMeta* meta, const int4* share, int nslots, double* rows, int row_width, LeafScal* scal) {
+  for (int s = blockIdx.x; s < nslots; s += gridDim.x) {
+    const int4 sh = share[s];
+    if (sh.x != SHARE_ALIAS) continue;
+    const int ld = meta[s].leaf, ls = meta[sh.y].leaf;
+    for (int k = threadIdx.x; k < row_width; k += blockDim.x) rows[(int64_t)ld * row_width + k] = rows[(int64_t)ls * row_width + k];
+    if (threadIdx.x == 0) scal[s] = scal[sh.y];
+  }
+}
+void launch_rows_alias(const LeafMeta* meta, const int4* share, int nslots, double* rows, int row_width, LeafScal* scal, cudaStream_t st) {
+  if (nslots <= 0) return;
+  rows_alias_kernel<<<nslots < 1184 ? nslots : 1184, 32, 0, st>>>(meta, share, nslots, rows, row_width, scal);
+}
+
 // ---- overlap matrix of getOverlap (fit.jl:12-39) -------------------------------------------------------------
 // D[n,m] = 1 - |obs_n \ obs_m| / |obs_n| = f(|obs_n ^ obs_m|) for experts whose lowest common ancestor is a sum node.
 // The reference xors N-bit sets for every pair (O(L^2 N)); here every POINT enumerates the pairs of experts that

@@ -35,22 +35,25 @@ struct PotrfGen {
   int nkc, I, J;
   int nc, nmain, nepi, c;
   bool diag, allready;       // allready: every k-block is known to be complete (tile (.,J-1) done implies all before it)
+  bool prefd;                // diagonal tile of a block column that already holds a valid factor (chol_continue / shared prefix)
   TaskHdr h;
   __device__ __forceinline__ int total() const { return nc + nmain + nepi; }
 
   __device__ __forceinline__ void load(const Potrf2Args& a, int ti) {
-    c = 0; nc = nmain = nepi = 0; diag = false; allready = false;
+    c = 0; nc = nmain = nepi = 0; diag = false; allready = false; prefd = false;
     const int4 tk = a.tasks[ti];
     const LeafMeta m = a.meta[tk.x];
     I = tk.y; J = tk.z; diag = (I == J);
     flags = a.flags + a.flag_off[tk.x];
+    const int js = (a.share != nullptr) ? a.share[tk.x].z : a.jstart;     // block rows < js hold a valid factor
     h.kind = diag ? 1 : 0; h.ti = ti; h.slot = tk.x; h.I = I; h.J = J;
-    h.wi = blk_width(m.np, I); h.wj = blk_width(m.np, J); h.n_c = 0; h.n_main = 0;
-    if (!diag && I < a.jstart) return;                    // tile already final (chol_continue)
+    h.wi = blk_width(m.np, I); h.wj = blk_width(m.np, J); h.n_c = 0; h.n_main = 0; h.pad0 = js;
+    if (!diag && I < js) return;                          // tile already final (chol_continue / copied from the source expert)
     nkc = m.nkc;
     F = a.F + m.foff; z = a.z + m.voff; Wj = a.W + m.woff + (int64_t)J * WBLK_D;
     nc = h.wj / 32;
-    nmain = (diag && J < a.jstart) ? 0 : (J * BLK) / KC;
+    prefd = diag && J < js;       // streams its block row for the forward solve z_J only (no MMA), then rebuilds W_J
+    nmain = (J * BLK) / KC;
     nepi = diag ? 0 : tri_epilogue_nstages(h.wj / 32);
     h.n_c = nc; h.n_main = nmain;
   }
@@ -63,6 +66,11 @@ struct PotrfGen {
       d.b = F + tile_off(I, J * 8 + 2 * c + 1, nkc); d.bbytes = TILE_BYTES;
     } else if (c < nc + nmain) {
       const int cc = c - nc, Kb = cc >> 3;
+      if ((cc & 7) == 0 && !allready && prefd) {
+        // the tiles (J, K) are final, but z_K is written by the diagonal task of column K: its flag orders all of them
+        if (J > 0) d.flag0 = flags + tile_flag_index(J - 1, J - 1);
+        allready = true;
+      }
       if ((cc & 7) == 0 && !allready) {
         if (cc == 0 && J > 1) {                           // fast path: the last k-block's tiles complete => all are
           int v0 = 1, v1 = 1;                             // both loads in flight before either is consumed
@@ -101,6 +109,7 @@ __device__ __forceinline__ void potrf2_producer(Pipe& p, const Potrf2Args& a) {
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
     const int ti = __shfl_sync(0xffffffffu, t, 0);
     if (ti >= a.ntasks) break;
+    if (a.share != nullptr && a.share[a.tasks[ti].x].x == SHARE_ALIAS) continue;     // the source expert's results are reused
     gen.load(a, ti);
     if (gen.total() == 0) {                               // already final: publish and move on
       if ((threadIdx.x & 31) == 0) st_release(const_cast<int*>(gen.flags) + tile_flag_index(gen.I, gen.J), 1);
@@ -147,7 +156,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
     const int nkc = m.nkc;
     const bool diag = (hd.kind == 1);
     const bool active = r0 < wi;
-    const bool prefactored = (J < a.jstart);     // chol_continue: column already final, diag only rebuilds W
+    const bool prefactored = (J < hd.pad0);      // chol_continue / shared prefix: column already final, diag only rebuilds W and z
     const int n_c = hd.n_c, n_main = hd.n_main;
     long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)hd.ti * 8 : nullptr;
     if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = (long long)sm | ((long long)I << 16) | ((long long)J << 32); }
@@ -186,7 +195,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
         st = p.wait();
         if (active) {
           const double* sA = p.A(st);
-          switch (ng) {
+          if (!prefactored) switch (ng) {
             case 1: mma_chunk16<1>(acc, sA, sA, r0); break;
             case 2: mma_chunk16<2>(acc, sA, sA, r0); break;
             case 3: mma_chunk16<3>(acc, sA, sA, r0); break;

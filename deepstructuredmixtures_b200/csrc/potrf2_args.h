@@ -13,6 +13,8 @@ struct Potrf2Args {
   const int4* tasks; int ntasks;                   // (slot, I, J, unused)
   int* counter; int* gerr;
   int jstart;                                      // chol_continue: block columns < jstart hold a valid factor
+  const int4* share;                               // per slot sharing plan or null: aliased experts are skipped, SHARE_PREFIX
+                                                   // experts continue behind their copied block rows (per-slot jstart = share.z)
   long long* trace;                                // optional [ntasks][8] clock stamps (DSMGP_TRACE_FILE), else null
 };
 

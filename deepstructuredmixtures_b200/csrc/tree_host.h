@@ -139,6 +139,37 @@ inline double update_weights(const HostTree& t, const double* rows, int64_t rw, 
   return val[t.root];
 }
 
+// infer! common.jl:336-355: kernel-mixture sum nodes (children are GPNodes, :339-345) keep normalised posterior weights, sum
+// nodes over sub-trees are reset to -log K after their evidence z is computed (:347-353).
+inline double infer_weights(const HostTree& t, const double* rows, int64_t rw, double* logw, double* zval) {
+  std::vector<double> val(t.n_nodes);
+  for (int64_t i = 0; i < t.n_nodes; i++) {
+    const int ty = t.type[i];
+    if (ty == DSMGP_NODE_LEAF) val[i] = rows[t.leaf_of_node[i] * rw];
+    else if (ty == DSMGP_NODE_SPLIT) {
+      double s = val[t.child(i, 0)];
+      for (int64_t k = 1; k < t.nchild(i); k++) s = s + val[t.child(i, k)];
+      val[i] = s;
+    } else {
+      const int64_t K = t.nchild(i);
+      double* lw = logw + t.child_ptr[i];
+      for (int64_t k = 0; k < K; k++) lw[k] = -std::log((double)K) + val[t.child(i, k)];
+      const double z = logsumexp(lw, K);
+      if (ty == DSMGP_NODE_KSUM) { for (int64_t k = 0; k < K; k++) lw[k] = lw[k] - z; }
+      else { for (int64_t k = 0; k < K; k++) lw[k] = -std::log((double)K); }
+      val[i] = z;
+    }
+  }
+  if (zval) *zval = val[t.root];
+  return val[t.root];
+}
+
+// reset_weights! common.jl:357-363
+inline void reset_weights(const HostTree& t, double* logw) {
+  for (int64_t i = 0; i < t.n_nodes; i++)
+    if (t.type[i] >= DSMGP_NODE_SUM) for (int64_t k = 0; k < t.nchild(i); k++) logw[t.child_ptr[i] + k] = -std::log((double)t.nchild(i));
+}
+
 // common.jl:101-122 for one point; returns child position or -1 (x above the last threshold / NaN)
 inline int64_t getchild(const HostTree& t, int64_t node, const double* xtest, int64_t T, int64_t p) {
   const int d = t.split_dim[node];

@@ -54,6 +54,18 @@ def allreduce_rows_(rows) -> None:
         dist.all_reduce(rows, op=dist.ReduceOp.SUM)
 
 
+def init_library_comm(model) -> None:
+    """Attach the model's handle to an NCCL communicator owned by libdsmgp (`dsmgp_comm_init`): afterwards `evaluate`,
+    `fit_`, `update_` and `predict` work on the sharded model exactly as on a single GPU -- the row table is all-reduced
+    inside the library.  The 128-byte NCCL id is created by rank 0 (`dsmgp_comm_unique_id`) and distributed through the
+    default process group's store (plumbing only; a Julia host would use MPI.jl or a file)."""
+    import torch.distributed as dist
+    from ._handle import comm_unique_id
+    ids = [comm_unique_id() if dist.get_rank() == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    model.handle.comm_init(ids[0])
+
+
 def evaluate_distributed(model, theta, leaf_scale=None) -> Tuple[float, np.ndarray]:
     """One LML+gradient evaluation of a model whose leaves are sharded over the ranks of the default process group
     (the model must have been created with rank=dist.get_rank(), world=dist.get_world_size())."""

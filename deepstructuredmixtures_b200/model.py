@@ -237,13 +237,20 @@ def _model_of(obj) -> Model:
 
 
 def fit_(model: Model, tau: float = 0.05) -> float:
-    """fit!(model; τ) fit.jl:67-122.  Every leaf gets the exact factor of update_cholesky! (fit.jl:105 always
-    runs it; the sharing branches never change the result).  Returns device seconds."""
-    _, sec = model.handle.fit()
+    """fit!(model; τ) fit.jl:67-122 with the model's overlap matrix D: the shared Cholesky (identical experts factored
+    once, common leading block rows reused; every result is the exact factor of update_cholesky!).  The plan stays in the
+    handle for the following evaluations, like train! calling fit!(spn, D, gpmap) every iteration.  Returns device seconds."""
+    if model.handle.world > 1 or len(model.leaves) == 1 or len(model.leaves) > 8192:
+        _, sec = model.handle.fit()          # (a dense 8192 x 8192 overlap matrix is where the plan stops paying for itself)
+    else:
+        _, sec = model.handle.fit(model.D, tau)
     return sec
 
 
-fit_naive_ = fit_                                             # fit.jl:294-304
+def fit_naive_(model: Model) -> float:
+    """fit_naive!(spn) fit.jl:294-304: every expert factored on its own."""
+    _, sec = model.handle.fit()
+    return sec
 
 
 def update_cholesky_(gp: LeafGP) -> LeafGP:                   # gaussianprocess.jl:82-108
@@ -290,6 +297,33 @@ def update_(model: Model) -> float:
 
     rec(model.root)
     return z
+
+
+def _write_logweights(model: Model, lw: np.ndarray):
+    ft = model.flat
+
+    def rec(n: Node):
+        if isinstance(n, GPNode):
+            return
+        if isinstance(n, GPSumNode):
+            n.logweights = [float(v) for v in lw[ft.child_ptr[n.id]:ft.child_ptr[n.id + 1]]]
+        for c in n.children:
+            rec(c)
+
+    rec(model.root)
+
+
+def infer_(model: Model) -> float:
+    """infer!(model) common.jl:336-355: kernel-mixture sum nodes keep posterior weights, the other sum nodes are reset to
+    uniform after their evidence is computed; returns z."""
+    lw, z = model.handle.infer()
+    _write_logweights(model, lw)
+    return z
+
+
+def reset_weights_(model: Model) -> None:
+    """reset_weights!(model) common.jl:357-363."""
+    _write_logweights(model, model.handle.reset_weights())
 
 
 def predict(model: Model, x) -> Tuple[np.ndarray, np.ndarray]:

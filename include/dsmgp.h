@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSMGP_VERSION 100
+#define DSMGP_VERSION 200
 
 typedef struct dsmgp_handle dsmgp_handle;
 
@@ -113,10 +113,25 @@ int64_t dsmgp_leaf_size(const dsmgp_handle* h, int64_t leaf);
 /* ---- fit -----------------------------------------------------------------------------------
  * fit!(spn, D, gpmap; tau) fit.jl:71-122 / fit_naive! :294-304 -> update_cholesky! gaussianprocess.jl:82-108
  * for every (local) leaf:  F = K + (exp(2 logNoise) + 1e-8) I ; L = potrf('L', F) ; alpha = L' \ (L \ y).
+ * `overlap` = the L x L matrix D of getOverlap (fit.jl:12-39, column-major) and `tau` the minimal relative overlap of
+ * fit!: the SHARED CHOLESKY.  The library repeats fit!'s scheduling (main expert = argmax D[:,j] .* D[j,:], :78-86) and
+ * its case split (fitcontained!, :124-292):  identical experts are factored once (their factor, alpha, LML, gradients and
+ * predictions are the source's);  an expert that shares its leading observations with its main expert (j inside main with
+ * fewer than tau*n_j rows to delete, or main a leading part of j) takes the factor tiles of the common leading 128-row blocks
+ * from the main expert and continues the factorisation behind them (chol_continue!).  Every result is the exact factor of
+ * update_cholesky! (the parity target: fit.jl:105 always runs it; the reference's own row-deletion is numerically wrong,
+ * SURVEY App. B Q7).  The plan is kept in the handle and used by every later fit / eval / grad until it is replaced;
+ * it is suspended while experts hold different theta (dsmgp_set_leaf_params).  overlap == NULL: fit_naive! (this call
+ * factors every expert on its own; a stored plan is kept).
  * `info[L]` (may be NULL): LAPACK potrf convention per leaf (0 ok, k>0 first non-positive pivot, 1-based;
  * chol_continue! returns the same, AdvancedCholeskey.jl:171-173).  `seconds` (may be NULL): device time of
  * the call, the value fit! returns (fit.jl:88,121). */
-int32_t dsmgp_fit(dsmgp_handle* h, int32_t* info, double* seconds);
+int32_t dsmgp_fit(dsmgp_handle* h, double tau, const double* overlap, int32_t* info, double* seconds);
+/* Store (overlap != NULL) or clear (NULL) the sharing plan without fitting. */
+int32_t dsmgp_set_sharing(dsmgp_handle* h, const double* overlap, double tau);
+/* The stored plan per leaf (any pointer may be NULL): kind 0 = factored on its own, 1 = identical to `source` (fit.jl:132-143),
+ * 2 = continues behind `blocks` leading 128-row blocks copied from `source` (fit.jl:145-292); source = leaf number or -1. */
+int32_t dsmgp_get_sharing(const dsmgp_handle* h, int32_t* kind, int32_t* source, int32_t* blocks);
 
 /* mll!(spn, L) optimize.jl:27-39 (leaf: mll(gp) gaussianprocess.jl:163): fills the per-node table
  * (AxisArray keyed by node id -> node_lml[n_nodes]); returns the root value in node_lml[root]. */
@@ -165,10 +180,27 @@ int32_t dsmgp_eval_finish_dev(dsmgp_handle* h, const double* leaf_scale, double*
 int32_t dsmgp_leaf_rows(const dsmgp_handle* h, double* rows);
 int32_t dsmgp_leaf_owner(const dsmgp_handle* h, int32_t* owner); /* rank owning each leaf (LPT on n^3) */
 
+/* ---- multi-GPU inside the library -------------------------------------------------------------
+ * One process (or thread) per GPU, handles created with rank/world in dsmgp_opts.  The only exchange of an evaluation is the
+ * table of per-leaf rows; with a communicator attached, dsmgp_fit / dsmgp_eval / dsmgp_grad / dsmgp_lml / dsmgp_update_weights
+ * and dsmgp_predict work at world > 1 exactly like at world == 1: the library all-reduces (NCCL SUM, on its own stream) and every
+ * rank finishes the O(L) tree passes.  NCCL is loaded with dlopen("libnccl.so.2") at the first of these two calls; the library
+ * has no link-time dependency on it.  `id` is NCCL's 128-byte ncclUniqueId: rank 0 creates it, the caller distributes it to the
+ * other ranks by any means (MPI.jl / sockets / a file), every rank passes it to dsmgp_comm_init (collective call). */
+#define DSMGP_COMM_ID_BYTES 128
+int32_t dsmgp_comm_unique_id(void* id /* DSMGP_COMM_ID_BYTES */);
+int32_t dsmgp_comm_init(dsmgp_handle* h, const void* id);
+
 /* ---- posterior weights and prediction --------------------------------------------------------
  * update!(spn) common.jl:323-334: sum_logweights receives, for every sum node in node order, its
  * normalised child log-weights (CSR by child_ptr; pass NULL to skip), *z the root evidence. */
 int32_t dsmgp_update_weights(dsmgp_handle* h, double* sum_logweights, double* z);
+/* infer!(spn) common.jl:336-355: like update!, but only the kernel-mixture sum nodes (GPSumNode{T,GPNode}, :339-345) keep their
+ * posterior weights; every sum node over sub-trees is reset to the uniform -log K after its evidence is computed (:347-353).
+ * The weights are stored in the handle (used by dsmgp_predict) and returned like dsmgp_update_weights. */
+int32_t dsmgp_infer(dsmgp_handle* h, double* sum_logweights, double* z);
+/* reset_weights!(spn) common.jl:357-363: every sum node's log-weights = -log K. */
+int32_t dsmgp_reset_weights(dsmgp_handle* h, double* sum_logweights);
 
 enum { DSMGP_PREDICT_DSMGP = 0, DSMGP_PREDICT_POE = 1, DSMGP_PREDICT_GPOE = 2, DSMGP_PREDICT_RBCM = 3 };
 /* predict(model, x) common.jl:294-307 -> prediction(gp, xtest) gaussianprocess.jl:110-137.
@@ -219,6 +251,10 @@ int32_t dsmgp_host_tree_eval(const dsmgp_tree* tree, int64_t L, const int32_t* l
                              const dsmgp_kernel_desc* kernels, int32_t n_kernels,
                              const double* rows, int64_t row_width, const double* leaf_scale,
                              double* node_lml, double* grad, double* sum_logweights, double* z);
+/* The sharing plan dsmgp_set_sharing / dsmgp_fit(tau, overlap) derives from a structure (fit.jl:71-122): kind / source / blocks
+ * per leaf as in dsmgp_get_sharing. */
+int32_t dsmgp_host_sharing_plan(int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs, const int32_t* leaf_kernel_id,
+                                const double* overlap, double tau, int32_t* kind, int32_t* source, int32_t* blocks);
 /* LPT bin packing of leaves by n^3 onto `world` ranks (deterministic). */
 int32_t dsmgp_host_shard(int64_t L, const int64_t* leaf_ptr, int32_t world, int32_t* owner);
 

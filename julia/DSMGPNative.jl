@@ -125,12 +125,20 @@ end
 setparams!(h::Handle, hyp::Vector{Float64}) =
     check(ccall((:dsmgp_set_params, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, hyp, length(hyp)), h.ptr)
 
-"fit!(spn, D, gpmap; τ): returns elapsed seconds like fit.jl:88,121."
-function fit!(h::Handle)
+"fit!(spn, D, gpmap; τ): the shared Cholesky with the overlap matrix D; returns elapsed seconds like fit.jl:88,121."
+function fit!(h::Handle, D::Matrix{Float64}; τ::Float64 = 0.05)
     sec = Ref{Float64}(0.0)
-    check(ccall((:dsmgp_fit, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ref{Float64}), h.ptr, C_NULL, sec), h.ptr)
+    check(ccall((:dsmgp_fit, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Int32}, Ref{Float64}), h.ptr, τ, D, C_NULL, sec), h.ptr)
     return sec[]
 end
+
+"fit_naive!(spn) fit.jl:294-304: every expert factored on its own."
+function fit_naive!(h::Handle)
+    sec = Ref{Float64}(0.0)
+    check(ccall((:dsmgp_fit, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Int32}, Ref{Float64}), h.ptr, 0.05, C_NULL, C_NULL, sec), h.ptr)
+    return sec[]
+end
+fit!(h::Handle) = fit_naive!(h)
 
 "mll!(spn, ℓ): fills the AxisArray keyed by node id (optimize.jl:27-39)."
 function mll!(h::Handle, ℓ)
@@ -172,6 +180,46 @@ function update!(h::Handle, spn)
     end
     return z[]
 end
+
+function _write_logweights!(h::Handle, spn, lw::Vector{Float64})
+    off = 0; order = sort(collect(h.nodeindex), by = last)
+    byid = Dict(n.id => n for n in getOrderedNodes(spn))
+    for (id, _) in order
+        n = byid[id]; n isa GPNode && continue
+        k = length(children(n))
+        n isa GPSumNode && (n.logweights[:] = lw[off + 1:off + k])
+        off += k
+    end
+end
+
+"infer!(spn) common.jl:336-355."
+function infer!(h::Handle, spn)
+    total = sum(length(children(n)) for n in getOrderedNodes(spn) if !(n isa GPNode))
+    lw = zeros(max(total, 1)); z = Ref{Float64}(0.0)
+    check(ccall((:dsmgp_infer, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ref{Float64}), h.ptr, lw, z), h.ptr)
+    _write_logweights!(h, spn, lw)
+    return z[]
+end
+
+"reset_weights!(spn) common.jl:357-363."
+function reset_weights!(h::Handle, spn)
+    total = sum(length(children(n)) for n in getOrderedNodes(spn) if !(n isa GPNode))
+    lw = zeros(max(total, 1))
+    check(ccall((:dsmgp_reset_weights, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h.ptr, lw), h.ptr)
+    _write_logweights!(h, spn, lw)
+end
+
+"""
+Multi-GPU, one Julia process per GPU (handle created with rank/world): rank 0 calls `comm_unique_id()`, ships the 128 bytes to the
+other ranks (MPI.jl bcast, a socket, a file), every rank calls `comm_init!(h, id)`.  After that fit! / evaluate! / update! / predict
+are the same calls as on one GPU: the library all-reduces the per-leaf rows over NCCL itself.
+"""
+function comm_unique_id()
+    id = zeros(UInt8, 128)
+    check(ccall((:dsmgp_comm_unique_id, LIB), Int32, (Ptr{UInt8},), id))
+    return id
+end
+comm_init!(h::Handle, id::Vector{UInt8}) = check(ccall((:dsmgp_comm_init, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), h.ptr, id), h.ptr)
 
 """
 train!(spn, D, gpmap, optim; iterations, λ, earlystop) optimisers.jl:40-83 as one call.  `optimiser`: 0 Descent(η), 1 ADAM(η, (β1, β2)),

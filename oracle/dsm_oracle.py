@@ -275,6 +275,13 @@ class GaussianProcess:
     # -- gradients ------------------------------------------------------------------
     def W(self) -> np.ndarray:
         """ααinvcK! :219-226:  out = -I ; ldiv!(cK, out) ; ger!(1, α, α, out)  =>  αα' - F^{-1}."""
+        if self.N > 3000:
+            # same matrix through LAPACK dpotri (F^-1 from the factor, 2/3 n^3 instead of the 2 n^3 of potrs with n right-hand
+            # sides): keeps the full-size parity tests (experts of 5,000-8,500 points) within seconds
+            Fi, info = sla.lapack.dpotri(self.L, lower=1)
+            assert info == 0
+            Fi = np.tril(Fi) + np.tril(Fi, -1).T
+            return np.outer(self.alpha, self.alpha) - Fi
         out = -np.eye(self.N)
         out = sla.cho_solve((self.L, True), out, check_finite=False)
         out += np.outer(self.alpha, self.alpha)
@@ -632,6 +639,90 @@ def update_weights(node: Node) -> float:
     z = logsumexp(lw)
     node.logweights = lw - z
     return z
+
+
+def infer_weights(node: Node) -> float:
+    """infer!(node) common.jl:336-355.  Kernel-mixture sum nodes (GPSumNode{T,GPNode}, :339-345) keep normalised posterior
+    weights; sum nodes over sub-trees (:347-353) are reset to the uniform -log K after z is computed.  Returns z."""
+    if node.type == NODE_LEAF:
+        return node.gp.mll()
+    if node.type == NODE_SPLIT:
+        v = 0.0
+        for c in node.children:
+            v = v + infer_weights(c)
+        return v
+    K = len(node.children)
+    lw = np.array([-math.log(K) + infer_weights(c) for c in node.children])
+    z = logsumexp(lw)
+    node.logweights = lw - z if node.type == NODE_KSUM else np.full(K, -math.log(K))
+    return z
+
+
+def reset_weights(node: Node) -> None:
+    """reset_weights!(spn) common.jl:357-363: every sum node's logweights = -log K."""
+    if node.type >= NODE_SUM:
+        node.logweights = np.full(len(node.children), -math.log(len(node.children)))
+    for c in node.children:
+        reset_weights(c)
+
+
+def fit_plan(root: Node, D: np.ndarray, tau: float = 0.05) -> List[Tuple[str, int]]:
+    """The scheduling and case split of fit!(spn, D, gpmap; τ) fit.jl:71-122 and fitcontained! :124-292, WITHOUT the
+    arithmetic: for every leaf (getLeaves order) the branch the reference takes and its main leaf:
+        'main'      factored as somebody's main expert (:97-100) before being visited itself
+        'self'      its own main / kernel ids differ / first(obs) < first(main.obs)      -> update_cholesky! (:107-112)
+        'copy'      (true, true)    :132-143
+        'delete'    (false, true)   :145-206 with length(toupdate)/nobs < τ  (else 'full')
+        'continue'  (true, false)   :208-292 with the prefix test :246-248 and the τ test (else 'full')
+        'full'      any branch that ends in update_cholesky!(jGP)"""
+    leaves = getLeaves(root)
+    n = len(leaves)
+    S = [0] * n
+    counts = [0] * n
+    for j in range(n):
+        i = int(np.argmax(D[:, j] * D[j, :]))                      # :79
+        counts[i] += 1
+        S[j] = i
+    order = sorted(range(n), key=lambda l: counts[l])              # :86 (stable)
+    processed = [False] * n
+    out: List[Tuple[str, int]] = [("", -1)] * n
+    for j in order:
+        if processed[j]:
+            continue
+        i = S[j]
+        if not processed[i]:
+            processed[i] = True
+            if i != j:
+                out[i] = ("main", i)
+        processed[j] = True
+        jn, mn = leaves[j], leaves[i]
+        jo, mo = jn.obs, mn.obs
+        if i == j or mn.kernelid != jn.kernelid or jo[0] < mo[0]:  # :107-112
+            out[j] = ("self", i)
+            continue
+        ione, jone = D[i, j] == 1.0, D[j, i] == 1.0
+        if ione and jone:
+            out[j] = ("copy", i)
+        elif (not ione) and jone:
+            minJ, maxJ, minM, maxM = jo[0], jo[-1], mo[0], mo[-1]
+            assert minJ >= minM and maxJ <= maxM                    # :162-163
+            e = len(mo) if maxJ == maxM else int(np.nonzero(mo == maxJ)[0][0]) + 1
+            toupdate = np.setdiff1d(mo[:e], jo)
+            out[j] = ("delete", i) if len(toupdate) / len(jo) < tau else ("full", i)
+        elif ione and (not jone):
+            minJ, maxJ, minM, maxM = jo[0], jo[-1], mo[0], mo[-1]
+            assert minJ >= minM and maxJ >= maxM                    # :232-233
+            s = 0 if minJ == minM else int(np.nonzero(mo == minJ)[0][0])
+            k1 = int(np.nonzero(jo == maxM)[0][0]) + 1
+            s1, s2 = jo[:k1], mo[s:]
+            toupdate = np.setdiff1d(mo, s1)
+            if len(s1) != len(s2) and minJ == minM:
+                out[j] = ("full", i)
+            else:
+                out[j] = ("continue", i) if len(toupdate) / len(jo) < tau else ("full", i)
+        else:
+            out[j] = ("full", i)
+    return out
 
 
 def getchild(node: Node, x: np.ndarray) -> np.ndarray:

@@ -43,8 +43,18 @@ def check_eval(model, theta, mathematical=False, leaf_scale=None):
             assert np.all(g == 0.0)          # zero-weight experts skip the gradient kernels (include/dsmgp.h: dsmgp_finetune_eval)
             continue
         assert np.all(np.abs(g - orow[1:]) <= GRAD_TOL * np.maximum(np.abs(orow[1:]), scale)), (l, g, orow[1:])
-    gs = np.maximum(np.abs(o_grad), 1e-6 * np.max(np.abs(o_grad)) + 1e-300)
-    assert np.all(np.abs(grad - o_grad) <= 1e-8 * np.maximum(gs, 1.0)), (grad, o_grad)
+    # model gradient (optimize.jl:42-89: sum_l w_l g_l): 1e-9 relative, where a component that is a cancelling sum of leaf
+    # gradients is compared with the natural scale sum_l w_l scale_l of its terms (the down-pass applied to the leaf scales)
+    leaves = orc.getLeaves(root)
+    nat_scale = np.zeros_like(o_grad)
+    orc.grad_down(root, 0.0, 0.0, o_ell, o_ell[root.id], nat_scale,
+                  {lf.leaf_index: np.full(lf.gp.nparams(), max(float(lf.gp.alpha @ lf.gp.alpha), float(lf.gp.N)) * max(1.0, lf.gp.noise()))
+                   for lf in leaves}, leaf_scale)
+    err_scaled = np.max(np.abs(grad - o_grad) / np.maximum(np.abs(o_grad), nat_scale))
+    nz = np.abs(o_grad) > 0
+    err_rel = np.max(np.abs(grad - o_grad)[nz] / np.abs(o_grad)[nz]) if nz.any() else 0.0
+    print(f"\n[parity] L={len(leaves)} lml rel {abs(lml - o_lml) / abs(o_lml):.1e}  model grad rel {err_rel:.1e} (rel to natural scale {err_scaled:.1e})")
+    assert err_scaled <= GRAD_TOL, (grad, o_grad)
     return lml, grad
 
 
@@ -54,7 +64,7 @@ def test_single_gp_isose():
     gp = dsm.GaussianProcess(x, y, kernel=dsm.IsoSE(0.1, -0.2), logNoise=-1.0, run_cholesky=True)
     o = orc.GaussianProcess(x, y, kernel=orc.IsoSE(0.1, -0.2), logNoise=-1.0, run_cholesky=True)
     assert abs(gp.mll() - o.mll()) <= LML_TOL * abs(o.mll())
-    assert relerr(gp.alpha, o.alpha) < 1e-7
+    assert np.max(np.abs(gp.alpha - o.alpha)) <= 1e-9 * np.max(np.abs(o.alpha))      # norm-wise: entries of alpha cross zero
     Lf = gp.factors
     assert np.max(np.abs(Lf - np.tril(o.L))) < 1e-11
     g = dsm.grad_mll(gp)
@@ -300,12 +310,12 @@ def test_single_gp_multiblock(n, ktype):
     o = orc.GaussianProcess(x, y, kernel=okern, logNoise=-1.0, run_cholesky=True)
     assert abs(gp.mll() - o.mll()) <= LML_TOL * abs(o.mll())
     assert np.max(np.abs(gp.factors - np.tril(o.L))) < 1e-10
-    assert relerr(gp.alpha, o.alpha) < 1e-6
+    assert np.max(np.abs(gp.alpha - o.alpha)) <= 1e-9 * np.max(np.abs(o.alpha))
     g = dsm.grad_mll(gp)
     og = o.grad_mll()
     scale = max(float(o.alpha @ o.alpha), float(n))
     assert np.all(np.abs(g - og) <= GRAD_TOL * np.maximum(np.abs(og), scale)), (g, og)
-    assert relerr(gp.alpha, o.alpha) < 1e-6          # alpha as produced by the gradient path (X^T z)
+    assert np.max(np.abs(gp.alpha - o.alpha)) <= 1e-9 * np.max(np.abs(o.alpha))          # alpha as produced by the gradient path (X^T z)
     xt = np.random.default_rng(n).random((300, D))
     mu, var = gp.prediction(xt)
     omu, ovar = o.prediction(xt)
@@ -339,7 +349,7 @@ def test_golden_vectors_gpu(name):
     lml, grad = dsm.evaluate(model, np.array(case["theta"]))
     assert abs(lml - gold["lml"]) <= LML_TOL * abs(gold["lml"])
     og = np.array(gold["grad"])
-    assert np.all(np.abs(grad - og) <= 1e-8 * np.maximum(np.abs(og), 1.0))
+    assert np.all(np.abs(grad - og) <= GRAD_TOL * np.maximum(np.abs(og), 1e-3 * np.max(np.abs(og)))), (grad, og)
     rows = model.handle.leaf_rows()
     assert relerr(rows[:, 0], np.array(gold["leaf_lml"])) < LML_TOL
     z = dsm.update_(model)

@@ -1,0 +1,474 @@
+"""GPU parity, round 2: the independent mpmath pin, oracle comparisons at the BENCHMARKED sizes (cfg3 / cfg4 / cfg5), the
+shared Cholesky of fit!, infer! / reset_weights!, repeated multi-rank evaluations and the in-library NCCL collective.
+Everything goes through the C ABI (ctypes).  Tolerances are BASELINE.json north_star's: LML and gradients 1e-9 relative,
+predictions 1e-8 relative; every test prints the error it achieved so the margin is on record."""
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, oracle_tree, orc, relerr, synth
+
+pytestmark = pytest.mark.gpu
+
+LML_TOL = 1e-9
+GRAD_TOL = 1e-9
+PRED_TOL = 1e-8
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def grad_scale(gp):
+    """Natural scale of a leaf gradient: its entries are differences alpha' dK alpha - tr(F^-1 dK) of two terms of size
+    ~ max(alpha'alpha, n) * max(1, noise) (compare relative to the larger term)."""
+    return max(float(gp.alpha @ gp.alpha), float(gp.N)) * max(1.0, gp.noise())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 1. the independent pin (tests/golden/make_mp_golden.py: 50-digit mpmath, no oracle import)
+# ---------------------------------------------------------------------------------------------------------------------
+def _mp_handle(doc, m, as_written):
+    from deepstructuredmixtures_b200 import _native as nat, kernels as kr
+    from deepstructuredmixtures_b200._handle import Handle
+    x = np.asarray(doc["x"]); y = np.asarray(doc["y"])
+    fl = m["flat"]
+    D = x.shape[1]
+    mk = {0: lambda: kr.IsoSE(0.0, 0.0), 1: lambda: kr.ArdSE(np.zeros(D), 0.0), 2: lambda: kr.IsoLinear(0.0),
+          3: lambda: kr.ArdLinear(np.zeros(D))}
+    kernels = [mk[k]() for k in m["kernels"]]
+    ft = nat.FlatTree(fl["node_type"], fl["child_ptr"], fl["child_idx"], fl["leaf_of_node"], fl["split_dim"], fl["split_ptr"],
+                      fl["split_val"], fl["root"])
+    lp = fl["leaf_ptr"]
+    obs = [np.asarray(fl["leaf_obs"][lp[l]:lp[l + 1]], dtype=np.int64) for l in range(len(lp) - 1)]
+    yc = [y[o - 1] - fl["leaf_mean"][l] for l, o in enumerate(obs)]
+    return Handle(x, obs, yc, fl["leaf_mean"], fl["leaf_kernel_id"], kernels, ft, as_written_grads=as_written), kernels
+
+
+@pytest.mark.parametrize("name", ["dsmgp_isose", "dsmgp_ardse", "dsmgp_isolinear", "dsmgp_ardlinear", "dsmgp_mixture", "poe_isose"])
+def test_gpu_against_independent_mpmath_vectors(name):
+    from deepstructuredmixtures_b200 import _native as nat
+    doc = json.load(open(os.path.join(GOLD, "mp_golden.json")))
+    m = [mm for mm in doc["models"] if mm["name"] == name][0]
+    xt = np.asarray(doc["xtest"])
+    worst = dict(lml=0.0, grad=0.0, model_grad=0.0, pred=0.0)
+    for mode, aw in (("as_written", True), ("mathematical", False)):
+        H, kernels = _mp_handle(doc, m, aw)
+        for ev in m["evals"]:
+            th = np.asarray(ev["theta"])
+            lml, grad, nodes = H.eval(th, want_nodes=True)
+            rows = H.leaf_rows()
+            root_lml = ev["node_lml"][m["flat"]["root"]]
+            worst["lml"] = max(worst["lml"], abs(lml - root_lml) / abs(root_lml), relerr(rows[:, 0], ev["leaf_lml"]))
+            assert abs(lml - root_lml) <= LML_TOL * abs(root_lml)
+            assert relerr(nodes, ev["node_lml"]) <= LML_TOL
+            assert relerr(rows[:, 0], ev["leaf_lml"]) <= LML_TOL
+            for l, g in enumerate(ev["leaf_grad_" + mode]):
+                g = np.asarray(g)
+                a = np.asarray(ev["leaf_alpha"][l])
+                scale = max(float(a @ a), float(a.size))
+                e = np.max(np.abs(rows[l, 1:1 + g.size] - g) / np.maximum(np.abs(g), scale))
+                worst["grad"] = max(worst["grad"], e)
+                assert e <= GRAD_TOL, (name, mode, l, rows[l, 1:1 + g.size], g)
+            G = np.asarray(ev["grad_" + mode])
+            e = np.max(np.abs(grad - G) / np.maximum(np.abs(G), 1e-6 * np.max(np.abs(G))))
+            worst["model_grad"] = max(worst["model_grad"], e)
+            assert e <= GRAD_TOL, (name, mode, grad, G)
+            _, gf = H.eval(th, leaf_scale=np.asarray(ev["finetune_row"]))
+            Gf = np.asarray(ev["grad_" + mode + "_finetune"])
+            assert np.max(np.abs(gf - Gf) / np.maximum(np.abs(Gf), 1e-6 * np.max(np.abs(Gf)))) <= GRAD_TOL
+            H.eval(th)
+            mu0, var0 = H.leaf_predict(0, xt)
+            e = max(relerr(mu0, ev["leaf0_mu"]), relerr(var0, ev["leaf0_var"]))
+            worst["pred"] = max(worst["pred"], e)
+            assert e <= PRED_TOL
+            if name.startswith("dsmgp"):
+                lw, z = H.update_weights()
+                assert abs(z - ev["update_z"]) <= LML_TOL * abs(z)
+                cp = m["flat"]["child_ptr"]
+                for nid, w in enumerate(ev["update_logw"]):
+                    if w:
+                        assert np.allclose(lw[cp[nid]:cp[nid + 1]], w, rtol=1e-9, atol=1e-11)
+                mu, var = H.predict(xt, nat.PREDICT_DSMGP)
+                e = max(relerr(mu, ev["predict_mu"]), relerr(var, ev["predict_var"]))
+                worst["pred"] = max(worst["pred"], e)
+                assert e <= PRED_TOL, (mu, ev["predict_mu"])
+                lw, z = H.infer()
+                assert abs(z - ev["infer_z"]) <= LML_TOL * abs(z)
+                for nid, w in enumerate(ev["infer_logw"]):
+                    if w:
+                        assert np.allclose(lw[cp[nid]:cp[nid + 1]], w, rtol=1e-9, atol=1e-11)
+            else:
+                for key, pm in (("poe", nat.PREDICT_POE), ("gpoe", nat.PREDICT_GPOE), ("rbcm", nat.PREDICT_RBCM)):
+                    mu, var = H.predict(xt, pm)
+                    e = max(relerr(mu, ev[key + "_mu"]), relerr(var, ev[key + "_var"]))
+                    worst["pred"] = max(worst["pred"], e)
+                    assert e <= PRED_TOL, key
+        H.close()
+    print(f"\n[mp pin] {name}: max rel err  LML {worst['lml']:.1e}  leaf grad {worst['grad']:.1e}  model grad {worst['model_grad']:.1e}"
+          f"  predictions {worst['pred']:.1e}")
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2. oracle comparison at the benchmarked sizes
+# ---------------------------------------------------------------------------------------------------------------------
+def _bench():
+    sys.path.insert(0, ROOT)
+    import bench
+    return bench
+
+
+def _oracle_kernel(pk, th):
+    """oracle kernel with the parameters of the product kernel slice th = [logl..., logs, logn]"""
+    nl = pk.logl.size
+    return orc.Kernel(pk.type, np.array(th[:nl], dtype=np.float64), float(th[nl]))
+
+
+def _compare_leaf(H, model, l, pk, th, xt, tag, mathematical=False, predict=True):
+    """rows[l] and a 256-point prediction of expert l against the oracle on the same points."""
+    lf = model.leaves[l]
+    nl = pk.logl.size
+    t0 = time.time()
+    gp = orc.GaussianProcess(model.x[lf.obs - 1], model.y[lf.obs - 1], mean=lf.mean, kernel=_oracle_kernel(pk, th), logNoise=float(th[nl + 1]),
+                             run_cholesky=True)
+    o_lml = gp.mll()
+    o_g = gp.grad_mll(mathematical=mathematical)
+    rows = H.leaf_rows()
+    e_lml = abs(rows[l, 0] - o_lml) / abs(o_lml)
+    g = rows[l, 1:1 + o_g.size]
+    sc = grad_scale(gp)
+    e_g_scaled = float(np.max(np.abs(g - o_g) / np.maximum(np.abs(o_g), sc)))
+    nzm = np.abs(o_g) > 0
+    e_g_rel = float(np.max(np.abs(g - o_g)[nzm] / np.abs(o_g)[nzm])) if nzm.any() else 0.0
+    msg = f"[full size] {tag} expert {l} n={lf.nobs}: LML rel {e_lml:.1e}, grad rel-to-scale {e_g_scaled:.1e} (pure rel {e_g_rel:.1e})"
+    e_mu = e_var = 0.0
+    if predict:
+        mu, var = H.leaf_predict(l, xt)
+        omu, ovar = gp.prediction(xt)
+        ysc = float(np.std(model.y))
+        e_mu = float(np.max(np.abs(mu - omu) / np.maximum(np.abs(omu), ysc)))
+        e_var = relerr(var, ovar)
+        msg += f", predict mean {e_mu:.1e} var {e_var:.1e}"
+    print("\n" + msg + f"  (oracle {time.time() - t0:.1f} s)")
+    assert e_lml <= LML_TOL, msg
+    assert e_g_scaled <= GRAD_TOL, msg
+    assert e_mu <= PRED_TOL and e_var <= PRED_TOL, msg
+    return e_lml, e_g_scaled, e_mu, e_var
+
+
+def test_full_size_cfg3_against_oracle():
+    """BASELINE config 3 at FULL size (40,000 x 8 ArdSE, 144 experts): the smallest, a median and the LARGEST expert
+    (n = 5008: 40 block columns, the longest dependency chain of the benchmarked run) against the oracle -- per-leaf LML and
+    gradient rows of the as-written evaluation that bench.py times, the mathematical gradient, and a 256-point prediction."""
+    bench = _bench()
+    from deepstructuredmixtures_b200 import model as mdl
+    w = bench.WORKLOADS["cfg3"]
+    x, y, root, kern = bench.build_structure(w)
+    th = bench.thetas([kern.nparams], w["seed"])[1]
+    xt = np.random.default_rng(11).random((256, w["D"]))
+    for mathematical in (False, True):
+        model = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, as_written_grads=not mathematical)
+        H = model.handle
+        lml, grad = H.eval(th)
+        sizes = np.diff(H.leaf_ptr)
+        order = np.argsort(sizes)
+        picks = [int(order[0]), int(order[len(order) // 2]), int(order[-1])]
+        assert sizes[picks[-1]] == sizes.max()
+        for l in picks:
+            _compare_leaf(H, model, l, kern, th, xt, "cfg3 " + ("mathematical" if mathematical else "as-written"),
+                          mathematical=mathematical, predict=not mathematical)
+        model.close()
+
+
+def test_full_size_cfg4_against_oracle():
+    """BASELINE config 4 at full size (45,730 x 9, KernelFunction[IsoSE, IsoLinear], V=4 K=4 M=1000: 512 experts up to ~8.5k
+    points): the largest IsoSE and the largest IsoLinear expert against the oracle (LAUUM path for IsoSE)."""
+    bench = _bench()
+    from deepstructuredmixtures_b200 import model as mdl
+    w = bench.WORKLOADS["cfg4"]
+    x, y, root, kern = bench.build_structure(w)
+    th = bench.thetas([k.nparams for k in kern], w["seed"])[1]
+    model = mdl.DSMGP(root, x, y, [k.copy() for k in kern], -1.0)
+    H = model.handle
+    lml, grad = H.eval(th)
+    assert np.isfinite(lml) and np.all(np.isfinite(grad))
+    sizes = np.diff(H.leaf_ptr)
+    kid = np.array([lf.kernelid - 1 for lf in model.leaves])
+    xt = np.random.default_rng(12).random((256, w["D"]))
+    off = 0
+    for k, pk in enumerate(kern):
+        cand = np.nonzero(kid == k)[0]
+        l = int(cand[np.argmax(sizes[cand])])
+        _compare_leaf(H, model, l, pk, th[off:off + pk.nparams], xt, f"cfg4 kernel {k}")
+        off += pk.nparams
+    model.close()
+
+
+def test_full_size_cfg5_streamed_against_oracle():
+    """BASELINE config 5 (scale run): 1,000,000 x 8 ArdSE, 20,736 experts, factors STREAMED through the production arena
+    (keep_factors=0: factor -> reduce -> discard, ~50 batches).  One full evaluation; the rows of the largest, a median and
+    the smallest expert -- three different streaming batches (slots are sorted by size) -- against the oracle."""
+    bench = _bench()
+    from deepstructuredmixtures_b200 import model as mdl
+    w = bench.WORKLOADS["cfg5"]
+    t0 = time.time()
+    x, y, root, kern = bench.build_structure(w)
+    t1 = time.time()
+    model = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, keep_factors=False)
+    H = model.handle
+    th = bench.thetas([kern.nparams], w["seed"])[1]
+    lml, grad = H.eval(th)
+    t2 = time.time()
+    print(f"\n[full size] cfg5: tree {t1 - t0:.1f} s, create + one streamed evaluation {t2 - t1:.1f} s, L = {H.L}, lml = {lml:.6e}")
+    assert np.isfinite(lml) and np.all(np.isfinite(grad)) and np.all(H.leaf_info() == 0)
+    sizes = np.diff(H.leaf_ptr)
+    order = np.argsort(sizes)
+    for l in (int(order[-1]), int(order[len(order) // 2]), int(order[0])):
+        _compare_leaf(H, model, l, kern, th, None, "cfg5 streamed", predict=False)
+    model.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 3. the shared Cholesky of fit! (fit.jl:71-122)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["sorted1d", "eps0", "eps0_ard"])
+def test_shared_cholesky_equals_full_refactorisation(case):
+    """dsmgp_fit(tau, overlap): identical experts factored once, common leading block rows copied, the rest continued --
+    every result against the naive fit (every expert on its own) to 1e-12: LML table, alpha, factors, gradients, predictions."""
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import model as mdl, structure as st
+    cfgs = {"sorted1d": dict(N=6000, D=1, V=3, K=4, M=100, eps=0.5, seed=2, kern=dsm.IsoSE(0.0, 0.0)),
+            "eps0": dict(N=4000, D=1, V=3, K=3, M=200, eps=0.0, seed=5, kern=dsm.IsoSE(0.0, 0.0)),
+            "eps0_ard": dict(N=5000, D=2, V=3, K=3, M=200, eps=0.0, seed=8, kern=dsm.ArdSE(np.zeros(2), 0.0))}
+    c = cfgs[case]
+    x, y = synth(c["N"], c["D"], c["seed"], sorted1d=True)
+    cfg = st.DSMGPConfig(None, c["kern"], -1.0, c["M"], c["K"], c["V"], 2, c["eps"], True)
+    root = st.buildTree(x, y, cfg, np.random.default_rng(c["seed"]))
+    th = np.concatenate([0.1 * np.arange(c["kern"].logl.size) - 0.2, [0.15, -1.1]])
+    naive = mdl.DSMGP(root, x, y, [c["kern"].copy()], -1.0)
+    shared = mdl.DSMGP(root, x, y, [c["kern"].copy()], -1.0)
+    Dm = shared.D
+    naive.handle.set_params(th); shared.handle.set_params(th)
+    info_n, _ = naive.handle.fit()                       # fit_naive!
+    info_s, sec = shared.handle.fit(Dm, 0.5)             # fit!(spn, D, gpmap; tau)
+    kind, src, blocks = shared.handle.get_sharing()
+    n_alias, n_prefix = int((kind == 1).sum()), int((kind == 2).sum())
+    print(f"\n[shared cholesky] {case}: {len(kind)} experts, {n_alias} identical (factored once), {n_prefix} continue behind "
+          f"{int(blocks.sum())} copied block rows")
+    assert n_alias + n_prefix > 0
+    if case.startswith("eps0"):
+        assert n_alias > 0
+    if case == "sorted1d":
+        assert n_prefix > 0
+    assert np.array_equal(info_n, info_s)
+    ln, ls = naive.handle.lml(), shared.handle.lml()
+    assert np.max(np.abs(ln - ls) / np.abs(ln)) <= 1e-12
+    xt = np.random.default_rng(4).random((300, c["D"]))
+    worst = 0.0
+    for l in range(len(kind)):
+        if kind[l] == 0 and l % 7:
+            continue
+        a_n, a_s = naive.handle.leaf_alpha(l), shared.handle.leaf_alpha(l)
+        F_n, F_s = naive.handle.leaf_factor(l), shared.handle.leaf_factor(l)
+        worst = max(worst, np.max(np.abs(a_n - a_s)) / np.max(np.abs(a_n)), np.max(np.abs(F_n - F_s)) / np.max(np.abs(F_n)))
+    assert worst <= 1e-12, worst
+    dsm.update_(naive); dsm.update_(shared)
+    mu_n, var_n = dsm.predict(naive, xt); mu_s, var_s = dsm.predict(shared, xt)
+    assert np.max(np.abs(mu_n - mu_s)) <= 1e-12 * np.max(np.abs(mu_n)) and relerr(var_s, var_n) <= 1e-12
+    # the plan stays in the handle: evaluations (fit! + gradients) use it
+    l_n, g_n = naive.handle.eval(th); l_s, g_s = shared.handle.eval(th)
+    assert abs(l_n - l_s) <= 1e-12 * abs(l_n) and np.max(np.abs(g_n - g_s)) <= 1e-12 * np.max(np.abs(g_n))
+    rn, rs = naive.handle.leaf_rows(), shared.handle.leaf_rows()
+    assert np.max(np.abs(rn - rs)) <= 1e-12 * np.max(np.abs(rn))
+    tn, ts = naive.handle.timings(), shared.handle.timings()
+    print(f"[shared cholesky] {case}: evaluation {tn['total_ms']:.3f} ms naive -> {ts['total_ms']:.3f} ms shared "
+          f"(potrf flops {tn['potrf_flops']:.3e} -> {ts['potrf_flops']:.3e})")
+    # per-expert theta suspends the plan (source and dependent no longer share theta) ...
+    th2 = th.copy(); th2[0] += 0.3
+    l_alias = int(np.nonzero(kind != 0)[0][0])
+    for m in (naive, shared):
+        m.handle.set_leaf_params(l_alias, th2)
+    l_n, g_n = naive.handle.eval(); l_s, g_s = shared.handle.eval()
+    assert l_n == l_s and np.array_equal(g_n, g_s)
+    # ... and a global theta brings it back; against the oracle as well
+    l_s, g_s = shared.handle.eval(th)
+    o_root = oracle_tree(shared, th)
+    o_lml, o_grad, _, _ = orc.evaluate(o_root, th)
+    assert abs(l_s - o_lml) <= LML_TOL * abs(o_lml)
+    assert np.all(np.abs(g_s - o_grad) <= GRAD_TOL * np.maximum(np.abs(o_grad), 1e-6 * np.max(np.abs(o_grad)) + 1.0))
+    naive.close(); shared.close()
+
+
+def test_all_three_sharing_branches_on_a_hand_made_structure():
+    """Three experts under one sum node: A = rows 1..400, B = rows 1..700 (A is its leading part: chol_continue!, fit.jl:208-292),
+    C = rows 1..400 (identical to A: copy, :132-143).  B must produce ITS OWN z = L^-1 y, log-det, LML and alpha behind the
+    three block rows it takes from A; C reads A's results."""
+    from deepstructuredmixtures_b200 import _native as nat, kernels as kr
+    from deepstructuredmixtures_b200._handle import Handle
+    rng = np.random.default_rng(3)
+    N = 700
+    x = np.sort(rng.random((N, 1)), axis=0); y = np.sin(6 * x[:, 0]) + 0.1 * rng.standard_normal(N)
+    obs = [np.arange(1, 401, dtype=np.int64), np.arange(1, 701, dtype=np.int64), np.arange(1, 401, dtype=np.int64)]
+    means = [float(np.mean(y[o - 1])) for o in obs]
+    ft = nat.FlatTree([0, 0, 0, 2], [0, 0, 0, 0, 3], [0, 1, 2], [0, 1, 2, -1], [-1, -1, -1, -1], [0, 0, 0, 0, 0], [0.0], 3)
+    r = 400.0 / 700.0
+    D = np.array([[0.0, 1.0, 1.0], [r, 0.0, r], [1.0, 1.0, 0.0]])          # D[n,m] = 1 - |obs_n \ obs_m| / |obs_n|
+    k = kr.IsoSE(0.0, 0.0)
+    mk = lambda: Handle(x, obs, [y[o - 1] - m for o, m in zip(obs, means)], means, [0, 0, 0], [k.copy()], ft)
+    a, b = mk(), mk()
+    th = np.array([-1.5, 0.2, -1.0])
+    a.set_params(th); b.set_params(th)
+    a.fit(); b.fit(D, 0.05)
+    kind, src, blocks = b.get_sharing()
+    assert list(kind) == [0, 2, 1] and src[1] == 0 and blocks[1] == 3 and src[2] == 0      # 400 // 128 leading block rows reused
+    assert np.max(np.abs(a.leaf_rows() - b.leaf_rows())) <= 1e-12 * np.max(np.abs(a.leaf_rows()))
+    for l in range(3):
+        assert np.max(np.abs(a.leaf_alpha(l) - b.leaf_alpha(l))) <= 1e-12 * np.max(np.abs(a.leaf_alpha(l)))
+        assert np.max(np.abs(a.leaf_factor(l) - b.leaf_factor(l))) <= 1e-13 * np.max(np.abs(a.leaf_factor(l)))
+    la, ga = a.eval(th); lb, gb = b.eval(th)
+    assert abs(la - lb) <= 1e-13 * abs(la) and np.max(np.abs(ga - gb)) <= 1e-12 * np.max(np.abs(ga))
+    xt = rng.random((40, 1))
+    for l in range(3):
+        (m1, v1), (m2, v2) = a.leaf_predict(l, xt), b.leaf_predict(l, xt)
+        assert np.max(np.abs(m1 - m2)) <= 1e-12 * np.max(np.abs(m1)) and relerr(v2, v1) <= 1e-12
+    a.close(); b.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 4. infer! / reset_weights!, gradient state after masked evaluations
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mixture", [False, True])
+def test_infer_and_reset_weights(mixture):
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(900, 2, 13)
+    kern = [dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)] if mixture else dsm.IsoSE(0.0, 0.0)
+    model = dsm.buildDSMGP(x, y, 2, 3, M=60, kernel=kern, logNoise=-1.0, rng=13)
+    th = np.array([0.1, 0.2, -1.0, 0.3, 0.0, -0.9]) if mixture else np.array([0.1, 0.2, -1.0])
+    dsm.evaluate(model, th)
+    o_root = oracle_tree(model, th)
+    orc.fit(o_root)
+    z = dsm.infer_(model)
+    oz = orc.infer_weights(o_root)
+    assert abs(z - oz) <= LML_TOL * abs(oz)
+
+    def cmp(n, on):
+        if on.type >= orc.NODE_SUM:
+            assert np.allclose(n.logweights, on.logweights, rtol=1e-9, atol=1e-11)
+        for c, oc in zip(getattr(n, "children", []), on.children):
+            cmp(c, oc)
+    cmp(model.root, o_root)
+    xt = np.random.default_rng(2).random((50, 2))
+    mu, var = dsm.predict(model, xt)                       # predicts with the infer! weights
+    omu, ovar = orc.predict_dsmgp(o_root, xt)
+    assert np.max(np.abs(mu - omu)) <= PRED_TOL * max(np.max(np.abs(omu)), float(np.std(y))) and relerr(var, ovar) <= PRED_TOL
+    dsm.update_(model); orc.update_weights(o_root)
+    cmp(model.root, o_root)
+    dsm.reset_weights_(model); orc.reset_weights(o_root)
+    cmp(model.root, o_root)
+    mu, var = dsm.predict(model, xt)
+    omu, ovar = orc.predict_dsmgp(o_root, xt)
+    assert np.max(np.abs(mu - omu)) <= PRED_TOL * max(np.max(np.abs(omu)), float(np.std(y))) and relerr(var, ovar) <= PRED_TOL
+    model.close()
+
+
+def test_grad_after_masked_evaluation_is_recomputed():
+    """dsmgp_eval with a leaf_scale containing zeros skips those experts' gradient kernels; a following dsmgp_grad with
+    another weighting must not reuse the incomplete rows."""
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(800, 2, 17)
+    model = dsm.buildDSMGP(x, y, 2, 2, M=80, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, rng=17)
+    th = np.array([0.0, 0.1, -1.0])
+    L = len(model.leaves)
+    scale = np.zeros(L); scale[0] = 1.0
+    lml, g_masked = model.handle.eval(th, leaf_scale=scale)
+    g_after = model.handle.grad()
+    lml2, g_full = model.handle.eval(th)
+    assert lml == lml2 and np.array_equal(g_after, g_full) and not np.array_equal(g_masked, g_full)
+    model.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 5. multi-rank: repeated evaluations, the collective inside the library
+# ---------------------------------------------------------------------------------------------------------------------
+def test_multirank_rows_are_rezeroed_between_evaluations():
+    """Two ranks (both on this GPU), two evaluations with DIFFERENT theta through eval_local_dev + SUM + eval_finish_dev:
+    the in-place sum leaves every rank with the other ranks' rows, which must not leak into the next evaluation."""
+    import torch
+    from deepstructuredmixtures_b200 import model as mdl, structure as st
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200.distributed import _DevPtr
+    x, y = synth(2000, 3, 23)
+    kern = dsm.ArdSE(np.zeros(3), 0.0)
+    cfg = st.DSMGPConfig(None, kern, -1.0, 100, 3, 2, 2, 0.5, True)
+    root = st.buildTree(x, y, cfg, np.random.default_rng(23))
+    single = mdl.DSMGP(root, x, y, [kern.copy()], -1.0)
+    ranks = [mdl.DSMGP(root, x, y, [kern.copy()], -1.0, rank=r, world=2) for r in range(2)]
+    n = single.handle.L * single.handle.row_width
+    for th in (np.array([0.1, -0.2, 0.0, 0.2, -1.0]), np.array([-0.3, 0.1, 0.2, -0.1, -0.7]), np.array([0.0, 0.0, 0.1, 0.3, -1.2])):
+        l0, g0 = single.handle.eval(th)
+        tens = [torch.as_tensor(_DevPtr(m.handle.eval_local_dev(th), n), device="cuda:0") for m in ranks]
+        tot = torch.stack(tens).sum(0)
+        for t in tens:
+            t.copy_(tot)
+        torch.cuda.synchronize()
+        for m in ranks:
+            l, g = m.handle.eval_finish_dev()
+            assert l == l0 and np.array_equal(g, g0), (l, l0)
+    for m in ranks + [single]:
+        m.close()
+
+
+def test_library_collective_two_gpus():
+    """world = 2 through the C ABI only: one handle per GPU, dsmgp_comm_unique_id / dsmgp_comm_init, then the SAME calls as on
+    one GPU (dsmgp_eval, dsmgp_update_weights, dsmgp_predict) -- the row table is all-reduced by the library over NCCL.
+    No torch.distributed; the two ranks are two threads of this process."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import model as mdl, structure as st
+    from deepstructuredmixtures_b200._handle import comm_unique_id
+    x, y = synth(4000, 4, 29)
+    kern = dsm.ArdSE(np.zeros(4), 0.0)
+    cfg = st.DSMGPConfig(None, kern, -1.0, 150, 3, 3, 2, 0.5, True)
+    root = st.buildTree(x, y, cfg, np.random.default_rng(29))
+    ths = [np.array([0.1, -0.2, 0.0, 0.2, 0.1, -1.0]), np.array([-0.1, 0.3, 0.1, -0.2, 0.0, -0.8])]
+    xt = np.random.default_rng(3).random((700, 4))
+    single = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, device=0)
+    ref = []
+    for th in ths:
+        l0, g0 = single.handle.eval(th)
+        z0 = dsm.update_(single)
+        ref.append((l0, g0, z0) + dsm.predict(single, xt))
+    uid = comm_unique_id()
+    out, errs = {}, []
+
+    def rank_main(r):
+        try:
+            m = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, rank=r, world=2, device=r)
+            m.handle.comm_init(uid)
+            res = []
+            for th in ths:
+                l, g = m.handle.eval(th)
+                z = dsm.update_(m)
+                res.append((l, g, z) + dsm.predict(m, xt))
+            out[r] = res
+            m.close()
+        except Exception as e:      # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    threads = [threading.Thread(target=rank_main, args=(r,)) for r in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errs, errs
+    for r in range(2):
+        for (l0, g0, z0, mu0, var0), (l, g, z, mu, var) in zip(ref, out[r]):
+            assert abs(l - l0) <= 1e-12 * abs(l0) and np.max(np.abs(g - g0)) <= 1e-12 * np.max(np.abs(g0))
+            assert abs(z - z0) <= 1e-12 * abs(z0)
+            assert np.max(np.abs(mu - mu0)) <= 1e-12 * np.max(np.abs(mu0)) and relerr(var, var0) <= 1e-12
+    single.close()

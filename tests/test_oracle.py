@@ -188,3 +188,88 @@ def test_table_exp_restated_accuracy():
     ref = np.array([float(mp.e ** mp.mpf(float(v))) for v in x])
     assert np.max(np.abs(exp_neg(x) - ref) / ref) < 4.5e-16
     assert exp_neg(np.array([-709.0]))[0] == 0.0 and exp_neg(np.array([0.0]))[0] == 1.0
+
+
+# ---- the independent pin: 50-digit mpmath vectors that do not share code with the oracle -------------------------------
+def _mp_models():
+    with open(os.path.join(GOLD, "mp_golden.json")) as f:
+        doc = json.load(f)
+    return doc, {m["name"]: m for m in doc["models"]}
+
+
+def mp_oracle_root(doc, model, theta):
+    flat = {k: np.asarray(v) for k, v in model["flat"].items() if k != "root"}
+    flat["root"] = model["flat"]["root"]
+    D = len(doc["x"][0])
+    kernels = []
+    for kt in model["kernels"]:
+        nl = 1 if kt in (orc.ISO_SE, orc.ISO_LINEAR) else D
+        kernels.append(orc.Kernel(kt, np.zeros(nl), 0.0))
+    root = orc.tree_from_flat(flat, np.asarray(doc["x"]), np.asarray(doc["y"]), kernels, -1.0)
+    return root
+
+
+MP_NAMES = ["dsmgp_isose", "dsmgp_ardse", "dsmgp_isolinear", "dsmgp_ardlinear", "dsmgp_mixture", "poe_isose"]
+
+
+@pytest.mark.parametrize("name", MP_NAMES)
+def test_oracle_against_independent_mpmath_vectors(name):
+    """tests/golden/mp_golden.json is written by make_mp_golden.py, which evaluates the Julia formulas in mpmath at 50 digits
+    and imports nothing from oracle/: LML, as-written and mathematical gradients, mll!, the down-pass (plain and finetune),
+    update!, infer!, DSMGP / PoE / gPoE / rBCM predictions of the oracle must agree with it."""
+    doc, models = _mp_models()
+    m = models[name]
+    xt = np.asarray(doc["xtest"])
+    worst = 0.0
+    for ev in m["evals"]:
+        theta = np.asarray(ev["theta"])
+        root = mp_oracle_root(doc, m, theta)
+        for mode, math_ in (("as_written", False), ("mathematical", True)):
+            lml, grad, ell, rows = orc.evaluate(root, theta, mathematical=math_, as_written_dense=not math_ and "ardlinear" not in name)
+            assert abs(lml - ev["node_lml"][m["flat"]["root"]]) <= 1e-12 * abs(lml)
+            for nid, v in ell.items():
+                assert abs(v - ev["node_lml"][nid]) <= 1e-12 * max(1.0, abs(v))
+            for l, r in rows.items():
+                g = np.asarray(ev["leaf_grad_" + mode][l])
+                scale = np.maximum(np.abs(g), 1e-10 * max(1.0, np.max(np.abs(g))))
+                err = np.max(np.abs(r[1:] - g) / np.maximum(scale, 1e-3))
+                worst = max(worst, err)
+                assert err <= 1e-9, (name, mode, l, r[1:], g)
+                assert abs(r[0] - ev["leaf_lml"][l]) <= 1e-12 * abs(r[0])
+            G = np.asarray(ev["grad_" + mode])
+            assert np.all(np.abs(grad - G) <= 1e-9 * np.maximum(np.abs(G), 1e-3)), (name, mode, grad, G)
+            _, gradf, _, _ = orc.evaluate(root, theta, Drow=np.asarray(ev["finetune_row"]), mathematical=math_)
+            Gf = np.asarray(ev["grad_" + mode + "_finetune"])
+            assert np.all(np.abs(gradf - Gf) <= 1e-9 * np.maximum(np.abs(Gf), 1e-3))
+        orc.evaluate(root, theta)
+        mu0, var0 = orc.getLeaves(root)[0].gp.prediction(xt)
+        assert np.allclose(mu0, ev["leaf0_mu"], rtol=1e-10, atol=1e-12) and np.allclose(var0, ev["leaf0_var"], rtol=1e-10)
+        if name.startswith("dsmgp"):
+            z = orc.update_weights(root)
+            assert abs(z - ev["update_z"]) <= 1e-12 * abs(z)
+            for nid, lw in enumerate(ev["update_logw"]):
+                if lw:
+                    node = _node_by_id(root, nid)
+                    assert np.allclose(node.logweights, lw, rtol=1e-10, atol=1e-12)
+            mu, var = orc.predict_dsmgp(root, xt)
+            assert np.allclose(mu, ev["predict_mu"], rtol=1e-9, atol=1e-11) and np.allclose(var, ev["predict_var"], rtol=1e-9)
+            zi = orc.infer_weights(root)
+            assert abs(zi - ev["infer_z"]) <= 1e-12 * abs(zi)
+            for nid, lw in enumerate(ev["infer_logw"]):
+                if lw:
+                    assert np.allclose(_node_by_id(root, nid).logweights, lw, rtol=1e-10, atol=1e-12)
+        else:
+            for fn, key in ((orc.predict_poe, "poe"), (orc.predict_gpoe, "gpoe"), (orc.predict_rbcm, "rbcm")):
+                mu, var = fn(root, xt)
+                assert np.allclose(mu, ev[key + "_mu"], rtol=1e-9, atol=1e-11) and np.allclose(var, ev[key + "_var"], rtol=1e-9), key
+    print(f"{name}: worst leaf-gradient error vs mpmath {worst:.2e}")
+
+
+def _node_by_id(root, nid):
+    if root.id == nid:
+        return root
+    for c in root.children:
+        r = _node_by_id(c, nid)
+        if r is not None:
+            return r
+    return None
