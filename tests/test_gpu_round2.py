@@ -69,7 +69,7 @@ def test_gpu_against_independent_mpmath_vectors(name):
             for l, g in enumerate(ev["leaf_grad_" + mode]):
                 g = np.asarray(g)
                 a = np.asarray(ev["leaf_alpha"][l])
-                scale = max(float(a @ a), float(a.size))
+                scale = 1e-4 * max(float(a @ a), float(a.size))
                 e = np.max(np.abs(rows[l, 1:1 + g.size] - g) / np.maximum(np.abs(g), scale))
                 worst["grad"] = max(worst["grad"], e)
                 assert e <= GRAD_TOL, (name, mode, l, rows[l, 1:1 + g.size], g)
@@ -154,7 +154,8 @@ def _compare_leaf(H, model, l, pk, th, xt, tag, mathematical=False, predict=True
         msg += f", predict mean {e_mu:.1e} var {e_var:.1e}"
     print("\n" + msg + f"  (oracle {time.time() - t0:.1f} s)")
     assert e_lml <= LML_TOL, msg
-    assert e_g_scaled <= GRAD_TOL, msg
+    # 1e-9 RELATIVE (north_star); only a component below 1e-4 of its two cancelling terms is compared with that floor
+    assert np.all(np.abs(g - o_g) <= GRAD_TOL * np.maximum(np.abs(o_g), 1e-4 * sc)), msg
     assert e_mu <= PRED_TOL and e_var <= PRED_TOL, msg
     return e_lml, e_g_scaled, e_mu, e_var
 
