@@ -513,13 +513,12 @@ static void prepare_masks(dsmgp_handle* h, const double* leaf_scale, bool with_g
 //   naive       ignore the sharing plan (fit_naive!)
 //   first       first pipeline of an API call: clears the scheduler error word (a later pipeline of the same call must not
 //               erase the error of an earlier one; finish_pipeline reads it once at the end)
-static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad);
-static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_scale = nullptr, bool defer_sync = false,
-                            bool naive = false, bool first = true) {
+int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_scale, bool defer_sync, bool naive, bool first) {
   cudaStream_t st = h->stream;
   const int sms = num_sms(h->device);
   const bool lau = with_grad && needs_lauum(h);
-  const bool shr = !naive && h->share.active && h->theta_global && (h->share.n_alias + h->share.n_prefix) > 0;
+  const bool shr = !naive && !h->capturing && h->share.active && h->theta_global && (h->share.n_alias + h->share.n_prefix) > 0;
+  #define EV_RECORD(e) do { if (!h->capturing) cudaEventRecord((e), st); } while (0)
   h->tm = dsmgp_timings{};
   h->share_applied = shr;
   prepare_masks(h, with_grad ? leaf_scale : nullptr, with_grad, shr);
@@ -537,17 +536,17 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
     Batch& b = h->batches[bi];
     cudaEvent_t* ev = h->ev.data() + 8 * bi;
     const int nsl = b.s1 - b.s0;
-    CUDA_TRY(h, cudaEventRecord(ev[0], st));
-    if (nsl == 0) { for (int k = 1; k < 8; k++) cudaEventRecord(ev[k], st); continue; }
+    EV_RECORD(ev[0]);
+    if (nsl == 0) { for (int k = 1; k < 8; k++) EV_RECORD(ev[k]); continue; }
     const LeafMeta* meta = h->d_meta.p + b.s0;
     LeafScal* scal = h->d_scal.p + b.s0;
     const int4* share_b = share_all ? share_all + b.s0 : nullptr;
     CUDA_TRY(h, cudaMemsetAsync(scal, 0, nsl * sizeof(LeafScal), st));
-    cudaEventRecord(ev[1], st);
+    EV_RECORD(ev[1]);
     GramArgs ga{meta, h->d_xg.p, h->d_prm.p, h->d_F.p, b.d_tile_off, nsl, (int)h->D, share_b};
     launch_gram_fit(ga, b.ntiles, st);
     h->tm.launches++;
-    cudaEventRecord(ev[2], st);
+    EV_RECORD(ev[2]);
     {
       CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
       CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
@@ -567,7 +566,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
         }
       } else {
         long long* d_trace = nullptr;
-        const char* trace_file = getenv("DSMGP_TRACE_FILE");
+        const char* trace_file = h->capturing ? nullptr : getenv("DSMGP_TRACE_FILE");
         if (trace_file) { cudaMalloc(&d_trace, (size_t)b.n_potrf2 * 64); cudaMemsetAsync(d_trace, 0, (size_t)b.n_potrf2 * 64, st); pa.trace = d_trace; }
         launch_potrf2(pa, std::min(sms, b.n_potrf2), st);
         if (trace_file) {
@@ -579,7 +578,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
         }
         h->tm.launches++;
       }
-      cudaEventRecord(ev[3], st);
+      EV_RECORD(ev[3]);
       if (!with_grad) {       // fit only: alpha by block back-substitution (the forward solve was fused above)
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         SolveArgs sa{meta, h->d_F.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_flags.p, b.d_flag_off, b.d_solve_tasks, b.n_solve,
@@ -587,7 +586,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
         launch_solve(sa, std::max(1, std::min(solve_max_ctas(sms), b.n_solve)), st);
         h->tm.launches++;
       }
-      cudaEventRecord(ev[4], st);
+      EV_RECORD(ev[4]);
       if (with_grad) {
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
@@ -597,7 +596,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
         h->tm.launches += 2;
       }
     }
-    cudaEventRecord(ev[5], st);
+    EV_RECORD(ev[5]);
     if (lau) {
       LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
                    h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + GERR,
@@ -605,7 +604,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
       launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
       h->tm.launches++;
     }
-    cudaEventRecord(ev[6], st);
+    EV_RECORD(ev[6]);
     RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,
                 h->d_rows.p, h->row_width, h->opts.as_written_grads, with_grad ? 1 : 0, lau ? 1 : 0,
                 h->d_ldpart.p, h->d_zzpart.p, h->d_alpha.p, mask_all ? mask_all + b.s0 : nullptr, share_b};
@@ -613,7 +612,7 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
     h->tm.launches++;
     if (shr && h->share.n_alias > 0) { launch_rows_alias(meta, share_b, nsl, h->d_rows.p, h->row_width, scal, st); h->tm.launches++; }
     CUDA_TRY(h, cudaGetLastError());
-    cudaEventRecord(ev[7], st);
+    EV_RECORD(ev[7]);
     double pf = b.potrf_flops, gb = b.gram_bytes;
     if (shr) {                 // work that the plan removed is not counted
       for (int s = b.s0; s < b.s1; s++) {
@@ -627,11 +626,12 @@ static int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_
     h->tm.inverse_flops += with_grad ? pf * (lau ? 2.0 : 1.0) : 0.0;
     h->tm.gram_bytes += gb;
   }
+  #undef EV_RECORD
   if (defer_sync) return DSMGP_OK;
   return finish_pipeline(h, with_grad);
 }
 
-static int32_t finish_pipeline(dsmgp_handle* h, bool with_grad) {
+int32_t dsm::finish_pipeline(dsmgp_handle* h, bool with_grad) {
   cudaStream_t st = h->stream;
   const int ns = (int)h->slot_leaf.size();
   if (ns) CUDA_TRY(h, cudaMemcpyAsync(h->pin_scal, h->d_scal.p, ns * sizeof(LeafScal), cudaMemcpyDeviceToHost, st));
@@ -855,7 +855,7 @@ extern "C" int32_t dsmgp_get_sharing(const dsmgp_handle* h, int32_t* kind, int32
 
 // After the pipeline: per-leaf rows on the host.  With a communicator (dsmgp_comm_init) the table is first assembled by a
 // SUM all-reduce on the library's stream (every rank filled only its own experts' rows).
-static int32_t fetch_rows(dsmgp_handle* h) {
+int32_t dsm::fetch_rows(dsmgp_handle* h) {
   const size_t count = (size_t)h->L * h->row_width;
   if (h->opts.world > 1 && h->comm != nullptr && !h->rows_complete) {
     int32_t rc = comm_allreduce_sum(h, h->d_rows.p, count);
@@ -868,7 +868,7 @@ static int32_t fetch_rows(dsmgp_handle* h) {
   return DSMGP_OK;
 }
 
-static int32_t check_pd(dsmgp_handle* h) {
+int32_t dsm::check_pd(dsmgp_handle* h) {
   if (!h->opts.strict_pd) return DSMGP_OK;
   for (int64_t l = 0; l < h->L; l++)
     if (h->h_info[l] != 0) {
@@ -1001,57 +1001,6 @@ extern "C" int32_t dsmgp_finetune_eval(dsmgp_handle* h, int64_t G, const int64_t
     tree_grad(h, scale.data(), grads + g * H);                               // finetuning.jl:53
   }
   h->rows_complete = true;
-  return DSMGP_OK;
-}
-
-// train!(spn, D, gpmap, optim; iterations, lambda, earlystop) optimisers.jl:40-83 as ONE call: the loop stays inside the
-// library (no per-iteration host round trip through the binding).  Optimisers = Flux.Optimise Descent / ADAM / RMSProp;
-// `state_by_identity` reproduces the reference's `hyp += grad` rebinding, which gives apply! a fresh state every iteration
-// (SURVEY App. B Q9).  The update is gradient ASCENT.  Returns the number of iterations executed in *n_done.
-extern "C" int32_t dsmgp_train(dsmgp_handle* h, int32_t optimiser, double eta, double beta1, double beta2,
-                               int32_t state_by_identity, int64_t iterations, double lambda, int64_t earlystop,
-                               double* theta, double* ell, int64_t* n_done) {
-  if (!h) return DSMGP_ERR_ARG;
-  if (!theta || !ell || iterations <= 0 || optimiser < 0 || optimiser > 2) { h->err = "train: bad argument"; return DSMGP_ERR_ARG; }
-  if (h->opts.world != 1) { h->err = "train: single-process handles only"; return DSMGP_ERR_STATE; }
-  const int64_t H = h->H;
-  std::vector<double> hyp(theta, theta + H), grad(H), mt(H, 0.0), vt(H, 0.0), acc(H, 0.0);
-  double bp1 = beta1, bp2 = beta2;
-  int64_t c = 0, it = 0;
-  if (n_done) *n_done = 0;
-  for (it = 0; it < iterations; it++) {
-    double lml = 0.0;
-    int32_t rc = dsmgp_eval(h, hyp.data(), H, nullptr, &lml, grad.data(), nullptr);     // :43-49, 68-77
-    if (rc) return rc;
-    ell[it] = lml;
-    double delta = std::numeric_limits<double>::infinity();
-    if (it >= 10) { double mean = 0.0; for (int64_t k = it - 9; k < it; k++) mean += ell[k]; delta = std::fabs(ell[it] - mean / 9.0); }   // :53
-    c = (delta < lambda) ? c + 1 : 0;                                                    // :57-61
-    if (c >= earlystop) { it++; break; }                                                 // :63-66 (returns before the update)
-    if (state_by_identity) { std::fill(mt.begin(), mt.end(), 0.0); std::fill(vt.begin(), vt.end(), 0.0); std::fill(acc.begin(), acc.end(), 0.0); bp1 = beta1; bp2 = beta2; }
-    for (int64_t k = 0; k < H; k++) {                                                    // Flux.Optimise.apply!  :78
-      double d = grad[k];
-      if (optimiser == 0) d *= eta;
-      else if (optimiser == 1) {
-        mt[k] = beta1 * mt[k] + (1.0 - beta1) * d;
-        vt[k] = beta2 * vt[k] + (1.0 - beta2) * d * d;
-        d = mt[k] / (1.0 - bp1) / (std::sqrt(vt[k] / (1.0 - bp2)) + 1e-8) * eta;
-      } else {
-        acc[k] = beta1 * acc[k] + (1.0 - beta1) * d * d;                                 // RMSProp: beta1 = rho
-        d = d * (eta / (std::sqrt(acc[k]) + 1e-8));
-      }
-      hyp[k] = hyp[k] + d;                                                               // :79
-    }
-    if (optimiser == 1) { bp1 *= beta1; bp2 *= beta2; }
-  }
-  std::copy(hyp.begin(), hyp.end(), theta);
-  if (n_done) *n_done = it;
-  if (it >= iterations) {                                                                // :82-83 final setparams! + fit!
-    int32_t rc = dsmgp_set_params(h, hyp.data(), H);
-    if (rc) return rc;
-    if ((rc = run_pipeline(h, false))) return rc;
-    return fetch_rows(h);
-  }
   return DSMGP_OK;
 }
 

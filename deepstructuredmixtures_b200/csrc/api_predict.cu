@@ -1,5 +1,6 @@
 // libdsmgp.so : prediction entry points (common.jl:101-122, 134-313; gaussianprocess.jl:110-137).
 #include "handle.h"
+#include "route_args.h"
 
 using namespace dsm;
 #define g_create_error (dsm::create_error())
@@ -281,9 +282,180 @@ static int32_t predict_mix(dsmgp_handle* h, const double* xtest, int64_t T, int3
                            const std::vector<std::vector<double>>& lmu, const std::vector<std::vector<double>>& lvar,
                            double* mu, double* var);
 
+// ---- large batches: route, predict and mix on the device ------------------------------------------------------------------
+// The host path above walks the tree with std::vector recursion, packs the routed points per expert, uploads them and mixes
+// on the host: for 40,000 points that costs 50 ms next to a 130 ms kernel.  Here x_test is uploaded ONCE, one thread per point
+// routes it (route.cuh), predict3 gathers its test tiles through the index lists, and one thread per point mixes
+// (common.jl:134-313).  Only the per-expert counts (L ints) visit the host in between, to size the task list.
+static int tree_metrics(const HostTree& t, int64_t node, bool poe, int depth, int* maxdepth, int* maxk, int frames, int* maxframes) {
+  *maxdepth = std::max(*maxdepth, depth);
+  const int ty = t.type[node];
+  if (ty == DSMGP_NODE_LEAF) { *maxframes = std::max(*maxframes, frames); return 1; }
+  *maxk = std::max(*maxk, (int)t.nchild(node));
+  const bool fan = (ty != DSMGP_NODE_SPLIT) || poe;            // every child is visited
+  const int fr = frames + ((ty != DSMGP_NODE_SPLIT) != poe ? 1 : 0);   // DSMGP: frames are sum nodes; PoE: split nodes
+  int reach = 0;
+  for (int64_t k = 0; k < t.nchild(node); k++) {
+    const int r = tree_metrics(t, t.child(node, k), poe, depth + 1, maxdepth, maxk, fr, maxframes);
+    reach = fan ? reach + r : std::max(reach, r);
+  }
+  return reach;
+}
+
+int32_t dsm::ensure_dev_tree(dsmgp_handle* h) {
+  if (h->tree_on_device) return DSMGP_OK;
+  const HostTree& t = h->tree;
+  const int64_t nn = t.n_nodes, nc = t.child_ptr[nn], nsv = t.split_ptr[nn];
+  std::vector<int> buf;
+  auto push = [&](auto& v, int64_t n) { for (int64_t i = 0; i < n; i++) buf.push_back((int)v[i]); };
+  push(t.type, nn); push(t.child_ptr, nn + 1); push(t.child_idx, nc); push(t.leaf_of_node, nn); push(t.split_dim, nn); push(t.split_ptr, nn + 1);
+  CUDA_TRY(h, h->t_int.alloc(buf.size()));
+  CUDA_TRY(h, cudaMemcpy(h->t_int.p, buf.data(), buf.size() * sizeof(int), cudaMemcpyHostToDevice));
+  CUDA_TRY(h, h->t_split_val.alloc(std::max<int64_t>(nsv, 1)));
+  if (nsv) CUDA_TRY(h, cudaMemcpy(h->t_split_val.p, t.split_val.data(), nsv * sizeof(double), cudaMemcpyHostToDevice));
+  int md = 0, mk = 0, mf = 0, md2 = 0, mk2 = 0, mf2 = 0;
+  h->reach_dsmgp = tree_metrics(t, t.root, false, 1, &md, &mk, 0, &mf);
+  h->reach_poe = tree_metrics(t, t.root, true, 1, &md2, &mk2, 0, &mf2);
+  h->tree_depth = md; h->tree_maxk = mk; h->tree_frames = std::max(mf, mf2);
+  h->tree_on_device = true;
+  return DSMGP_OK;
+}
+
+DevTree dsm::dev_tree(const dsmgp_handle* h) {
+  const HostTree& t = h->tree;
+  const int64_t nn = t.n_nodes, nc = t.child_ptr[nn];
+  DevTree d;
+  d.n_nodes = (int)nn; d.root = (int)t.root;
+  const int* p = h->t_int.p;
+  d.type = p; p += nn; d.child_ptr = p; p += nn + 1; d.child_idx = p; p += nc; d.leaf_of_node = p; p += nn; d.split_dim = p; p += nn; d.split_ptr = p;
+  d.split_val = h->t_split_val.p;
+  return d;
+}
+
+// Can (and should) this prediction run on the device path?
+static bool predict_on_device(dsmgp_handle* h, int64_t T, int32_t mode) {
+  if (h->opts.world != 1 || !h->fitted || !h->opts.keep_factors || h->batches.size() != 1) return false;
+  const char* force = getenv("DSMGP_PREDICT_DEVICE");       // tests: "0" / "1" force the path
+  if (force && force[0] == '0') return false;
+  if (ensure_dev_tree(h) != DSMGP_OK) return false;
+  const bool poe = mode != DSMGP_PREDICT_DSMGP;
+  const int R = poe ? h->reach_poe : h->reach_dsmgp;
+  if (h->tree_maxk > MIX_KMAX || h->tree_frames > MIX_FRAMES || h->tree_depth * std::max(h->tree_maxk, 1) > ROUTE_STACK) return false;
+  if ((double)T * R > 1.5e9) return false;
+  if (poe) for (int64_t i = 0; i < h->tree.n_nodes; i++) if (h->tree.type[i] >= DSMGP_NODE_SUM) return false;   // MethodError path: host reports it
+  if (force && force[0] == '1') return true;
+  return T * R >= 3ll * num_sms(h->device) * BLK;           // enough (expert, 128-point block) tasks to fill the GPU
+}
+
+static int32_t predict_device(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
+  cudaStream_t st = h->stream;
+  const HostTree& t = h->tree;
+  const int64_t L = h->L, D = h->D;
+  const bool poe = mode != DSMGP_PREDICT_DSMGP;
+  if (poe && t.type[t.root] != DSMGP_NODE_SPLIT) { h->err = "predict: PoE/gPoE/rBCM need a split root (buildPoE/buildBCM model)"; return DSMGP_ERR_ARG; }
+  { int32_t rr = refine_alpha(h); if (rr) return rr; }
+  if (!poe && !h->have_weights) {       // the reference predicts with whatever logweights the sum nodes hold (uniform after build)
+    h->sum_logw.assign(t.child_ptr[t.n_nodes], 0.0);
+    reset_weights(t, h->sum_logw.data());
+  }
+  const int R = poe ? h->reach_poe : h->reach_dsmgp;
+  CUDA_TRY(h, h->p_xtest.ensure((size_t)T * D));
+  CUDA_TRY(h, cudaMemcpyAsync(h->p_xtest.p, xtest, (size_t)T * D * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, h->p_cnt.ensure(3 * L + 1));
+  CUDA_TRY(h, cudaMemsetAsync(h->p_cnt.p, 0, (3 * L + 1) * sizeof(int), st));
+  CUDA_TRY(h, h->p_reach.ensure((size_t)T * R));
+  CUDA_TRY(h, cudaMemsetAsync(h->p_reach.p, 0xFF, (size_t)T * R * sizeof(int), st));
+  RouteArgs ra{dev_tree(h), h->p_xtest.p, T, (int)D, poe ? 1 : 0, R, h->p_cnt.p, h->p_cnt.p + 2 * L, h->p_cnt.p + L, nullptr,
+               h->p_reach.p, h->p_cnt.p + 3 * L};
+  launch_route(ra, false, st);
+  std::vector<int> cnt(3 * L + 1);
+  CUDA_TRY(h, cudaMemcpyAsync(cnt.data(), h->p_cnt.p, (3 * L + 1) * sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (cnt[3 * L] == 1) { h->err = "predict: non-finite input"; return DSMGP_ERR_ARG; }
+  if (cnt[3 * L] == 2) { h->err = "predict: a test point lies outside every split interval"; return DSMGP_ERR_ARG; }
+  // experts with points, largest first (slots are sorted by size); outputs of an expert are padded to whole 128-point blocks
+  std::vector<int64_t> order;
+  for (int64_t l = 0; l < L; l++) if (cnt[l] > 0) {
+    if (h->exec_slot[l] < 0) { h->err = "predict: leaf owned by another rank"; return DSMGP_ERR_STATE; }
+    order.push_back(l);
+  }
+  std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return h->meta[h->exec_slot[a]].np > h->meta[h->exec_slot[b]].np; });
+  std::vector<PredLeaf> pls; std::vector<int2> tasks; std::vector<int> ooff(L, 0);
+  int64_t oo = 0; int max_nkc = 0;
+  for (int64_t l : order) {
+    PredLeaf pl; pl.slot = h->exec_slot[l]; pl.T = cnt[l]; pl.Tp = (pl.T + BLK - 1) / BLK * BLK; pl.pad_ = 0;
+    pl.xtoff = 0; pl.vtoff = 0; pl.ooff = oo;
+    ooff[l] = (int)oo; oo += pl.Tp;
+    max_nkc = std::max(max_nkc, (int)h->meta[pl.slot].nkc);
+    for (int q = 0; q < pl.Tp / BLK; q++) tasks.push_back(make_int2((int)pls.size(), q));
+    pls.push_back(pl);
+  }
+  if (oo >= (int64_t(1) << 31)) { h->err = "predict: too many (expert, point) pairs for the device path"; return DSMGP_ERR_ARG; }
+  const int sms = num_sms(h->device);
+  const int nctas = std::max(1, std::min(sms, (int)tasks.size()));
+  const int64_t vt_stride = (int64_t)max_nkc * TILE_D;
+  CUDA_TRY(h, h->p_pl.ensure(pls.size())); CUDA_TRY(h, h->p_tasks.ensure(tasks.size()));
+  CUDA_TRY(h, h->p_pidx.ensure(oo)); CUDA_TRY(h, h->p_mu.ensure(oo)); CUDA_TRY(h, h->p_var.ensure(oo));
+  CUDA_TRY(h, h->p_VT.ensure((size_t)nctas * vt_stride));
+  CUDA_TRY(h, h->p_outmu.ensure(T)); CUDA_TRY(h, h->p_outvar.ensure(T));
+  CUDA_TRY(h, h->p_logw.ensure(std::max<size_t>(h->sum_logw.size(), 1)));
+  CUDA_TRY(h, cudaMemcpyAsync(h->p_pl.p, pls.data(), pls.size() * sizeof(PredLeaf), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->p_tasks.p, tasks.data(), tasks.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(h->p_cnt.p + 2 * L, ooff.data(), L * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (!h->sum_logw.empty()) CUDA_TRY(h, cudaMemcpyAsync(h->p_logw.p, h->sum_logw.data(), h->sum_logw.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemsetAsync(h->p_pidx.p, 0xFF, oo * sizeof(int), st));
+  ra.pidx = h->p_pidx.p;
+  launch_route(ra, true, st);
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p, 0, 16 * sizeof(int), st));
+  CUDA_TRY(h, cudaMemsetAsync(h->d_counter.p + GERR, 0, sizeof(int), st));
+  PredArgs pa{h->d_meta.p, h->p_pl.p, h->p_tasks.p, (int)tasks.size(), h->d_counter.p + 2, h->d_F.p, h->d_W.p, h->d_xg.p,
+              h->d_alpha.p, h->d_prm.p, h->d_leaf_mean.p, nullptr, h->p_VT.p, h->p_mu.p, h->p_var.p, (int)D, h->d_counter.p + GERR,
+              0, nullptr, nullptr, nullptr, nullptr, 0, h->p_pidx.p, h->p_xtest.p, T, 1, vt_stride, nullptr};
+  long long* d_trace = nullptr;
+  const char* trace_file = getenv("DSMGP_PTRACE_FILE");       // development: per-task phase cycle counts (tools/trace_predict.py)
+  if (trace_file) { cudaMalloc(&d_trace, tasks.size() * 64); cudaMemsetAsync(d_trace, 0, tasks.size() * 64, st); pa.trace = d_trace; }
+  cudaEventRecord(h->ev[0], st);
+  launch_predict3(pa, nctas, st);
+  cudaEventRecord(h->ev[1], st);
+  if (trace_file) {
+    std::vector<long long> tr(tasks.size() * 8);
+    cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    if (FILE* f = fopen(trace_file, "wb")) { fwrite(tr.data(), 8, tr.size(), f); fclose(f); }
+    cudaFree(d_trace);
+  }
+  h->tm.launches = 4;
+  // rBCM prior: the left-most expert's kernel (common.jl:226-227)
+  int64_t nd = t.root;
+  while (t.type[nd] != DSMGP_NODE_LEAF) nd = t.child(nd, 0);
+  const int s0 = h->exec_slot[t.leaf_of_node[nd]];
+  MixArgs ma{dev_tree(h), h->p_xtest.p, T, (int)D, mode, R, h->p_reach.p, h->p_mu.p, h->p_var.p, h->p_logw.p,
+             s0 >= 0 ? h->meta[s0].ktype : 0, s0 >= 0 ? h->d_prm.p + h->meta[s0].poff : h->d_prm.p, h->p_outmu.p, h->p_outvar.p};
+  launch_mix(ma, st);
+  CUDA_TRY(h, cudaGetLastError());
+  CUDA_TRY(h, cudaMemcpyAsync(mu, h->p_outmu.p, T * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaMemcpyAsync(var, h->p_outvar.p, T * sizeof(double), cudaMemcpyDeviceToHost, st));
+  int gerr = 0;
+  CUDA_TRY(h, cudaMemcpyAsync(&gerr, h->d_counter.p + GERR, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (gerr != 0) { h->err = "predict: device scheduler timeout (code " + std::to_string(gerr) + ")"; return DSMGP_ERR_STATE; }
+  h->tm.predict_ms = ev_ms(h->ev[0], h->ev[1]);
+  h->tm.predict_flops = 0.0; h->tm.predict_bytes = 0.0;
+  for (auto& pl : pls) {
+    const double n = h->meta[pl.slot].n, Tl = pl.T;
+    h->tm.predict_flops += n * n * Tl + 2.0 * n * Tl;
+    h->tm.predict_bytes += 8.0 * (n * (n + 1) / 2.0) * (pl.Tp / BLK) + 8.0 * (n + Tl) * (double)D + 16.0 * Tl;
+  }
+  return DSMGP_OK;
+}
+
 extern "C" int32_t dsmgp_predict(dsmgp_handle* h, const double* xtest, int64_t T, int32_t mode, double* mu, double* var) {
   if (!h) return DSMGP_ERR_ARG;
   if (!mu || !var) { h->err = "predict: bad argument"; return DSMGP_ERR_ARG; }
+  if (xtest && T > 0 && mode >= 0 && mode <= 3) {
+    cudaSetDevice(h->device);
+    if (predict_on_device(h, T, mode)) return predict_device(h, xtest, T, mode, mu, var);
+  }
   std::vector<std::vector<int64_t>> pts;
   int32_t rc = predict_route(h, xtest, T, mode, pts);
   if (rc) return rc;

@@ -125,6 +125,13 @@ struct PredArgs {
   double* part;            // [slot][2][BLK]: mean partial, sum-of-squares partial
   const int4* wcols;       // (pred leaf index, Q, base, nb) per (pl, Q), for the final reduction
   int nwcols;
+  // device-routed test points (large batches): the points of (expert, position) are gathered through pidx from the caller's
+  // T x D matrix instead of a packed copy; position = PredLeaf.ooff + q, pidx < 0 on the padding
+  const int* pidx;         // or null: xt holds the packed points
+  const double* xtest; int64_t T_all;
+  // V^T scratch per CTA (a task's V^T row block is written and read back by the CTA that owns the task only)
+  int vt_per_cta; int64_t vt_stride;
+  long long* trace;        // optional [ntasks][8] cycle counts per phase (DSMGP_PTRACE_FILE), else null
 };
 
 // ---- launchers (defined next to their kernels) ------------------------------------------------
@@ -149,6 +156,10 @@ void launch_ov_pairs(const int64_t* poff, const int* plist, int64_t N, int64_t L
 void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
                       int64_t L, double* D, cudaStream_t st);
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
+struct RouteArgs;
+struct MixArgs;
+void launch_route(const RouteArgs& a, bool fill, cudaStream_t st);
+void launch_mix(const MixArgs& a, cudaStream_t st);
 void launch_share_copy(const LeafMeta* meta, const int4* share, const int* slots, int nslots, int max_jb, double* F, cudaStream_t st);
 void launch_rows_alias(const LeafMeta* meta, const int4* share, int nslots, double* rows, int row_width, LeafScal* scal, cudaStream_t st);
 

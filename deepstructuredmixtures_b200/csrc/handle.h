@@ -178,6 +178,18 @@ struct dsmgp_handle {
   DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
   DevBuf<double> p_xt, p_VT, p_mu, p_var, p_part; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
   DevBuf<int4> p_wtasks, p_wcols; DevBuf<int> p_flags;
+  // device-side routing / mixing of large prediction batches (route.cuh)
+  DevBuf<int> t_int;                    // flattened tree, integer arrays back to back
+  DevBuf<double> t_split_val, p_logw, p_xtest, p_outmu, p_outvar;
+  DevBuf<int> p_cnt, p_pidx, p_reach;   // p_cnt: [cnt L | fill L | ooff L | err 1]
+  bool tree_on_device = false;
+  bool capturing = false;               // the pipeline is being recorded into a CUDA graph: no event records, no host copies
+  DevBuf<int> t_lvl;                    // level lists and per-leaf tables of the device tree passes (tree.cuh)
+  int n_up = 0, n_dn = 0; size_t lvl_off[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  bool lvl_on_device = false;
+  DevBuf<double> g_dbl;                 // fused train loop: theta, out, optimiser state, tree scratch, trace, history
+  DevBuf<int> g_int;
+  int reach_dsmgp = 0, reach_poe = 0, tree_depth = 0, tree_maxk = 0, tree_frames = 0;
   DevBuf<int> d_mask; std::vector<int> h_mask; bool use_mask = false;   // per-slot gradient mask (finetune: zero-overlap experts)
   double* pin_multi = nullptr; size_t pin_multi_doubles = 0;             // rows of a multi-theta call [G][L][row_width]
   LeafScal* pin_scal_multi = nullptr; size_t pin_scal_multi_n = 0;       // per-slot scalars of a multi-theta call [G][slots]
@@ -211,6 +223,8 @@ struct dsmgp_handle {
     d_flags.free(); d_ldpart.free(); d_zzpart.free(); d_apart.free(); d_tpart.free();
     p_xt.free(); p_VT.free(); p_mu.free(); p_var.free(); p_pl.free(); p_tasks.free();
     p_part.free(); p_wtasks.free(); p_wcols.free(); p_flags.free();
+    t_lvl.free(); g_dbl.free(); g_int.free();
+    t_int.free(); t_split_val.free(); p_logw.free(); p_xtest.free(); p_outmu.free(); p_outvar.free(); p_cnt.free(); p_pidx.free(); p_reach.free();
     d_prm.free(); d_trpart.free(); d_gpart.free(); d_rows.free(); d_leaf_mean.free(); d_scal.free(); d_counter.free();
     d_mask.free();
     if (pin_multi) cudaFreeHost(pin_multi);
@@ -238,6 +252,15 @@ void shard_lpt(int64_t L, const int64_t* leaf_ptr, int world, int32_t* owner);
 void derive_params(const dsmgp_handle* h, int kid, const double* th, double* prm);
 inline float ev_ms(cudaEvent_t a, cudaEvent_t b) { float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
 int32_t refine_alpha(dsmgp_handle* h);
+int32_t ensure_dev_tree(dsmgp_handle* h);       // api_predict.cu: the flattened region graph in device memory
+struct DevTree;
+DevTree dev_tree(const dsmgp_handle* h);
+// api.cu: the evaluation pipeline (gram -> potrf -> inverse -> rows) enqueued on the handle's stream
+int32_t run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_scale = nullptr, bool defer_sync = false,
+                     bool naive = false, bool first = true);
+int32_t finish_pipeline(dsmgp_handle* h, bool with_grad);
+int32_t fetch_rows(dsmgp_handle* h);
+int32_t check_pd(dsmgp_handle* h);
 // potrf2 task list of one batch in topological look-ahead order, restricted to the slots with keep[slot - b.s0] != 0
 std::vector<int4> build_potrf2_tasks(const dsmgp_handle* h, const Batch& b, const std::vector<char>& keep, int sms);
 int32_t standalone_device_check(std::string& err);

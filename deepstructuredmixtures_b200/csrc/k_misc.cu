@@ -1,4 +1,16 @@
 #include "args.h"
+#include "route.cuh"
+#include "tree.cuh"
+namespace dsm {
+void launch_route(const RouteArgs& a, bool fill, cudaStream_t st) {
+  const unsigned nb = (unsigned)((a.T + 255) / 256);
+  if (fill) route_kernel<true><<<nb, 256, 0, st>>>(a); else route_kernel<false><<<nb, 256, 0, st>>>(a);
+}
+void launch_tree_eval(const TreeEvalArgs& a, cudaStream_t st) { tree_eval_kernel<<<1, 256, 0, st>>>(a); }
+void launch_derive(const DeriveArgs& a, cudaStream_t st) { if (a.nslots > 0) derive_kernel<<<(a.nslots + 127) / 128, 128, 0, st>>>(a); }
+void launch_opt_step(const OptArgs& a, cudaStream_t st) { opt_step_kernel<<<1, (a.H + 63) / 64 * 64, 0, st>>>(a); }
+void launch_mix(const MixArgs& a, cudaStream_t st) { mix_kernel<<<(unsigned)((a.T + 127) / 128), 128, 0, st>>>(a); }
+}  // namespace dsm
 namespace dsm {
 // Givens rank-1 update of the trailing block for every deleted row (one CTA; column sweep is sequential).
 __global__ void __launch_bounds__(NTHREADS) delete_rows_kernel(double* Lf, int n, const int64_t* rows, int nrows, double* v) {

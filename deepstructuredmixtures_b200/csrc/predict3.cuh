@@ -62,7 +62,7 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
     const LeafMeta m = a.meta[pl.slot];
     Pred3Gen gen;
     gen.F = a.F + m.foff; gen.W = a.W + m.woff; gen.np = m.np; gen.nb = a.wave ? wt.z + 1 : m.nb; gen.nkc = m.nkc;
-    gen.VT = a.VT + pl.vtoff + (int64_t)tk.y * m.nkc * TILE_D;
+    gen.VT = a.vt_per_cta ? a.VT + (int64_t)blockIdx.x * a.vt_stride : a.VT + pl.vtoff + (int64_t)tk.y * m.nkc * TILE_D;
     gen.I = a.wave ? wt.z : 0; gen.c = 0;
     TaskHdr h; h.kind = 0; h.ti = ti; h.slot = tk.x; h.I = gen.I; h.J = tk.y; h.wi = 0; h.wj = 0; h.n_c = 0; h.n_main = 0; h.pad0 = wt.w;
     int stored = a.wave ? gen.I : 0;             // blocks of V^T in memory (wave mode: ordered by the flags below instead)
@@ -105,7 +105,15 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
 }
 
 // Kernel values of one group of 2 test points (rows rb, rb+1 of the test tile) x 4 consecutive training rows (cb .. cb+3).
-__device__ __forceinline__ void kernel_group(int ktype, int D, const double* sxq, const double* sxi, const double* scf,
+#ifndef DSM_KG_INLINE
+#define DSM_KG_INLINE 0
+#endif
+#if DSM_KG_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__        // one copy of the (large) kernel-evaluation code instead of eight per call site: instruction cache
+#endif
+void kernel_group(int ktype, int D, const double* sxq, const double* sxi, const double* scf,
                                              const double* sT, double v, int rb, int cb, double (&kv)[2][4]) {
 #pragma unroll
   for (int mm = 0; mm < 2; mm++)
@@ -194,7 +202,8 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     const double* xt = a.xt + pl.xtoff;
     const double* al = a.alpha + m.voff;
     const double* prm = a.prm + m.poff;
-    double* VT = a.VT + pl.vtoff + (int64_t)Q * m.nkc * TILE_D;
+    double* VT = a.vt_per_cta ? a.VT + (int64_t)blockIdx.x * a.vt_stride : a.VT + pl.vtoff + (int64_t)Q * m.nkc * TILE_D;
+    const int* pidx = a.pidx != nullptr ? a.pidx + pl.ooff + q0 : nullptr;       // device-routed points: gather from xtest
     const int ktype = m.ktype;
     const double v = prm[PRM_V];
     const bool c0ok = q0 + acc_row(0) < pl.T, c1ok = q0 + acc_row(1) < pl.T;
@@ -203,11 +212,16 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
     const bool active = q0 + r0 < pl.T;
     const bool strip = pl.T - q0 <= 16;              // only slab 0 (= warp 0) holds real test points
     double mu0 = 0.0, mu1 = 0.0, sq0 = 0.0, sq1 = 0.0;
+    // optional per-task cycle counts: [0] start, [1] contraction, [2] staging, [3] kernel values, [4] TRSM epilogue, [5] store, [6] end, [7] I count
+    long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)hd.ti * 8 : nullptr;
+    long long tc0 = 0, t_con = 0, t_stage = 0, t_eval = 0, t_epi = 0, t_store = 0;
+    if (trc) { trc[0] = clock64(); }
     if (!borrow) {
       csync();                                       // previous task's readers are done with the static tiles
       for (int u = tid; u < D * BLK; u += NCONS) {
         const int d = u / BLK, q = u % BLK;
-        sxq[u] = (q0 + q < pl.Tp) ? xt[(int64_t)d * ldv + q0 + q] : 0.0;
+        if (pidx != nullptr) { const int gp = (q0 + q < pl.Tp) ? pidx[q] : -1; sxq[u] = gp >= 0 ? a.xtest[(int64_t)d * a.T_all + gp] : 0.0; }
+        else sxq[u] = (q0 + q < pl.Tp) ? xt[(int64_t)d * ldv + q0 + q] : 0.0;
       }
       if (tid < D) scf[tid] = (m.nl > 1) ? prm[PRM_COEF + tid] : prm[PRM_COEF];
     }
@@ -223,6 +237,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
 #pragma unroll
       for (int mm = 0; mm < 2; mm++) { sacc[mm][0][0] = 0.0; sacc[mm][0][1] = 0.0; sacc[mm][1][0] = 0.0; sacc[mm][1][1] = 0.0; }
       const bool wact = strip && 16 * warp < wi;     // strip mode: this warp's 16 columns exist in block I
+      if (trc) tc0 = clock64();
       for (int c = 0; c < I * (BLK / KC); c++) {     // (I == 0 has no contraction: the header chunk is its first epilogue stage)
         st = p.wait();                                 // (idempotent for the header chunk, which is still unreleased)
         if (strip) { if (wact) strip_chunk(sacc, p.A(st), p.B(st), 16 * warp); }
@@ -230,11 +245,13 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
         p.release();
       }
       // stage the point tiles of block I (and, when borrowing the ring, of the test block too)
+      if (trc) { const long long t1 = clock64(); t_con += t1 - tc0; tc0 = t1; }
       csync();
       if (borrow) {
         for (int u = tid; u < D * BLK; u += NCONS) {
           const int d = u / BLK, q = u % BLK;
-          sxq[u] = (q0 + q < pl.Tp) ? xt[(int64_t)d * ldv + q0 + q] : 0.0;
+          if (pidx != nullptr) { const int gp = (q0 + q < pl.Tp) ? pidx[q] : -1; sxq[u] = gp >= 0 ? a.xtest[(int64_t)d * a.T_all + gp] : 0.0; }
+          else sxq[u] = (q0 + q < pl.Tp) ? xt[(int64_t)d * ldv + q0 + q] : 0.0;
         }
         if (tid < D) scf[tid] = (m.nl > 1) ? prm[PRM_COEF + tid] : prm[PRM_COEF];
       }
@@ -244,6 +261,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       }
       if (tid < BLK) sal[tid] = (tid < wi && i0 + tid < m.n) ? al[i0 + tid] : 0.0;
       csync();
+      if (trc) { const long long t1 = clock64(); t_stage += t1 - tc0; tc0 = t1; }
       // OUT = Knt_IQ^T - OUT ; mean partial sum_r Knt[r][c] alpha[r].  Groups of 2 test points x 4 consecutive rows r.
       if (strip) {
         if (wact) {
@@ -312,7 +330,9 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
         csync();
         if (tid == 0) mbar_arrive(&p.aux[0]);
       }
+      if (trc) { const long long t1 = clock64(); t_eval += t1 - tc0; tc0 = t1; }
       tri_epilogue(p, acc, wi / 32, active, 1.0);     // V_IQ^T = S^T W_I^T
+      if (trc) { const long long t1 = clock64(); t_epi += t1 - tc0; tc0 = t1; }
       if (active) acc2_store(acc, VT, m.nkc, 0, i0, BLK, wi);
       fence_proxy_async();
       csync();
@@ -320,6 +340,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
         if (a.wave) { __threadfence(); st_release(a.flags + hd.pad0 + I, 1); }     // other CTAs read this block of V^T
         else mbar_arrive(&p.aux[1]);
       }
+      if (trc) { const long long t1 = clock64(); t_store += t1 - tc0; tc0 = t1; }
 #pragma unroll
       for (int nb = 0; nb < 16; nb++)
         if (8 * nb < wi) {
@@ -327,6 +348,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
           for (int e = 0; e < 2; e++) { sq0 = fma(acc[0][nb][e], acc[0][nb][e], sq0); sq1 = fma(acc[1][nb][e], acc[1][nb][e], sq1); }
         }
     }
+    if (trc) { trc[1] = t_con; trc[2] = t_stage; trc[3] = t_eval; trc[4] = t_epi; trc[5] = t_store; trc[6] = clock64(); trc[7] = I_end - I_begin; }
     // finish: mu = m + Knt' alpha ; var = k(x_t, x_t) - sum V^2 + eta      (gaussianprocess.jl:117-126)
     mu0 += __shfl_xor_sync(0xffffffffu, mu0, 1); mu0 += __shfl_xor_sync(0xffffffffu, mu0, 2);
     mu1 += __shfl_xor_sync(0xffffffffu, mu1, 1); mu1 += __shfl_xor_sync(0xffffffffu, mu1, 2);
@@ -361,7 +383,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
           else {
             ktt = 0.0;
             for (int d = 0; d < D; d++) {
-              const double xv = xt[(int64_t)d * ldv + q0 + c];
+              const double xv = pidx != nullptr ? a.xtest[(int64_t)d * a.T_all + pidx[c]] : xt[(int64_t)d * ldv + q0 + c];
               const double cf = (ktype == ISO_LINEAR) ? prm[PRM_COEF] : prm[PRM_COEF + d];
               ktt = fma(cf * xv, xv, ktt);
             }

@@ -473,3 +473,101 @@ def test_library_collective_two_gpus():
             assert abs(z - z0) <= 1e-12 * abs(z0)
             assert np.max(np.abs(mu - mu0)) <= 1e-12 * np.max(np.abs(mu0)) and relerr(var, var0) <= 1e-12
     single.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 6. prediction routed and mixed on the device (large batches) == the host recursion (small batches)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["dsmgp_ard", "dsmgp_mixture", "dsmgp_deep", "poe", "gpoe", "rbcm", "single_gp"])
+def test_device_routing_and_mixing_match_host_path(kind, monkeypatch):
+    """dsmgp_predict has two implementations of common.jl:101-122,134-313: the host recursion (few points) and the device
+    path (route.cuh: one thread per point routes and mixes; predict3 gathers its test tiles through index lists).  Both must
+    give the same predictions, and both must match the oracle."""
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(2400, 3, 61)
+    T = 1500
+    xt = np.random.default_rng(8).random((T, 3))
+    if kind == "dsmgp_ard":
+        model = dsm.buildDSMGP(x, y, 3, 3, M=80, kernel=dsm.ArdSE(np.zeros(3), 0.0), logNoise=-1.0, rng=61)
+        th = np.array([0.1, -0.2, 0.0, 0.2, -1.0])
+    elif kind == "dsmgp_mixture":
+        model = dsm.buildDSMGP(x, y, 2, 3, M=150, kernel=[dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)], logNoise=-1.0, rng=61)
+        th = np.array([0.1, 0.2, -1.0, 0.3, 0.0, -0.9])
+    elif kind == "dsmgp_deep":
+        model = dsm.buildDSMGP(x, y, 2, 2, M=40, D=3, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, rng=61)
+        th = np.array([-0.5, 0.2, -1.0])
+    elif kind == "poe":
+        model = dsm.buildPoE(x, y, 3, M=150, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, rng=61)
+        th = np.array([-0.5, 0.2, -1.0])
+    elif kind == "gpoe":
+        model = dsm.buildPoE(x, y, 3, M=150, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, generalized=True, rng=61)
+        th = np.array([-0.5, 0.2, -1.0])
+    elif kind == "rbcm":
+        model = dsm.buildBCM(x, y, 3, M=150, kernel=dsm.ArdSE(np.zeros(3), 0.0), logNoise=-1.0, rng=61)
+        th = np.array([0.1, -0.2, 0.0, 0.2, -1.0])
+    else:
+        model = dsm.GaussianProcess(x[:700], y[:700], kernel=dsm.IsoSE(-0.5, 0.1), logNoise=-1.0, run_cholesky=True).model
+        th = np.array([-0.5, 0.1, -1.0])
+    dsm.evaluate(model, th)
+    if kind.startswith("dsmgp"):
+        dsm.update_(model)
+    monkeypatch.setenv("DSMGP_PREDICT_DEVICE", "0")
+    mu_h, var_h = dsm.predict(model, xt)
+    monkeypatch.setenv("DSMGP_PREDICT_DEVICE", "1")
+    mu_d, var_d = dsm.predict(model, xt)
+    e = max(float(np.max(np.abs(mu_d - mu_h)) / np.max(np.abs(mu_h))), relerr(var_d, var_h))
+    print(f"\n[device predict] {kind}: device vs host path {e:.1e}")
+    assert e <= 1e-12
+    o_root = oracle_tree(model, th)
+    orc.fit(o_root)
+    if kind.startswith("dsmgp") or kind == "single_gp":
+        if kind != "single_gp":
+            orc.update_weights(o_root)
+        omu, ovar = orc.predict_dsmgp(o_root, xt)
+    else:
+        omu, ovar = {"poe": orc.predict_poe, "gpoe": orc.predict_gpoe, "rbcm": orc.predict_rbcm}[kind](o_root, xt)
+    assert np.max(np.abs(mu_d - omu)) <= PRED_TOL * max(float(np.max(np.abs(omu))), float(np.std(y))) and relerr(var_d, ovar) <= PRED_TOL
+    # error reporting of the device path
+    bad = xt.copy(); bad[7, 1] = np.nan
+    with pytest.raises(dsm.DsmgpError):
+        dsm.predict(model, bad)
+    model.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 7. the train! loop as a CUDA graph (tree passes + Flux step on the device) == the host loop
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["readme", "mixture"])
+def test_fused_train_loop_matches_host_loop(kind, monkeypatch):
+    """dsmgp_train runs a whole iteration (theta -> parameters -> Gram -> Cholesky -> inverse -> rows -> mll! -> nabla-mll! ->
+    Flux step) as one CUDA graph with theta, optimiser state and LML trace on the device; DSMGP_TRAIN_FUSED=0 is the loop of
+    dsmgp_eval calls with host tree passes.  Same traces, same final theta, same early-stopping iteration (also when the
+    stopping iteration lies inside a chunk the device has already run past)."""
+    import deepstructuredmixtures_b200 as dsm
+    rng = np.random.default_rng(1)
+    if kind == "readme":
+        x = np.linspace(0, 1, 100).reshape(-1, 1)
+        y = np.sin(x[:, 0] * 4 * np.pi + rng.standard_normal(100) * 0.2)
+        make = lambda: dsm.buildDSMGP(x, y, 3, 4, M=10, kernel=dsm.IsoSE(1.0, 1.0), meanFun=dsm.ConstMean(float(np.mean(x))), rng=1)
+    else:
+        x, y = synth(900, 2, 19)
+        make = lambda: dsm.buildDSMGP(x, y, 2, 3, M=60, kernel=[dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)], logNoise=-1.0, rng=19)
+    for opt, iters, lam, es in ((lambda: dsm.ADAM(0.01, state_by_identity=False), 70, 1e-12, 10),
+                                (lambda: dsm.ADAM(0.001), 45, 1e-12, 10),
+                                (lambda: dsm.RMSProp(0.01, state_by_identity=False), 50, 1e-12, 10),
+                                (lambda: dsm.Descent(1e-9), 90, 1e3, 27)):            # stops at iteration 10 + 27 - 1 (inside chunk 2)
+        res = {}
+        for fused in ("1", "0"):
+            monkeypatch.setenv("DSMGP_TRAIN_FUSED", fused)
+            m = make()
+            t0 = time.perf_counter()
+            _, ell = dsm.train_(m, opt(), iterations=iters, randinit=False, lam=lam, earlystop=es)
+            dt = time.perf_counter() - t0
+            res[fused] = (ell, m.handle.get_leaf_params(0), m.handle.lml()[m.flat.root], dt)
+            m.close()
+        (e1, th1, l1, t1), (e0, th0, l0, t0_) = res["1"], res["0"]
+        assert e1.size == e0.size, (e1.size, e0.size)
+        assert np.max(np.abs(e1 - e0)) <= 1e-10 * np.max(np.abs(e0))
+        assert np.max(np.abs(th1 - th0)) <= 1e-10 and abs(l1 - l0) <= 1e-10 * abs(l0)
+        print(f"\n[fused train] {kind}: {e1.size} iterations, graph loop {1e3 * t1 / e1.size:.3f} ms/iteration, host loop {1e3 * t0_ / e0.size:.3f} ms/iteration")
+    assert e1.size == 36 + 1                 # 10 + 27 - 1 = 36 is the stopping iteration (0-based)
