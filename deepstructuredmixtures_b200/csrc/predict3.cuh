@@ -104,46 +104,60 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
   p.issue(d, &h);
 }
 
-// Kernel values of one group of 2 test points (rows rb, rb+1 of the test tile) x 4 consecutive training rows (cb .. cb+3).
-#ifndef DSM_KG_INLINE
-#define DSM_KG_INLINE 0
-#endif
-#if DSM_KG_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__        // one copy of the (large) kernel-evaluation code instead of eight per call site: instruction cache
-#endif
-void kernel_group(int ktype, int D, const double* sxq, const double* sxi, const double* scf,
-                                             const double* sT, double v, int rb, int cb, double (&kv)[2][4]) {
+// Kernel values of NG groups of 2 test points (rows rb, rb+1 of the test tile) x 4 consecutive training rows (cb + 16 g .. + 3).
+// The exp chains of the SE kernels are long (10 dependent FP64 operations + a table load) and a CTA has only two MMA warps per
+// scheduler, so the groups are evaluated NG = 2 at a time: 16 independent chains per thread keep the FP64 pipe busy (measured with
+// the per-task trace: 70.7 -> see profiles/ us per 128 x 128 ArdSE tile).  One out-of-line copy per kernel type instead of eight inlined
+// ones keeps the kernel inside the instruction cache (383 KB -> 172 KB of SASS, +4.5 % / +10 % on cfg3 / cfg4).
+template <int KT, int NG>
+__device__ __noinline__ void kernel_groups(int D, const double* sxq, const double* sxi, const double* scf,
+                                           const double* sT, double v, int rb, int cb, double (&kv)[NG][2][4]) {
 #pragma unroll
-  for (int mm = 0; mm < 2; mm++)
+  for (int g = 0; g < NG; g++)
 #pragma unroll
-    for (int k = 0; k < 4; k++) kv[mm][k] = 0.0;
+    for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+      for (int k = 0; k < 4; k++) kv[g][mm][k] = 0.0;
 #pragma unroll 2
   for (int d = 0; d < D; d++) {
     const double2 xq = *reinterpret_cast<const double2*>(sxq + d * BLK + rb);
-    const double2 xi0 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb), xi1 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb + 2);
-    const double xqv[2] = {xq.x, xq.y}, xiv[4] = {xi0.x, xi0.y, xi1.x, xi1.y};
+    const double xqv[2] = {xq.x, xq.y};
     const double cf = scf[d];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      const double2 xi0 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb + 16 * g), xi1 = *reinterpret_cast<const double2*>(sxi + d * BLK + cb + 16 * g + 2);
+      const double xiv[4] = {xi0.x, xi0.y, xi1.x, xi1.y};
+#pragma unroll
+      for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (KT == ISO_SE) { const double t = xqv[mm] - xiv[k]; kv[g][mm][k] = fma(t, t, kv[g][mm][k]); }
+          else if (KT == ARD_SE) { const double t = xqv[mm] - xiv[k]; kv[g][mm][k] += exp_neg(cf * (t * t), sT); }
+          else if (KT == ISO_LINEAR) kv[g][mm][k] = fma(xqv[mm], xiv[k], kv[g][mm][k]);
+          else kv[g][mm][k] = fma(cf * xqv[mm], xiv[k], kv[g][mm][k]);
+        }
+    }
+  }
+  const double cf0 = scf[0];
+#pragma unroll
+  for (int g = 0; g < NG; g++)
 #pragma unroll
     for (int mm = 0; mm < 2; mm++)
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        if (ktype == ISO_SE) { const double t = xqv[mm] - xiv[k]; kv[mm][k] = fma(t, t, kv[mm][k]); }
-        else if (ktype == ARD_SE) { const double t = xqv[mm] - xiv[k]; kv[mm][k] += exp_neg(cf * (t * t), sT); }
-        else if (ktype == ISO_LINEAR) kv[mm][k] = fma(xqv[mm], xiv[k], kv[mm][k]);
-        else kv[mm][k] = fma(cf * xqv[mm], xiv[k], kv[mm][k]);
+        if (KT == ISO_SE) kv[g][mm][k] = v * exp_neg(cf0 * kv[g][mm][k], sT);
+        else if (KT == ARD_SE) kv[g][mm][k] = v * kv[g][mm][k];
+        else if (KT == ISO_LINEAR) kv[g][mm][k] = cf0 * kv[g][mm][k];
       }
-  }
-  const double cf0 = scf[0];
-#pragma unroll
-  for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      if (ktype == ISO_SE) kv[mm][k] = v * exp_neg(cf0 * kv[mm][k], sT);
-      else if (ktype == ARD_SE) kv[mm][k] = v * kv[mm][k];
-      else if (ktype == ISO_LINEAR) kv[mm][k] = cf0 * kv[mm][k];
-    }
+}
+
+template <int NG>
+__device__ __forceinline__ void kernel_groups_any(int ktype, int D, const double* sxq, const double* sxi, const double* scf,
+                                                  const double* sT, double v, int rb, int cb, double (&kv)[NG][2][4]) {
+  if (ktype == ISO_SE) kernel_groups<ISO_SE, NG>(D, sxq, sxi, scf, sT, v, rb, cb, kv);
+  else if (ktype == ARD_SE) kernel_groups<ARD_SE, NG>(D, sxq, sxi, scf, sT, v, rb, cb, kv);
+  else if (ktype == ISO_LINEAR) kernel_groups<ISO_LINEAR, NG>(D, sxq, sxi, scf, sT, v, rb, cb, kv);
+  else kernel_groups<ARD_LINEAR, NG>(D, sxq, sxi, scf, sT, v, rb, cb, kv);
 }
 
 // STRIP mode (at most 16 real test points in the block, i.e. only slab 0 is live): the 128 columns of the 16-row strip are
@@ -266,15 +280,15 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
       if (strip) {
         if (wact) {
           const int rbs = 2 * g8, cb = 16 * warp + 4 * t4;
-          double kv[2][4];
-          kernel_group(ktype, D, sxq, sxi, scf, sT, v, rbs, cb, kv);
+          double kv[1][2][4];
+          kernel_groups_any<1>(ktype, D, sxq, sxi, scf, sT, v, rbs, cb, kv);
           const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
           const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
 #pragma unroll
           for (int mm = 0; mm < 2; mm++)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-              double kk = kv[mm][k];
+              double kk = kv[0][mm][k];
               if (!(q0 + rbs + mm < pl.T && i0 + cb + k < m.n)) kk = 0.0;
               if (mm) mu1 = fma(kk, alv[k], mu1); else mu0 = fma(kk, alv[k], mu0);
               sacc[mm][k & 1][k >> 1] = kk - sacc[mm][k & 1][k >> 1];
@@ -306,22 +320,26 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
         }
       } else {
 #pragma unroll
-      for (int nbp = 0; nbp < 8; nbp++) {
-        if (active && 16 * nbp < wi) {
-          const int cb = 16 * nbp + 4 * t4;
-          double kv[2][4];
-          kernel_group(ktype, D, sxq, sxi, scf, sT, v, rb, cb, kv);
-          const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
-          const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
+      for (int nbp2 = 0; nbp2 < 4; nbp2++) {
+        if (active && 32 * nbp2 < wi) {                 // wi is a multiple of 64: both 16-column groups of the pair exist
+          const int cb0 = 32 * nbp2 + 4 * t4;
+          double kv[2][2][4];
+          kernel_groups_any<2>(ktype, D, sxq, sxi, scf, sT, v, rb, cb0, kv);
 #pragma unroll
-          for (int mm = 0; mm < 2; mm++)
+          for (int g = 0; g < 2; g++) {
+            const int nbp = 2 * nbp2 + g, cb = cb0 + 16 * g;
+            const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
+            const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-              double kk = kv[mm][k];
-              if (!((mm ? c1ok : c0ok) && i0 + cb + k < m.n)) kk = 0.0;
-              if (mm) mu1 = fma(kk, alv[k], mu1); else mu0 = fma(kk, alv[k], mu0);
-              acc[mm][2 * nbp + (k & 1)][k >> 1] = kk - acc[mm][2 * nbp + (k & 1)][k >> 1];
-            }
+            for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+              for (int k = 0; k < 4; k++) {
+                double kk = kv[g][mm][k];
+                if (!((mm ? c1ok : c0ok) && i0 + cb + k < m.n)) kk = 0.0;
+                if (mm) mu1 = fma(kk, alv[k], mu1); else mu0 = fma(kk, alv[k], mu0);
+                acc[mm][2 * nbp + (k & 1)][k >> 1] = kk - acc[mm][2 * nbp + (k & 1)][k >> 1];
+              }
+          }
         }
       }
       }
