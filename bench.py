@@ -145,8 +145,10 @@ def oracle_kernel(w):
     return [orc.IsoSE(0.0, 0.0), orc.IsoLinear(0.0)]
 
 
-def build_structure(w):
-    """Region graph on the host (no GPU): returns x, y, root, kernels (product types)."""
+def build_structure(w, device=False):
+    """Region graph: returns x, y, root, kernels (product types).  device=False: the host builder (no GPU; the CPU reference
+    arm).  device=True: the same recursion and random draws with the data passes on the GPU (dsmgp_part_*) --
+    bit-identical graph (tests/test_gpu_round2.py::test_device_tree_construction_is_bit_identical)."""
     from deepstructuredmixtures_b200 import kernels as kr, structure as st
     x, y = make_data(w)
     if w["kernel"] == "isose":
@@ -156,7 +158,7 @@ def build_structure(w):
     else:
         kern = [kr.IsoSE(0.0, 0.0), kr.IsoLinear(0.0)]
     cfg = st.DSMGPConfig(None, kern, -1.0, w["M"], w["K"], w["V"], w["depth"], w["eps"], True)
-    root = st.buildTree(x, y, cfg, np.random.default_rng(w["seed"]))
+    root = (st.buildTree_device if device else st.buildTree)(x, y, cfg, np.random.default_rng(w["seed"]))
     return x, y, root, kern
 
 
@@ -267,7 +269,7 @@ def main():
     from deepstructuredmixtures_b200 import model as mdl
 
     t_build0 = time.perf_counter()
-    x, y, root, kern = build_structure(w)
+    x, y, root, kern = build_structure(w, device=True)
     klist = kern if isinstance(kern, list) else [kern]
     t_tree = time.perf_counter() - t_build0
     keep = args.workload != "cfg5"
@@ -457,7 +459,7 @@ def scale_record(args, rank, world, local):
     from deepstructuredmixtures_b200 import model as mdl
     w = WORKLOADS["cfg5"]
     t0 = time.perf_counter()
-    x, y, root, kern = build_structure(w)
+    x, y, root, kern = build_structure(w, device=True)
     t_tree = time.perf_counter() - t0
     t0 = time.perf_counter()
     model = mdl.DSMGP(root, x, y, [kern.copy()], -1.0, rank=rank, world=world, device=local, keep_factors=False)

@@ -66,6 +66,8 @@ EXPORTS = [
     "dsmgp_leaf_info", "dsmgp_kernelmatrix", "dsmgp_overlap", "dsmgp_release_cache", "dsmgp_chol_continue", "dsmgp_chol_delete_rows", "dsmgp_potrf",
     "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling",
     "dsmgp_set_sharing", "dsmgp_get_sharing", "dsmgp_infer", "dsmgp_reset_weights", "dsmgp_comm_unique_id", "dsmgp_comm_init", "dsmgp_host_sharing_plan",
+    "dsmgp_part_create", "dsmgp_part_destroy", "dsmgp_part_size", "dsmgp_part_range", "dsmgp_part_sorted_column", "dsmgp_part_split",
+    "dsmgp_part_rows",
 ]
 COMM_ID_BYTES = 128
 
@@ -127,6 +129,13 @@ def lib() -> C.CDLL:
         "dsmgp_potrf": (I32, [pd, I64, pi32]),
         "dsmgp_host_tree_eval": (I32, [C.POINTER(Tree), I64, pi32, C.POINTER(KernelDesc), I32, pd, I64, pd, pd, pd, pd, pd]),
         "dsmgp_host_shard": (I32, [I64, pi64, I32, pi32]),
+        "dsmgp_part_create": (I32, [pd, I64, I64, C.POINTER(P)]),
+        "dsmgp_part_destroy": (None, [P]),
+        "dsmgp_part_size": (I64, [P, I64]),
+        "dsmgp_part_range": (I32, [P, I64, pd, pd]),
+        "dsmgp_part_sorted_column": (I32, [P, I64, I64, pd]),
+        "dsmgp_part_split": (I32, [P, I64, I64, pd, pd, I64, pi64, pi64]),
+        "dsmgp_part_rows": (I32, [P, I64, pi64]),
         "dsmgp_host_sharing_plan": (I32, [I64, pi64, pi64, pi32, pd, D, pi32, pi32, pi32]),
         "dsmgp_get_timings": (I32, [P, C.POINTER(Timings)]),
         "dsmgp_set_profiling": (I32, [P, I32]),

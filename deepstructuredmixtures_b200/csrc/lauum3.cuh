@@ -16,6 +16,84 @@ namespace dsm {
 
 constexpr int LAUUM_DSTAGE = 8;
 
+// sum_ij M_ij dK_ij / dlog l_h for NG groups of 2 rows x 4 consecutive columns (rows rb, rb+1; columns cb + 16 g .. + 3) and the
+// hyper-parameters h0 .. h0+3, added to g[0..3].  M = sym * (alpha_i alpha_j - F^-1_ij) comes from the accumulators.
+// Out of line and NG = 2 groups at a time for the same reasons as predict3's kernel_groups: one copy per kernel type (instruction
+// cache), 16 independent exp chains per thread (two MMA warps per scheduler cannot hide a 10-operation FP64 chain otherwise).
+template <int KT, int NG>
+__device__ __noinline__ void lauum_groups(int D, int h0, int nl, const double* sxi, const double* sxj, const double* scf,
+                                          const double* sT, double v, int rb, int cb, const double (&mij)[NG][2][4], double (&g)[4]) {
+  if (KT == ISO_SE || KT == ISO_LINEAR) {
+    double r2[NG][2][4];
+#pragma unroll
+    for (int q = 0; q < NG; q++)
+#pragma unroll
+      for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) r2[q][mm][k] = 0.0;
+#pragma unroll 2
+    for (int d = 0; d < D; d++) {
+      const double2 xi = *reinterpret_cast<const double2*>(sxi + d * BLK + rb);
+      const double xiv[2] = {xi.x, xi.y};
+#pragma unroll
+      for (int q = 0; q < NG; q++) {
+        const double2 xj0 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb + 16 * q), xj1 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb + 16 * q + 2);
+        const double xjv[4] = {xj0.x, xj0.y, xj1.x, xj1.y};
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (KT == ISO_SE) { const double tt = xiv[mm] - xjv[k]; r2[q][mm][k] = fma(tt, tt, r2[q][mm][k]); }
+            else r2[q][mm][k] = fma(xiv[mm], xjv[k], r2[q][mm][k]);
+          }
+      }
+    }
+    double gs[NG] = {};
+#pragma unroll
+    for (int q = 0; q < NG; q++)
+#pragma unroll
+      for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          if (KT == ISO_SE) {
+            const double u = scf[0] * r2[q][mm][k];                                  // -0.5 r2 / l^2
+            gs[q] = fma(mij[q][mm][k], v * exp_neg(u, sT) * (-2.0 * u), gs[q]);       // K * r2 / l^2
+          } else {
+            gs[q] = fma(mij[q][mm][k], -2.0 * scf[0] * r2[q][mm][k], gs[q]);
+          }
+        }
+#pragma unroll
+    for (int q = 0; q < NG; q++) g[0] += gs[q];
+  } else {
+    for (int hh = 0; hh < 4 && h0 + hh < nl; hh++) {
+      const int d = h0 + hh;
+      const double cf = scf[d];
+      const double2 xi = *reinterpret_cast<const double2*>(sxi + d * BLK + rb);
+      const double xiv[2] = {xi.x, xi.y};
+      double gs[NG] = {};
+#pragma unroll
+      for (int q = 0; q < NG; q++) {
+        const double2 xj0 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb + 16 * q), xj1 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb + 16 * q + 2);
+        const double xjv[4] = {xj0.x, xj0.y, xj1.x, xj1.y};
+#pragma unroll
+        for (int mm = 0; mm < 2; mm++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            if (KT == ARD_SE) {
+              const double tt = xiv[mm] - xjv[k];
+              const double u = cf * (tt * tt);
+              gs[q] = fma(mij[q][mm][k], v * exp_neg(u, sT) * (-2.0 * u), gs[q]);
+            } else {
+              gs[q] = fma(mij[q][mm][k], -2.0 * cf * xiv[mm] * xjv[k], gs[q]);
+            }
+          }
+      }
+#pragma unroll
+      for (int q = 0; q < NG; q++) g[hh] += gs[q];
+    }
+  }
+}
+
 struct Lauum3Gen {
   const double* A0; const double* B0;   // K = I block operands (WT_I tiles / X_IJ^T tiles)
   const double* A1; const double* B1;   // remaining k range: tiles (I, kc), (J, kc)
@@ -131,75 +209,29 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
       double g[4] = {0.0, 0.0, 0.0, 0.0};
       if (active) {
 #pragma unroll
-        for (int nbp = 0; nbp < 8; nbp++) {
-          if (16 * nbp < wj) {
-            const int cb = 16 * nbp + 4 * t4;
-            double mij[2][4];
-            {
-              const double2 ai = *reinterpret_cast<const double2*>(sai + rb);
+        for (int nbp2 = 0; nbp2 < 4; nbp2++) {
+          if (32 * nbp2 < wj) {                         // wj is a multiple of 64: both 16-column groups of the pair exist
+            const int cb0 = 32 * nbp2 + 4 * t4;
+            double mij[2][2][4];
+            const double2 ai = *reinterpret_cast<const double2*>(sai + rb);
+            const double aiv[2] = {ai.x, ai.y};
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+              const int nbp = 2 * nbp2 + q, cb = cb0 + 16 * q;
               const double2 aj0 = *reinterpret_cast<const double2*>(saj + cb), aj1 = *reinterpret_cast<const double2*>(saj + cb + 2);
-              const double aiv[2] = {ai.x, ai.y}, ajv[4] = {aj0.x, aj0.y, aj1.x, aj1.y};
+              const double ajv[4] = {aj0.x, aj0.y, aj1.x, aj1.y};
 #pragma unroll
               for (int mm = 0; mm < 2; mm++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) {
                   const bool ok = (i0 + rb + mm < m.n) && (j0 + cb + k < m.n);
-                  mij[mm][k] = ok ? sym * (aiv[mm] * ajv[k] - acc[mm][2 * nbp + (k & 1)][k >> 1]) : 0.0;
+                  mij[q][mm][k] = ok ? sym * (aiv[mm] * ajv[k] - acc[mm][2 * nbp + (k & 1)][k >> 1]) : 0.0;
                 }
             }
-            if (ktype == ISO_SE || ktype == ISO_LINEAR) {
-              double r2[2][4];
-#pragma unroll
-              for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) r2[mm][k] = 0.0;
-#pragma unroll 2
-              for (int d = 0; d < D; d++) {
-                const double2 xi = *reinterpret_cast<const double2*>(sxi + d * BLK + rb);
-                const double2 xj0 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb), xj1 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb + 2);
-                const double xiv[2] = {xi.x, xi.y}, xjv[4] = {xj0.x, xj0.y, xj1.x, xj1.y};
-#pragma unroll
-                for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-                  for (int k = 0; k < 4; k++) {
-                    if (ktype == ISO_SE) { const double tt = xiv[mm] - xjv[k]; r2[mm][k] = fma(tt, tt, r2[mm][k]); }
-                    else r2[mm][k] = fma(xiv[mm], xjv[k], r2[mm][k]);
-                  }
-              }
-#pragma unroll
-              for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                  if (ktype == ISO_SE) {
-                    const double u = scf[0] * r2[mm][k];                      // -0.5 r2 / l^2
-                    g[0] = fma(mij[mm][k], v * exp_neg(u, sT) * (-2.0 * u), g[0]);     // K * r2 / l^2
-                  } else {
-                    g[0] = fma(mij[mm][k], -2.0 * scf[0] * r2[mm][k], g[0]);
-                  }
-                }
-            } else {
-              for (int hh = 0; hh < 4 && h0 + hh < nl; hh++) {
-                const int d = h0 + hh;
-                const double cf = scf[d];
-                const double2 xi = *reinterpret_cast<const double2*>(sxi + d * BLK + rb);
-                const double2 xj0 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb), xj1 = *reinterpret_cast<const double2*>(sxj + d * BLK + cb + 2);
-                const double xiv[2] = {xi.x, xi.y}, xjv[4] = {xj0.x, xj0.y, xj1.x, xj1.y};
-                double gs = 0.0;
-#pragma unroll
-                for (int mm = 0; mm < 2; mm++)
-#pragma unroll
-                  for (int k = 0; k < 4; k++) {
-                    if (ktype == ARD_SE) {
-                      const double tt = xiv[mm] - xjv[k];
-                      const double u = cf * (tt * tt);
-                      gs = fma(mij[mm][k], v * exp_neg(u, sT) * (-2.0 * u), gs);
-                    } else {
-                      gs = fma(mij[mm][k], -2.0 * cf * xiv[mm] * xjv[k], gs);
-                    }
-                  }
-                g[hh] += gs;
-              }
-            }
+            if (ktype == ISO_SE) lauum_groups<ISO_SE, 2>(D, h0, nl, sxi, sxj, scf, sT, v, rb, cb0, mij, g);
+            else if (ktype == ISO_LINEAR) lauum_groups<ISO_LINEAR, 2>(D, h0, nl, sxi, sxj, scf, sT, v, rb, cb0, mij, g);
+            else if (ktype == ARD_SE) lauum_groups<ARD_SE, 2>(D, h0, nl, sxi, sxj, scf, sT, v, rb, cb0, mij, g);
+            else lauum_groups<ARD_LINEAR, 2>(D, h0, nl, sxi, sxj, scf, sT, v, rb, cb0, mij, g);
           }
         }
       }

@@ -109,6 +109,9 @@ __device__ __forceinline__ void predict3_producer(Pipe& p, const PredArgs& a) {
 // scheduler, so the groups are evaluated NG = 2 at a time: 16 independent chains per thread keep the FP64 pipe busy (measured with
 // the per-task trace: 70.7 -> see profiles/ us per 128 x 128 ArdSE tile).  One out-of-line copy per kernel type instead of eight inlined
 // ones keeps the kernel inside the instruction cache (383 KB -> 172 KB of SASS, +4.5 % / +10 % on cfg3 / cfg4).
+#ifndef DSM_KG_NG
+#define DSM_KG_NG 2
+#endif
 template <int KT, int NG>
 __device__ __noinline__ void kernel_groups(int D, const double* sxq, const double* sxi, const double* scf,
                                            const double* sT, double v, int rb, int cb, double (&kv)[NG][2][4]) {
@@ -320,14 +323,14 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) predict3_kernel(PredArgs a) {
         }
       } else {
 #pragma unroll
-      for (int nbp2 = 0; nbp2 < 4; nbp2++) {
-        if (active && 32 * nbp2 < wi) {                 // wi is a multiple of 64: both 16-column groups of the pair exist
-          const int cb0 = 32 * nbp2 + 4 * t4;
-          double kv[2][2][4];
-          kernel_groups_any<2>(ktype, D, sxq, sxi, scf, sT, v, rb, cb0, kv);
+      for (int nbp2 = 0; nbp2 < 8 / DSM_KG_NG; nbp2++) {
+        if (active && 16 * DSM_KG_NG * nbp2 < wi) {     // wi is a multiple of 64: every 16-column group of the set exists
+          const int cb0 = 16 * DSM_KG_NG * nbp2 + 4 * t4;
+          double kv[DSM_KG_NG][2][4];
+          kernel_groups_any<DSM_KG_NG>(ktype, D, sxq, sxi, scf, sT, v, rb, cb0, kv);
 #pragma unroll
-          for (int g = 0; g < 2; g++) {
-            const int nbp = 2 * nbp2 + g, cb = cb0 + 16 * g;
+          for (int g = 0; g < DSM_KG_NG; g++) {
+            const int nbp = DSM_KG_NG * nbp2 + g, cb = cb0 + 16 * g;
             const double2 al0 = *reinterpret_cast<const double2*>(sal + cb), al1 = *reinterpret_cast<const double2*>(sal + cb + 2);
             const double alv[4] = {al0.x, al0.y, al1.x, al1.y};
 #pragma unroll

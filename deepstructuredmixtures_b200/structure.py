@@ -190,6 +190,170 @@ def _buildSum(X, y, lowerBound, upperBound, config: DSMGPConfig, depth: int, obs
     return node
 
 
+# ---------------------------------------------------------------------------------------------
+# The same construction with the data passes on the device (`dsmgp_part_*`): X stays in HBM, every node of
+# the recursion is an index list there.  The recursion and EVERY random draw are the code above (same order, same generator),
+# so the region graph is bit-identical to the host builder's; what changes is that getSplits works on the node's SORTED column
+# (min / max / median / counts become binary searches), `findall` becomes a stable K-way partition kernel and X[idx,:] is never
+# copied.
+class DevicePartition:
+    def __init__(self, X: np.ndarray):
+        import ctypes as C
+        self._C = C
+        self._lib = nat.lib()
+        self._p = C.c_void_p()
+        self.X = nat.colmajor(X)
+        self.N, self.D = self.X.shape
+        nat.check(self._lib.dsmgp_part_create(nat.p_d(self.X), self.N, self.D, C.byref(self._p)))
+
+    def close(self):
+        if self._p and self._p.value:
+            self._lib.dsmgp_part_destroy(self._p)
+            self._p = self._C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def size(self, node: int) -> int:
+        return int(self._lib.dsmgp_part_size(self._p, node))
+
+    def range(self, node: int):
+        mn = np.zeros(self.D); mx = np.zeros(self.D)
+        nat.check(self._lib.dsmgp_part_range(self._p, node, nat.p_d(mn), nat.p_d(mx)))
+        return mn, mx
+
+    def sorted_column(self, node: int, d: int) -> np.ndarray:
+        out = np.zeros(self.size(node))
+        nat.check(self._lib.dsmgp_part_sorted_column(self._p, node, d, nat.p_d(out)))
+        return out
+
+    def split(self, node: int, d: int, lower, upper):
+        lo = nat.f64(lower); up = nat.f64(upper)
+        K = lo.size
+        ch = np.zeros(K, dtype=np.int64); sz = np.zeros(K, dtype=np.int64)
+        nat.check(self._lib.dsmgp_part_split(self._p, node, d, nat.p_d(lo), nat.p_d(up), K, nat.p_i64(ch), nat.p_i64(sz)))
+        return ch, sz
+
+    def rows(self, node: int) -> np.ndarray:
+        out = np.zeros(self.size(node), dtype=np.int64)
+        nat.check(self._lib.dsmgp_part_rows(self._p, node, nat.p_i64(out)))
+        return out
+
+
+def _getSplits_sorted(col: np.ndarray, lowerBound, upperBound, minData: int, eps: float, K: int, d: int,
+                      rng: np.random.Generator, depth: int = 1) -> List[float]:
+    """getSplits (treeStructure.jl:23-129) on the node's SORTED column: identical draws and results to `getSplits`."""
+    K_ = depth ** 2
+    s: List[float] = []
+    l = max(lowerBound[d], col[0])
+    u = min(upperBound[d], col[-1])
+    v = u - l
+    i0 = int(np.searchsorted(col, l, side="right"))          # (col > l)
+    i1 = int(np.searchsorted(col, u, side="right"))          # (col <= u)
+    sel = col[i0:i1]
+    if sel.size > minData * 2:
+        n = sel.size
+        m = float(sel[n // 2]) if n % 2 else float((sel[n // 2 - 1] + sel[n // 2]) / 2.0)      # median(sel) :49
+        z1 = z2 = 0
+        c = 0
+        s_new = 0.0
+        while z1 == 0 or z2 == 0:
+            a = rng.beta(2.0, 2.0) * v + l
+            s_new = float(eps * a + (1 - eps) * m)
+            z1 = int(np.searchsorted(sel, s_new, side="right"))
+            z2 = n - z1
+            c += 1
+            if c > 100:
+                return s
+        zi = int(rng.integers(1, 3))
+
+        def left():
+            ub = np.array(upperBound, dtype=float); ub[d] = s_new
+            return _getSplits_sorted(col, lowerBound, ub, minData, eps, K, d, rng, depth + 1)
+
+        def right():
+            lb = np.array(upperBound, dtype=float); lb[d] = s_new
+            return _getSplits_sorted(col, lb, upperBound, minData, eps, K, d, rng, depth + 1)
+
+        if zi == 1:
+            if z1 > minData and K_ < K:
+                s.extend(left()); K_ += 1
+            if z2 > minData and K_ < K:
+                s.extend(right())
+        else:
+            if z2 > minData and K_ < K:
+                s.extend(right()); K_ += 1
+            if z1 > minData and K_ < K:
+                s.extend(left())
+        s.append(s_new)
+    return s
+
+
+def _buildGP_dev(part: DevicePartition, y, lb, ub, config: DSMGPConfig, node: int, rng) -> Node:
+    obs = part.rows(node)
+    return _buildGP(None, y[obs - 1], lb, ub, config, obs, rng)
+
+
+def _buildSplit_dev(part: DevicePartition, y, lowerBound, upperBound, config: DSMGPConfig, depth: int, node: int, rng, d: int = 0) -> Node:
+    col = part.sorted_column(node, d)
+    s = sorted(_getSplits_sorted(col, lowerBound, upperBound, config.minData, config.bnoise, config.K, d, rng))
+    split = [(d + 1, si) for si in s] + [(d + 1, float(upperBound[d]))]
+    out = GPSplitNode(lowerBound=np.array(lowerBound), upperBound=np.array(upperBound), split=split)
+    lb = np.array(lowerBound, dtype=float)
+    ub = np.array(upperBound, dtype=float)
+    if s:
+        lows, ups, bounds = [], [], []
+        for (_, si) in split:
+            lb_ = lb.copy(); ub_ = ub.copy(); ub_[d] = si
+            lows.append(lb_[d]); ups.append(ub_[d]); bounds.append((lb_, ub_))
+            lb[d] = si
+        children, sizes = part.split(node, d, lows, ups)
+        for (lb_, ub_), ch, n in zip(bounds, children, sizes):
+            if depth < config.depth and n > config.minData:
+                if config.sumRoot:
+                    child = _buildSum_dev(part, y, lb_, ub_, config, depth, int(ch), rng)
+                else:
+                    child = _buildSplit_dev(part, y, lb_, ub_, config, depth, int(ch), rng)
+            else:
+                child = _buildGP_dev(part, y, lb_, ub_, config, int(ch), rng)
+            out.children.append(child)
+        return out
+    children, _ = part.split(node, d, [lowerBound[d]], [upperBound[d]])
+    return _buildGP_dev(part, y, np.array(lowerBound), np.array(upperBound), config, int(children[0]), rng)
+
+
+def _buildSum_dev(part: DevicePartition, y, lowerBound, upperBound, config: DSMGPConfig, depth: int, node: int, rng) -> Node:
+    V = config.V
+    out = GPSumNode()
+    mn, mx = part.range(node)
+    phi = mx - mn
+    phi = phi / phi.sum()
+    for _ in range(V):
+        d = int(rng.choice(len(phi), p=phi))
+        out.add(_buildSplit_dev(part, y, lowerBound, upperBound, config, depth + 1, node, rng, d=d), -math.log(V))
+    return out
+
+
+def buildTree_device(X: np.ndarray, y: np.ndarray, config: DSMGPConfig, rng) -> Node:
+    """buildTree (treeStructure.jl:4-21) with the data passes on the device; same graph as `buildTree` for the same generator."""
+    N, D = X.shape
+    assert N == len(y)
+    assert np.all(np.isfinite(X))
+    y = np.asarray(y, dtype=np.float64)
+    part = DevicePartition(X)
+    try:
+        lb = np.full(D, -np.inf)
+        ub = np.full(D, np.inf)
+        if config.sumRoot:
+            return _buildSum_dev(part, y, lb, ub, config, 0, 0, rng)
+        return _buildSplit_dev(part, y, lb, ub, config, 0, 0, rng)
+    finally:
+        part.close()
+
+
 def buildTree(X: np.ndarray, y: np.ndarray, config: DSMGPConfig, rng) -> Node:
     """treeStructure.jl:4-21."""
     N, D = X.shape

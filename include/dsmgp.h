@@ -244,6 +244,26 @@ int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, 
 /* plain batched-size-1 potrf('L') on a host matrix (LAPACK.potrf! as used at gaussianprocess.jl:101) */
 int32_t dsmgp_potrf(double* A, int64_t n, int32_t* info);
 
+/* ---- region-graph construction on the device ---------------------------------
+ * The data passes of buildTree (treeStructure.jl:23-243) on index lists in device memory; the recursion and every random draw
+ * (Beta(2,2), rand(1:2), Categorical) stay with the caller, so the partitions are bit-identical to the host builder's.
+ * A partition owns a device copy of x (N x D column-major) and a list of nodes; node 0 holds all rows. */
+typedef struct dsmgp_partition dsmgp_partition;
+int32_t dsmgp_part_create(const double* x, int64_t N, int64_t D, dsmgp_partition** out);
+void    dsmgp_part_destroy(dsmgp_partition* p);
+int64_t dsmgp_part_size(const dsmgp_partition* p, int64_t node);
+/* X.max - X.min per dimension over the node's rows (_buildSum, treeStructure.jl:233-235): mins[D], maxs[D] */
+int32_t dsmgp_part_range(dsmgp_partition* p, int64_t node, double* mins, double* maxs);
+/* column d of the node's rows in ascending order (n values): min / max / median of a sub-range / sum(. <= s) of getSplits
+ * (treeStructure.jl:36-57) are binary searches on it */
+int32_t dsmgp_part_sorted_column(dsmgp_partition* p, int64_t node, int64_t d, double* sorted);
+/* the children of _buildSplit (treeStructure.jl:176-199): child k = rows with lower[k] < x_d <= upper[k] in the node's own
+ * (ascending) order; K <= 32 new node numbers in children[], their sizes in sizes[] */
+int32_t dsmgp_part_split(dsmgp_partition* p, int64_t node, int64_t d, const double* lower, const double* upper, int64_t K,
+                         int64_t* children, int64_t* sizes);
+/* GPNode.obs of a leaf: the node's rows, 1-based ascending (n values) */
+int32_t dsmgp_part_rows(dsmgp_partition* p, int64_t node, int64_t* obs);
+
 /* ---- HOST-ONLY helpers (no GPU needed; used by the multi-process plumbing and its CPU tests) ---
  * Tree passes over a table of per-leaf rows (layout of dsmgp_leaf_rows): up-pass mll! optimize.jl:27-39,
  * down-pass nabla-mll! :42-150, update! common.jl:323-334. */

@@ -571,3 +571,38 @@ def test_fused_train_loop_matches_host_loop(kind, monkeypatch):
         assert np.max(np.abs(th1 - th0)) <= 1e-10 and abs(l1 - l0) <= 1e-10 * abs(l0)
         print(f"\n[fused train] {kind}: {e1.size} iterations, graph loop {1e3 * t1 / e1.size:.3f} ms/iteration, host loop {1e3 * t0_ / e0.size:.3f} ms/iteration")
     assert e1.size == 36 + 1                 # 10 + 27 - 1 = 36 is the stopping iteration (0-based)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 8. region-graph construction with the data passes on the device == the host builder, bit for bit
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["d1_sorted", "d4", "d8_deep", "mixture", "poe", "eps0"])
+def test_device_tree_construction_is_bit_identical(case):
+    """buildTree_device (dsmgp_part_*: sorted columns, per-dimension ranges, stable K-way partition on index lists in HBM; the
+    recursion and every random draw stay on the host) must produce exactly the region graph of buildTree
+    (treeStructure.jl:4-243 restated): same nodes, same split thresholds, same observation lists, same leaf means."""
+    import deepstructuredmixtures_b200 as dsm
+    from deepstructuredmixtures_b200 import structure as st
+    cfgs = {"d1_sorted": dict(N=20000, D=1, V=3, K=4, M=100, depth=2, eps=0.5, sumRoot=True, kern=dsm.IsoSE(0.0, 0.0)),
+            "d4": dict(N=30000, D=4, V=3, K=4, M=200, depth=2, eps=0.5, sumRoot=True, kern=dsm.ArdSE(np.zeros(4), 0.0)),
+            "d8_deep": dict(N=60000, D=8, V=2, K=3, M=300, depth=3, eps=0.1, sumRoot=True, kern=dsm.ArdSE(np.zeros(8), 0.0)),
+            "mixture": dict(N=8000, D=3, V=2, K=3, M=150, depth=2, eps=0.5, sumRoot=True, kern=[dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)]),
+            "poe": dict(N=9000, D=2, V=1, K=4, M=200, depth=2, eps=0.0, sumRoot=False, kern=dsm.IsoSE(0.0, 0.0)),
+            "eps0": dict(N=12000, D=2, V=3, K=3, M=200, depth=2, eps=0.0, sumRoot=True, kern=dsm.IsoSE(0.0, 0.0))}
+    c = cfgs[case]
+    x, y = synth(c["N"], c["D"], 71, sorted1d=True)
+    cfg = st.DSMGPConfig(None, c["kern"], -1.0, c["M"], c["K"], c["V"], c["depth"], c["eps"], c["sumRoot"])
+    t0 = time.perf_counter()
+    r_host = st.buildTree(x, y, cfg, np.random.default_rng(5))
+    t1 = time.perf_counter()
+    r_dev = st.buildTree_device(x, y, cfg, np.random.default_rng(5))
+    t2 = time.perf_counter()
+    fh, lh = st.flatten(r_host)
+    fd, ld = st.flatten(r_dev)
+    for k, v in fh.as_dict().items():
+        assert np.array_equal(np.asarray(v), np.asarray(fd.as_dict()[k])), k
+    assert len(lh) == len(ld)
+    for a, b in zip(lh, ld):
+        assert np.array_equal(a.obs, b.obs) and a.mean == b.mean and a.kernelid == b.kernelid and a.nobs == b.nobs
+        assert np.array_equal(a.lb, b.lb) and np.array_equal(a.ub, b.ub)
+    print(f"\n[device tree] {case}: {len(lh)} experts, host builder {t1 - t0:.3f} s, device-backed builder {t2 - t1:.3f} s")
