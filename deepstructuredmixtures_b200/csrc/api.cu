@@ -4,6 +4,10 @@
 
 using namespace dsm;
 
+#ifndef DSM_TRTRI_GROUP_DEFAULT
+#define DSM_TRTRI_GROUP_DEFAULT 1
+#endif
+
 namespace dsm {
 std::string& create_error() { static thread_local std::string e; return e; }
 BufCache g_cache;
@@ -264,6 +268,37 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
         if (a.grp != c.grp) return a.grp < c.grp;
         if (a.slot != c.slot) return a.slot < c.slot;
         return a.J < c.J; });
+      // L2 reuse by task order (DSMGP_TRTRI_GROUP = G > 1): consecutive tasks are claimed by different SMs at nearly the same
+      // time and stream their k-blocks in lockstep, so tasks that READ THE SAME TILES should be neighbours in the list.  Tile
+      // (I, J) reads X^T of block column J and L of block row I: the tiles of a G x G group of the (I, J) plane share each
+      // operand G ways.  Groups are ordered by THEIR anti-diagonal (still topological: a tile only depends on tiles above it in
+      // its own column, which lie in the same group -- row-major inside a group -- or in a group of a smaller anti-diagonal).
+      {
+        const char* ge = getenv("DSMGP_TRTRI_GROUP");
+        const int G = ge ? std::max(1, atoi(ge)) : (stretch ? 1 : DSM_TRTRI_GROUP_DEFAULT);
+        if (G > 1) {
+          struct GK { int level, slot, gi, gj, I, J; };
+          std::vector<GK> gv;
+          const int max_ng = (b.max_nb + G - 1) / G;
+          for (int s = b.s0; s < b.s1; s++) {
+            const LeafMeta& m = h->meta[s];
+            const int sl = s - b.s0, ng = (m.nb + G - 1) / G, shift = max_ng - ng;
+            for (int J = 0; J < m.nb; J++)
+              for (int I = J + 1; I < m.nb; I++) {
+                const int gi = I / G, gj = J / G, gd = gi - gj;
+                const int level = start_together ? gd : stretch ? (int)(((int64_t)gd * 64 * max_ng) / ng) : (gd + shift) * 64;
+                gv.push_back({level, sl, gi, gj, I, J});
+              }
+          }
+          std::stable_sort(gv.begin(), gv.end(), [](const GK& a, const GK& c) {
+            if (a.level != c.level) return a.level < c.level;
+            if (a.slot != c.slot) return a.slot < c.slot;
+            if (a.gj != c.gj) return a.gj < c.gj;
+            if (a.I != c.I) return a.I < c.I;
+            return a.J < c.J; });
+          for (size_t i = 0; i < gv.size(); i++) iv[i] = {0, 0, gv[i].slot, gv[i].I, gv[i].J};
+        }
+      }
       std::vector<int4> it(iv.size());
       for (size_t i = 0; i < iv.size(); i++) it[i] = make_int4(iv[i].slot, iv[i].I, iv[i].J, 0);
       b.n_trtri3 = (int)it.size();
@@ -806,6 +841,26 @@ extern "C" int32_t dsmgp_set_sharing(dsmgp_handle* h, const double* overlap, dou
   // map to local slots: source and dependent must live in the same batch of the same rank
   std::vector<int> slot_batch(std::max(ns, 1), -1);
   for (size_t bi = 0; bi < h->batches.size(); bi++) for (int s = h->batches[bi].s0; s < h->batches[bi].s1; s++) slot_batch[s] = (int)bi;
+  // Continuing behind copied block rows costs a copy kernel and a second Cholesky launch per batch (~0.3 ms of launch and tail
+  // latency, measured on the 10,000 x 1 model): the branch is only taken when the factorisation work it removes from a batch is
+  // worth more than that (DSMGP_SHARE_MIN_FLOPS, default 1.5e10 flop ~ 0.5 ms at 30 TFLOP/s).  Aliases always pay.
+  {
+    const char* mf = getenv("DSMGP_SHARE_MIN_FLOPS");
+    const double min_flops = mf ? atof(mf) : 1.5e10;
+    std::vector<double> saved(h->batches.size(), 0.0);
+    for (int64_t l = 0; l < L; l++) {
+      const int s = h->leaf_slot[l];
+      if (sp.leaf_kind[l] != SHARE_PREFIX || s < 0) continue;
+      const int ss = h->leaf_slot[sp.leaf_src[l]];
+      if (ss < 0 || slot_batch[s] != slot_batch[ss]) continue;
+      const double k = (double)blocks[l] * BLK;
+      saved[slot_batch[s]] += k * k * k / 3.0;
+    }
+    for (int64_t l = 0; l < L; l++) {
+      const int s = h->leaf_slot[l];
+      if (sp.leaf_kind[l] == SHARE_PREFIX && s >= 0 && saved[slot_batch[s]] < min_flops) { sp.leaf_kind[l] = SHARE_NONE; sp.leaf_src[l] = -1; blocks[l] = 0; }
+    }
+  }
   for (int64_t l = 0; l < L; l++) {
     const int s = h->leaf_slot[l];
     if (sp.leaf_kind[l] == SHARE_NONE) continue;

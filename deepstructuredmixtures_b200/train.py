@@ -15,6 +15,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from .model import LeafGP, Model, fit_, leftGP, update_cholesky_
+from .structure import GPSumNode
 
 
 class _Optimiser:
@@ -146,30 +147,60 @@ def train_gp_(gp: LeafGP, *, optim=None, iterations: int = 10_000, lam: float = 
     return gp, ell
 
 
-def finetune_(model: Model, optim=None, *, iterations: int = 1000, lam: float = 0.5, batch: int = 256):
+def finetune_(model: Model, optim=None, *, iterations: int = 1000, lam: float = 0.5, batch: int = 256,
+              strict_reference: bool = False):
     """finetune!(model, optim; iterations, λ) finetuning.jl:3-88: per-leaf hyper-parameters.  For every leaf g the
     WHOLE model is evaluated under θ_g and the leaf gradients are weighted by the overlap row D[g,:]
     (optimize.jl:92-102; the diagonal of D is 0, so a leaf's own gradient has weight 0).
-    Kernel mixtures raise, as in the reference (App. B Q10).
+
+    Kernel mixtures (`KernelFunction[...]`): the reference indexes a single kernel's 3-vector as if it held every kernel's
+    parameters and throws a BoundsError (finetuning.jl:41; `strict_reference=True` reproduces that).  The
+    library defines the semantics the code was reaching for: every expert keeps ITS OWN kernel's theta; the evaluation anchored at
+    expert g sets, for every kernel k, theta_k of the whole model to the theta of the kernel-k expert of g's REGION (the siblings
+    under g's kernel-mixture sum node, treeStructure.jl:258-286), and g is updated from the slice of the gradient that belongs to
+    its own kernel (optimize.jl:76-89).  BASELINE.json config 4 ("gPoE warm-start then DSMGP finetune!") runs this way.
 
     The L evaluations of one iteration are independent (hyp[g] is only updated from its own gradient), so they go to the
     device as ONE `dsmgp_finetune_eval` call; `batch` bounds how many anchors share a call."""
     optim = ADAM() if optim is None else optim
-    if len(model.kernels) != 1:
+    nk = len(model.kernels)
+    if nk != 1 and strict_reference:
         raise IndexError("finetune! with a kernel vector is a BoundsError in the reference (finetuning.jl:41)")
     L = len(model.leaves)
     D = model.D
     hyp = [model.handle.get_leaf_params(g).copy() for g in range(L)]         # :24
+    # region of every expert: the experts (one per kernel, in kernel order) under its kernel-mixture sum node, or itself
+    koff = np.concatenate([[0], np.cumsum([k.nparams for k in model.kernels])])
+    region = {}
+    if nk > 1:
+        def rec(n):
+            if isinstance(n, GPSumNode) and n.kernel_mixture:
+                ids = [c.leaf_index for c in n.children]
+                for g in ids:
+                    region[g] = ids
+                return
+            for c in getattr(n, "children", []):
+                rec(c)
+        rec(model.root)
+
+    def full_theta(g):
+        return hyp[g] if nk == 1 else np.concatenate([hyp[s] for s in region[g]])
+
+    def own_slice(g, grad):
+        if nk == 1:
+            return grad
+        k = model.leaves[g].kernelid - 1
+        return grad[koff[k]:koff[k + 1]]
     ell = np.zeros(iterations)
     c = 0
     for it in range(iterations):
         l = 0.0
         for g0 in range(0, L, batch):
             gs = list(range(g0, min(L, g0 + batch)))
-            leaf_lml, grads, _ = model.handle.finetune_eval(gs, np.stack([hyp[g] for g in gs]), D)   # :41-54
+            leaf_lml, grads, _ = model.handle.finetune_eval(gs, np.stack([full_theta(g) for g in gs]), D)   # :41-54
             for i, g in enumerate(gs):
                 l += leaf_lml[i]                                             # :51
-                grad = grads[i].copy()
+                grad = own_slice(g, grads[i]).copy()
                 optim.apply_(hyp[g], grad)
                 hyp[g] = hyp[g] + grad
         ell[it] = l

@@ -236,7 +236,7 @@ def test_full_size_cfg5_streamed_against_oracle():
 # 3. the shared Cholesky of fit! (fit.jl:71-122)
 # ---------------------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("case", ["sorted1d", "eps0", "eps0_ard"])
-def test_shared_cholesky_equals_full_refactorisation(case):
+def test_shared_cholesky_equals_full_refactorisation(case, monkeypatch):
     """dsmgp_fit(tau, overlap): identical experts factored once, common leading block rows copied, the rest continued --
     every result against the naive fit (every expert on its own) to 1e-12: LML table, alpha, factors, gradients, predictions."""
     import deepstructuredmixtures_b200 as dsm
@@ -245,6 +245,7 @@ def test_shared_cholesky_equals_full_refactorisation(case):
             "eps0": dict(N=4000, D=1, V=3, K=3, M=200, eps=0.0, seed=5, kern=dsm.IsoSE(0.0, 0.0)),
             "eps0_ard": dict(N=5000, D=2, V=3, K=3, M=200, eps=0.0, seed=8, kern=dsm.ArdSE(np.zeros(2), 0.0))}
     c = cfgs[case]
+    monkeypatch.setenv("DSMGP_SHARE_MIN_FLOPS", "0")      # these models are small: take the continue branch however little it saves
     x, y = synth(c["N"], c["D"], c["seed"], sorted1d=True)
     cfg = st.DSMGPConfig(None, c["kern"], -1.0, c["M"], c["K"], c["V"], 2, c["eps"], True)
     root = st.buildTree(x, y, cfg, np.random.default_rng(c["seed"]))
@@ -303,12 +304,13 @@ def test_shared_cholesky_equals_full_refactorisation(case):
     naive.close(); shared.close()
 
 
-def test_all_three_sharing_branches_on_a_hand_made_structure():
+def test_all_three_sharing_branches_on_a_hand_made_structure(monkeypatch):
     """Three experts under one sum node: A = rows 1..400, B = rows 1..700 (A is its leading part: chol_continue!, fit.jl:208-292),
     C = rows 1..400 (identical to A: copy, :132-143).  B must produce ITS OWN z = L^-1 y, log-det, LML and alpha behind the
     three block rows it takes from A; C reads A's results."""
     from deepstructuredmixtures_b200 import _native as nat, kernels as kr
     from deepstructuredmixtures_b200._handle import Handle
+    monkeypatch.setenv("DSMGP_SHARE_MIN_FLOPS", "0")
     rng = np.random.default_rng(3)
     N = 700
     x = np.sort(rng.random((N, 1)), axis=0); y = np.sin(6 * x[:, 0]) + 0.1 * rng.standard_normal(N)
@@ -606,3 +608,43 @@ def test_device_tree_construction_is_bit_identical(case):
         assert np.array_equal(a.obs, b.obs) and a.mean == b.mean and a.kernelid == b.kernelid and a.nobs == b.nobs
         assert np.array_equal(a.lb, b.lb) and np.array_equal(a.ub, b.ub)
     print(f"\n[device tree] {case}: {len(lh)} experts, host builder {t1 - t0:.3f} s, device-backed builder {t2 - t1:.3f} s")
+
+
+def test_finetune_on_a_kernel_mixture_cfg4_workflow():
+    """BASELINE config 4's workflow at reduced size: gPoE warm start, then a DSMGP over KernelFunction[IsoSE, IsoLinear] fine-tuned
+    with per-expert theta.  The reference throws a BoundsError for kernel vectors (finetuning.jl:41, App. B Q10); the library's
+    semantics (an anchor expert evaluates the model under its REGION's theta, one slice per kernel) are checked against the
+    oracle evaluated anchor by anchor."""
+    import deepstructuredmixtures_b200 as dsm
+    x, y = synth(1500, 3, 83)
+    kern = [dsm.IsoSE(0.0, 0.0), dsm.IsoLinear(0.0)]
+    warm = dsm.buildPoE(x, y, 3, M=200, kernel=dsm.IsoSE(0.0, 0.0), logNoise=-1.0, generalized=True, rng=83)
+    _, ell_w = dsm.train_(warm, dsm.ADAM(0.01), iterations=5, randinit=False)
+    th_w = warm.handle.get_leaf_params(0)
+    warm.close()
+    model = dsm.buildDSMGP(x, y, 2, 3, M=150, kernel=kern, logNoise=-1.0, rng=83)
+    with pytest.raises(IndexError):
+        dsm.finetune_(model, dsm.ADAM(), iterations=1, strict_reference=True)
+    L = len(model.leaves)
+    theta0 = np.concatenate([th_w, [0.2, 0.0, -0.9]])
+    model.setparams_(theta0)
+    D = model.D
+    # one finetune iteration by hand through the oracle: anchor g, region theta, weights D[g,:], own-kernel slice
+    hyp = [model.handle.get_leaf_params(g).copy() for g in range(L)]
+    g = 3
+    region = [l for l in range(L) if np.array_equal(model.leaves[l].obs, model.leaves[g].obs)]
+    region.sort(key=lambda l: model.leaves[l].kernelid)
+    th_g = np.concatenate([hyp[l] for l in region])
+    o_root = oracle_tree(model)
+    o_lml, o_grad, o_ell, _ = orc.evaluate(o_root, th_g, Drow=D[g, :])
+    ll, gr, rl = model.handle.finetune_eval([g], th_g[None, :], D)
+    assert abs(rl[0] - o_lml) <= LML_TOL * abs(o_lml)
+    assert np.all(np.abs(gr[0] - o_grad) <= GRAD_TOL * np.maximum(np.abs(o_grad), 1e-6 * np.max(np.abs(o_grad)) + 1e-12))
+    m2, ell = dsm.finetune_(model, dsm.ADAM(0.01), iterations=2)
+    assert ell.size == 2 and np.all(np.isfinite(ell))
+    k = model.leaves[g].kernelid - 1
+    assert not np.array_equal(m2.handle.get_leaf_params(g), theta0[3 * k:3 * k + 3])      # per-expert theta moved
+    dsm.update_(model)
+    mu, var = dsm.predict(model, np.random.default_rng(1).random((40, 3)))
+    assert np.all(np.isfinite(mu)) and np.all(var > 0)
+    model.close()
