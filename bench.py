@@ -438,6 +438,7 @@ def main():
                     ph[k] += tmm[k] / nrep
             line["mathematical"] = {"value": nrep / (ms * 1e-3), "unit": "evals/s", "ms_per_step": ms / nrep, "steps": nrep,
                                     "phases_ms_per_step": ph,
+                                    "lauum_tflops": tmm["potrf_flops"] / (ph["grad_ms"] * 1e-3) * 1e-12 if ph["grad_ms"] > 0 else None,
                                     "what": "same workload with as_written_grads=0: true d LML / d theta (adds the LAUUM pass with the fused dK traces)"}
             m3.close()
         if args.workload == "cfg3":

@@ -296,6 +296,42 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
             if (a.gj != c.gj) return a.gj < c.gj;
             if (a.I != c.I) return a.I < c.I;
             return a.J < c.J; });
+          // Stagger: inside a group the tile (I+1, J) needs (I, J) for its LAST k-block; two rows of one group claimed back to
+          // back reach that point together and the lower one would wait out the upper one's epilogue and store (measured:
+          // +11 % kernel time with plain row-major groups).  So the rows of DSMGP_TRTRI_STAGGER (default 4) consecutive groups
+          // are interleaved: row r of every group of the chunk, then row r+1, ... -- successors in a column are then >= 12
+          // list positions (~ 10 us of claim time) apart while the tiles they share are still in L2.
+          const char* se = getenv("DSMGP_TRTRI_STAGGER");
+          const int C = se ? std::max(1, atoi(se)) : 4;
+          if (C > 1) {
+            std::vector<GK> out; out.reserve(gv.size());
+            size_t i = 0;
+            while (i < gv.size()) {
+              // chunk = up to C groups of the same level
+              std::vector<std::pair<size_t, size_t>> grp;      // [begin, end) of each group in gv
+              const int lvl = gv[i].level;
+              size_t j = i;
+              while (j < gv.size() && gv[j].level == lvl && (int)grp.size() < C) {
+                size_t e = j;
+                while (e < gv.size() && gv[e].level == lvl && gv[e].slot == gv[j].slot && gv[e].gj == gv[j].gj) e++;
+                grp.push_back({j, e}); j = e;
+              }
+              std::vector<size_t> cur(grp.size());
+              for (size_t q = 0; q < grp.size(); q++) cur[q] = grp[q].first;
+              bool any = true;
+              while (any) {
+                any = false;
+                for (size_t q = 0; q < grp.size(); q++) {
+                  if (cur[q] >= grp[q].second) continue;
+                  const int row = gv[cur[q]].I;
+                  while (cur[q] < grp[q].second && gv[cur[q]].I == row) out.push_back(gv[cur[q]++]);
+                  any = true;
+                }
+              }
+              i = j;
+            }
+            gv.swap(out);
+          }
           for (size_t i = 0; i < gv.size(); i++) iv[i] = {0, 0, gv[i].slot, gv[i].I, gv[i].J};
         }
       }
@@ -658,7 +694,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
       }
     }
     h->tm.potrf_flops += pf;
-    h->tm.inverse_flops += with_grad ? pf * (lau ? 2.0 : 1.0) : 0.0;
+    h->tm.inverse_flops += with_grad ? pf : 0.0;      // the triangular inverse (inverse_ms); a LAUUM pass (grad_ms) is n^3/3 once more
     h->tm.gram_bytes += gb;
   }
   #undef EV_RECORD

@@ -281,7 +281,8 @@ int32_t dsmgp_host_shard(int64_t L, const int64_t* leaf_ptr, int32_t world, int3
 /* ---- instrumentation ------------------------------------------------------------------------ */
 typedef struct {
   double gram_ms, potrf_ms, solve_ms, inverse_ms, grad_ms, tree_ms, total_ms;
-  double potrf_flops, inverse_flops, gram_bytes;   /* algorithmic work of the last eval (local leaves) */
+  double potrf_flops, inverse_flops, gram_bytes;   /* algorithmic work of the last eval (local leaves): Cholesky (potrf_ms), triangular
+                                                      inverse (inverse_ms; the LAUUM pass inside grad_ms is the same count again), Gram */
   int64_t launches;                                 /* kernels launched by the last call */
   double predict_ms, predict_flops, predict_bytes;  /* last dsmgp_predict / dsmgp_leaf_predict: device time of predict_kernel,
                                                        sum_l (n_l^2 T_l + 2 n_l T_l) flop, bytes of L + x + xt read */
