@@ -344,6 +344,10 @@ def main():
         potrf_tf /= world; inv_tf /= world; gram_gbs /= world
         dom = "trtri3_kernel" if phase["inverse_ms"] >= phase["potrf_ms"] else "potrf2_kernel"
         ach = inv_tf if dom == "trtri3_kernel" else potrf_tf
+        if inv_fl > 0 and phase["inverse_ms"] < 0.02 * phase["potrf_ms"]:
+            # small shards run the factorisation and the inverse as ONE persistent launch (csrc/fused2.cuh): one phase, one rate
+            dom = "eval2_kernel"
+            ach = potrf_tf = inv_tf = (potrf_fl + inv_fl) * args.steps / ((phase["potrf_ms"] + phase["inverse_ms"]) * 1e-3) * 1e-12 / world
         # DRAM bytes per launch from `ncu --set full` (profiles/ncu_full_*_r01e.csv); only known for the profiled config
         traffic, traffic_src = ncu_traffic_gb(dom, args.workload, world)
         pk = fp64_peaks()

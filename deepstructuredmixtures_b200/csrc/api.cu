@@ -339,6 +339,25 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       for (size_t i = 0; i < iv.size(); i++) it[i] = make_int4(iv[i].slot, iv[i].I, iv[i].J, 0);
       b.n_trtri3 = (int)it.size();
       CUDA_TRY(h, upload(&b.d_trtri3_tasks, it));
+      {   // the same tiles in the order of the fused launch: level of block row I in the factorisation's order, then row-major
+        std::vector<TK> mv;
+        for (int s = b.s0; s < b.s1; s++) {
+          const LeafMeta& m = h->meta[s];
+          const int sl = s - b.s0, shift = b.max_nb - m.nb;
+          for (int I = 1; I < m.nb; I++) {
+            const int lvl = start_together ? I * 1024 : stretch ? (int)(((int64_t)I * 1024 * b.max_nb) / m.nb) : (I + shift) * 1024;
+            for (int J = 0; J < I; J++) mv.push_back({lvl, I, sl, I, J});
+          }
+        }
+        std::stable_sort(mv.begin(), mv.end(), [](const TK& a, const TK& c) {
+          if (a.s != c.s) return a.s < c.s;
+          if (a.slot != c.slot) return a.slot < c.slot;
+          if (a.I != c.I) return a.I < c.I;
+          return a.J < c.J; });
+        std::vector<int4> mt(mv.size());
+        for (size_t i = 0; i < mv.size(); i++) mt[i] = make_int4(mv[i].slot, mv[i].I, mv[i].J, 0);
+        CUDA_TRY(h, upload(&b.d_trtri3m_tasks, mt));
+      }
       // back-substitution tasks (slot, J): level = distance from the bottom (a task depends on the tasks below it)
       std::vector<TK> sv;
       for (int s = b.s0; s < b.s1; s++) {
@@ -386,6 +405,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
   h->share.slot.assign(std::max(ns, 1), make_int4(0, 0, 0, 0));
   h->exec_slot = h->leaf_slot;
   CUDA_TRY(h, h->d_flags.alloc(std::max<int64_t>(maxFlags, 1)));
+  CUDA_TRY(h, h->d_flags2.alloc(std::max<int64_t>(maxFlags, 1)));
   CUDA_TRY(h, h->d_ldpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
   CUDA_TRY(h, h->d_zzpart.alloc(std::max<int64_t>(maxTr / 2, 1)));
   CUDA_TRY(h, h->d_apart.alloc(std::max<int64_t>(maxFlags, 1) * BLK));
@@ -624,6 +644,20 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
       Potrf2Args pa{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_y.p, h->d_z.p, scal, h->d_trpart.p, b.d_trpart_off,
                     h->d_ldpart.p, h->d_zzpart.p, h->d_flags.p, b.d_flag_off, b.d_potrf2_tasks, b.n_potrf2,
                     h->d_counter.p + 4, h->d_counter.p + GERR, 0, share_b, nullptr};
+      // One launch for the factorisation and the inverse (fused2.cuh) when the batch is small enough for the tails of two
+      // separate launches to matter (multi-GPU shards): DSMGP_FUSED_EVAL=0|1 overrides.
+      const char* fe = getenv("DSMGP_FUSED_EVAL");
+      const bool fused = with_grad && !shr && b.n_trtri3 > 0 && !getenv("DSMGP_TRACE_FILE") &&
+                         (fe ? fe[0] == '1' : nsl * 4 < sms);
+      if (fused) {
+        CUDA_TRY(h, cudaMemsetAsync(h->d_flags2.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
+        Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
+                      h->d_flags2.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, b.d_trtri3m_tasks, b.n_trtri3,
+                      h->d_counter.p, h->d_counter.p + GERR, mask_all ? mask_all + b.s0 : nullptr};
+        launch_eval2(pa, ta, std::min(sms, b.n_potrf2 + b.n_trtri3), b.d_trtri_tasks, b.n_trtri, st);
+        h->tm.launches += 2;
+        EV_RECORD(ev[3]); EV_RECORD(ev[4]);
+      } else {
       if (shr) {
         // shared Cholesky (fit.jl:71-122): the experts that are factored on their own first, then the leading block rows
         // of the SHARE_PREFIX experts are copied from their sources and their factorisation continues behind them
@@ -666,6 +700,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
         launch_trtri3(ta, std::max(1, std::min(sms, b.n_trtri3)), b.d_trtri_tasks, b.n_trtri, st);
         h->tm.launches += 2;
       }
+      }   // !fused
     }
     EV_RECORD(ev[5]);
     if (lau) {

@@ -45,6 +45,8 @@ struct Batch {
   int4* d_potrf2_B = nullptr; int n_potrf2_B = 0;
   int* d_prefix_slots = nullptr; int n_prefix = 0, max_jb = 0;   // batch-relative slots of the SHARE_PREFIX experts
   int4* d_trtri3_tasks = nullptr; int n_trtri3 = 0;     // inverse: tile tasks by anti-diagonal
+  int4* d_trtri3m_tasks = nullptr;                      // inverse tiles in the order of the fused launch (fused2.cuh): by the level at
+                                                        // which their block row completes in the factorisation, then row-major
   int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
@@ -174,6 +176,7 @@ struct dsmgp_handle {
   DevBuf<LeafScal> d_scal;
   DevBuf<int> d_counter;
   DevBuf<int> d_flags;
+  DevBuf<int> d_flags2;              // second per-tile flag array: the inverse's flags when it shares a launch with the factorisation
   DevBuf<double> d_ldpart, d_zzpart;
   DevBuf<double> d_apart, d_tpart;   // per-tile partials of the tile-pipelined inverse
   DevBuf<double> p_xt, p_VT, p_mu, p_var, p_part; DevBuf<PredLeaf> p_pl; DevBuf<int2> p_tasks;   // predict scratch (grow-only)
@@ -215,8 +218,9 @@ struct dsmgp_handle {
     for (auto& b : batches) {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
       cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
-      cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots);
+      cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots); cudaFree(b.d_trtri3m_tasks);
     }
+    d_flags2.free();
     d_share.free(); d_comm_buf.free();
     dsm::comm_destroy(comm);
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();

@@ -101,6 +101,27 @@ struct PotrfGen {
 // Producer warp: claims tasks in list order and streams their chunks into the ring, running ahead of the MMA warps by
 // up to NS2 stages ACROSS task boundaries.  A diagonal tile reuses the ring as scratch for its factorisation, so after
 // the last chunk of a diagonal task the producer waits until the consumers hand the ring back (aux[0]).
+// One claimed task: stream its chunks into the ring.  Returns false when the kernel must stop (abort).
+__device__ __forceinline__ bool potrf2_produce_task(Pipe& p, const Potrf2Args& a, PotrfGen& gen, int ti, uint32_t& scratch_phase) {
+  if (a.share != nullptr && a.share[a.tasks[ti].x].x == SHARE_ALIAS) return true;     // the source expert's results are reused
+  gen.load(a, ti);
+  if (gen.total() == 0) {                               // already final: publish and move on
+    if ((threadIdx.x & 31) == 0) st_release(const_cast<int*>(gen.flags) + tile_flag_index(gen.I, gen.J), 1);
+    return true;
+  }
+  ChunkDesc d;
+  bool first = true;
+  while (gen.next(d)) { p.issue(d, first ? &gen.h : nullptr); first = false; }
+  if (gen.diag) { p.wait_bar(&p.aux[0], scratch_phase & 1, 5); scratch_phase++; }
+  return !*p.abort;
+}
+
+__device__ __forceinline__ void pipe_end(Pipe& p) {       // header with kind < 0 ends the consumers
+  TaskHdr h; h.kind = -1;
+  ChunkDesc d; d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
+  p.issue(d, &h);
+}
+
 __device__ __forceinline__ void potrf2_producer(Pipe& p, const Potrf2Args& a) {
   PotrfGen gen;
   uint32_t scratch_phase = 0;
@@ -109,21 +130,174 @@ __device__ __forceinline__ void potrf2_producer(Pipe& p, const Potrf2Args& a) {
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
     const int ti = __shfl_sync(0xffffffffu, t, 0);
     if (ti >= a.ntasks) break;
-    if (a.share != nullptr && a.share[a.tasks[ti].x].x == SHARE_ALIAS) continue;     // the source expert's results are reused
-    gen.load(a, ti);
-    if (gen.total() == 0) {                               // already final: publish and move on
-      if ((threadIdx.x & 31) == 0) st_release(const_cast<int*>(gen.flags) + tile_flag_index(gen.I, gen.J), 1);
-      continue;
-    }
-    ChunkDesc d;
-    bool first = true;
-    while (gen.next(d)) { p.issue(d, first ? &gen.h : nullptr); first = false; }
-    if (gen.diag) { p.wait_bar(&p.aux[0], scratch_phase & 1, 5); scratch_phase++; }
-    if (*p.abort) break;
+    if (!potrf2_produce_task(p, a, gen, ti, scratch_phase)) break;
   }
-  TaskHdr h; h.kind = -1;
-  ChunkDesc d; d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
-  p.issue(d, &h);
+  pipe_end(p);
+}
+
+// Consumer side of one task (all 8 MMA warps): `st` = stage of the task's first chunk, `hd` its header.
+// done_flags (or null): per-tile flag array in which a diagonal task marks entry (J, J) once EVERYTHING it writes (L_JJ, W_J,
+// W_J^T, z_J, the partial sums) is in memory -- the inverse tiles of the fused evaluation kernel wait on it.
+__device__ __forceinline__ void potrf2_consume(Pipe& p, const Potrf2Args& a, const TaskHdr& hd, int st, double* smem,
+                                               double* s_red, double* s_v, int* s_info_p, int* done_flags) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slab = warp_slab(), r0 = 16 * slab;
+  int& s_info = *s_info_p;
+  const LeafMeta m = a.meta[hd.slot];
+  const int I = hd.I, J = hd.J;
+  const int i0 = I * BLK, j0 = J * BLK;
+  const int wi = hd.wi, wj = hd.wj;
+  double* F = a.F + m.foff;
+  int* flags = a.flags + a.flag_off[hd.slot];
+  double* Wj = a.W + m.woff + (int64_t)J * WBLK_D;
+  const int nkc = m.nkc;
+  const bool diag = (hd.kind == 1);
+  const bool active = r0 < wi;
+  const bool prefactored = (J < hd.pad0);      // chol_continue / shared prefix: column already final, diag only rebuilds W and z
+  const int n_c = hd.n_c, n_main = hd.n_main;
+  long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)hd.ti * 8 : nullptr;
+  if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = (long long)sm | ((long long)I << 16) | ((long long)J << 32); }
+
+  // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
+  Acc2 acc;
+  acc2_zero(acc);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    if (e < n_c) {
+      if (e > 0) st = p.wait();
+      if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
+      p.release();
+    }
+  }
+
+  if (trc) trc[1] = clock64();
+  if (!diag) {
+    // ---------------- panel tile ----------------
+    for (int c = 0; c < n_main; c++) {
+      st = p.wait();
+      if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
+      p.release();
+    }
+    if (trc) trc[2] = clock64();
+    // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
+    tri_epilogue(p, acc, wj / 32, active, -1.0);
+    if (trc) trc[3] = clock64();
+    acc2_store(acc, F, nkc, i0, j0, wi, wj);
+  } else {
+  // ---------------- diagonal tile ----------------
+  double gemv = 0.0;                                  // row r0 + (lane & 15), k-half lane >> 4
+  {
+    const int ng = min(wj / 16, slab + 1);            // lower triangle only: 16-column groups 0 .. slab
+    for (int c = 0; c < n_main; c++) {
+      st = p.wait();
+      if (active) {
+        const double* sA = p.A(st);
+        if (!prefactored) switch (ng) {
+          case 1: mma_chunk16<1>(acc, sA, sA, r0); break;
+          case 2: mma_chunk16<2>(acc, sA, sA, r0); break;
+          case 3: mma_chunk16<3>(acc, sA, sA, r0); break;
+          case 4: mma_chunk16<4>(acc, sA, sA, r0); break;
+          case 5: mma_chunk16<5>(acc, sA, sA, r0); break;
+          case 6: mma_chunk16<6>(acc, sA, sA, r0); break;
+          case 7: mma_chunk16<7>(acc, sA, sA, r0); break;
+          default: mma_chunk16<8>(acc, sA, sA, r0); break;
+        }
+        const double* zs = p.B(st);
+        const double* ar = sA + r0 + (lane & 15) + (lane >> 4) * 8 * LDS;
+#pragma unroll
+        for (int k = 0; k < 8; k++) gemv = fma(ar[k * LDS], zs[(lane >> 4) * 8 + k], gemv);
+      }
+      p.release();
+    }
+  }
+  if (trc) trc[2] = clock64();
+  gemv += __shfl_xor_sync(0xffffffffu, gemv, 16);
+  csync();                                             // every warp is done with the ring: stages become scratch
+  double* S = smem;                                    // resident tile [c][LDS] (stages 0..3)
+  double* aux = smem + 4 * STAGE_DOUBLES;              // stage 4: scratch
+  if (active) {
+#pragma unroll
+    for (int n = 0; n < 16; n++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int c = acc_col(n, e);
+        if (c < wj) *reinterpret_cast<double2*>(S + c * LDS + acc_row(0)) = make_double2(-acc[0][n][e], -acc[1][n][e]);
+      }
+    if (lane < 16) s_v[r0 + lane] = gemv;
+  }
+  csync();
+  {
+    const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info, trc ? trc + 6 : nullptr);
+    if (tid == 0 && info != 0) atomicCAS(&a.scal[hd.slot].info, 0, j0 + info);
+  }
+  if (trc) trc[3] = clock64();
+  const double* DI = aux;
+  // Critical path first: the panel tiles of this column wait for W_J and the next diagonal tile (transitively) for
+  // z_J, so those two are stored and the tile is PUBLISHED before the factor, W_J^T and the reductions are written.
+  double tr = 0.0;
+  for (int c = warp; c < BLK; c += NCONS / 32)
+    for (int r = lane; r < BLK; r += 32) {
+      double v = 0.0;
+      if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
+      Wj[widx(r, c)] = v;
+      if (j0 + r < m.n && j0 + c < m.n) tr += v * v;
+    }
+  // forward solve block: z_J = W_J (y_J - sum_K L_JK z_K)
+  if (tid < BLK) s_v[tid] = (tid < wj) ? a.y[m.voff + j0 + tid] - s_v[tid] : 0.0;
+  csync();
+  double zz = 0.0;
+  {
+    const int r = tid >> 1, h = tid & 1;              // 2 threads per row
+    double s = 0.0;
+    if (r < wj)
+      for (int k = h; k <= r; k += 2) s = fma(diag_W(S, DI, r, k), s_v[k], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    if (r < wj && h == 0) {
+      a.z[m.voff + j0 + r] = s;
+      if (j0 + r < m.n) zz = s * s;
+    }
+  }
+  csync();
+  if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
+  // off the critical path: L_JJ, W_J^T, log-det and the partial sums
+  if (!prefactored) {
+    for (int c = warp; c < wj; c += NCONS / 32) {
+      double* dst = F + tidx(j0, j0 + c, nkc);
+      for (int r = lane; r < wj; r += 32)
+        if (r >= c) dst[r] = S[c * LDS + r];
+    }
+  }
+  double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;
+  for (int r = warp; r < BLK; r += NCONS / 32)
+    for (int c = lane; c < BLK; c += 32) {
+      double v = 0.0;
+      if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
+      WTj[widx(c, r)] = v;
+    }
+  double ld = 0.0;
+  for (int r = tid; r < wj; r += NCONS)
+    if (j0 + r < m.n) ld += log(S[r * LDS + r]);
+  ld = block_sum_c(ld, s_red);
+  tr = block_sum_c(tr, s_red);
+  zz = block_sum_c(zz, s_red);
+  if (tid == 0) {
+    const int64_t po = a.trpart_off[hd.slot];
+    a.trpart[po + J] = tr;
+    a.ldpart[po / 2 + J] = 2.0 * ld;
+    a.zzpart[po / 2 + J] = zz;
+  }
+  fence_proxy_async();                                 // generic writes to the stages precede the next bulk copies
+  }   // diagonal tile
+  // ---------------- task boundary: publish a panel tile / hand the ring back to the producer after a diagonal tile
+  csync();
+  if (tid == 0) {
+    if (!diag) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
+    else {
+      if (done_flags != nullptr) { __threadfence(); st_release(done_flags + a.flag_off[hd.slot] + tile_flag_index(J, J), 1); }
+      mbar_arrive(&p.aux[0]);
+    }
+  }
+  if (trc) trc[4] = clock64();
 }
 
 __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
@@ -131,8 +305,7 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
   __shared__ double s_red[16];
   __shared__ double s_v[BLK];
   __shared__ int s_info;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slab = warp_slab(), r0 = 16 * slab;
+  const int warp = threadIdx.x >> 5;
   Pipe p;
   p.init(smem, a.gerr);
   if (warp >= NCONS / 32) {                          // producer warpgroup: one working warp, three that only donate registers
@@ -143,161 +316,10 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) potrf2_kernel(Potrf2Args a) {
   setmaxnreg_inc<REGS_CONSUMER>();
   for (;;) {
     // the first chunk of a task carries its header
-    int st = p.wait();
+    const int st = p.wait();
     const TaskHdr hd = p.hdr[st];
     if (hd.kind < 0 || *p.abort) return;
-    const LeafMeta m = a.meta[hd.slot];
-    const int I = hd.I, J = hd.J;
-    const int i0 = I * BLK, j0 = J * BLK;
-    const int wi = hd.wi, wj = hd.wj;
-    double* F = a.F + m.foff;
-    int* flags = a.flags + a.flag_off[hd.slot];
-    double* Wj = a.W + m.woff + (int64_t)J * WBLK_D;
-    const int nkc = m.nkc;
-    const bool diag = (hd.kind == 1);
-    const bool active = r0 < wi;
-    const bool prefactored = (J < hd.pad0);      // chol_continue / shared prefix: column already final, diag only rebuilds W and z
-    const int n_c = hd.n_c, n_main = hd.n_main;
-    long long* trc = (a.trace != nullptr && tid == 0) ? a.trace + (long long)hd.ti * 8 : nullptr;
-    if (trc) { trc[0] = clock64(); unsigned sm; asm("mov.u32 %0, %%smid;" : "=r"(sm)); trc[5] = (long long)sm | ((long long)I << 16) | ((long long)J << 32); }
-
-    // acc = -F_IJ: the tile arrives through the ring as the first wj/32 stages (two 16-column tiles per stage)
-    Acc2 acc;
-    acc2_zero(acc);
-#pragma unroll
-    for (int e = 0; e < 4; e++) {
-      if (e < n_c) {
-        if (e > 0) st = p.wait();
-        if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
-        p.release();
-      }
-    }
-
-    if (trc) trc[1] = clock64();
-    if (!diag) {
-      // ---------------- panel tile ----------------
-      for (int c = 0; c < n_main; c++) {
-        st = p.wait();
-        if (active) { if (wj == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0); }
-        p.release();
-      }
-      if (trc) trc[2] = clock64();
-      // X = C W_J^T = (-acc) W_J^T, in registers (M = W_J streamed through the ring)
-      tri_epilogue(p, acc, wj / 32, active, -1.0);
-      if (trc) trc[3] = clock64();
-      acc2_store(acc, F, nkc, i0, j0, wi, wj);
-    } else {
-    // ---------------- diagonal tile ----------------
-    double gemv = 0.0;                                  // row r0 + (lane & 15), k-half lane >> 4
-    {
-      const int ng = min(wj / 16, slab + 1);            // lower triangle only: 16-column groups 0 .. slab
-      for (int c = 0; c < n_main; c++) {
-        st = p.wait();
-        if (active) {
-          const double* sA = p.A(st);
-          if (!prefactored) switch (ng) {
-            case 1: mma_chunk16<1>(acc, sA, sA, r0); break;
-            case 2: mma_chunk16<2>(acc, sA, sA, r0); break;
-            case 3: mma_chunk16<3>(acc, sA, sA, r0); break;
-            case 4: mma_chunk16<4>(acc, sA, sA, r0); break;
-            case 5: mma_chunk16<5>(acc, sA, sA, r0); break;
-            case 6: mma_chunk16<6>(acc, sA, sA, r0); break;
-            case 7: mma_chunk16<7>(acc, sA, sA, r0); break;
-            default: mma_chunk16<8>(acc, sA, sA, r0); break;
-          }
-          const double* zs = p.B(st);
-          const double* ar = sA + r0 + (lane & 15) + (lane >> 4) * 8 * LDS;
-#pragma unroll
-          for (int k = 0; k < 8; k++) gemv = fma(ar[k * LDS], zs[(lane >> 4) * 8 + k], gemv);
-        }
-        p.release();
-      }
-    }
-    if (trc) trc[2] = clock64();
-    gemv += __shfl_xor_sync(0xffffffffu, gemv, 16);
-    csync();                                             // every warp is done with the ring: stages become scratch
-    double* S = smem;                                    // resident tile [c][LDS] (stages 0..3)
-    double* aux = smem + 4 * STAGE_DOUBLES;              // stage 4: scratch
-    if (active) {
-#pragma unroll
-      for (int n = 0; n < 16; n++)
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int c = acc_col(n, e);
-          if (c < wj) *reinterpret_cast<double2*>(S + c * LDS + acc_row(0)) = make_double2(-acc[0][n][e], -acc[1][n][e]);
-        }
-      if (lane < 16) s_v[r0 + lane] = gemv;
-    }
-    csync();
-    {
-      const int info = diag_factor_invert(S, wj, aux, !prefactored, &s_info, trc ? trc + 6 : nullptr);
-      if (tid == 0 && info != 0) atomicCAS(&a.scal[hd.slot].info, 0, j0 + info);
-    }
-    if (trc) trc[3] = clock64();
-    const double* DI = aux;
-    // Critical path first: the panel tiles of this column wait for W_J and the next diagonal tile (transitively) for
-    // z_J, so those two are stored and the tile is PUBLISHED before the factor, W_J^T and the reductions are written.
-    double tr = 0.0;
-    for (int c = warp; c < BLK; c += NCONS / 32)
-      for (int r = lane; r < BLK; r += 32) {
-        double v = 0.0;
-        if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
-        Wj[widx(r, c)] = v;
-        if (j0 + r < m.n && j0 + c < m.n) tr += v * v;
-      }
-    // forward solve block: z_J = W_J (y_J - sum_K L_JK z_K)
-    if (tid < BLK) s_v[tid] = (tid < wj) ? a.y[m.voff + j0 + tid] - s_v[tid] : 0.0;
-    csync();
-    double zz = 0.0;
-    {
-      const int r = tid >> 1, h = tid & 1;              // 2 threads per row
-      double s = 0.0;
-      if (r < wj)
-        for (int k = h; k <= r; k += 2) s = fma(diag_W(S, DI, r, k), s_v[k], s);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      if (r < wj && h == 0) {
-        a.z[m.voff + j0 + r] = s;
-        if (j0 + r < m.n) zz = s * s;
-      }
-    }
-    csync();
-    if (tid == 0) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
-    // off the critical path: L_JJ, W_J^T, log-det and the partial sums
-    if (!prefactored) {
-      for (int c = warp; c < wj; c += NCONS / 32) {
-        double* dst = F + tidx(j0, j0 + c, nkc);
-        for (int r = lane; r < wj; r += 32)
-          if (r >= c) dst[r] = S[c * LDS + r];
-      }
-    }
-    double* WTj = a.WT + m.woff + (int64_t)J * WBLK_D;
-    for (int r = warp; r < BLK; r += NCONS / 32)
-      for (int c = lane; c < BLK; c += 32) {
-        double v = 0.0;
-        if (r < wj && c < wj && r >= c) v = diag_W(S, DI, r, c);
-        WTj[widx(c, r)] = v;
-      }
-    double ld = 0.0;
-    for (int r = tid; r < wj; r += NCONS)
-      if (j0 + r < m.n) ld += log(S[r * LDS + r]);
-    ld = block_sum_c(ld, s_red);
-    tr = block_sum_c(tr, s_red);
-    zz = block_sum_c(zz, s_red);
-    if (tid == 0) {
-      const int64_t po = a.trpart_off[hd.slot];
-      a.trpart[po + J] = tr;
-      a.ldpart[po / 2 + J] = 2.0 * ld;
-      a.zzpart[po / 2 + J] = zz;
-    }
-    fence_proxy_async();                                 // generic writes to the stages precede the next bulk copies
-    }   // diagonal tile
-    // ---------------- task boundary: publish a panel tile / hand the ring back to the producer after a diagonal tile
-    csync();
-    if (tid == 0) {
-      if (!diag) { __threadfence(); st_release(flags + tile_flag_index(I, J), 1); }
-      else mbar_arrive(&p.aux[0]);
-    }
-    if (trc) trc[4] = clock64();
+    potrf2_consume(p, a, hd, st, smem, s_red, s_v, &s_info, nullptr);
   }
 }
 

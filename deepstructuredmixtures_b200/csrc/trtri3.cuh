@@ -31,14 +31,16 @@ struct Trtri3Gen {
   const double* F; const double* W; const double* WT; const int* flags;
   int nkc, I, J, nmain, nepi, c;
   bool allready;
+  const int* done;            // fused evaluation kernel: flags (J, J) / (I, I) of the factorisation's diagonal tasks, else null
   TaskHdr h;
-  __device__ __forceinline__ void load(const Trtri3Args& a, int ti) {
+  __device__ __forceinline__ void load(const Trtri3Args& a, int ti, int kind = 0, bool wait_factor = false) {
     const int4 tk = a.tasks[ti];
     const LeafMeta m = a.meta[tk.x];
     I = tk.y; J = tk.z; c = 0; allready = false;
     F = a.F + m.foff; W = a.W + m.woff; WT = a.WT + m.woff; nkc = m.nkc;
     flags = a.flags + a.flag_off[tk.x];
-    h.kind = 0; h.ti = ti; h.slot = tk.x; h.I = I; h.J = J;
+    done = wait_factor ? flags : nullptr;
+    h.kind = kind; h.ti = ti; h.slot = tk.x; h.I = I; h.J = J;
     h.wi = blk_width(m.np, I); h.wj = blk_width(m.np, J);
     nmain = (I - J) * (BLK / KC);
     nepi = tri_epilogue_nstages(h.wi / 32);
@@ -51,6 +53,9 @@ struct Trtri3Gen {
     if (c < n1) {                                        // K = J block: X_JJ = W_J
       d.a = WT + (int64_t)J * WBLK_D + c * TILE_D; d.abytes = TILE_BYTES;
       d.b = F + tile_off(I, J * n1 + c, nkc); d.bbytes = TILE_BYTES;
+      if (c == 0 && done != nullptr) {                   // fused kernel: block row I of L, W_I, z_I and W_J^T must be final
+        d.flag0 = done + tri_tile_index(J, J); d.flag1 = done + tri_tile_index(I, I);
+      }
     } else if (c < nmain) {
       const int kc = J * n1 + c, K = kc / n1;
       if ((c & (n1 - 1)) == 0 && !allready) {
@@ -72,6 +77,15 @@ struct Trtri3Gen {
   }
 };
 
+__device__ __forceinline__ bool trtri3_produce_task(Pipe& p, const Trtri3Args& a, Trtri3Gen& gen, int ti, int kind, bool wait_factor) {
+  if (a.mask != nullptr && a.mask[a.tasks[ti].x] == 0) return true;      // expert without a gradient request
+  gen.load(a, ti, kind, wait_factor);
+  ChunkDesc d;
+  bool first = true;
+  while (gen.next(d)) { p.issue(d, first ? &gen.h : nullptr); first = false; }
+  return !*p.abort;
+}
+
 __device__ __forceinline__ void trtri3_producer(Pipe& p, const Trtri3Args& a) {
   Trtri3Gen gen;
   for (;;) {
@@ -79,24 +93,78 @@ __device__ __forceinline__ void trtri3_producer(Pipe& p, const Trtri3Args& a) {
     if ((threadIdx.x & 31) == 0) t = atomicAdd(a.counter, 1);
     const int ti = __shfl_sync(0xffffffffu, t, 0);
     if (ti >= a.ntasks) break;
-    if (a.mask != nullptr && a.mask[a.tasks[ti].x] == 0) continue;      // expert without a gradient request
-    gen.load(a, ti);
-    ChunkDesc d;
-    bool first = true;
-    while (gen.next(d)) { p.issue(d, first ? &gen.h : nullptr); first = false; }
-    if (*p.abort) break;
+    if (!trtri3_produce_task(p, a, gen, ti, 0, false)) break;
   }
   TaskHdr h; h.kind = -1;
   ChunkDesc d; d.a = nullptr; d.b = nullptr; d.abytes = 0; d.bbytes = 0; d.flag0 = nullptr; d.flag1 = nullptr;
   p.issue(d, &h);
 }
 
+// Consumer side of one inverse tile (all 8 MMA warps): `st` = stage of the task's first chunk, `hd` its header.
+__device__ __forceinline__ void trtri3_consume(Pipe& p, const Trtri3Args& a, const TaskHdr& hd, int st, double* s_red, double (*s_z)[BLK]) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int slab = warp_slab(), r0 = 16 * slab;
+  const LeafMeta m = a.meta[hd.slot];
+  const int I = hd.I, J = hd.J, i0 = I * BLK, j0 = J * BLK, wi = hd.wi;
+  double* F = a.F + m.foff;
+  const double* z = a.z + m.voff;
+  Acc2 acc;
+  acc2_zero(acc);
+  {   // z_I for the fused alpha partial: latency hidden behind the contraction
+    double4 zv = make_double4(0.0, 0.0, 0.0, 0.0);
+    if (4 * lane < wi) {          // through L2: in the fused kernel z_I was written by another CTA of the same launch
+      const double2 za = __ldcg(reinterpret_cast<const double2*>(z + i0 + 4 * lane)), zb = __ldcg(reinterpret_cast<const double2*>(z + i0 + 4 * lane + 2));
+      zv = make_double4(za.x, za.y, zb.x, zb.y);
+    }
+    __syncwarp();
+    *reinterpret_cast<double4*>(&s_z[warp][4 * lane]) = zv;
+    __syncwarp();
+  }
+  for (int c = 0; c < hd.n_main; c++) {
+    if (c > 0) st = p.wait();
+    // K = J block: the A operand is W_J^T (A[row][k] = W_J[k][row] = 0 for k < row): chunk c is all zero for slabs > c
+    if (c >= BLK / KC || c >= slab) {
+      if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
+    }
+    p.release();
+  }
+  tri_epilogue(p, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
+  acc2_store(acc, F, m.nkc, j0, i0, BLK, wi);
+  // publish as early as possible: the tile below in this column is waiting for exactly this
+  csync();
+  int* flags = a.flags + a.flag_off[hd.slot];
+  const int64_t tile = a.flag_off[hd.slot] + tri_tile_index(I, J);
+  if (tid == 0) { __threadfence(); st_release(flags + tri_tile_index(I, J), 1); }
+  // fused partials: ||X_IJ||_F^2 over real rows/cols, (X_IJ^T z_I)[c]
+  double tr = 0.0, p0 = 0.0, p1 = 0.0;
+  const bool row0 = (j0 + acc_row(0)) < m.n, row1 = (j0 + acc_row(1)) < m.n;
+#pragma unroll
+  for (int n = 0; n < 16; n++) {
+    if (8 * n < wi) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int col = i0 + acc_col(n, e);
+        if (col < m.n) {
+          const double zi = s_z[warp][col - i0];
+          const double v0 = acc[0][n][e], v1 = acc[1][n][e];
+          if (row0) { tr = fma(v0, v0, tr); p0 = fma(v0, zi, p0); }
+          if (row1) { tr = fma(v1, v1, tr); p1 = fma(v1, zi, p1); }
+        }
+      }
+    }
+  }
+  p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
+  p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
+  if ((lane & 3) == 0) *reinterpret_cast<double2*>(a.apart + tile * BLK + acc_row(0)) = make_double2(p0, p1);   // rows 2g, 2g+1 adjacent
+  tr = block_sum_c(tr, s_red);
+  if (tid == 0) a.tpart[tile] = tr;
+}
+
 __global__ void __launch_bounds__(NTHREADS_PW, 1) trtri3_kernel(Trtri3Args a) {
   extern __shared__ __align__(16) double smem[];
   __shared__ double s_red[16];
   __shared__ __align__(32) double s_z[NCONS / 32][BLK];     // per-warp copy of z_I
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int slab = warp_slab(), r0 = 16 * slab;
+  const int warp = threadIdx.x >> 5;
   Pipe p;
   p.init(smem, a.gerr);
   if (warp >= NCONS / 32) {                          // producer warpgroup: one working warp, three that only donate registers
@@ -106,59 +174,10 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) trtri3_kernel(Trtri3Args a) {
   }
   setmaxnreg_inc<REGS_CONSUMER>();
   for (;;) {
-    int st = p.wait();                               // the first chunk of a task carries its header
+    const int st = p.wait();                         // the first chunk of a task carries its header
     const TaskHdr hd = p.hdr[st];
     if (hd.kind < 0 || *p.abort) return;
-    const LeafMeta m = a.meta[hd.slot];
-    const int I = hd.I, J = hd.J, i0 = I * BLK, j0 = J * BLK, wi = hd.wi;
-    double* F = a.F + m.foff;
-    const double* z = a.z + m.voff;
-    Acc2 acc;
-    acc2_zero(acc);
-    {   // z_I for the fused alpha partial: latency hidden behind the contraction
-      const double4 zv = (4 * lane < wi) ? *reinterpret_cast<const double4*>(z + i0 + 4 * lane) : make_double4(0.0, 0.0, 0.0, 0.0);
-      __syncwarp();
-      *reinterpret_cast<double4*>(&s_z[warp][4 * lane]) = zv;
-      __syncwarp();
-    }
-    for (int c = 0; c < hd.n_main; c++) {
-      if (c > 0) st = p.wait();
-      // K = J block: the A operand is W_J^T (A[row][k] = W_J[k][row] = 0 for k < row): chunk c is all zero for slabs > c
-      if (c >= BLK / KC || c >= slab) {
-        if (wi == BLK) mma_chunk<4>(acc, p.A(st), p.B(st), r0); else mma_chunk<2>(acc, p.A(st), p.B(st), r0);
-      }
-      p.release();
-    }
-    tri_epilogue(p, acc, wi / 32, true, -1.0);      // OUT = X_IJ^T  (rows c of block J, cols r of block I)
-    acc2_store(acc, F, m.nkc, j0, i0, BLK, wi);
-    // publish as early as possible: the tile below in this column is waiting for exactly this
-    csync();
-    int* flags = a.flags + a.flag_off[hd.slot];
-    const int64_t tile = a.flag_off[hd.slot] + tri_tile_index(I, J);
-    if (tid == 0) { __threadfence(); st_release(flags + tri_tile_index(I, J), 1); }
-    // fused partials: ||X_IJ||_F^2 over real rows/cols, (X_IJ^T z_I)[c]
-    double tr = 0.0, p0 = 0.0, p1 = 0.0;
-    const bool row0 = (j0 + acc_row(0)) < m.n, row1 = (j0 + acc_row(1)) < m.n;
-#pragma unroll
-    for (int n = 0; n < 16; n++) {
-      if (8 * n < wi) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const int col = i0 + acc_col(n, e);
-          if (col < m.n) {
-            const double zi = s_z[warp][col - i0];
-            const double v0 = acc[0][n][e], v1 = acc[1][n][e];
-            if (row0) { tr = fma(v0, v0, tr); p0 = fma(v0, zi, p0); }
-            if (row1) { tr = fma(v1, v1, tr); p1 = fma(v1, zi, p1); }
-          }
-        }
-      }
-    }
-    p0 += __shfl_xor_sync(0xffffffffu, p0, 1); p0 += __shfl_xor_sync(0xffffffffu, p0, 2);
-    p1 += __shfl_xor_sync(0xffffffffu, p1, 1); p1 += __shfl_xor_sync(0xffffffffu, p1, 2);
-    if ((lane & 3) == 0) *reinterpret_cast<double2*>(a.apart + tile * BLK + acc_row(0)) = make_double2(p0, p1);   // rows 2g, 2g+1 adjacent
-    tr = block_sum_c(tr, s_red);
-    if (tid == 0) a.tpart[tile] = tr;
+    trtri3_consume(p, a, hd, st, s_red, s_z);
   }
 }
 
