@@ -67,7 +67,7 @@ EXPORTS = [
     "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling",
     "dsmgp_set_sharing", "dsmgp_get_sharing", "dsmgp_infer", "dsmgp_reset_weights", "dsmgp_comm_unique_id", "dsmgp_comm_init", "dsmgp_host_sharing_plan",
     "dsmgp_part_create", "dsmgp_part_destroy", "dsmgp_part_size", "dsmgp_part_range", "dsmgp_part_sorted_column", "dsmgp_part_split",
-    "dsmgp_part_rows",
+    "dsmgp_part_rows", "dsmgp_overlap_csr",
 ]
 COMM_ID_BYTES = 128
 
@@ -111,6 +111,7 @@ def lib() -> C.CDLL:
         "dsmgp_predict_finish": (I32, [P, pd, I64, I32, pd, pd, pd]),
         "dsmgp_train": (I32, [P, I32, D, D, D, I32, I64, D, I64, pd, pd, pi64]),
         "dsmgp_overlap": (I32, [I64, I64, pi64, pi64, pi32, C.POINTER(Tree), pd]),
+        "dsmgp_overlap_csr": (I32, [I64, I64, pi64, pi64, pi32, C.POINTER(Tree), pi64, pi32, pd]),
         "dsmgp_release_cache": (None, []),
         "dsmgp_row_width": (I64, [P]),
         "dsmgp_eval_local_dev": (I32, [P, pd, I64, C.POINTER(C.c_void_p)]),

@@ -48,9 +48,10 @@ done:
 // potrf / chol_continue on one host matrix.  k = number of leading rows/cols that already hold a valid factor.
 // Runs the same persistent tile scheduler as the batched path (potrf2_kernel) on a one-expert batch.
 // getOverlap(spn, D, gpmap) fit.jl:12-39 on the device.
-extern "C" int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
-                                 const int32_t* leaf_kernel_id, const dsmgp_tree* tree, double* D) {
-  if (N <= 0 || L <= 0 || !leaf_ptr || !leaf_obs || !leaf_kernel_id || !tree || !D) { g_create_error = "overlap: bad argument"; return DSMGP_ERR_ARG; }
+// dense == true: D is the L x L column-major matrix.  dense == false: CSR by row (row_ptr[L+1] always; col / val when non-null).
+static int32_t overlap_core(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs, const int32_t* leaf_kernel_id,
+                            const dsmgp_tree* tree, bool dense, double* D, int64_t* row_ptr, int32_t* col, double* val) {
+  if (N <= 0 || L <= 0 || !leaf_ptr || !leaf_obs || !leaf_kernel_id || !tree || (dense && !D) || (!dense && !row_ptr)) { g_create_error = "overlap: bad argument"; return DSMGP_ERR_ARG; }
   HostTree t; std::string err;
   if (!t.load(tree, L, err)) { g_create_error = err; return DSMGP_ERR_ARG; }
   const int64_t total = leaf_ptr[L];
@@ -96,13 +97,52 @@ extern "C" int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, 
   OTRY(cudaMalloc(&d_kid, L * 4)); OTRY(cudaMemcpy(d_kid, kid.data(), L * 4, cudaMemcpyHostToDevice));
   OTRY(cudaMalloc(&d_anc, anc.size() * 4)); OTRY(cudaMemcpy(d_anc, anc.data(), anc.size() * 4, cudaMemcpyHostToDevice));
   OTRY(cudaMalloc(&d_nt, ntype.size() * 4)); OTRY(cudaMemcpy(d_nt, ntype.data(), ntype.size() * 4, cudaMemcpyHostToDevice));
-  OTRY(cudaMalloc(&d_D, (size_t)L * L * 8));
-  launch_ov_finish(d_inter, d_lp, d_kid, d_anc, AD, d_nt, L, d_D, nullptr);
-  OTRY(cudaGetLastError());
-  OTRY(cudaMemcpy(D, d_D, (size_t)L * L * 8, cudaMemcpyDeviceToHost));
+  if (dense) {
+    OTRY(cudaMalloc(&d_D, (size_t)L * L * 8));
+    launch_ov_finish(d_inter, d_lp, d_kid, d_anc, AD, d_nt, L, d_D, nullptr);
+    OTRY(cudaGetLastError());
+    OTRY(cudaMemcpy(D, d_D, (size_t)L * L * 8, cudaMemcpyDeviceToHost));
+  } else {
+    // sparse: only the non-zero entries leave the device (experts under different children of a common sum node that share
+    // observations, or differ in kernel id) -- the dense L x L double matrix (3.4 GB at L = 20,736) is never formed
+    int* d_rc = nullptr; int64_t* d_rp = nullptr; int32_t* d_col = nullptr; double* d_val = nullptr;
+    auto cleanup2 = [&]() { cudaFree(d_rc); cudaFree(d_rp); cudaFree(d_col); cudaFree(d_val); };
+    cudaError_t ce;
+    std::vector<int> rc(L);
+    if ((ce = cudaMalloc(&d_rc, L * 4)) == cudaSuccess) {
+      launch_ov_csr(d_inter, d_lp, d_kid, d_anc, AD, d_nt, L, d_rc, nullptr, nullptr, nullptr, nullptr);
+      ce = cudaMemcpy(rc.data(), d_rc, L * 4, cudaMemcpyDeviceToHost);
+    }
+    if (ce == cudaSuccess) {
+      row_ptr[0] = 0;
+      for (int64_t n = 0; n < L; n++) row_ptr[n + 1] = row_ptr[n] + rc[n];
+      if (col && val && row_ptr[L] > 0) {
+        if ((ce = cudaMalloc(&d_rp, (L + 1) * 8)) == cudaSuccess && (ce = cudaMalloc(&d_col, row_ptr[L] * 4)) == cudaSuccess &&
+            (ce = cudaMalloc(&d_val, row_ptr[L] * 8)) == cudaSuccess && (ce = cudaMemcpy(d_rp, row_ptr, (L + 1) * 8, cudaMemcpyHostToDevice)) == cudaSuccess) {
+          launch_ov_csr(d_inter, d_lp, d_kid, d_anc, AD, d_nt, L, nullptr, d_rp, d_col, d_val, nullptr);
+          if ((ce = cudaMemcpy(col, d_col, row_ptr[L] * 4, cudaMemcpyDeviceToHost)) == cudaSuccess)
+            ce = cudaMemcpy(val, d_val, row_ptr[L] * 8, cudaMemcpyDeviceToHost);
+        }
+      }
+    }
+    cleanup2();
+    OTRY(ce);
+  }
 #undef OTRY
   cleanup();
   return DSMGP_OK;
+}
+
+extern "C" int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
+                                 const int32_t* leaf_kernel_id, const dsmgp_tree* tree, double* D) {
+  return overlap_core(N, L, leaf_ptr, leaf_obs, leaf_kernel_id, tree, true, D, nullptr, nullptr, nullptr);
+}
+
+// The same matrix in CSR form (row n: the experts m with D[n,m] != 0, ascending).  Call once with col = val = NULL to get
+// row_ptr[L+1] (row_ptr[L] = number of non-zeros), then again with col[nnz] (int32) and val[nnz].
+extern "C" int32_t dsmgp_overlap_csr(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
+                                     const int32_t* leaf_kernel_id, const dsmgp_tree* tree, int64_t* row_ptr, int32_t* col, double* val) {
+  return overlap_core(N, L, leaf_ptr, leaf_obs, leaf_kernel_id, tree, false, nullptr, row_ptr, col, val);
 }
 
 static int32_t chol_host_matrix(double* A, int64_t n, int64_t k, int32_t* info) {

@@ -156,6 +156,8 @@ void launch_ov_fill(const int64_t* obs, const int64_t* leaf_ptr, int L, const in
 void launch_ov_pairs(const int64_t* poff, const int* plist, int64_t N, int64_t L, int* inter, cudaStream_t st);
 void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
                       int64_t L, double* D, cudaStream_t st);
+void launch_ov_csr(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type, int64_t L,
+                   int* row_cnt, const int64_t* row_ptr, int32_t* col, double* val, cudaStream_t st);
 void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
 struct RouteArgs;
 struct MixArgs;

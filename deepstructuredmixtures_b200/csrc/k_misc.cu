@@ -118,26 +118,43 @@ __global__ void ov_pairs_kernel(const int64_t* poff, const int* plist, int64_t N
     }
   }
 }
-// anc: [L][AD] node ids from the root down to the expert (-1 padded).  D is L x L column-major.
+// anc: [L][AD] node ids from the root down to the expert (-1 padded).  D[n,m] of getOverlap (fit.jl:12-39).
+__device__ __forceinline__ double ov_value(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD,
+                                           const int* node_type, int64_t L, int64_t n, int64_t m) {
+  if (n == m) return 0.0;
+  int lca = -1;
+  for (int d = 0; d < AD; d++) {
+    const int an = anc[n * AD + d], am = anc[m * AD + d];
+    if (an < 0 || an != am) break;
+    lca = an;
+  }
+  if (lca < 0 || node_type[lca] < 2) return 0.0;                   // DSMGP_NODE_SUM / DSMGP_NODE_KSUM
+  const int64_t cn = leaf_ptr[n + 1] - leaf_ptr[n];
+  const int64_t dn = (kid[n] == kid[m]) ? cn - (int64_t)inter[n + m * L] : 0;      // sum(xor & obs_n) * (kernelid equal)
+  return 1.0 - (double)dn / (double)cn;                            // fit.jl:31
+}
+// D is L x L column-major.
 __global__ void ov_finish_kernel(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD,
                                  const int* node_type, int64_t L, double* D) {
-  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < L * L; e += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t n = e % L, m = e / L;
-    double v = 0.0;
-    if (n != m) {
-      int lca = -1;
-      for (int d = 0; d < AD; d++) {
-        const int an = anc[n * AD + d], am = anc[m * AD + d];
-        if (an < 0 || an != am) break;
-        lca = an;
-      }
-      if (lca >= 0 && node_type[lca] >= 2) {                       // DSMGP_NODE_SUM / DSMGP_NODE_KSUM
-        const int64_t cn = leaf_ptr[n + 1] - leaf_ptr[n];
-        const int64_t dn = (kid[n] == kid[m]) ? cn - (int64_t)inter[e] : 0;      // sum(xor & obs_n) * (kernelid equal)
-        v = 1.0 - (double)dn / (double)cn;                         // fit.jl:31
-      }
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < L * L; e += (int64_t)gridDim.x * blockDim.x)
+    D[e] = ov_value(inter, leaf_ptr, kid, anc, AD, node_type, L, e % L, e / L);
+}
+// Sparse form (CSR by row n, columns ascending): one warp per row.  col == nullptr: count pass (row_cnt[n] = non-zeros of row n).
+__global__ void ov_csr_kernel(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
+                              int64_t L, int* row_cnt, const int64_t* row_ptr, int32_t* col, double* val) {
+  const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int64_t n = warp; n < L; n += nw) {
+    int64_t pos = col != nullptr ? row_ptr[n] : 0;
+    int cnt = 0;
+    for (int64_t m0 = 0; m0 < L; m0 += 32) {
+      const int64_t m = m0 + lane;
+      const double v = m < L ? ov_value(inter, leaf_ptr, kid, anc, AD, node_type, L, n, m) : 0.0;
+      const unsigned mask = __ballot_sync(0xffffffffu, v != 0.0);
+      if (col != nullptr && v != 0.0) { const int r = __popc(mask & ((1u << lane) - 1u)); col[pos + r] = (int32_t)m; val[pos + r] = v; }
+      pos += __popc(mask); cnt += __popc(mask);
     }
-    D[e] = v;
+    if (col == nullptr && lane == 0) row_cnt[n] = cnt;
   }
 }
 void launch_ov_count(const int64_t* obs, int64_t total, int* cntp, cudaStream_t st) { ov_count_kernel<<<1184, 256, 0, st>>>(obs, total, cntp); }
@@ -146,6 +163,10 @@ void launch_ov_fill(const int64_t* obs, const int64_t* leaf_ptr, int L, const in
 }
 void launch_ov_pairs(const int64_t* poff, const int* plist, int64_t N, int64_t L, int* inter, cudaStream_t st) {
   ov_pairs_kernel<<<1184, 256, 0, st>>>(poff, plist, N, L, inter);
+}
+void launch_ov_csr(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type, int64_t L,
+                   int* row_cnt, const int64_t* row_ptr, int32_t* col, double* val, cudaStream_t st) {
+  ov_csr_kernel<<<1184, 256, 0, st>>>(inter, leaf_ptr, kid, anc, AD, node_type, L, row_cnt, row_ptr, col, val);
 }
 void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type,
                       int64_t L, double* D, cudaStream_t st) {

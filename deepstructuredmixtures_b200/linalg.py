@@ -47,3 +47,21 @@ def overlap_matrix(N: int, leaf_obs: Sequence[np.ndarray], leaf_kernel_id: Seque
     nat.check(nat.lib().dsmgp_overlap(int(N), L, nat.p_i64(leaf_ptr), nat.p_i64(obs), nat.p_i32(kid),
                                       C.byref(tree.struct), nat.p_d(D)))
     return D
+
+
+def overlap_matrix_csr(N: int, leaf_obs: Sequence[np.ndarray], leaf_kernel_id: Sequence[int], tree: "nat.FlatTree"):
+    """getOverlap in CSR form (`dsmgp_overlap_csr`): (row_ptr[L+1], col[nnz], val[nnz]) -- only the non-zero entries leave the
+    device, for models whose dense L x L matrix is too large to move."""
+    L = len(leaf_obs)
+    leaf_ptr = np.zeros(L + 1, dtype=np.int64)
+    leaf_ptr[1:] = np.cumsum([len(o) for o in leaf_obs])
+    obs = np.ascontiguousarray(np.concatenate(leaf_obs), dtype=np.int64)
+    kid = np.ascontiguousarray(leaf_kernel_id, dtype=np.int32)
+    row_ptr = np.zeros(L + 1, dtype=np.int64)
+    args = (int(N), L, nat.p_i64(leaf_ptr), nat.p_i64(obs), nat.p_i32(kid), C.byref(tree.struct), nat.p_i64(row_ptr))
+    nat.check(nat.lib().dsmgp_overlap_csr(*args, None, None))
+    nnz = int(row_ptr[-1])
+    col = np.zeros(max(nnz, 1), dtype=np.int32); val = np.zeros(max(nnz, 1))
+    if nnz:
+        nat.check(nat.lib().dsmgp_overlap_csr(*args, nat.p_i32(col), nat.p_d(val)))
+    return row_ptr, col[:nnz], val[:nnz]

@@ -235,6 +235,11 @@ int32_t dsmgp_kernelmatrix(int32_t kernel_type, const double* theta, int64_t D,
  * letting every point enumerate the pairs of experts that contain it. */
 int32_t dsmgp_overlap(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
                       const int32_t* leaf_kernel_id, const dsmgp_tree* tree, double* D);
+/* The same matrix in CSR form by row (row n: the experts m with D[n,m] != 0, ascending), for models whose dense L x L matrix is
+ * too large to move (3.4 GB at L = 20,736): only the non-zeros leave the device.  Call once with col = val = NULL to obtain
+ * row_ptr[L+1] (row_ptr[L] = number of non-zeros), then again with col[nnz], val[nnz]. */
+int32_t dsmgp_overlap_csr(int64_t N, int64_t L, const int64_t* leaf_ptr, const int64_t* leaf_obs,
+                          const int32_t* leaf_kernel_id, const dsmgp_tree* tree, int64_t* row_ptr, int32_t* col, double* val);
 /* AdvancedCholesky.chol_continue!(A, ki) AdvancedCholeskey.jl:152-174 (ki 1-based): A n x n column-major in/out. */
 int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t* info);
 /* Row/column deletion from a lower Cholesky factor: the operation fit.jl:179-195 composes from

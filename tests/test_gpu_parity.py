@@ -162,6 +162,16 @@ def test_overlap_matrix_device_bit_exact(kernel):
     assert np.array_equal(D, orc.getOverlap(oracle_tree(model), x.shape[0]))
     assert np.array_equal(D, st.getOverlap(model.root, x.shape[0]))
     assert D.max() <= 1.0 and D.min() >= 0.0 and np.all(np.diag(D) == 0.0) and np.count_nonzero(D) > 0
+    # the sparse form (dsmgp_overlap_csr): exactly the non-zeros of D, row by row, columns ascending
+    from deepstructuredmixtures_b200.linalg import overlap_matrix_csr
+    rp, col, val = overlap_matrix_csr(x.shape[0], [lf.obs for lf in model.leaves], [lf.kernelid - 1 for lf in model.leaves], model.flat)
+    assert rp[-1] == np.count_nonzero(D) and rp[-1] < D.size
+    S = np.zeros_like(D)
+    for n in range(D.shape[0]):
+        c = col[rp[n]:rp[n + 1]]
+        assert np.all(np.diff(c) > 0)
+        S[n, c] = val[rp[n]:rp[n + 1]]
+    assert np.array_equal(S, D)
 
 
 @pytest.mark.parametrize("ktype,mathematical", [("isose", False), ("ardse", True), ("ardlin", False)])
