@@ -67,7 +67,7 @@ EXPORTS = [
     "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling",
     "dsmgp_set_sharing", "dsmgp_get_sharing", "dsmgp_infer", "dsmgp_reset_weights", "dsmgp_comm_unique_id", "dsmgp_comm_init", "dsmgp_host_sharing_plan",
     "dsmgp_part_create", "dsmgp_part_destroy", "dsmgp_part_size", "dsmgp_part_range", "dsmgp_part_sorted_column", "dsmgp_part_split",
-    "dsmgp_part_rows", "dsmgp_overlap_csr",
+    "dsmgp_part_rows", "dsmgp_overlap_csr", "dsmgp_chol_delete_rows_batched",
 ]
 COMM_ID_BYTES = 128
 
@@ -127,6 +127,7 @@ def lib() -> C.CDLL:
         "dsmgp_kernelmatrix": (I32, [I32, pd, I64, pd, I64, pd, I64, pd]),
         "dsmgp_chol_continue": (I32, [pd, I64, I64, pi32]),
         "dsmgp_chol_delete_rows": (I32, [pd, I64, pi64, I64, pd]),
+        "dsmgp_chol_delete_rows_batched": (I32, [I64, C.POINTER(pd), pi64, C.POINTER(pi64), pi64, C.POINTER(pd)]),
         "dsmgp_potrf": (I32, [pd, I64, pi32]),
         "dsmgp_host_tree_eval": (I32, [C.POINTER(Tree), I64, pi32, C.POINTER(KernelDesc), I32, pd, I64, pd, pd, pd, pd, pd]),
         "dsmgp_host_shard": (I32, [I64, pi64, I32, pi32]),

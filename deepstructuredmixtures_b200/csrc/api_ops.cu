@@ -216,28 +216,60 @@ extern "C" int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t
   return chol_host_matrix(A, n, ki - 1, info);
 }
 
-extern "C" int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, int64_t nrows, double* out) {
-  if (!A || n <= 0 || !rows || nrows < 0 || nrows >= n || !out) return DSMGP_ERR_ARG;
-  for (int64_t q = 0; q < nrows; q++)
-    if (rows[q] < 1 || rows[q] > n || (q > 0 && rows[q] <= rows[q - 1])) { g_create_error = "delete_rows: rows must be 1-based ascending"; return DSMGP_ERR_ARG; }
+namespace { struct DelJobH { double* L; int n; const int64_t* rows; int nrows; double* v; }; }
+
+// Row deletion for `count` factors in ONE launch per chunk of 64 deleted rows (one CTA per matrix, one column sweep for all rows
+// of a matrix): the device-resident, batched form of what fit.jl:167-195 composes from lowrankupdate!.
+extern "C" int32_t dsmgp_chol_delete_rows_batched(int64_t count, const double* const* A, const int64_t* n, const int64_t* const* rows,
+                                                  const int64_t* nrows, double* const* out) {
+  if (count <= 0 || !A || !n || !rows || !nrows || !out) return DSMGP_ERR_ARG;
+  for (int64_t m = 0; m < count; m++) {
+    if (!A[m] || n[m] <= 0 || nrows[m] < 0 || nrows[m] >= n[m] || !out[m] || (nrows[m] > 0 && !rows[m])) return DSMGP_ERR_ARG;
+    for (int64_t q = 0; q < nrows[m]; q++)
+      if (rows[m][q] < 1 || rows[m][q] > n[m] || (q > 0 && rows[m][q] <= rows[m][q - 1])) { g_create_error = "delete_rows: rows must be 1-based ascending"; return DSMGP_ERR_ARG; }
+  }
   int32_t rc = standalone_device_check(g_create_error);
   if (rc) return rc;
-  double *dL = nullptr, *dv = nullptr; int64_t* dr = nullptr;
-  std::vector<double> P((size_t)n * n);
-  SA_TRY(cudaMalloc(&dL, n * n * 8)); SA_TRY(cudaMalloc(&dv, n * 8)); SA_TRY(cudaMalloc(&dr, std::max<int64_t>(nrows, 1) * 8));
-  SA_TRY(cudaMemcpy(dL, A, n * n * 8, cudaMemcpyHostToDevice));
-  if (nrows) SA_TRY(cudaMemcpy(dr, rows, nrows * 8, cudaMemcpyHostToDevice));
-  launch_delete_rows(dL, (int)n, dr, (int)nrows, dv, 0);
-  SA_TRY(cudaGetLastError());
-  SA_TRY(cudaMemcpy(P.data(), dL, n * n * 8, cudaMemcpyDeviceToHost));
-  {
+  constexpr int QMAX = 64;
+  std::vector<double*> dL(count, nullptr), dV(count, nullptr); std::vector<int64_t*> dR(count, nullptr);
+  DelJobH* djobs = nullptr;
+  int64_t maxq = 0;
+  for (int64_t m = 0; m < count; m++) maxq = std::max(maxq, nrows[m]);
+  for (int64_t m = 0; m < count; m++) {
+    SA_TRY(cudaMalloc(&dL[m], n[m] * n[m] * 8));
+    SA_TRY(cudaMalloc(&dV[m], (size_t)std::min<int64_t>(std::max<int64_t>(nrows[m], 1), QMAX) * n[m] * 8));
+    SA_TRY(cudaMalloc(&dR[m], std::max<int64_t>(nrows[m], 1) * 8));
+    SA_TRY(cudaMemcpyAsync(dL[m], A[m], n[m] * n[m] * 8, cudaMemcpyHostToDevice, 0));
+    if (nrows[m]) SA_TRY(cudaMemcpyAsync(dR[m], rows[m], nrows[m] * 8, cudaMemcpyHostToDevice, 0));
+  }
+  SA_TRY(cudaMalloc(&djobs, count * sizeof(DelJobH)));
+  for (int64_t q0 = 0; q0 < maxq; q0 += QMAX) {          // later rows are taken from the factor the earlier chunks left behind
+    std::vector<DelJobH> jobs(count);
+    for (int64_t m = 0; m < count; m++) {
+      const int64_t nq = std::max<int64_t>(0, std::min<int64_t>(QMAX, nrows[m] - q0));
+      jobs[m] = DelJobH{dL[m], (int)n[m], dR[m] + std::min(q0, nrows[m]), (int)nq, dV[m]};
+    }
+    SA_TRY(cudaMemcpy(djobs, jobs.data(), count * sizeof(DelJobH), cudaMemcpyHostToDevice));
+    launch_delete_rows(djobs, (int)count, 0);
+    SA_TRY(cudaGetLastError());
+    SA_TRY(cudaDeviceSynchronize());
+  }
+  for (int64_t m = 0; m < count; m++) {
+    std::vector<double> P((size_t)n[m] * n[m]);
+    SA_TRY(cudaMemcpy(P.data(), dL[m], n[m] * n[m] * 8, cudaMemcpyDeviceToHost));
     std::vector<int64_t> keep;
-    for (int64_t i = 0, q = 0; i < n; i++) { if (q < nrows && rows[q] - 1 == i) { q++; continue; } keep.push_back(i); }
-    const int64_t m = (int64_t)keep.size();
-    for (int64_t c = 0; c < m; c++)
-      for (int64_t r = 0; r < m; r++) out[c * m + r] = (r >= c) ? P[keep[c] * n + keep[r]] : 0.0;
+    for (int64_t i = 0, q = 0; i < n[m]; i++) { if (q < nrows[m] && rows[m][q] - 1 == i) { q++; continue; } keep.push_back(i); }
+    const int64_t k = (int64_t)keep.size();
+    for (int64_t c = 0; c < k; c++)
+      for (int64_t r = 0; r < k; r++) out[m][c * k + r] = (r >= c) ? P[keep[c] * n[m] + keep[r]] : 0.0;
   }
 done:
-  cudaFree(dL); cudaFree(dv); cudaFree(dr);
+  for (int64_t m = 0; m < count; m++) { cudaFree(dL[m]); cudaFree(dV[m]); cudaFree(dR[m]); }
+  cudaFree(djobs);
   return rc;
+}
+
+extern "C" int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, int64_t nrows, double* out) {
+  if (!A || n <= 0 || !rows || nrows < 0 || nrows >= n || !out) return DSMGP_ERR_ARG;
+  return dsmgp_chol_delete_rows_batched(1, &A, &n, &rows, &nrows, &out);
 }

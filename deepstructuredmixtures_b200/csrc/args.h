@@ -158,7 +158,9 @@ void launch_ov_finish(const int* inter, const int64_t* leaf_ptr, const int* kid,
                       int64_t L, double* D, cudaStream_t st);
 void launch_ov_csr(const int* inter, const int64_t* leaf_ptr, const int* kid, const int* anc, int AD, const int* node_type, int64_t L,
                    int* row_cnt, const int64_t* row_ptr, int32_t* col, double* val, cudaStream_t st);
-void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st);
+// jobs_dev: device array of { double* L; int n; const int64_t* rows; int nrows; double* v } (k_misc.cu DelJob), one CTA per matrix,
+// at most DEL_QMAX = 64 deleted rows per job and launch
+void launch_delete_rows(const void* jobs_dev, int njobs, cudaStream_t st);
 struct RouteArgs;
 struct MixArgs;
 void launch_route(const RouteArgs& a, bool fill, cudaStream_t st);

@@ -12,30 +12,53 @@ void launch_opt_step(const OptArgs& a, cudaStream_t st) { opt_step_kernel<<<1, (
 void launch_mix(const MixArgs& a, cudaStream_t st) { mix_kernel<<<(unsigned)((a.T + 127) / 128), 128, 0, st>>>(a); }
 }  // namespace dsm
 namespace dsm {
-// Givens rank-1 update of the trailing block for every deleted row (one CTA; column sweep is sequential).
-__global__ void __launch_bounds__(NTHREADS) delete_rows_kernel(double* Lf, int n, const int64_t* rows, int nrows, double* v) {
-  __shared__ double cs[2];
-  const int tid = threadIdx.x;
-  for (int q = 0; q < nrows; q++) {
-    const int i = (int)rows[q] - 1;
-    for (int r = i + 1 + tid; r < n; r += NTHREADS) v[r] = Lf[(int64_t)i * n + r];
-    __syncthreads();
-    for (int k = i + 1; k < n; k++) {
+// Row / column deletion from lower Cholesky factors (the operation fit.jl:167-195 composes from lowrankupdate!,
+// AdvancedCholeskey.jl:20-59, implemented correctly: SURVEY App. B Q7).  Deleting row i turns the trailing block into the factor of
+// L33 L33' + u u' (u = L[i+1:, i]): a Givens rank-1 UPDATE that sweeps the columns behind i.  The reference runs one full sweep per
+// deleted row; here ONE sweep over the columns serves every deleted row of a matrix: at column k the rotations of all update
+// vectors that are already active are applied back to back while the column is in registers (the arithmetic and its order per
+// element are exactly those of the row-by-row sweeps, so the result is bit-identical), and when k is itself a deleted row its
+// freshly updated column becomes the next update vector.  Column traffic and barriers drop by the number of deleted rows.
+// One CTA per matrix: a batch of matrices is one launch (dsmgp_chol_delete_rows_batched).
+struct DelJob { double* L; int n; const int64_t* rows; int nrows; double* v; };      // v: [nrows][n] scratch
+constexpr int DEL_QMAX = 64;
+__global__ void __launch_bounds__(NTHREADS) delete_rows_kernel(const DelJob* jobs) {
+  __shared__ double cs[2 * DEL_QMAX];
+  const DelJob jb = jobs[blockIdx.x];
+  double* Lf = jb.L; const int n = jb.n; const int tid = threadIdx.x;
+  if (jb.nrows <= 0) return;
+  int nact = 0, next = 0;
+  for (int k = (int)jb.rows[0] - 1; k < n; k++) {
+    if (nact > 0) {
       if (tid == 0) {
-        const double f = Lf[(int64_t)k * n + k], g = v[k];
-        double c, s, r;
-        if (g == 0.0) { c = 1.0; s = 0.0; r = f; }
-        else if (f == 0.0) { c = 0.0; s = 1.0; r = g; }
-        else { r = hypot(f, g); if (fabs(f) > fabs(g) && f < 0) r = -r; c = f / r; s = g / r; }
-        Lf[(int64_t)k * n + k] = r; cs[0] = c; cs[1] = s;
+        double f = Lf[(int64_t)k * n + k];
+        for (int j = 0; j < nact; j++) {
+          const double g = jb.v[(int64_t)j * n + k];
+          double c, s, r;
+          if (g == 0.0) { c = 1.0; s = 0.0; r = f; }
+          else if (f == 0.0) { c = 0.0; s = 1.0; r = g; }
+          else { r = hypot(f, g); if (fabs(f) > fabs(g) && f < 0) r = -r; c = f / r; s = g / r; }
+          cs[2 * j] = c; cs[2 * j + 1] = s; f = r;
+        }
+        Lf[(int64_t)k * n + k] = f;
       }
       __syncthreads();
-      const double c = cs[0], s = cs[1];
       for (int r = k + 1 + tid; r < n; r += NTHREADS) {
-        const double a = Lf[(int64_t)k * n + r], b = v[r];
-        Lf[(int64_t)k * n + r] = c * a + s * b;
-        v[r] = -s * a + c * b;
+        double a = Lf[(int64_t)k * n + r];
+        for (int j = 0; j < nact; j++) {
+          const double c = cs[2 * j], s = cs[2 * j + 1];
+          const double b = jb.v[(int64_t)j * n + r];
+          const double a2 = c * a + s * b;
+          jb.v[(int64_t)j * n + r] = -s * a + c * b;
+          a = a2;
+        }
+        Lf[(int64_t)k * n + r] = a;
       }
+      __syncthreads();
+    }
+    if (next < jb.nrows && (int)jb.rows[next] - 1 == k) {          // column k (now final) is the update vector of its own deletion
+      for (int r = k + 1 + tid; r < n; r += NTHREADS) jb.v[(int64_t)nact * n + r] = Lf[(int64_t)k * n + r];
+      nact++; next++;
       __syncthreads();
     }
   }
@@ -47,8 +70,8 @@ __global__ void untile_kernel(const double* Ft, int nkc, int n, double* out) {
   for (int r = threadIdx.x; r < n; r += blockDim.x) out[(int64_t)c * n + r] = (r >= c) ? Ft[tidx(r, c, nkc)] : 0.0;
 }
 void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st) { untile_kernel<<<n, 256, 0, st>>>(Ft, nkc, n, out); }
-void launch_delete_rows(double* Lf, int n, const int64_t* rows, int nrows, double* v, cudaStream_t st) {
-  delete_rows_kernel<<<1, NTHREADS, 0, st>>>(Lf, n, rows, nrows, v);
+void launch_delete_rows(const void* jobs_dev, int njobs, cudaStream_t st) {
+  if (njobs > 0) delete_rows_kernel<<<njobs, NTHREADS, 0, st>>>(static_cast<const DelJob*>(jobs_dev));
 }
 
 // ---- shared Cholesky of fit! (fit.jl:132-143, 208-292): block rows I < jb of a SHARE_PREFIX expert are the source expert's

@@ -65,3 +65,20 @@ def overlap_matrix_csr(N: int, leaf_obs: Sequence[np.ndarray], leaf_kernel_id: S
     if nnz:
         nat.check(nat.lib().dsmgp_overlap_csr(*args, nat.p_i32(col), nat.p_d(val)))
     return row_ptr, col[:nnz], val[:nnz]
+
+
+def chol_delete_rows_batched(factors: Sequence[np.ndarray], rows: Sequence[Sequence[int]]):
+    """`dsmgp_chol_delete_rows_batched`: row deletion for several factors in one launch (one CTA per matrix, one column sweep per
+    matrix for all of its deleted rows).  Returns the list of reduced factors."""
+    Ls = [np.array(L, dtype=np.float64, order="F") for L in factors]
+    rs = [np.ascontiguousarray(sorted(r), dtype=np.int64) for r in rows]
+    cnt = len(Ls)
+    n = np.array([L.shape[0] for L in Ls], dtype=np.int64)
+    nr = np.array([r.size for r in rs], dtype=np.int64)
+    outs = [np.zeros((int(n[m] - nr[m]), int(n[m] - nr[m])), order="F") for m in range(cnt)]
+    PD, PI = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    a_arr = (PD * cnt)(*[nat.p_d(L) for L in Ls])
+    r_arr = (PI * cnt)(*[nat.p_i64(r) if r.size else C.cast(None, PI) for r in rs])
+    o_arr = (PD * cnt)(*[nat.p_d(o) for o in outs])
+    nat.check(nat.lib().dsmgp_chol_delete_rows_batched(cnt, a_arr, nat.p_i64(n), r_arr, nat.p_i64(nr), o_arr))
+    return outs

@@ -246,6 +246,10 @@ int32_t dsmgp_chol_continue(double* A, int64_t n, int64_t ki, int32_t* info);
  * lowrankupdate! (AdvancedCholeskey.jl:20-59), implemented CORRECTLY.
  * A: n x n in, (n-nrows) x (n-nrows) factor written to `out` (column-major, ld = n-nrows). rows 1-based ascending. */
 int32_t dsmgp_chol_delete_rows(const double* A, int64_t n, const int64_t* rows, int64_t nrows, double* out);
+/* The same for `count` factors at once: one CTA per matrix, ONE column sweep per matrix for all of its deleted rows (bit-identical
+ * to deleting them one after the other), one launch per 64 deleted rows.  A[m]: n[m] x n[m]; out[m]: (n[m]-nrows[m])^2. */
+int32_t dsmgp_chol_delete_rows_batched(int64_t count, const double* const* A, const int64_t* n, const int64_t* const* rows,
+                                       const int64_t* nrows, double* const* out);
 /* plain batched-size-1 potrf('L') on a host matrix (LAPACK.potrf! as used at gaussianprocess.jl:101) */
 int32_t dsmgp_potrf(double* A, int64_t n, int32_t* info);
 

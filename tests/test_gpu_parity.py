@@ -300,6 +300,19 @@ def test_chol_delete_rows_lrtest():
     ref = sla.cholesky(S[np.ix_(keep, keep)], lower=True)
     assert np.sum(np.abs(out - ref)) < 1e-9
     assert np.max(np.abs(out - orc.chol_delete_rows(Lf, missing.tolist()))) < 1e-11
+    # batched form: several factors, one launch, one column sweep per matrix for all of its rows (incl. > 64 rows: two chunks)
+    from deepstructuredmixtures_b200.linalg import chol_delete_rows_batched
+    mats, rws, refs = [], [], []
+    for D2, nd in ((150, 3), (333, 70), (64, 1), (200, 10)):
+        S2 = orc.gen_cov(D2, rng)
+        miss = np.sort(rng.permutation(D2 - 1)[:nd])
+        kp = np.setdiff1d(np.arange(D2), miss)
+        mats.append(sla.cholesky(S2, lower=True)); rws.append((miss + 1).tolist())
+        refs.append(sla.cholesky(S2[np.ix_(kp, kp)], lower=True))
+    outs = chol_delete_rows_batched(mats, rws)
+    for o, r_ in zip(outs, refs):
+        assert np.max(np.abs(o - r_)) < 1e-10 * np.max(np.abs(r_))
+    assert np.array_equal(outs[3], dsm.chol_delete_rows(mats[3], rws[3]))
 
 
 def test_not_positive_definite_reports_info():
