@@ -5,7 +5,7 @@
 using namespace dsm;
 
 #ifndef DSM_TRTRI_GROUP_DEFAULT
-#define DSM_TRTRI_GROUP_DEFAULT 1
+#define DSM_TRTRI_GROUP_DEFAULT 4      // measured on cfg3 (profiles/trtri3_group*_r02.csv): DRAM read 74.7 -> 27 GB at equal kernel time
 #endif
 
 namespace dsm {
@@ -299,10 +299,11 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
           // Stagger: inside a group the tile (I+1, J) needs (I, J) for its LAST k-block; two rows of one group claimed back to
           // back reach that point together and the lower one would wait out the upper one's epilogue and store (measured:
           // +11 % kernel time with plain row-major groups).  So the rows of DSMGP_TRTRI_STAGGER (default 4) consecutive groups
-          // are interleaved: row r of every group of the chunk, then row r+1, ... -- successors in a column are then >= 12
-          // list positions (~ 10 us of claim time) apart while the tiles they share are still in L2.
+          // are interleaved: row r of every group of the chunk, then row r+1, ... -- successors in a column are then dozens of
+          // list positions (> 10 us of claim time) apart while the tiles they share are still in L2.  Measured (cfg3, ms of the
+          // inverse): no grouping 31.92; G=4 without stagger 35.40; stagger 4: 33.94, 8: 32.48, 16: 32.01.
           const char* se = getenv("DSMGP_TRTRI_STAGGER");
-          const int C = se ? std::max(1, atoi(se)) : 4;
+          const int C = se ? std::max(1, atoi(se)) : 16;
           if (C > 1) {
             std::vector<GK> out; out.reserve(gv.size());
             size_t i = 0;
