@@ -298,7 +298,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
             return a.J < c.J; });
           // Stagger: inside a group the tile (I+1, J) needs (I, J) for its LAST k-block; two rows of one group claimed back to
           // back reach that point together and the lower one would wait out the upper one's epilogue and store (measured:
-          // +11 % kernel time with plain row-major groups).  So the rows of DSMGP_TRTRI_STAGGER (default 4) consecutive groups
+          // +11 % kernel time with plain row-major groups).  So the rows of DSMGP_TRTRI_STAGGER (default 16) consecutive groups
           // are interleaved: row r of every group of the chunk, then row r+1, ... -- successors in a column are then dozens of
           // list positions (> 10 us of claim time) apart while the tiles they share are still in L2.  Measured (cfg3, ms of the
           // inverse): no grouping 31.92; G=4 without stagger 35.40; stagger 4: 33.94, 8: 32.48, 16: 32.01.
@@ -646,10 +646,12 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
                     h->d_ldpart.p, h->d_zzpart.p, h->d_flags.p, b.d_flag_off, b.d_potrf2_tasks, b.n_potrf2,
                     h->d_counter.p + 4, h->d_counter.p + GERR, 0, share_b, nullptr};
       // One launch for the factorisation and the inverse (fused2.cuh) when the batch is small enough for the tails of two
-      // separate launches to matter (multi-GPU shards): DSMGP_FUSED_EVAL=0|1 overrides.
+      // separate launches to matter (multi-GPU shards; measured with every rank of a shard emulated on one GPU, slowest rank:
+      // 8-way 10.19 -> 9.57 ms, 4-way 18.95 -> 18.41 ms; neutral on the full 144-expert batch, which keeps the two launches and
+      // their per-phase timings): DSMGP_FUSED_EVAL=0|1 overrides.
       const char* fe = getenv("DSMGP_FUSED_EVAL");
       const bool fused = with_grad && !shr && b.n_trtri3 > 0 && !getenv("DSMGP_TRACE_FILE") &&
-                         (fe ? fe[0] == '1' : nsl * 4 < sms);
+                         (fe ? fe[0] == '1' : nsl * 3 < sms * 2);
       if (fused) {
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags2.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
         Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
