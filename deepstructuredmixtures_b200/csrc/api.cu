@@ -4,6 +4,9 @@
 
 using namespace dsm;
 
+#ifndef DSM_LAUUM_GROUP_DEFAULT
+#define DSM_LAUUM_GROUP_DEFAULT 1
+#endif
 #ifndef DSM_TRTRI_GROUP_DEFAULT
 #define DSM_TRTRI_GROUP_DEFAULT 4      // measured on cfg3 (profiles/trtri3_group*_r02.csv): DRAM read 74.7 -> 27 GB at equal kernel time
 #endif
@@ -236,8 +239,22 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     // cost-descending task order (dynamic LPT through the atomic task counter)
     std::stable_sort(tt.begin(), tt.end(), [&](const int2& a, const int2& c) {
       const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
-    std::stable_sort(lt.begin(), lt.end(), [&](const int4& a, const int4& c) {
-      const int ra = h->meta[b.s0 + a.x].nb - a.y, rc = h->meta[b.s0 + c.x].nb - c.y; return ra > rc; });
+    {
+      // LAUUM tiles have no dependencies at all; tile (I, J) reads X^T of block rows I and J behind column I.  DSMGP_LAUUM_GROUP
+      // = G orders them in G x G groups of the (I, J) plane (cost-descending by group, row-major inside) so that neighbours in the
+      // task list -- which run at the same time on different SMs -- read the same tiles out of L2 (G = 1: every row I on its own).
+      const char* lg = getenv("DSMGP_LAUUM_GROUP");
+      const int G = lg ? std::max(1, atoi(lg)) : DSM_LAUUM_GROUP_DEFAULT;
+      std::stable_sort(lt.begin(), lt.end(), [&](const int4& a, const int4& c) {
+        const int ra = h->meta[b.s0 + a.x].nb - (a.y / G) * G, rc = h->meta[b.s0 + c.x].nb - (c.y / G) * G;
+        if (ra != rc) return ra > rc;
+        if (G == 1) return false;
+        if (a.x != c.x) return a.x < c.x;
+        if (a.y / G != c.y / G) return a.y / G < c.y / G;
+        if (a.z / G != c.z / G) return a.z / G < c.z / G;
+        if (a.y != c.y) return a.y < c.y;
+        return a.z < c.z; });
+    }
     const char* ord_env = getenv("DSMGP_ORDER");           // development A/B: 0 = end together, 1 = stretch
     const bool stretch = ord_env ? (ord_env[0] == '1') : (nb_s * 4 < sms_plan);
     const bool start_together = ord_env && ord_env[0] == '2';     // experiment: no shift at all

@@ -5,8 +5,8 @@
 namespace dsm {
 
 constexpr int ROUTE_STACK = 96;     // pending nodes of the depth-first walk (checked on the host: depth * max fan-out)
-constexpr int MIX_KMAX = 16;        // children per sum node the device mixer supports (else: host mixer)
-constexpr int MIX_FRAMES = 12;      // nested sum nodes (DSMGP) / split nodes (PoE) on one root-to-leaf path
+constexpr int MIX_KMAX = 8;         // children per sum node the device mixer supports (else: host mixer)
+constexpr int MIX_FRAMES = 8;       // nested sum nodes (DSMGP) / split nodes (PoE) on one root-to-leaf path
 
 struct DevTree {
   int n_nodes, root;
