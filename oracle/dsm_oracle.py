@@ -6,11 +6,16 @@ This file restates, in NumPy/SciPy FP64, the arithmetic of the reference Julia p
 and `bench.py`'s cpu_baseline / `--impl reference` legs may import it.  The product
 package (`deepstructuredmixtures_b200/`) never imports anything from `oracle/`.
 
-PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures
+PARITY UNPINNED (by the reference): the reference ships no tests, golden vectors or fixtures
  and no Julia toolchain exists in this image, so the reference
-cannot be executed.  The pin is (i) this line-by-line restatement, each function citing
-the reference file:line it follows, (ii) finite-difference / mpmath / LAPACK self-checks
-in tests/test_oracle.py, and (iii) the restated in-source self tests
+cannot be executed.  What pins this file instead: (i) the line-by-line restatement, each function
+citing the reference file:line it follows, (ii) an INDEPENDENT 50-digit evaluation of small models
+straight from the Julia formulas (tests/golden/make_mp_golden.py: mpmath only, imports nothing
+from here; vectors committed as tests/golden/mp_golden.json and checked by
+tests/test_oracle.py::test_oracle_against_independent_mpmath_vectors -- LML, as-written and
+mathematical gradients of all four kernels and a mixture, mll!, the down-pass plain and
+finetune-weighted, update!, infer!, DSMGP / PoE / gPoE / rBCM predictions), (iii) finite-difference
+and LAPACK self-checks in tests/test_oracle.py, and (iv) the restated in-source self tests
 `test_chol_continue` and `lrtest` (AdvancedCholeskey.jl:61-135).
 
 Third-party arithmetic the reference delegates to (not vendored, versions unpinned:
