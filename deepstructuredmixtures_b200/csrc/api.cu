@@ -5,10 +5,10 @@
 using namespace dsm;
 
 #ifndef DSM_LAUUM_GROUP_DEFAULT
-#define DSM_LAUUM_GROUP_DEFAULT 1
+#define DSM_LAUUM_GROUP_DEFAULT 4      // measured: cfg3 mathematical LAUUM phase 45.09 -> 44.95 ms, cfg4 120.4 -> 119.8 ms
 #endif
 #ifndef DSM_TRTRI_GROUP_DEFAULT
-#define DSM_TRTRI_GROUP_DEFAULT 4      // measured on cfg3 (profiles/trtri3_group*_r02.csv): DRAM read 74.7 -> 27 GB at equal kernel time
+#define DSM_TRTRI_GROUP_DEFAULT 4      // measured on cfg3 (profiles/trtri3_default_r02.csv): DRAM 78.6 -> 41.3 GB per launch at equal kernel time
 #endif
 
 namespace dsm {
