@@ -8,7 +8,7 @@ CMDM="python bench.py --workload cfg3 --steps 1 --warmup 3 --no-cpu-baseline --n
 mkdir -p gpurun_out /tmp/prof
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 tail -1 gpurun_out/plain_$TAG.log | head -c 400; echo
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"potrf2|trtri3|gram_fit|rows_kernel|alpha_reduce|predict3|route_kernel|mix_kernel|solve3|lauum3|gather_kernel" -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_list_$TAG.log 2>&1
 echo "launch list rc=$?"
 summ() {   # kernel, rep
   { echo "# ncu --set full --clock-control none --import-source on -k regex:$1 (one launch of: $3)"; python tools/ncu_summary.py $2 12; echo; echo "# stall samples by CUDA source line"; python tools/ncu_lines.py $2 14; } > gpurun_out/ncu_full_$1_$TAG.txt 2>&1
