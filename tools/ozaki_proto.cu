@@ -21,6 +21,7 @@
 // Build (GPU box or here):  nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -o /tmp/ozaki_proto tools/ozaki_proto.cu -lcublas
 // Run:  /tmp/ozaki_proto [n] [K] [factor.bin]     (tools/ozaki_run.sh drives it on the GPU box)
 #include <cublas_v2.h>
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cmath>
 #include <cstdint>
@@ -33,10 +34,10 @@
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fprintf(stderr, "CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(2); } } while (0)
 
 constexpr int TM = 128;        // rows of A per tile (TMEM lanes)
-constexpr int TN = 64;         // rows of B per tile (accumulator columns per slice group)
+constexpr int TN = 128;        // rows of B per tile (accumulator columns per slice group)
 constexpr int KSTEP = 32;      // K of one tcgen05.mma kind::i8
 constexpr int A_TILE = TM * KSTEP;  // 4096 bytes: [2 k-chunks of 16 B][16 row groups][8 rows][16 B]
-constexpr int B_TILE = TN * KSTEP;  // 2048 bytes: [2][8][8][16]
+constexpr int B_TILE = TN * KSTEP;  // 4096 bytes, same layout
 constexpr int SMEM_BUDGET = 220 * 1024;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -130,32 +131,48 @@ __global__ void slice_kernel(const double* __restrict__ X, int R, int K, long lo
 // ------------------------------------------------------------------------------------------------------------------
 template <int S>
 struct GemmCfg {
+  static constexpr int NR = (S > 4) ? 2 : 1;                     // rounds: TMEM holds 4 accumulators of 128 columns
   static constexpr int STAGE = S * (A_TILE + B_TILE);
   static constexpr int NST = SMEM_BUDGET / STAGE;
   static constexpr int SMEM = NST * STAGE + 1024;
-  static constexpr int TCOLS = (S * TN <= 256) ? 256 : 512;
+  static constexpr int TCOLS = 512;
+  // round r: groups [glo, ghi], slices 0 .. nsl-1.  Low-weight groups first.
+  __host__ __device__ static constexpr int glo(int r) { return (NR == 2 && r == 0) ? S - 4 : 0; }
+  __host__ __device__ static constexpr int ghi(int r) { return (NR == 2 && r == 1) ? S - 5 : S - 1; }
+  __host__ __device__ static constexpr int nsl(int r) { return ghi(r) + 1; }
 };
 
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+
+// One CTA per 128 x 128 tile of C.  The S slice groups do not fit TMEM at N = 128 (S * 128 columns > 512), so the tile
+// is computed in two rounds over K: first the four lowest-weight groups (all slices), then the remaining S - 4 groups
+// (slices 0 .. S-5); the partial sum of the first round is parked in C and folded into the Horner sum of the second.
 template <int S>
 __global__ void __launch_bounds__(192, 1)
-ozaki_gemm_kernel(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl, const double* __restrict__ sa, const double* __restrict__ sb,
-                  double* __restrict__ C, long long ldc, int nk, int accumulate_sub) {
+ozaki_gemm_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                  const double* __restrict__ sa, const double* __restrict__ sb, double* __restrict__ C, long long ldc, int nk) {
   using Cfg = GemmCfg<S>;
   constexpr int NST = Cfg::NST;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty = full + NST;
   uint64_t* tfull = empty + NST;
-  uint32_t* tptr = reinterpret_cast<uint32_t*>(tfull + 1);
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty + 1);
   uint8_t* stage0 = smem + 1024;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cb = blockIdx.x, rb = blockIdx.y;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tfull, 1);
+    mbar_init(tfull, 1); mbar_init(tempty, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mapB)) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tptr)), "r"((uint32_t)Cfg::TCOLS) : "memory");
@@ -168,69 +185,93 @@ ozaki_gemm_kernel(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl
 
   if (warp == 0) {
     if (lane == 0) {
-      const int8_t* a = Asl + (long long)rb * nk * S * A_TILE;
-      const int8_t* b = Bsl + (long long)cb * nk * S * B_TILE;
-      for (int ks = 0; ks < nk; ++ks) {
-        int st = ks % NST;
-        if (ks >= NST) mbar_wait(&empty[st], ((ks / NST) - 1) & 1, 1);
-        uint8_t* dst = stage0 + st * Cfg::STAGE;
-        mbar_expect_tx(&full[st], Cfg::STAGE);
-        bulk_g2s(dst, a + (long long)ks * S * A_TILE, S * A_TILE, &full[st]);
-        bulk_g2s(dst + S * A_TILE, b + (long long)ks * S * B_TILE, S * B_TILE, &full[st]);
+      int step = 0;
+      for (int r = 0; r < Cfg::NR; ++r) {
+        const int nsl = Cfg::nsl(r);
+        for (int ks = 0; ks < nk; ++ks, ++step) {
+          int st = step % NST;
+          if (step >= NST) mbar_wait(&empty[st], ((step / NST) - 1) & 1, 1);
+          uint8_t* dst = stage0 + st * Cfg::STAGE;
+          mbar_expect_tx(&full[st], nsl * (A_TILE + B_TILE));
+          // tensor-map rows are 128-byte core matrices; one slice tile = 32 rows
+          int rowA = ((rb * nk + ks) * S) * 32, rowB = ((cb * nk + ks) * S) * 32;
+          for (int s = 0; s < nsl; ++s) {
+            tma_load_2d(dst + s * A_TILE, &mapA, 0, rowA + s * 32, &full[st]);
+            tma_load_2d(dst + S * A_TILE + s * B_TILE, &mapB, 0, rowB + s * 32, &full[st]);
+          }
+        }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor (cute::UMMA::InstrDescriptor): D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10),
-      // both K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
-      for (int ks = 0; ks < nk; ++ks) {
-        int st = ks % NST;
-        mbar_wait(&full[st], (ks / NST) & 1, 2);
-        tc_fence_after();
-        uint32_t sA = smem_u32(stage0 + st * Cfg::STAGE), sB = sA + S * A_TILE;
+      int step = 0;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-          uint64_t da = make_desc(sA + s * A_TILE, TM * 16, 128);
+      for (int r = 0; r < Cfg::NR; ++r) {
+        constexpr int dummy = 0; (void)dummy;
+        const int glo = Cfg::glo(r), ghi = Cfg::ghi(r), nsl = Cfg::nsl(r);
+        if (r > 0) { mbar_wait(tempty, (r - 1) & 1, 4); tc_fence_after(); }
+        for (int ks = 0; ks < nk; ++ks, ++step) {
+          int st = step % NST;
+          mbar_wait(&full[st], (step / NST) & 1, 2);
+          tc_fence_after();
+          uint32_t sA = smem_u32(stage0 + st * Cfg::STAGE), sB = sA + S * A_TILE;
+          uint32_t written = (ks > 0) ? 0xFFu : 0u;
 #pragma unroll
-          for (int t = 0; t < S - s; ++t) {
-            uint64_t db = make_desc(sB + t * B_TILE, TN * 16, 128);
-            tc_mma_i8(tbase + (uint32_t)((s + t) * TN), da, db, idesc, (ks > 0 || s > 0) ? 1u : 0u);
+          for (int s = 0; s < S; ++s) {
+            if (s >= nsl) continue;
+            uint64_t da = make_desc(sA + s * A_TILE, TM * 16, 128);
+#pragma unroll
+            for (int t = 0; t < S; ++t) {
+              int g = s + t;
+              if (t >= nsl || g < glo || g > ghi) continue;
+              uint64_t db = make_desc(sB + t * B_TILE, TN * 16, 128);
+              tc_mma_i8(tbase + (uint32_t)((g - glo) * TN), da, db, idesc, (written >> g) & 1u);
+              written |= 1u << g;
+            }
           }
+          tc_commit(&empty[st]);
         }
-        tc_commit(&empty[st]);
+        tc_commit(tfull);
       }
-      tc_commit(tfull);
     }
   } else {
     // epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 (rows of the tile)
     const int q = warp & 3;
-    mbar_wait(tfull, 0, 3);
-    tc_fence_after();
     const int row = rb * TM + q * 32 + lane;
     const double srow = sa[row];
     double* crow = C + (long long)row * ldc + (long long)cb * TN;
+#pragma unroll
+    for (int r = 0; r < Cfg::NR; ++r) {
+      const int glo = Cfg::glo(r), ghi = Cfg::ghi(r);
+      mbar_wait(tfull, r & 1, 3);
+      tc_fence_after();
 #pragma unroll 1
-    for (int c0 = 0; c0 < TN; c0 += 16) {
-      double acc[16];
+      for (int c0 = 0; c0 < TN; c0 += 16) {
+        double acc[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = 0.0;
+        for (int j = 0; j < 16; ++j) acc[j] = (r == 0) ? 0.0 : crow[c0 + j];   // partial Horner sum of the low groups
 #pragma unroll
-      for (int g = S - 1; g >= 0; --g) {          // smallest weight first
-        uint32_t v[16];
-        tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * TN + c0), v);
-        tc_wait_ld();
-        // acc = acc / 128 + G_g  (Horner in the slice weight: exact scalings)
+        for (int g = S - 1; g >= 0; --g) {        // smallest weight first: acc = acc / 128 + G_g
+          if (g < glo || g > ghi) continue;
+          uint32_t v[16];
+          tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * TN + c0), v);
+          tc_wait_ld();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.0078125, (double)(int)v[j]);
+          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.0078125, (double)(int)v[j]);
+        }
+        if (r == Cfg::NR - 1) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) crow[c0 + j] = acc[j] * srow * sb[cb * TN + c0 + j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) crow[c0 + j] = acc[j];
+        }
       }
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        double r = acc[j] * srow * sb[cb * TN + c0 + j];
-        crow[c0 + j] = accumulate_sub ? crow[c0 + j] - r : r;
-      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty)) : "memory");
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -238,7 +279,6 @@ ozaki_gemm_kernel(const int8_t* __restrict__ Asl, const int8_t* __restrict__ Bsl
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"((uint32_t)Cfg::TCOLS) : "memory");
   }
 }
-
 
 // ------------------------------------------------------------------------------------------------------------------
 // Issue-rate probe: one CTA per SM issues `count` kind::i8 MMAs of shape 128 x N x 32 from fixed shared-memory tiles
@@ -293,6 +333,29 @@ void run_rate(int sms, double ghz) {
   CK(cudaFree(d));
 }
 
+
+// 2-D tensor map over a slice array seen as rows of 128-byte core matrices; box = one slice tile (32 rows = 4096 bytes).
+// No swizzle / interleave: the box lands in shared memory exactly as it lies in global memory (the UMMA no-swizzle layout).
+static CUtensorMap make_map(const void* base, size_t bytes) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                               CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { fprintf(stderr, "cuTensorMapEncodeTiled not found\n"); exit(2); }
+  }
+  CUtensorMap m;
+  cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {128, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "cuTensorMapEncodeTiled failed: %d\n", (int)r); exit(2); }
+  return m;
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 struct Result { double ms_slice, ms_gemm, max_rel_norm, max_rel_comp; };
 
@@ -306,6 +369,7 @@ Result run_ozaki(const double* dA, const double* dB, double* dC, int M, int N, i
   CK(cudaMalloc(&dAs, (size_t)M * K * S)); CK(cudaMalloc(&dBs, (size_t)N * K * S));
   CK(cudaMalloc(&dsa, M * sizeof(double))); CK(cudaMalloc(&dsb, N * sizeof(double)));
   CK(cudaFuncSetAttribute(ozaki_gemm_kernel<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM));
+  CUtensorMap mapA = make_map(dAs, (size_t)M * K * S), mapB = make_map(dBs, (size_t)N * K * S);
   cudaEvent_t e0, e1, e2; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1)); CK(cudaEventCreate(&e2));
   float ts = 0, tg = 0;
   for (int it = 0; it < reps + 1; ++it) {
@@ -313,7 +377,7 @@ Result run_ozaki(const double* dA, const double* dB, double* dC, int M, int N, i
     slice_kernel<S, TM><<<(M + 7) / 8, 256>>>(dA, M, K, K, dAs, dsa);
     slice_kernel<S, TN><<<(N + 7) / 8, 256>>>(dB, N, K, K, dBs, dsb);
     CK(cudaEventRecord(e1));
-    ozaki_gemm_kernel<S><<<dim3(N / TN, M / TM), 192, Cfg::SMEM>>>(dAs, dBs, dsa, dsb, dC, N, nk, 0);
+    ozaki_gemm_kernel<S><<<dim3(N / TN, M / TM), 192, Cfg::SMEM>>>(mapA, mapB, dsa, dsb, dC, N, nk);
     CK(cudaEventRecord(e2));
     CK(cudaEventSynchronize(e2));
     CK(cudaGetLastError());
