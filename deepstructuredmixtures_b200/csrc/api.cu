@@ -31,6 +31,7 @@ cudaError_t dsm::engine_attrs() {
   std::lock_guard<std::mutex> g(g_attr_mu);
   if (dev >= 0 && dev < 256 && ((g_attr_done[dev >> 6] >> (dev & 63)) & 1)) return cudaSuccess;
   if ((e = init_v2_kernels())) return e;
+  if ((e = oz_init_kernels())) return e;
   if (dev >= 0 && dev < 256) g_attr_done[dev >> 6] |= (uint64_t(1) << (dev & 63));
   return cudaSuccess;
 }
@@ -356,6 +357,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       std::vector<int4> it(iv.size());
       for (size_t i = 0; i < iv.size(); i++) it[i] = make_int4(iv[i].slot, iv[i].I, iv[i].J, 0);
       b.n_trtri3 = (int)it.size();
+      b.h_trtri3 = it;
       CUDA_TRY(h, upload(&b.d_trtri3_tasks, it));
       {   // the same tiles in the order of the fused launch: level of block row I in the factorisation's order, then row-major
         std::vector<TK> mv;
@@ -464,7 +466,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       cudaFree(d_x); cudaFree(d_obs); cudaFree(d_obs_off);
     }
   }
-  return DSMGP_OK;
+  return oz_plan(h);
 }
 
 extern "C" int32_t dsmgp_create(const double* x, int64_t N, int64_t D, int64_t L, const int64_t* leaf_ptr,
@@ -717,8 +719,14 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
         Trtri3Args ta{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
                       h->d_flags.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, b.d_trtri3_tasks, b.n_trtri3,
                       h->d_counter.p, h->d_counter.p + GERR, mask_all ? mask_all + b.s0 : nullptr};
-        launch_trtri3(ta, std::max(1, std::min(sms, b.n_trtri3)), b.d_trtri_tasks, b.n_trtri, st);
-        h->tm.launches += 2;
+        // large experts: off-diagonal parts of the inverse as GEMMs on the INT8 tensor cores (api_ozaki.cu)
+        if (b.oz.active && !mask_all && !shr && !h->capturing) {
+          const int32_t rc = oz_run_inverse(h, b, ta, sms, st);
+          if (rc != DSMGP_OK) return rc;
+        } else {
+          launch_trtri3(ta, std::max(1, std::min(sms, b.n_trtri3)), b.d_trtri_tasks, b.n_trtri, st);
+          h->tm.launches += 2;
+        }
       }
       }   // !fused
     }

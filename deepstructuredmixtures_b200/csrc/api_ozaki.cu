@@ -1,0 +1,193 @@
+// Split triangular inverse with the off-diagonal products on the INT8 tensor cores (ozaki_args.h, ozaki.cuh).
+//
+// For an expert with nb block rows the block range [lo, hi) is split at mid (recursively, DSMGP_OZAKI_DEPTH levels):
+//     X[mid:hi, lo:mid] = -X22 (L21 X11),   X11 = X[lo:mid, lo:mid],  X22 = X[mid:hi, mid:hi],  L21 = L[mid:hi, lo:mid].
+// The tile pipeline (trtri3.cuh) computes only the tiles whose row and column block lie in the same leaf range; every
+// split then costs two batched GEMM launches with their slicing passes, deepest level first:
+//     stage 1:  T^T = X11^T L21^T      (A = rows of X^T in the upper block triangle / W^T, B = rows of L; K = [Jb, mid))
+//     stage 2:  X21^T = -T^T X22^T     (A = rows of T^T, B = rows of X22 read transposed / W; K = [mid, Ib]), written
+//               into the upper block triangle of the factor arena where the tile pipeline would have put it.
+// The fused partials of those tiles (||X_IJ||^2, X_IJ^T z_I) come from a small kernel afterwards.
+#include "handle.h"
+
+namespace dsm {
+
+namespace {
+struct Split { int slot, lo, mid, hi; };
+
+void collect_splits(int slot, int lo, int hi, int depth, int maxdepth, int min_nb, std::vector<std::vector<Split>>& levels,
+                    std::vector<int>& range_of, int& nranges) {
+  if (depth >= maxdepth || hi - lo < min_nb) {
+    for (int b = lo; b < hi; b++) range_of[b] = nranges;
+    nranges++;
+    return;
+  }
+  const int mid = lo + (hi - lo) / 2;
+  collect_splits(slot, lo, mid, depth + 1, maxdepth, min_nb, levels, range_of, nranges);
+  collect_splits(slot, mid, hi, depth + 1, maxdepth, min_nb, levels, range_of, nranges);
+  levels[depth].push_back({slot, lo, mid, hi});
+}
+}  // namespace
+
+int oz_env_slices() {
+  const char* e = getenv("DSMGP_OZAKI_SLICES");
+  const int s = e ? atoi(e) : 8;
+  return s == 7 ? 7 : 8;
+}
+
+// Builds the plan of every batch (sizes first, then the job / tile lists with final pointers).  Called at the end of
+// create; a handle without large experts, with several ranks' masks etc. simply keeps oz.active == false.
+int32_t oz_plan(dsmgp_handle* h) {
+  const char* en = getenv("DSMGP_OZAKI");
+  if (!en || en[0] != '1') return DSMGP_OK;
+  const char* de = getenv("DSMGP_OZAKI_DEPTH");
+  const char* me = getenv("DSMGP_OZAKI_MIN_NB");
+  const int maxdepth = de ? std::max(1, std::min(4, atoi(de))) : 1;
+  const int min_nb = me ? std::max(2, atoi(me)) : 8;
+  const int S = oz_env_slices();
+  h->oz_S = S;
+  struct Tmp { std::vector<std::vector<Split>> levels; std::vector<std::vector<int>> range_of; };
+  std::vector<Tmp> tmp(h->batches.size());
+  int64_t max_pool = 0, max_scratch = 0, max_scale = 0;
+  // pass 1: splits and sizes
+  for (size_t bi = 0; bi < h->batches.size(); bi++) {
+    Batch& b = h->batches[bi];
+    Tmp& t = tmp[bi];
+    t.levels.assign(maxdepth, {});
+    t.range_of.resize(b.s1 - b.s0);
+    bool any = false;
+    for (int s = b.s0; s < b.s1; s++) {
+      const int nb = h->meta[s].nb;
+      t.range_of[s - b.s0].assign(nb, 0);
+      int nr = 0;
+      collect_splits(s - b.s0, 0, nb, 0, maxdepth, min_nb, t.levels, t.range_of[s - b.s0], nr);
+      any |= nr > 1;
+    }
+    if (!any) continue;
+    b.oz.active = true;
+    for (auto& lv : t.levels) {
+      int64_t pool = 0, scratch = 0, scale = 0;
+      for (const Split& sp : lv) {
+        const int64_t J1 = sp.mid - sp.lo, J2 = sp.hi - sp.mid;
+        pool += (J1 * J1 + 2 * J1 * J2 + J2 * J2) * OZ_KSTEPS_PER_BLK * S;     // slice tiles: X11^T, L21, T^T, X22
+        scratch += J1 * J2 * WBLK_D;
+        scale += 2 * (J1 + J2) * BLK;
+      }
+      max_pool = std::max(max_pool, pool); max_scratch = std::max(max_scratch, scratch); max_scale = std::max(max_scale, scale);
+    }
+  }
+  if (max_pool == 0) return DSMGP_OK;
+  CUDA_TRY(h, h->oz_pool.alloc((size_t)max_pool * OZ_TILE_B));
+  CUDA_TRY(h, h->oz_scratch.alloc((size_t)max_scratch));
+  CUDA_TRY(h, h->oz_scale.alloc((size_t)max_scale));
+  CUDA_TRY(h, h->oz_rowmax.alloc((size_t)max_scale));
+  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)max_pool * OZ_TILE_B) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return DSMGP_ERR_CUDA; }
+  // pass 2: lists
+  for (size_t bi = 0; bi < h->batches.size(); bi++) {
+    Batch& b = h->batches[bi];
+    if (!b.oz.active) continue;
+    Tmp& t = tmp[bi];
+    // tile-pipeline tasks restricted to the leaf ranges (order of the full list kept: still topological)
+    std::vector<int4> keep;
+    for (const int4& tk : b.h_trtri3) {
+      const std::vector<int>& ro = t.range_of[tk.x];
+      if (ro[tk.y] == ro[tk.z]) keep.push_back(tk);
+    }
+    b.oz.n_tasks = (int)keep.size();
+    CUDA_TRY(h, upload(&b.oz.d_tasks, keep));
+    std::vector<OzPart> parts;
+    double flops = 0.0;
+    for (int lv = maxdepth - 1; lv >= 0; lv--) {         // deepest level first
+      if (t.levels[lv].empty()) continue;
+      OzLevel L;
+      std::vector<OzJob> j1, j2; std::vector<OzTile> t1, t2;
+      int64_t pool = 0, scratch = 0; int scale = 0;
+      for (const Split& sp : t.levels[lv]) {
+        const LeafMeta& m = h->meta[b.s0 + sp.slot];
+        const int J1 = sp.mid - sp.lo, J2 = sp.hi - sp.mid, KB = OZ_KSTEPS_PER_BLK;
+        const double* F = h->d_F.p + m.foff;
+        const double* W = h->d_W.p + m.woff; const double* WT = h->d_WT.p + m.woff;
+        auto wid = [&](int blk) { const int w = m.np - blk * BLK; return w < BLK ? w : BLK; };
+        auto fblk = [&](int rb, int cb) { return F + tile_off(rb, cb * (BLK / KC), m.nkc); };
+        // operand pools (tile indices) and scales
+        const int64_t pA1 = pool; pool += (int64_t)J1 * J1 * KB * S;      // X11^T : J1 row blocks x J1 k blocks
+        const int64_t pB1 = pool; pool += (int64_t)J2 * J1 * KB * S;      // L21   : J2 x J1
+        const int64_t pA2 = pool; pool += (int64_t)J1 * J2 * KB * S;      // T^T   : J1 x J2
+        const int64_t pB2 = pool; pool += (int64_t)J2 * J2 * KB * S;      // X22   : J2 x J2
+        const int sA1 = scale; scale += J1 * BLK;
+        const int sB1 = scale; scale += J2 * BLK;
+        const int sA2 = scale; scale += J1 * BLK;
+        const int sB2 = scale; scale += J2 * BLK;
+        double* T = h->oz_scratch.p + scratch; scratch += (int64_t)J1 * J2 * WBLK_D;
+        for (int a = 0; a < J1; a++) {                                       // a = Jb - lo
+          const int Jb = sp.lo + a;
+          for (int k = a; k < J1; k++) {                                     // X^T block (Jb, Kb), Kb >= Jb
+            const int Kb = sp.lo + k;
+            j1.push_back({Kb == Jb ? WT + (int64_t)Jb * WBLK_D : fblk(Jb, Kb), 0, BLK, BLK, sA1 + a * BLK, pA1 + ((int64_t)a * J1 + k) * KB * S});
+          }
+          for (int c = 0; c < J2; c++) {
+            const int Ib = sp.mid + c;
+            t1.push_back({(int)(pA1 + (int64_t)a * J1 * KB * S), (int)(pB1 + (int64_t)c * J1 * KB * S), a * KB, J1 * KB, sA1 + a * BLK, sB1 + c * BLK,
+                          BLK, wid(Ib), T + ((int64_t)a * J2 + c) * WBLK_D, 1.0});
+            j2.push_back({T + ((int64_t)a * J2 + c) * WBLK_D, 0, BLK, wid(Ib), sA2 + a * BLK, pA2 + ((int64_t)a * J2 + c) * KB * S});
+            // k-steps of a half-wide last block beyond its width hold zeros: stop before them
+            const int kend = c * KB + (wid(Ib) + OZ_KSTEP - 1) / OZ_KSTEP;
+            t2.push_back({(int)(pA2 + (int64_t)a * J2 * KB * S), (int)(pB2 + (int64_t)c * J2 * KB * S), 0, kend, sA2 + a * BLK, sB2 + c * BLK,
+                          BLK, wid(Ib), const_cast<double*>(fblk(Jb, Ib)), -1.0});
+            parts.push_back({sp.slot, Ib, Jb});
+            flops += 2.0 * BLK * BLK * OZ_KSTEP * ((double)(J1 - a) * KB + kend);
+          }
+        }
+        for (int c = 0; c < J2; c++) {
+          const int Ib = sp.mid + c;
+          for (int k = 0; k < J1; k++)                                       // L block (Ib, Kb)
+            j1.push_back({fblk(Ib, sp.lo + k), 0, wid(Ib), BLK, sB1 + c * BLK, pB1 + ((int64_t)c * J1 + k) * KB * S});
+          for (int k = 0; k <= c; k++) {                                     // X22 block (Ib, Kb), Kb <= Ib: stored transposed above the diagonal
+            const int Kb = sp.mid + k;
+            if (Kb == Ib) j2.push_back({W + (int64_t)Ib * WBLK_D, 0, wid(Ib), wid(Ib), sB2 + c * BLK, pB2 + ((int64_t)c * J2 + k) * KB * S});
+            else j2.push_back({fblk(Kb, Ib), 1, wid(Ib), BLK, sB2 + c * BLK, pB2 + ((int64_t)c * J2 + k) * KB * S});
+          }
+        }
+      }
+      // long blocks first: the hardware hands CTAs out in grid order
+      auto by_len = [](const OzTile& x, const OzTile& y) { return (x.k1 - x.k0) > (y.k1 - y.k0); };
+      std::stable_sort(t1.begin(), t1.end(), by_len);
+      std::stable_sort(t2.begin(), t2.end(), by_len);
+      L.n_jobs1 = (int)j1.size(); L.n_jobs2 = (int)j2.size(); L.n_tiles1 = (int)t1.size(); L.n_tiles2 = (int)t2.size(); L.n_scale = scale;
+      CUDA_TRY(h, upload(&L.d_jobs1, j1)); CUDA_TRY(h, upload(&L.d_jobs2, j2));
+      CUDA_TRY(h, upload(&L.d_tiles1, t1)); CUDA_TRY(h, upload(&L.d_tiles2, t2));
+      b.oz.levels[b.oz.n_levels++] = L;
+    }
+    b.oz.n_parts = (int)parts.size();
+    CUDA_TRY(h, upload(&b.oz.d_parts, parts));
+    b.oz.gemm_flops = flops;
+  }
+  return DSMGP_OK;
+}
+
+// The inverse of one batch: restricted tile pipeline, then per level  slice -> GEMM 1 -> slice -> GEMM 2,  then the
+// partials of the GEMM-written tiles and the block-column reduction (alpha, tr(F^-1)).
+int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st) {
+  Trtri3Args ta = full;
+  ta.tasks = b.oz.d_tasks; ta.ntasks = b.oz.n_tasks;
+  launch_trtri3_only(ta, std::max(1, std::min(sms, ta.ntasks)), st);
+  const int S = h->oz_S;
+  for (int li = 0; li < b.oz.n_levels; li++) {
+    const OzLevel& L = b.oz.levels[li];
+    CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)L.n_scale * sizeof(unsigned long long), st));
+    launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_gemm(S, h->oz_map, L.d_tiles1, L.n_tiles1, h->oz_scale.p, st);
+    launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_gemm(S, h->oz_map, L.d_tiles2, L.n_tiles2, h->oz_scale.p, st);
+    h->tm.launches += 6;
+  }
+  OzPartArgs pa{full.meta, full.F, full.z, full.flag_off, full.apart, full.tpart, b.oz.d_parts};
+  launch_oz_parts(pa, b.oz.n_parts, st);
+  launch_alpha_reduce(full, b.d_trtri_tasks, b.n_trtri, st);
+  h->tm.launches += 3;
+  return DSMGP_OK;
+}
+
+}  // namespace dsm

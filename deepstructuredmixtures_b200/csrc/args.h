@@ -149,6 +149,8 @@ struct Trtri3Args;
 cudaError_t init_v2_kernels();
 void launch_potrf2(const Potrf2Args& a, int nctas, cudaStream_t st);
 void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, cudaStream_t st);
+void launch_trtri3_only(const Trtri3Args& a, int nctas, cudaStream_t st);                      // without the block-column reduction
+void launch_alpha_reduce(const Trtri3Args& a, const int2* cols, int ncols, cudaStream_t st);
 void launch_eval2(const Potrf2Args& pa, const Trtri3Args& ta, int nctas, const int2* cols, int ncols, cudaStream_t st);
 void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st);
 void launch_ov_count(const int64_t* obs, int64_t total, int* cntp, cudaStream_t st);

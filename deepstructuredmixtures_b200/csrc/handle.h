@@ -12,6 +12,7 @@
 #include "../../include/dsmgp.h"
 #include "args.h"
 #include "potrf2_args.h"
+#include "ozaki_args.h"
 #include "tree_host.h"
 
 namespace dsm {
@@ -50,6 +51,8 @@ struct Batch {
   int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
+  std::vector<int4> h_trtri3;                           // host copy of d_trtri3_tasks (filtered by the INT8 split plan)
+  OzPlan oz;                                            // split inverse on the INT8 tensor cores (api_ozaki.cu), DSMGP_OZAKI=1
 };
 
 // Process-wide cache of large device buffers.  cudaMalloc / cudaFree of multi-GB arenas cost 10 ms ... 3 s each
@@ -212,6 +215,9 @@ struct dsmgp_handle {
   std::vector<int> exec_slot;             // global leaf -> slot that holds its results (the source's slot for an alias)
   void* comm = nullptr;                   // ncclComm_t (dsmgp_comm_init), or null
   DevBuf<double> d_comm_buf;              // device staging for the prediction all-reduce
+  // split inverse on the INT8 tensor cores: slice pool + its tensor map, T^T scratch, row scales
+  DevBuf<int8_t> oz_pool; DevBuf<double> oz_scratch, oz_scale; DevBuf<unsigned long long> oz_rowmax;
+  alignas(64) unsigned char oz_map[128]; int oz_S = 8;
   std::string err;
 
   ~dsmgp_handle() {
@@ -219,8 +225,11 @@ struct dsmgp_handle {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
       cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
       cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots); cudaFree(b.d_trtri3m_tasks);
+      cudaFree(b.oz.d_tasks); cudaFree(b.oz.d_parts);
+      for (int l = 0; l < b.oz.n_levels; l++) { cudaFree(b.oz.levels[l].d_jobs1); cudaFree(b.oz.levels[l].d_jobs2); cudaFree(b.oz.levels[l].d_tiles1); cudaFree(b.oz.levels[l].d_tiles2); }
     }
     d_flags2.free();
+    oz_pool.free(); oz_scratch.free(); oz_scale.free(); oz_rowmax.free();
     d_share.free(); d_comm_buf.free();
     dsm::comm_destroy(comm);
     d_meta.free(); d_xg.free(); d_y.free(); d_z.free(); d_alpha.free(); d_F.free(); d_W.free(); d_WT.free();
@@ -268,4 +277,7 @@ int32_t check_pd(dsmgp_handle* h);
 // potrf2 task list of one batch in topological look-ahead order, restricted to the slots with keep[slot - b.s0] != 0
 std::vector<int4> build_potrf2_tasks(const dsmgp_handle* h, const Batch& b, const std::vector<char>& keep, int sms);
 int32_t standalone_device_check(std::string& err);
+// api_ozaki.cu
+int32_t oz_plan(dsmgp_handle* h);
+int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st);
 }  // namespace dsm

@@ -1,0 +1,56 @@
+// Launchers of the INT8-tensor-core block products (ozaki.cuh).
+#include "ozaki.cuh"
+
+namespace dsm {
+
+cudaError_t oz_init_kernels() {
+  cudaError_t e;
+  if ((e = cudaFuncSetAttribute(oz::gemm_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<7>::SMEM))) return e;
+  if ((e = cudaFuncSetAttribute(oz::gemm_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, oz::Cfg<8>::SMEM))) return e;
+  return cudaSuccess;
+}
+
+// 2-D tensor map over the slice pool seen as rows of 128-byte core matrices; box = one slice tile (32 rows = 4096 bytes).
+// No swizzle, no interleave: a box lands in shared memory exactly as it lies in global memory, which is the UMMA
+// no-swizzle K-major layout the slicing kernel wrote.  cuTensorMapEncodeTiled comes from the driver through the runtime
+// (the library does not link libcuda).
+int oz_make_map(void* map128, const void* pool, size_t bytes) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void**)&fn, cudaEnableDefault, &q) != cudaSuccess || !fn ||
+        q != cudaDriverEntryPointSuccess) { fn = nullptr; return 1; }
+  }
+  static_assert(sizeof(CUtensorMap) == 128, "tensor map size");
+  cuuint64_t dims[2] = {128, (cuuint64_t)(bytes / 128)};
+  cuuint64_t strides[1] = {128};
+  cuuint32_t box[2] = {128, 32};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = fn(reinterpret_cast<CUtensorMap*>(map128), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(pool), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 2;
+}
+
+void launch_oz_slice(int S, const OzJob* jobs, int njobs, int pass, unsigned long long* rowmax, double* scale, int8_t* pool, cudaStream_t st) {
+  if (njobs <= 0) return;
+  if (S == 7) oz::slice_kernel<7><<<njobs, 256, 0, st>>>(jobs, pass, rowmax, scale, pool);
+  else oz::slice_kernel<8><<<njobs, 256, 0, st>>>(jobs, pass, rowmax, scale, pool);
+}
+
+void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, cudaStream_t st) {
+  if (ntiles <= 0) return;
+  CUtensorMap map;
+  memcpy(&map, map128, sizeof(map));
+  if (S == 7) oz::gemm_kernel<7><<<ntiles, 192, oz::Cfg<7>::SMEM, st>>>(map, tiles, scale);
+  else oz::gemm_kernel<8><<<ntiles, 192, oz::Cfg<8>::SMEM, st>>>(map, tiles, scale);
+}
+
+void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st) {
+  if (nparts <= 0) return;
+  oz::parts_kernel<<<nparts, BLK, 0, st>>>(a);
+}
+
+}  // namespace dsm

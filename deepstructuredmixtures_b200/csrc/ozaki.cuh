@@ -1,0 +1,298 @@
+// FP64-accurate block products on the INT8 tcgen05 tensor cores (sm_100a), used by the split triangular inverse
+// (ozaki_args.h, api_ozaki.cu).  Stand-alone prototype with the accuracy and rate measurements: tools/ozaki_proto.cu.
+//
+// Ozaki split, error-free: each operand row gets one power-of-two scale 2^e (its largest magnitude over K), the scaled
+// entries are cut into S signed 7-bit slices  x = 2^(e-6) * sum_s q_s 128^-s, |q_s| <= 64  (exact in FP64).  A product
+// of two slices accumulates EXACTLY in an int32 TMEM accumulator (|sum| <= 4096 * 8 * K < 2^31 for K <= 65,536); the
+// pairs with s + t = g share the weight 128^-g and one accumulator; pairs with s + t >= S are dropped (< 2^-7S of
+// rowmax * colmax per term).  S = 8 gives products that are MORE accurate than an FP64 FMA chain (measured: 2e-15 of
+// max|C| on Cholesky-factor operands against 4e-15 for cuBLAS DGEMM).
+//
+// GEMM kernel: one CTA per 128 x 128 output block.  warp 0 = TMA producer (cp.async.bulk.tensor.2d of 4 KB slice
+// tiles into a mbarrier ring), warp 1 = TMEM allocation + tcgen05.mma.kind::i8 issue (M = N = 128, K = 32), warps 2-5 =
+// epilogue (tcgen05.ld, int32 -> FP64, Horner sum over the slice groups, row scales, store in the factor-tile layout).
+// S groups of 128 columns do not fit TMEM (512 columns), so a block is computed in two rounds over K: the four
+// lowest-weight groups first, their partial sum parked in the output block, then the remaining S - 4 groups.
+#pragma once
+#include <cuda.h>
+#include "ozaki_args.h"
+
+namespace dsm {
+namespace oz {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol error must not hang the device; the trap surfaces as a CUDA error of the call
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+      " tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}\n"
+      ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle (UMMA SmemDescriptor, version 1): [0,14) address >> 4,
+// [16,30) byte offset between the two 16-byte K chunks >> 4, [32,46) byte offset between 8-row groups >> 4, [46,48) = 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((BLK * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+
+template <int S>
+struct Cfg {
+  static constexpr int NR = (S > 4) ? 2 : 1;
+  static constexpr int STAGE = 2 * S * OZ_TILE_B;
+  static constexpr int NST = (220 * 1024) / STAGE;
+  static constexpr int SMEM = NST * STAGE + 1024;
+  __host__ __device__ static constexpr int glo(int r) { return (NR == 2 && r == 0) ? S - 4 : 0; }
+  __host__ __device__ static constexpr int ghi(int r) { return (NR == 2 && r == 1) ? S - 5 : S - 1; }
+  __host__ __device__ static constexpr int nsl(int r) { return ghi(r) + 1; }
+};
+
+// ---- slicing ---------------------------------------------------------------------------------------------------------
+// grid = jobs, 256 threads: thread = (operand row i, 16-wide k chunk).  pass 0: row maxima (atomicMax on the bit pattern
+// of |x|, monotone for non-negative doubles); pass 1: the slices, 16 bytes per thread and slice.
+template <int S>
+__global__ void __launch_bounds__(256) slice_kernel(const OzJob* __restrict__ jobs, int pass, unsigned long long* __restrict__ rowmax,
+                                                    double* __restrict__ scale, int8_t* __restrict__ pool) {
+  const OzJob j = jobs[blockIdx.x];
+  const int i = threadIdx.x & 127;
+  double inv = 0.0;
+  if (pass == 1) {
+    const double m = __longlong_as_double((long long)rowmax[j.scale + i]);
+    int e = 0;
+    if (m > 0.0 && m < 1.0e300) frexp(m, &e);
+    inv = ldexp(64.0, -e);
+    scale[j.scale + i] = ldexp(1.0, e - 6);        // every block of the row writes the same value
+  }
+  double mx = 0.0;
+#pragma unroll 1
+  for (int kc = threadIdx.x >> 7; kc < BLK / 16; kc += 2) {
+    double v[16];
+    if (i < j.vr) {
+      if (!j.transposed) {
+        const double* p = j.src + kc * TILE_D + i;
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = (16 * kc + q < j.vk) ? p[q * LDS] : 0.0;
+      } else {
+        const double* p = j.src + (i >> 4) * TILE_D + (i & 15) * LDS + 16 * kc;
+#pragma unroll
+        for (int q = 0; q < 16; q++) v[q] = (16 * kc + q < j.vk) ? p[q] : 0.0;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; q++) v[q] = 0.0;
+    }
+    if (pass == 0) {
+#pragma unroll
+      for (int q = 0; q < 16; q++) mx = fmax(mx, fabs(v[q]));
+    } else {
+      int8_t* dst = pool + (j.dst + (int64_t)(kc >> 1) * S) * OZ_TILE_B + (kc & 1) * (BLK * 16) + (i >> 3) * 128 + (i & 7) * 16;
+#pragma unroll
+      for (int q = 0; q < 16; q++) v[q] *= inv;
+#pragma unroll
+      for (int s = 0; s < S; s++) {
+        uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+          const double r = rint(v[q]);
+          v[q] = (v[q] - r) * 128.0;
+          w[q >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)r) << ((q & 3) * 8);
+        }
+        *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_TILE_B) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+  }
+  if (pass == 0 && mx > 0.0) atomicMax(rowmax + j.scale + i, (unsigned long long)__double_as_longlong(mx));
+}
+
+// ---- block products ----------------------------------------------------------------------------------------------------
+template <int S>
+__global__ void __launch_bounds__(192, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ tiles, const double* __restrict__ scale) {
+  using C = Cfg<S>;
+  constexpr int NST = C::NST;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NST;
+  uint64_t* tfull = empty + NST;
+  uint64_t* tempty = tfull + 1;
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty + 1);
+  uint8_t* stage0 = smem + 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const OzTile t = tiles[blockIdx.x];
+  const int nk = t.k1 - t.k0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map)) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tptr)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tptr;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int step = 0;
+      for (int r = 0; r < C::NR; ++r) {
+        const int nsl = C::nsl(r);
+        for (int ks = t.k0; ks < t.k1; ++ks, ++step) {
+          const int st = step % NST;
+          if (step >= NST) mbar_wait(&empty[st], ((step / NST) - 1) & 1);
+          uint8_t* dst = stage0 + st * C::STAGE;
+          mbar_expect_tx(&full[st], nsl * 2 * OZ_TILE_B);
+          const int rowA = (t.a_tile + ks * S) * 32, rowB = (t.b_tile + ks * S) * 32;   // tensor-map rows = 128-byte core matrices
+          for (int s = 0; s < nsl; ++s) {
+            tma_load_2d(dst + s * OZ_TILE_B, &map, 0, rowA + s * 32, &full[st]);
+            tma_load_2d(dst + (S + s) * OZ_TILE_B, &map, 0, rowB + s * 32, &full[st]);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), K-major, N >> 3 at 17, M >> 4 at 24
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLK >> 3) << 17) | ((uint32_t)(BLK >> 4) << 24);
+      int step = 0;
+#pragma unroll
+      for (int r = 0; r < C::NR; ++r) {
+        const int glo = C::glo(r), ghi = C::ghi(r), nsl = C::nsl(r);
+        if (r > 0) { mbar_wait(tempty, (r - 1) & 1); tc_fence_after(); }
+        for (int ks = 0; ks < nk; ++ks, ++step) {
+          const int st = step % NST;
+          mbar_wait(&full[st], (step / NST) & 1);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(stage0 + st * C::STAGE), sB = sA + S * OZ_TILE_B;
+          uint32_t written = (ks > 0) ? 0xFFu : 0u;
+#pragma unroll
+          for (int s = 0; s < S; ++s) {
+            if (s >= nsl) continue;
+            const uint64_t da = make_desc(sA + s * OZ_TILE_B);
+#pragma unroll
+            for (int u = 0; u < S; ++u) {
+              const int g = s + u;
+              if (u >= nsl || g < glo || g > ghi) continue;
+              tc_mma_i8(tbase + (uint32_t)((g - glo) * BLK), da, make_desc(sB + u * OZ_TILE_B), idesc, (written >> g) & 1u);
+              written |= 1u << g;
+            }
+          }
+          tc_commit(&empty[st]);
+        }
+        tc_commit(tfull);
+      }
+    }
+  } else {
+    // epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 = rows of the block
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const bool rok = row < t.vr;
+    const double srow = rok ? scale[t.sa + row] * t.sign : 0.0;
+#pragma unroll
+    for (int r = 0; r < C::NR; ++r) {
+      const int glo = C::glo(r), ghi = C::ghi(r);
+      mbar_wait(tfull, r & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLK; c0 += 16) {
+        if (c0 >= t.vc) break;                                   // vc is a multiple of 16; uniform over the CTA
+        double* o = t.out + (c0 >> 4) * TILE_D + row;            // column c0 + j at o[j * LDS]
+        double acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j] = (r == 0 || !rok) ? 0.0 : o[j * LDS];   // partial Horner sum of the low groups
+#pragma unroll
+        for (int g = S - 1; g >= 0; --g) {                       // smallest weight first: acc = acc / 128 + G_g
+          if (g < glo || g > ghi) continue;
+          uint32_t v[16];
+          tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * BLK + c0), v);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.0078125, (double)(int)v[j]);
+        }
+        if (rok) {
+          if (r == C::NR - 1) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j * LDS] = acc[j] * srow * scale[t.sb + c0 + j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) o[j * LDS] = acc[j];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty)) : "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tbase), "r"(512u) : "memory");
+  }
+}
+
+// ---- fused partials of the inverse tiles written by the GEMMs (what trtri3_consume computes in its epilogue) ------------
+// tpart[tile] = ||X_IJ||_F^2 over real rows / columns, apart[tile][c] = (X_IJ^T z_I)[c].  The block holds X_IJ^T:
+// (r = column c of X_IJ, col = row i of X_IJ).  One CTA of BLK threads per tile, fixed summation order.
+__global__ void __launch_bounds__(BLK) parts_kernel(OzPartArgs a) {
+  __shared__ double s_red[BLK / 32];
+  const OzPart p = a.parts[blockIdx.x];
+  const LeafMeta m = a.meta[p.slot];
+  const int i0 = p.I * BLK, j0 = p.J * BLK, wi = blk_width(m.np, p.I), tid = threadIdx.x;
+  const double* blk = a.F + m.foff + tile_off(p.J, p.I * (BLK / KC), m.nkc);
+  const double* z = a.z + m.voff + i0;
+  const int64_t tile = a.flag_off[p.slot] + (int64_t)p.I * (p.I + 1) / 2 + p.J;
+  double tr = 0.0, s = 0.0;
+  const bool rowok = j0 + tid < m.n;
+  for (int i = 0; i < wi; i++) {
+    if (i0 + i < m.n && rowok) {
+      const double v = blk[(i >> 4) * TILE_D + (i & 15) * LDS + tid];
+      tr = fma(v, v, tr); s = fma(v, z[i], s);
+    }
+  }
+  a.apart[tile * BLK + tid] = s;
+  tr = warp_sum(tr);
+  if ((tid & 31) == 0) s_red[tid >> 5] = tr;
+  __syncthreads();
+  if (tid == 0) a.tpart[tile] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+}
+
+}  // namespace oz
+}  // namespace dsm

@@ -1,0 +1,69 @@
+// Argument blocks of the INT8-tensor-core path of the triangular inverse (ozaki.cuh, api_ozaki.cu).
+//
+// X = L^-1 of one expert is split recursively:  X = [X11 0; X21 X22],  X21 = -X22 (L21 X11).  The diagonal parts stay
+// on the tile pipeline (trtri3.cuh, FP64 DMMA); the two products per split are GEMMs without dependencies between
+// their tiles and run on the INT8 tcgen05 tensor cores through an error-free Ozaki split of the FP64 operands
+// (tools/ozaki_proto.cu is the stand-alone prototype with the accuracy / rate measurements).
+#pragma once
+#include <cstdint>
+#include "common.cuh"
+
+namespace dsm {
+
+constexpr int OZ_KSTEP = 32;                 // K of one tcgen05.mma kind::i8
+constexpr int OZ_TILE_B = BLK * OZ_KSTEP;    // bytes of one slice tile: 128 rows x 32 k, UMMA canonical K-major, no swizzle:
+                                             //   [2 chunks of 16 k][16 groups of 8 rows][8 rows][16 bytes]
+constexpr int OZ_KSTEPS_PER_BLK = BLK / OZ_KSTEP;
+
+// Slice one 128 x 128 block of an operand.  `src` is a block in the factor-tile layout: (r, c) at
+// (c >> 4) * TILE_D + (c & 15) * LDS + r  (8 consecutive factor tiles, or a W / W^T block, or a scratch block).
+struct OzJob {
+  const double* src;
+  int transposed;        // operand(i, k) = src(k, i) instead of src(i, k)
+  int vr, vk;            // valid operand rows / k entries; everything else is sliced as zero (and never read)
+  int scale;             // index of operand row 0 of this block in the row-scale arrays
+  int64_t dst;           // slice-pool tile index of (row block, first k-step of this block), slice 0
+};
+
+// One 128 x 128 output block:  out = sign * A[k0 .. k1) B[k0 .. k1)^T
+struct OzTile {
+  int a_tile, b_tile;    // slice-pool tile index of k-step 0, slice 0 of the A / B row block
+  int k0, k1;            // k-steps
+  int sa, sb;            // row-scale indices of the A rows (output rows) / B rows (output columns)
+  int vr, vc;            // valid rows / columns of the output block
+  double* out;           // factor-tile layout block
+  double sign;
+};
+
+struct OzPart { int slot, I, J; };      // inverse tile (I, J) written by a GEMM: its fused partials are computed afterwards
+
+struct OzPartArgs {
+  const LeafMeta* meta;
+  const double* F; const double* z;
+  const int64_t* flag_off;
+  double* apart; double* tpart;
+  const OzPart* parts;
+};
+
+// host side plan of one batch (api_ozaki.cu)
+struct OzLevel {
+  OzJob* d_jobs1 = nullptr; int n_jobs1 = 0; OzTile* d_tiles1 = nullptr; int n_tiles1 = 0;     // stage 1: T^T = X11^T L21^T
+  OzJob* d_jobs2 = nullptr; int n_jobs2 = 0; OzTile* d_tiles2 = nullptr; int n_tiles2 = 0;     // stage 2: X21^T = -T^T X22^T
+  int n_scale = 0;
+};
+struct OzPlan {
+  bool active = false;
+  int4* d_tasks = nullptr; int n_tasks = 0;        // tile-pipeline tasks restricted to the diagonal ranges
+  OzLevel levels[4]; int n_levels = 0;             // deepest level first
+  OzPart* d_parts = nullptr; int n_parts = 0;
+  double gemm_flops = 0.0;
+};
+
+// launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).
+cudaError_t oz_init_kernels();
+int oz_make_map(void* map128, const void* pool, size_t bytes);          // 0 on success
+void launch_oz_slice(int S, const OzJob* jobs, int njobs, int pass, unsigned long long* rowmax, double* scale, int8_t* pool, cudaStream_t st);
+void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, cudaStream_t st);
+void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st);
+
+}  // namespace dsm
