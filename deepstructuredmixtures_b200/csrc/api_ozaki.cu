@@ -177,7 +177,26 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
     CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)L.n_scale * sizeof(unsigned long long), st));
     launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
     launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-    launch_oz_gemm(S, h->oz_map, L.d_tiles1, L.n_tiles1, h->oz_scale.p, st);
+    long long* d_trace = nullptr;
+    const char* tf = (li == 0) ? getenv("DSMGP_OZAKI_TRACE") : nullptr;     // clock stamps per block product of the first GEMM
+    if (tf) { cudaMalloc(&d_trace, (size_t)L.n_tiles1 * 64); cudaMemsetAsync(d_trace, 0, (size_t)L.n_tiles1 * 64, st); }
+    launch_oz_gemm(S, h->oz_map, L.d_tiles1, L.n_tiles1, h->oz_scale.p, st, d_trace);
+    if (tf) {
+      std::vector<long long> tr((size_t)L.n_tiles1 * 8);
+      std::vector<OzTile> tl(L.n_tiles1);
+      cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
+      cudaMemcpyAsync(tl.data(), L.d_tiles1, tl.size() * sizeof(OzTile), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      if (FILE* f = fopen(tf, "w")) {
+        for (int i = 0; i < L.n_tiles1; i++) {
+          fprintf(f, "%d", tl[i].k1 - tl[i].k0);
+          for (int q = 1; q < 8; q++) fprintf(f, " %lld", tr[(size_t)i * 8 + q] - tr[(size_t)i * 8]);
+          fprintf(f, "\n");
+        }
+        fclose(f);
+      }
+      cudaFree(d_trace);
+    }
     launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
     launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
     launch_oz_gemm(S, h->oz_map, L.d_tiles2, L.n_tiles2, h->oz_scale.p, st);

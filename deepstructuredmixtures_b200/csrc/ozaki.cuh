@@ -10,9 +10,9 @@
 //
 // GEMM kernel: one CTA per 128 x 128 output block.  warp 0 = TMA producer (cp.async.bulk.tensor.2d of 4 KB slice
 // tiles into a mbarrier ring), warp 1 = TMEM allocation + tcgen05.mma.kind::i8 issue (M = N = 128, K = 32), warps 2-5 =
-// epilogue (tcgen05.ld, int32 -> FP64, Horner sum over the slice groups, row scales, store in the factor-tile layout).
+// 8 epilogue warps (tcgen05.ld, int32 -> FP64, Horner sum over the slice groups, row scales, store in the factor-tile layout).
 // S groups of 128 columns do not fit TMEM (512 columns), so a block is computed in two rounds over K: the four
-// lowest-weight groups first, their partial sum parked in the output block, then the remaining S - 4 groups.
+// lowest-weight groups first (their partial sums stay in the epilogue warps' registers), then the remaining S - 4 groups.
 #pragma once
 #include <cuda.h>
 #include "ozaki_args.h"
@@ -137,25 +137,30 @@ __global__ void __launch_bounds__(256) slice_kernel(const OzJob* __restrict__ jo
 }
 
 // ---- block products ----------------------------------------------------------------------------------------------------
+constexpr int OZ_THREADS = 64 + 256;      // producer warp, MMA warp, 8 epilogue warps
+
 template <int S>
-__global__ void __launch_bounds__(192, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ tiles, const double* __restrict__ scale) {
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ tiles, const double* __restrict__ scale, long long* __restrict__ trace) {
   using C = Cfg<S>;
-  constexpr int NST = C::NST;
+  constexpr int RING = C::NST * C::STAGE;                     // bytes of the operand ring
+  constexpr int MAXST = 8;
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + NST;
-  uint64_t* tfull = empty + NST;
+  // per round its own ring geometry (a stage = the slices that round needs for one k-step) and its own barriers
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);         // [round][full MAXST | empty MAXST]
+  uint64_t* tfull = bars + 4 * MAXST;
   uint64_t* tempty = tfull + 1;
   uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty + 1);
-  uint8_t* stage0 = smem + 1024;
+  uint8_t* ring = smem + 1024;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const OzTile t = tiles[blockIdx.x];
   const int nk = t.k1 - t.k0;
+  long long* trc = trace ? trace + (int64_t)blockIdx.x * 8 : nullptr;      // optional clock stamps (DSMGP_OZAKI_TRACE)
+  if (trc && threadIdx.x == 0) trc[0] = clock64();
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(tfull, 1); mbar_init(tempty, 4);
+    for (int i = 0; i < 4 * MAXST; ++i) mbar_init(&bars[i], 1);
+    mbar_init(tfull, 1); mbar_init(tempty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map)) : "memory");
@@ -168,21 +173,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tptr;
+  if (trc && threadIdx.x == 0) trc[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
-      int step = 0;
+#pragma unroll
       for (int r = 0; r < C::NR; ++r) {
         const int nsl = C::nsl(r);
-        for (int ks = t.k0; ks < t.k1; ++ks, ++step) {
-          const int st = step % NST;
-          if (step >= NST) mbar_wait(&empty[st], ((step / NST) - 1) & 1);
-          uint8_t* dst = stage0 + st * C::STAGE;
-          mbar_expect_tx(&full[st], nsl * 2 * OZ_TILE_B);
+        const int stage = 2 * nsl * OZ_TILE_B;
+        const int nst = (RING / stage) < MAXST ? (RING / stage) : MAXST;
+        uint64_t* full = bars + r * 2 * MAXST; uint64_t* empty = full + MAXST;
+        // the ring changes its geometry: it is free once the previous round's last MMAs have completed (tfull); the loads of
+        // this round then overlap the epilogue of the previous one
+        if (r > 0) mbar_wait(tfull, (r - 1) & 1);
+        for (int i = 0; i < nk; ++i) {
+          const int st = i % nst, ks = t.k0 + i;
+          if (i >= nst) mbar_wait(&empty[st], ((i / nst) - 1) & 1);
+          uint8_t* dst = ring + st * stage;
+          mbar_expect_tx(&full[st], stage);
           const int rowA = (t.a_tile + ks * S) * 32, rowB = (t.b_tile + ks * S) * 32;   // tensor-map rows = 128-byte core matrices
           for (int s = 0; s < nsl; ++s) {
             tma_load_2d(dst + s * OZ_TILE_B, &map, 0, rowA + s * 32, &full[st]);
-            tma_load_2d(dst + (S + s) * OZ_TILE_B, &map, 0, rowB + s * 32, &full[st]);
+            tma_load_2d(dst + (nsl + s) * OZ_TILE_B, &map, 0, rowB + s * 32, &full[st]);
           }
         }
       }
@@ -191,17 +203,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
     if (lane == 0) {
       // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), K-major, N >> 3 at 17, M >> 4 at 24
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLK >> 3) << 17) | ((uint32_t)(BLK >> 4) << 24);
-      int step = 0;
 #pragma unroll
       for (int r = 0; r < C::NR; ++r) {
         const int glo = C::glo(r), ghi = C::ghi(r), nsl = C::nsl(r);
+        const int stage = 2 * nsl * OZ_TILE_B;
+        const int nst = (RING / stage) < MAXST ? (RING / stage) : MAXST;
+        uint64_t* full = bars + r * 2 * MAXST; uint64_t* empty = full + MAXST;
         if (r > 0) { mbar_wait(tempty, (r - 1) & 1); tc_fence_after(); }
-        for (int ks = 0; ks < nk; ++ks, ++step) {
-          const int st = step % NST;
-          mbar_wait(&full[st], (step / NST) & 1);
+        for (int i = 0; i < nk; ++i) {
+          const int st = i % nst;
+          mbar_wait(&full[st], (i / nst) & 1);
+          if (trc && r == 0 && i == 0) trc[2] = clock64();
           tc_fence_after();
-          const uint32_t sA = smem_u32(stage0 + st * C::STAGE), sB = sA + S * OZ_TILE_B;
-          uint32_t written = (ks > 0) ? 0xFFu : 0u;
+          const uint32_t sA = smem_u32(ring + st * stage), sB = sA + nsl * OZ_TILE_B;
+          uint32_t written = (i > 0) ? 0xFFu : 0u;
 #pragma unroll
           for (int s = 0; s < S; ++s) {
             if (s >= nsl) continue;
@@ -217,49 +232,50 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
           tc_commit(&empty[st]);
         }
         tc_commit(tfull);
+        if (trc && r == 0) trc[3] = clock64();
       }
     }
   } else {
-    // epilogue: warp q = warp % 4 owns TMEM lanes 32q .. 32q+31 = rows of the block
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
+    // epilogue: 8 warps.  Warp w may touch TMEM lanes 32 (w % 4) .. +31 = rows of the block; the two warps of a lane quarter
+    // split the 128 columns.  The Horner sum over the slice groups stays in registers across the two rounds.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int row = q * 32 + lane, cbase = half * 64;
     const bool rok = row < t.vr;
     const double srow = rok ? scale[t.sa + row] * t.sign : 0.0;
+    double acc[64];
+#pragma unroll
+    for (int j = 0; j < 64; ++j) acc[j] = 0.0;
 #pragma unroll
     for (int r = 0; r < C::NR; ++r) {
       const int glo = C::glo(r), ghi = C::ghi(r);
       mbar_wait(tfull, r & 1);
+      if (trc && threadIdx.x == 64) trc[4 + 2 * r] = clock64();
       tc_fence_after();
-#pragma unroll 1
-      for (int c0 = 0; c0 < BLK; c0 += 16) {
-        if (c0 >= t.vc) break;                                   // vc is a multiple of 16; uniform over the CTA
-        double* o = t.out + (c0 >> 4) * TILE_D + row;            // column c0 + j at o[j * LDS]
-        double acc[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) acc[j] = (r == 0 || !rok) ? 0.0 : o[j * LDS];   // partial Horner sum of the low groups
+      for (int c0 = 0; c0 < 64; c0 += 16) {
 #pragma unroll
         for (int g = S - 1; g >= 0; --g) {                       // smallest weight first: acc = acc / 128 + G_g
           if (g < glo || g > ghi) continue;
           uint32_t v[16];
-          tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * BLK + c0), v);
+          tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * BLK + cbase + c0), v);
           tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = fma(acc[j], 0.0078125, (double)(int)v[j]);
-        }
-        if (rok) {
-          if (r == C::NR - 1) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j * LDS] = acc[j] * srow * scale[t.sb + c0 + j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) o[j * LDS] = acc[j];
-          }
+          for (int j = 0; j < 16; ++j) acc[c0 + j] = fma(acc[c0 + j], 0.0078125, (double)(int)v[j]);
         }
       }
       tc_fence_before();
       __syncwarp();
+      if (trc && threadIdx.x == 64) trc[5 + 2 * r] = clock64();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty)) : "memory");
     }
+    if (rok) {
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int c = cbase + j;
+        if (c < t.vc) t.out[(c >> 4) * TILE_D + (c & 15) * LDS + row] = acc[j] * srow * scale[t.sb + c];
+      }
+    }
+    if (trc && threadIdx.x == 64) trc[7] = clock64();
   }
   __syncthreads();
   if (warp == 1) {
