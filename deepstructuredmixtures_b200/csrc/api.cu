@@ -389,6 +389,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
       for (size_t i = 0; i < sv.size(); i++) st2[i] = make_int2(sv[i].slot, sv[i].J);
       b.n_solve = (int)st2.size();
       CUDA_TRY(h, upload(&b.d_solve_tasks, st2));
+      b.h_potrf2 = pt;
       CUDA_TRY(h, upload(&b.d_potrf2_tasks, pt));
       CUDA_TRY(h, upload(&b.d_flag_off, foff));
       maxFlags = std::max(maxFlags, fo);
@@ -647,6 +648,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
     Batch& b = h->batches[bi];
     cudaEvent_t* ev = h->ev.data() + 8 * bi;
     const int nsl = b.s1 - b.s0;
+    h->oz_l21_ready = false;
     EV_RECORD(ev[0]);
     if (nsl == 0) { for (int k = 1; k < 8; k++) EV_RECORD(ev[k]); continue; }
     const LeafMeta* meta = h->d_meta.p + b.s0;
@@ -695,6 +697,10 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
         long long* d_trace = nullptr;
         const char* trace_file = h->capturing ? nullptr : getenv("DSMGP_TRACE_FILE");
         if (trace_file) { cudaMalloc(&d_trace, (size_t)b.n_potrf2 * 64); cudaMemsetAsync(d_trace, 0, (size_t)b.n_potrf2 * 64, st); pa.trace = d_trace; }
+        if (b.oz.active && b.oz.potrf && !trace_file && !h->capturing) {
+          const int32_t rc = oz_run_potrf(h, b, pa, sms, st);        // split factorisation, SYRK on the INT8 tensor cores
+          if (rc != DSMGP_OK) return rc;
+        } else
         launch_potrf2(pa, std::min(sms, b.n_potrf2), st);
         if (trace_file) {
           std::vector<long long> tr((size_t)b.n_potrf2 * 8);

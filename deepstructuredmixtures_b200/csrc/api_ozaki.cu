@@ -48,7 +48,9 @@ int32_t oz_plan(dsmgp_handle* h) {
   h->oz_S = S;
   struct Tmp { std::vector<std::vector<Split>> levels; std::vector<std::vector<int>> range_of; };
   std::vector<Tmp> tmp(h->batches.size());
-  int64_t max_pool = 0, max_scratch = 0, max_scale = 0;
+  int64_t max_pool = 0, max_scratch = 0, max_scale = 0, max_l21_pool = 0, max_l21_scale = 0;
+  const char* pe = getenv("DSMGP_OZAKI_POTRF");
+  const bool want_potrf = !(pe && pe[0] == '0');
   // pass 1: splits and sizes
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
     Batch& b = h->batches[bi];
@@ -75,13 +77,17 @@ int32_t oz_plan(dsmgp_handle* h) {
       }
       max_pool = std::max(max_pool, pool); max_scratch = std::max(max_scratch, scratch); max_scale = std::max(max_scale, scale);
     }
+    // the L21 slices of the root splits live in their own region: the factorisation phase makes them, the inverse reuses them
+    int64_t lp = 0, ls = 0;
+    for (const Split& sp : t.levels[0]) { lp += (int64_t)(sp.hi - sp.mid) * (sp.mid - sp.lo) * OZ_KSTEPS_PER_BLK * S; ls += (int64_t)(sp.hi - sp.mid) * BLK; }
+    max_l21_pool = std::max(max_l21_pool, lp); max_l21_scale = std::max(max_l21_scale, ls);
   }
   if (max_pool == 0) return DSMGP_OK;
-  CUDA_TRY(h, h->oz_pool.alloc((size_t)max_pool * OZ_TILE_B));
+  CUDA_TRY(h, h->oz_pool.alloc((size_t)(max_pool + max_l21_pool) * OZ_TILE_B));
   CUDA_TRY(h, h->oz_scratch.alloc((size_t)max_scratch));
-  CUDA_TRY(h, h->oz_scale.alloc((size_t)max_scale));
-  CUDA_TRY(h, h->oz_rowmax.alloc((size_t)max_scale));
-  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)max_pool * OZ_TILE_B) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return DSMGP_ERR_CUDA; }
+  CUDA_TRY(h, h->oz_scale.alloc((size_t)(max_scale + max_l21_scale)));
+  CUDA_TRY(h, h->oz_rowmax.alloc((size_t)(max_scale + max_l21_scale)));
+  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return DSMGP_ERR_CUDA; }
   // pass 2: lists
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
     Batch& b = h->batches[bi];
@@ -97,6 +103,9 @@ int32_t oz_plan(dsmgp_handle* h) {
     CUDA_TRY(h, upload(&b.oz.d_tasks, keep));
     std::vector<OzPart> parts;
     double flops = 0.0;
+    std::vector<OzJob> jL; std::vector<OzTile> tS;
+    std::vector<int> kskip(b.s1 - b.s0, 0);
+    int64_t l21_pool = max_pool; int l21_scale = (int)max_scale;
     for (int lv = maxdepth - 1; lv >= 0; lv--) {         // deepest level first
       if (t.levels[lv].empty()) continue;
       OzLevel L;
@@ -111,14 +120,17 @@ int32_t oz_plan(dsmgp_handle* h) {
         auto fblk = [&](int rb, int cb) { return F + tile_off(rb, cb * (BLK / KC), m.nkc); };
         // operand pools (tile indices) and scales
         const int64_t pA1 = pool; pool += (int64_t)J1 * J1 * KB * S;      // X11^T : J1 row blocks x J1 k blocks
-        const int64_t pB1 = pool; pool += (int64_t)J2 * J1 * KB * S;      // L21   : J2 x J1
+        int64_t pB1;                                                      // L21   : J2 x J1
+        if (lv == 0) { pB1 = l21_pool; l21_pool += (int64_t)J2 * J1 * KB * S; } else { pB1 = pool; pool += (int64_t)J2 * J1 * KB * S; }
         const int64_t pA2 = pool; pool += (int64_t)J1 * J2 * KB * S;      // T^T   : J1 x J2
         const int64_t pB2 = pool; pool += (int64_t)J2 * J2 * KB * S;      // X22   : J2 x J2
         const int sA1 = scale; scale += J1 * BLK;
-        const int sB1 = scale; scale += J2 * BLK;
+        int sB1;
+        if (lv == 0) { sB1 = l21_scale; l21_scale += J2 * BLK; } else { sB1 = scale; scale += J2 * BLK; }
         const int sA2 = scale; scale += J1 * BLK;
         const int sB2 = scale; scale += J2 * BLK;
         double* T = h->oz_scratch.p + scratch; scratch += (int64_t)J1 * J2 * WBLK_D;
+        if (lv == 0) kskip[sp.slot] = sp.mid;
         for (int a = 0; a < J1; a++) {                                       // a = Jb - lo
           const int Jb = sp.lo + a;
           for (int k = a; k < J1; k++) {                                     // X^T block (Jb, Kb), Kb >= Jb
@@ -128,12 +140,12 @@ int32_t oz_plan(dsmgp_handle* h) {
           for (int c = 0; c < J2; c++) {
             const int Ib = sp.mid + c;
             t1.push_back({(int)(pA1 + (int64_t)a * J1 * KB * S), (int)(pB1 + (int64_t)c * J1 * KB * S), a * KB, J1 * KB, sA1 + a * BLK, sB1 + c * BLK,
-                          BLK, wid(Ib), T + ((int64_t)a * J2 + c) * WBLK_D, 1.0});
+                          BLK, wid(Ib), T + ((int64_t)a * J2 + c) * WBLK_D, 1.0, 0, 0});
             j2.push_back({T + ((int64_t)a * J2 + c) * WBLK_D, 0, BLK, wid(Ib), sA2 + a * BLK, pA2 + ((int64_t)a * J2 + c) * KB * S});
             // k-steps of a half-wide last block beyond its width hold zeros: stop before them
             const int kend = c * KB + (wid(Ib) + OZ_KSTEP - 1) / OZ_KSTEP;
             t2.push_back({(int)(pA2 + (int64_t)a * J2 * KB * S), (int)(pB2 + (int64_t)c * J2 * KB * S), 0, kend, sA2 + a * BLK, sB2 + c * BLK,
-                          BLK, wid(Ib), const_cast<double*>(fblk(Jb, Ib)), -1.0});
+                          BLK, wid(Ib), const_cast<double*>(fblk(Jb, Ib)), -1.0, 0, 0});
             parts.push_back({sp.slot, Ib, Jb});
             flops += 2.0 * BLK * BLK * OZ_KSTEP * ((double)(J1 - a) * KB + kend);
           }
@@ -141,7 +153,11 @@ int32_t oz_plan(dsmgp_handle* h) {
         for (int c = 0; c < J2; c++) {
           const int Ib = sp.mid + c;
           for (int k = 0; k < J1; k++)                                       // L block (Ib, Kb)
-            j1.push_back({fblk(Ib, sp.lo + k), 0, wid(Ib), BLK, sB1 + c * BLK, pB1 + ((int64_t)c * J1 + k) * KB * S});
+            (lv == 0 ? jL : j1).push_back({fblk(Ib, sp.lo + k), 0, wid(Ib), BLK, sB1 + c * BLK, pB1 + ((int64_t)c * J1 + k) * KB * S});
+          if (lv == 0)                                                       // A22 -= L21 L21^T, lower block triangle (root split: lo = 0)
+            for (int c2 = 0; c2 <= c; c2++)
+              tS.push_back({(int)(pB1 + (int64_t)c * J1 * KB * S), (int)(pB1 + (int64_t)c2 * J1 * KB * S), 0, J1 * KB, sB1 + c * BLK, sB1 + c2 * BLK,
+                            wid(Ib), wid(sp.mid + c2), const_cast<double*>(fblk(Ib, sp.mid + c2)), -1.0, 1, 0});
           for (int k = 0; k <= c; k++) {                                     // X22 block (Ib, Kb), Kb <= Ib: stored transposed above the diagonal
             const int Kb = sp.mid + k;
             if (Kb == Ib) j2.push_back({W + (int64_t)Ib * WBLK_D, 0, wid(Ib), wid(Ib), sB2 + c * BLK, pB2 + ((int64_t)c * J2 + k) * KB * S});
@@ -158,10 +174,41 @@ int32_t oz_plan(dsmgp_handle* h) {
       CUDA_TRY(h, upload(&L.d_tiles1, t1)); CUDA_TRY(h, upload(&L.d_tiles2, t2));
       b.oz.levels[b.oz.n_levels++] = L;
     }
+    {   // factorisation phase of the root splits
+      auto by_len = [](const OzTile& x, const OzTile& y) { return (x.k1 - x.k0) > (y.k1 - y.k0); };
+      std::stable_sort(tS.begin(), tS.end(), by_len);
+      b.oz.n_jobsL = (int)jL.size(); b.oz.n_syrk = (int)tS.size();
+      b.oz.l21_scale0 = (int)max_scale; b.oz.l21_nscale = l21_scale - (int)max_scale;
+      CUDA_TRY(h, upload(&b.oz.d_jobsL, jL)); CUDA_TRY(h, upload(&b.oz.d_syrk, tS));
+      std::vector<int4> pA, pB;
+      for (const int4& tk : b.h_potrf2) (kskip[tk.x] > 0 && tk.z >= kskip[tk.x] ? pB : pA).push_back(tk);
+      b.oz.n_potrfA = (int)pA.size(); b.oz.n_potrfB = (int)pB.size();
+      CUDA_TRY(h, upload(&b.oz.d_potrfA, pA)); CUDA_TRY(h, upload(&b.oz.d_potrfB, pB));
+      CUDA_TRY(h, upload(&b.oz.d_kskip, kskip));
+      b.oz.potrf = want_potrf && !pB.empty();
+    }
     b.oz.n_parts = (int)parts.size();
     CUDA_TRY(h, upload(&b.oz.d_parts, parts));
     b.oz.gemm_flops = flops;
   }
+  return DSMGP_OK;
+}
+
+// The factorisation of one batch split at the root: block columns < mid, then A22 -= L21 L21^T as block products on the INT8
+// tensor cores, then block columns >= mid whose contractions start at mid.  The tile flags persist across the two launches.
+int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, int sms, cudaStream_t st) {
+  const int S = h->oz_S;
+  Potrf2Args pa = full;
+  pa.tasks = b.oz.d_potrfA; pa.ntasks = b.oz.n_potrfA;
+  launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
+  launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+  launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+  launch_oz_gemm(S, h->oz_map, b.oz.d_syrk, b.oz.n_syrk, h->oz_scale.p, st);
+  pa.tasks = b.oz.d_potrfB; pa.ntasks = b.oz.n_potrfB; pa.counter = full.counter + 1; pa.kskip = b.oz.d_kskip;
+  launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  h->tm.launches += 5;
+  h->oz_l21_ready = true;
   return DSMGP_OK;
 }
 
@@ -177,6 +224,11 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
     CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)L.n_scale * sizeof(unsigned long long), st));
     launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
     launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    if (li == b.oz.n_levels - 1 && !h->oz_l21_ready) {      // root level: L21 not sliced by the factorisation phase
+      CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
+      launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+      launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    }
     long long* d_trace = nullptr;
     const char* tf = (li == 0) ? getenv("DSMGP_OZAKI_TRACE") : nullptr;     // clock stamps per block product of the first GEMM
     if (tf) { cudaMalloc(&d_trace, (size_t)L.n_tiles1 * 64); cudaMemsetAsync(d_trace, 0, (size_t)L.n_tiles1 * 64, st); }

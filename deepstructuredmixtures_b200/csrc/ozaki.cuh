@@ -272,7 +272,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const int c = cbase + j;
-        if (c < t.vc) t.out[(c >> 4) * TILE_D + (c & 15) * LDS + row] = acc[j] * srow * scale[t.sb + c];
+        if (c < t.vc) {
+          double* o = t.out + (c >> 4) * TILE_D + (c & 15) * LDS + row;
+          const double v = acc[j] * srow * scale[t.sb + c];
+          *o = t.accum ? *o + v : v;
+        }
       }
     }
     if (trc && threadIdx.x == 64) trc[7] = clock64();

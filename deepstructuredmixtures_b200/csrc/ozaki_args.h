@@ -33,6 +33,8 @@ struct OzTile {
   int vr, vc;            // valid rows / columns of the output block
   double* out;           // factor-tile layout block
   double sign;
+  int accum;             // 1: out += sign * product (right-looking update of the factorisation), 0: out = sign * product
+  int pad_;
 };
 
 struct OzPart { int slot, I, J; };      // inverse tile (I, J) written by a GEMM: its fused partials are computed afterwards
@@ -57,6 +59,14 @@ struct OzPlan {
   OzLevel levels[4]; int n_levels = 0;             // deepest level first
   OzPart* d_parts = nullptr; int n_parts = 0;
   double gemm_flops = 0.0;
+  // right-looking split of the factorisation at the root split: columns < mid (launch A), A22 -= L21 L21^T on the INT8 tensor
+  // cores, columns >= mid with the contraction starting at mid (launch B).  The L21 slices are reused by the inverse.
+  bool potrf = false;
+  int4* d_potrfA = nullptr; int n_potrfA = 0; int4* d_potrfB = nullptr; int n_potrfB = 0;
+  int* d_kskip = nullptr;
+  OzJob* d_jobsL = nullptr; int n_jobsL = 0;         // L21 blocks
+  OzTile* d_syrk = nullptr; int n_syrk = 0;
+  int l21_scale0 = 0, l21_nscale = 0;
 };
 
 // launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).

@@ -33,7 +33,7 @@ __device__ __forceinline__ bool flag_is_set(const int* f) {
 struct PotrfGen {
   const double* F; const double* z; const double* Wj; const int* flags;
   int nkc, I, J;
-  int nc, nmain, nepi, c;
+  int nc, nmain, nepi, c, cc0;
   bool diag, allready;       // allready: every k-block is known to be complete (tile (.,J-1) done implies all before it)
   bool prefd;                // diagonal tile of a block column that already holds a valid factor (chol_continue / shared prefix)
   TaskHdr h;
@@ -47,13 +47,18 @@ struct PotrfGen {
     flags = a.flags + a.flag_off[tk.x];
     const int js = (a.share != nullptr) ? a.share[tk.x].z : a.jstart;     // block rows < js hold a valid factor
     h.kind = diag ? 1 : 0; h.ti = ti; h.slot = tk.x; h.I = I; h.J = J;
-    h.wi = blk_width(m.np, I); h.wj = blk_width(m.np, J); h.n_c = 0; h.n_main = 0; h.pad0 = js;
+    h.wi = blk_width(m.np, I); h.wj = blk_width(m.np, J); h.n_c = 0; h.n_main = 0; h.pad0 = js; h.pad1 = 0; cc0 = 0;
     if (!diag && I < js) return;                          // tile already final (chol_continue / copied from the source expert)
     nkc = m.nkc;
     F = a.F + m.foff; z = a.z + m.voff; Wj = a.W + m.woff + (int64_t)J * WBLK_D;
     nc = h.wj / 32;
     prefd = diag && J < js;       // streams its block row for the forward solve z_J only (no MMA), then rebuilds W_J
-    nmain = (J * BLK) / KC;
+    // right-looking split: the leading k-blocks are already in the tile.  Panel tiles skip them; a diagonal tile still
+    // streams its whole block row for the forward solve z_J but runs no MMA on the first pad1 chunks
+    const int ks = (a.kskip != nullptr) ? a.kskip[tk.x] : 0;
+    const int skip = (ks > 0 && J >= ks && !prefd) ? ks * (BLK / KC) : 0;
+    cc0 = diag ? 0 : skip; h.pad1 = diag ? skip : 0;
+    nmain = (J * BLK) / KC - cc0;
     nepi = diag ? 0 : tri_epilogue_nstages(h.wj / 32);
     h.n_c = nc; h.n_main = nmain;
   }
@@ -65,14 +70,14 @@ struct PotrfGen {
       d.a = F + tile_off(I, J * 8 + 2 * c, nkc); d.abytes = TILE_BYTES;
       d.b = F + tile_off(I, J * 8 + 2 * c + 1, nkc); d.bbytes = TILE_BYTES;
     } else if (c < nc + nmain) {
-      const int cc = c - nc, Kb = cc >> 3;
+      const int cc = cc0 + c - nc, Kb = cc >> 3;
       if ((cc & 7) == 0 && !allready && prefd) {
         // the tiles (J, K) are final, but z_K is written by the diagonal task of column K: its flag orders all of them
         if (J > 0) d.flag0 = flags + tile_flag_index(J - 1, J - 1);
         allready = true;
       }
       if ((cc & 7) == 0 && !allready) {
-        if (cc == 0 && J > 1) {                           // fast path: the last k-block's tiles complete => all are
+        if (c == nc && J > 1) {                           // fast path: the last k-block's tiles complete => all are
           int v0 = 1, v1 = 1;                             // both loads in flight before either is consumed
           if ((threadIdx.x & 31) == 0) {
             v0 = ld_acquire(flags + tile_flag_index(I, J - 1));
@@ -192,7 +197,7 @@ __device__ __forceinline__ void potrf2_consume(Pipe& p, const Potrf2Args& a, con
       st = p.wait();
       if (active) {
         const double* sA = p.A(st);
-        if (!prefactored) switch (ng) {
+        if (!prefactored && c >= hd.pad1) switch (ng) {
           case 1: mma_chunk16<1>(acc, sA, sA, r0); break;
           case 2: mma_chunk16<2>(acc, sA, sA, r0); break;
           case 3: mma_chunk16<3>(acc, sA, sA, r0); break;

@@ -16,6 +16,9 @@ struct Potrf2Args {
   const int4* share;                               // per slot sharing plan or null: aliased experts are skipped, SHARE_PREFIX
                                                    // experts continue behind their copied block rows (per-slot jstart = share.z)
   long long* trace;                                // optional [ntasks][8] clock stamps (DSMGP_TRACE_FILE), else null
+  const int* kskip;                                // per slot block index ks or null: for block columns >= ks the k-blocks < ks have
+                                                   // already been subtracted from the tiles (right-looking SYRK on the INT8 tensor
+                                                   // cores, api_ozaki.cu), the contraction starts at ks
 };
 
 // tile-pipelined inverse (trtri3): tasks (slot, I, J, unused), I > J, ordered by anti-diagonal
