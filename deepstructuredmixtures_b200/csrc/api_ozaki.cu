@@ -194,19 +194,63 @@ int32_t oz_plan(dsmgp_handle* h) {
   return DSMGP_OK;
 }
 
+// DSMGP_OZAKI_TIMING=1: CUDA-event time of every launch of the split phases, printed to stderr (synchronises: diagnostics only)
+struct OzTimer {
+  bool on; cudaStream_t st; std::vector<cudaEvent_t> ev; std::vector<const char*> names;
+  OzTimer(cudaStream_t s, bool capturing) : on(!capturing && getenv("DSMGP_OZAKI_TIMING") != nullptr), st(s) { mark("start"); }
+  void mark(const char* name) { if (!on) return; cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); ev.push_back(e); names.push_back(name); }
+  void report(const char* what) {
+    if (!on) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[ozaki %s]", what);
+    for (size_t i = 1; i < ev.size(); i++) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s %.3f", names[i], ms); }
+    float tot = 0; cudaEventElapsedTime(&tot, ev.front(), ev.back()); fprintf(stderr, " | total %.3f ms\n", tot);
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
+
+// optional clock stamps of one GEMM launch (DSMGP_OZAKI_TRACE / DSMGP_OZAKI_TRACE_SYRK = file): tools/ozaki_trace.py
+static void traced_gemm(dsmgp_handle* h, int S, const OzTile* d_tiles, int n, const char* file, cudaStream_t st) {
+  const int nctas = num_sms(h->device);
+  if (!file) { launch_oz_gemm(S, h->oz_map, d_tiles, n, h->oz_scale.p, nctas, st); return; }
+  long long* d_trace = nullptr;
+  cudaMalloc(&d_trace, (size_t)n * 128); cudaMemsetAsync(d_trace, 0, (size_t)n * 128, st);
+  launch_oz_gemm(S, h->oz_map, d_tiles, n, h->oz_scale.p, nctas, st, d_trace);
+  std::vector<long long> tr((size_t)n * 16);
+  std::vector<OzTile> tl(n);
+  cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
+  cudaMemcpyAsync(tl.data(), d_tiles, tl.size() * sizeof(OzTile), cudaMemcpyDeviceToHost, st);
+  cudaStreamSynchronize(st);
+  if (FILE* f = fopen(file, "w")) {
+    for (int i = 0; i < n; i++) {
+      fprintf(f, "%d", tl[i].k1 - tl[i].k0);
+      for (int q = 1; q < 9; q++) fprintf(f, " %lld", tr[(size_t)i * 16 + q] - tr[(size_t)i * 16]);
+      fprintf(f, "\n");
+    }
+    fclose(f);
+  }
+  cudaFree(d_trace);
+}
+
 // The factorisation of one batch split at the root: block columns < mid, then A22 -= L21 L21^T as block products on the INT8
 // tensor cores, then block columns >= mid whose contractions start at mid.  The tile flags persist across the two launches.
 int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, int sms, cudaStream_t st) {
   const int S = h->oz_S;
+  OzTimer tm(st, h->capturing);
   Potrf2Args pa = full;
   pa.tasks = b.oz.d_potrfA; pa.ntasks = b.oz.n_potrfA;
   launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  tm.mark("potrfA");
   CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
   launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
   launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-  launch_oz_gemm(S, h->oz_map, b.oz.d_syrk, b.oz.n_syrk, h->oz_scale.p, st);
+  tm.mark("sliceL21");
+  traced_gemm(h, S, b.oz.d_syrk, b.oz.n_syrk, getenv("DSMGP_OZAKI_TRACE_SYRK"), st);
+  tm.mark("syrk");
   pa.tasks = b.oz.d_potrfB; pa.ntasks = b.oz.n_potrfB; pa.counter = full.counter + 1; pa.kskip = b.oz.d_kskip;
   launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  tm.mark("potrfB");
+  tm.report("potrf");
   h->tm.launches += 5;
   h->oz_l21_ready = true;
   return DSMGP_OK;
@@ -217,7 +261,9 @@ int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, int sms,
 int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st) {
   Trtri3Args ta = full;
   ta.tasks = b.oz.d_tasks; ta.ntasks = b.oz.n_tasks;
+  OzTimer tm(st, h->capturing);
   launch_trtri3_only(ta, std::max(1, std::min(sms, ta.ntasks)), st);
+  tm.mark("trtri3");
   const int S = h->oz_S;
   for (int li = 0; li < b.oz.n_levels; li++) {
     const OzLevel& L = b.oz.levels[li];
@@ -229,34 +275,21 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
       launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
       launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
     }
-    long long* d_trace = nullptr;
-    const char* tf = (li == 0) ? getenv("DSMGP_OZAKI_TRACE") : nullptr;     // clock stamps per block product of the first GEMM
-    if (tf) { cudaMalloc(&d_trace, (size_t)L.n_tiles1 * 64); cudaMemsetAsync(d_trace, 0, (size_t)L.n_tiles1 * 64, st); }
-    launch_oz_gemm(S, h->oz_map, L.d_tiles1, L.n_tiles1, h->oz_scale.p, st, d_trace);
-    if (tf) {
-      std::vector<long long> tr((size_t)L.n_tiles1 * 8);
-      std::vector<OzTile> tl(L.n_tiles1);
-      cudaMemcpyAsync(tr.data(), d_trace, tr.size() * 8, cudaMemcpyDeviceToHost, st);
-      cudaMemcpyAsync(tl.data(), L.d_tiles1, tl.size() * sizeof(OzTile), cudaMemcpyDeviceToHost, st);
-      cudaStreamSynchronize(st);
-      if (FILE* f = fopen(tf, "w")) {
-        for (int i = 0; i < L.n_tiles1; i++) {
-          fprintf(f, "%d", tl[i].k1 - tl[i].k0);
-          for (int q = 1; q < 8; q++) fprintf(f, " %lld", tr[(size_t)i * 8 + q] - tr[(size_t)i * 8]);
-          fprintf(f, "\n");
-        }
-        fclose(f);
-      }
-      cudaFree(d_trace);
-    }
+    tm.mark("slice1");
+    traced_gemm(h, S, L.d_tiles1, L.n_tiles1, (li == 0 && !h->capturing) ? getenv("DSMGP_OZAKI_TRACE") : nullptr, st);
+    tm.mark("gemm1");
     launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
     launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-    launch_oz_gemm(S, h->oz_map, L.d_tiles2, L.n_tiles2, h->oz_scale.p, st);
+    tm.mark("slice2");
+    launch_oz_gemm(S, h->oz_map, L.d_tiles2, L.n_tiles2, h->oz_scale.p, num_sms(h->device), st);
+    tm.mark("gemm2");
     h->tm.launches += 6;
   }
   OzPartArgs pa{full.meta, full.F, full.z, full.flag_off, full.apart, full.tpart, b.oz.d_parts};
   launch_oz_parts(pa, b.oz.n_parts, st);
   launch_alpha_reduce(full, b.d_trtri_tasks, b.n_trtri, st);
+  tm.mark("parts+reduce");
+  tm.report("inverse");
   h->tm.launches += 3;
   return DSMGP_OK;
 }

@@ -40,12 +40,13 @@ void launch_oz_slice(int S, const OzJob* jobs, int njobs, int pass, unsigned lon
   else oz::slice_kernel<8><<<njobs, 256, 0, st>>>(jobs, pass, rowmax, scale, pool);
 }
 
-void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, cudaStream_t st, long long* trace) {
+void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, int nctas, cudaStream_t st, long long* trace) {
   if (ntiles <= 0) return;
   CUtensorMap map;
   memcpy(&map, map128, sizeof(map));
-  if (S == 7) oz::gemm_kernel<7><<<ntiles, oz::OZ_THREADS, oz::Cfg<7>::SMEM, st>>>(map, tiles, scale, trace);
-  else oz::gemm_kernel<8><<<ntiles, oz::OZ_THREADS, oz::Cfg<8>::SMEM, st>>>(map, tiles, scale, trace);
+  const int grid = ntiles < nctas ? ntiles : nctas;
+  if (S == 7) oz::gemm_kernel<7><<<grid, oz::OZ_THREADS, oz::Cfg<7>::SMEM, st>>>(map, tiles, ntiles, scale, trace);
+  else oz::gemm_kernel<8><<<grid, oz::OZ_THREADS, oz::Cfg<8>::SMEM, st>>>(map, tiles, ntiles, scale, trace);
 }
 
 void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st) {

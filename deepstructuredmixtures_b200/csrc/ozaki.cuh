@@ -8,7 +8,7 @@
 // rowmax * colmax per term).  S = 8 gives products that are MORE accurate than an FP64 FMA chain (measured: 2e-15 of
 // max|C| on Cholesky-factor operands against 4e-15 for cuBLAS DGEMM).
 //
-// GEMM kernel: one CTA per 128 x 128 output block.  warp 0 = TMA producer (cp.async.bulk.tensor.2d of 4 KB slice
+// GEMM kernel: persistent CTAs, one 128 x 128 output block at a time.  warp 0 = TMA producer (cp.async.bulk.tensor.2d of 4 KB slice
 // tiles into a mbarrier ring), warp 1 = TMEM allocation + tcgen05.mma.kind::i8 issue (M = N = 128, K = 32), warps 2-5 =
 // 8 epilogue warps (tcgen05.ld, int32 -> FP64, Horner sum over the slice groups, row scales, store in the factor-tile layout).
 // S groups of 128 columns do not fit TMEM (512 columns), so a block is computed in two rounds over K: the four
@@ -139,9 +139,14 @@ __global__ void __launch_bounds__(256) slice_kernel(const OzJob* __restrict__ jo
 // ---- block products ----------------------------------------------------------------------------------------------------
 constexpr int OZ_THREADS = 64 + 256;      // producer warp, MMA warp, 8 epilogue warps
 
+// Persistent: CTA b works on the blocks b, b + gridDim.x, ... of the list (sorted by length, so the strided assignment is
+// balanced to within one block).  TMEM is allocated once; the operand ring and the barriers run on across blocks.  The
+// epilogue warps release TMEM as soon as they have read it, so the global-memory part of a block's epilogue (scales, old
+// values of an accumulating block, stores) overlaps the MMAs of the next block.
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ tiles, const double* __restrict__ scale, long long* __restrict__ trace) {
+gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ tiles, int ntiles, const double* __restrict__ scale,
+            long long* __restrict__ trace) {
   using C = Cfg<S>;
   constexpr int RING = C::NST * C::STAGE;                     // bytes of the operand ring
   constexpr int MAXST = 8;
@@ -153,10 +158,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
   uint32_t* tptr = reinterpret_cast<uint32_t*>(tempty + 1);
   uint8_t* ring = smem + 1024;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const OzTile t = tiles[blockIdx.x];
-  const int nk = t.k1 - t.k0;
-  long long* trc = trace ? trace + (int64_t)blockIdx.x * 8 : nullptr;      // optional clock stamps (DSMGP_OZAKI_TRACE)
-  if (trc && threadIdx.x == 0) trc[0] = clock64();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4 * MAXST; ++i) mbar_init(&bars[i], 1);
@@ -173,28 +174,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = *tptr;
-  if (trc && threadIdx.x == 0) trc[1] = clock64();
 
   if (warp == 0) {
     if (lane == 0) {
+      int it[2] = {0, 0};          // steps issued into the ring of each round so far
+      int nround = 0;              // (block, round) pairs started so far
+      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const OzTile t = tiles[ti];
+        const int nk = t.k1 - t.k0;
 #pragma unroll
-      for (int r = 0; r < C::NR; ++r) {
-        const int nsl = C::nsl(r);
-        const int stage = 2 * nsl * OZ_TILE_B;
-        const int nst = (RING / stage) < MAXST ? (RING / stage) : MAXST;
-        uint64_t* full = bars + r * 2 * MAXST; uint64_t* empty = full + MAXST;
-        // the ring changes its geometry: it is free once the previous round's last MMAs have completed (tfull); the loads of
-        // this round then overlap the epilogue of the previous one
-        if (r > 0) mbar_wait(tfull, (r - 1) & 1);
-        for (int i = 0; i < nk; ++i) {
-          const int st = i % nst, ks = t.k0 + i;
-          if (i >= nst) mbar_wait(&empty[st], ((i / nst) - 1) & 1);
-          uint8_t* dst = ring + st * stage;
-          mbar_expect_tx(&full[st], stage);
-          const int rowA = (t.a_tile + ks * S) * 32, rowB = (t.b_tile + ks * S) * 32;   // tensor-map rows = 128-byte core matrices
-          for (int s = 0; s < nsl; ++s) {
-            tma_load_2d(dst + s * OZ_TILE_B, &map, 0, rowA + s * 32, &full[st]);
-            tma_load_2d(dst + (nsl + s) * OZ_TILE_B, &map, 0, rowB + s * 32, &full[st]);
+        for (int r = 0; r < C::NR; ++r, ++nround) {
+          const int nsl = C::nsl(r);
+          const int stage = 2 * nsl * OZ_TILE_B;
+          const int nst = (RING / stage) < MAXST ? (RING / stage) : MAXST;
+          uint64_t* full = bars + r * 2 * MAXST; uint64_t* empty = full + MAXST;
+          // the ring changes its geometry between rounds: it is free once the previous round's last MMAs have completed
+          // (tfull); the loads of this round then overlap the epilogue of the previous one
+          if (C::NR > 1 && nround > 0) mbar_wait(tfull, (nround - 1) & 1);
+          for (int i = 0; i < nk; ++i, ++it[r]) {
+            const int st = it[r] % nst, ks = t.k0 + i;
+            if (it[r] >= nst) mbar_wait(&empty[st], ((it[r] / nst) - 1) & 1);
+            uint8_t* dst = ring + st * stage;
+            mbar_expect_tx(&full[st], stage);
+            const int rowA = (t.a_tile + ks * S) * 32, rowB = (t.b_tile + ks * S) * 32;   // tensor-map rows = 128-byte core matrices
+            for (int s = 0; s < nsl; ++s) {
+              tma_load_2d(dst + s * OZ_TILE_B, &map, 0, rowA + s * 32, &full[st]);
+              tma_load_2d(dst + (nsl + s) * OZ_TILE_B, &map, 0, rowB + s * 32, &full[st]);
+            }
           }
         }
       }
@@ -203,36 +209,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
     if (lane == 0) {
       // instruction descriptor: D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), K-major, N >> 3 at 17, M >> 4 at 24
       const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLK >> 3) << 17) | ((uint32_t)(BLK >> 4) << 24);
+      int it[2] = {0, 0};
+      int nround = 0;
+      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const int nk = tiles[ti].k1 - tiles[ti].k0;
+        long long* trc = trace ? trace + (int64_t)ti * 16 : nullptr;
 #pragma unroll
-      for (int r = 0; r < C::NR; ++r) {
-        const int glo = C::glo(r), ghi = C::ghi(r), nsl = C::nsl(r);
-        const int stage = 2 * nsl * OZ_TILE_B;
-        const int nst = (RING / stage) < MAXST ? (RING / stage) : MAXST;
-        uint64_t* full = bars + r * 2 * MAXST; uint64_t* empty = full + MAXST;
-        if (r > 0) { mbar_wait(tempty, (r - 1) & 1); tc_fence_after(); }
-        for (int i = 0; i < nk; ++i) {
-          const int st = i % nst;
-          mbar_wait(&full[st], (i / nst) & 1);
-          if (trc && r == 0 && i == 0) trc[2] = clock64();
-          tc_fence_after();
-          const uint32_t sA = smem_u32(ring + st * stage), sB = sA + nsl * OZ_TILE_B;
-          uint32_t written = (i > 0) ? 0xFFu : 0u;
+        for (int r = 0; r < C::NR; ++r, ++nround) {
+          const int glo = C::glo(r), ghi = C::ghi(r), nsl = C::nsl(r);
+          const int stage = 2 * nsl * OZ_TILE_B;
+          const int nst = (RING / stage) < MAXST ? (RING / stage) : MAXST;
+          uint64_t* full = bars + r * 2 * MAXST; uint64_t* empty = full + MAXST;
+          if (nround > 0) { mbar_wait(tempty, (nround - 1) & 1); tc_fence_after(); }     // the epilogue has read the accumulators
+          if (trc && r == 0) trc[0] = clock64();
+          for (int i = 0; i < nk; ++i, ++it[r]) {
+            const int st = it[r] % nst;
+            mbar_wait(&full[st], (it[r] / nst) & 1);
+            if (trc && r == 0 && i == 0) trc[2] = clock64();
+            tc_fence_after();
+            const uint32_t sA = smem_u32(ring + st * stage), sB = sA + nsl * OZ_TILE_B;
+            uint32_t written = (i > 0) ? 0xFFu : 0u;
 #pragma unroll
-          for (int s = 0; s < S; ++s) {
-            if (s >= nsl) continue;
-            const uint64_t da = make_desc(sA + s * OZ_TILE_B);
+            for (int s = 0; s < S; ++s) {
+              if (s >= nsl) continue;
+              const uint64_t da = make_desc(sA + s * OZ_TILE_B);
 #pragma unroll
-            for (int u = 0; u < S; ++u) {
-              const int g = s + u;
-              if (u >= nsl || g < glo || g > ghi) continue;
-              tc_mma_i8(tbase + (uint32_t)((g - glo) * BLK), da, make_desc(sB + u * OZ_TILE_B), idesc, (written >> g) & 1u);
-              written |= 1u << g;
+              for (int u = 0; u < S; ++u) {
+                const int g = s + u;
+                if (u >= nsl || g < glo || g > ghi) continue;
+                tc_mma_i8(tbase + (uint32_t)((g - glo) * BLK), da, make_desc(sB + u * OZ_TILE_B), idesc, (written >> g) & 1u);
+                written |= 1u << g;
+              }
             }
+            tc_commit(&empty[st]);
           }
-          tc_commit(&empty[st]);
+          tc_commit(tfull);
+          if (trc) trc[3 + 2 * r] = clock64();
         }
-        tc_commit(tfull);
-        if (trc && r == 0) trc[3] = clock64();
       }
     }
   } else {
@@ -240,46 +253,56 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
     // split the 128 columns.  The Horner sum over the slice groups stays in registers across the two rounds.
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int row = q * 32 + lane, cbase = half * 64;
-    const bool rok = row < t.vr;
-    const double srow = rok ? scale[t.sa + row] * t.sign : 0.0;
-    double acc[64];
+    int nround = 0;
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+      const OzTile t = tiles[ti];
+      long long* trc = (trace && threadIdx.x == 64) ? trace + (int64_t)ti * 16 : nullptr;
+      const bool rok = row < t.vr;
+      const double srow = rok ? scale[t.sa + row] * t.sign : 0.0;
+      double acc[64];
 #pragma unroll
-    for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+      for (int j = 0; j < 64; ++j) acc[j] = 0.0;
 #pragma unroll
-    for (int r = 0; r < C::NR; ++r) {
-      const int glo = C::glo(r), ghi = C::ghi(r);
-      mbar_wait(tfull, r & 1);
-      if (trc && threadIdx.x == 64) trc[4 + 2 * r] = clock64();
-      tc_fence_after();
+      for (int r = 0; r < C::NR; ++r, ++nround) {
+        const int glo = C::glo(r), ghi = C::ghi(r);
+        mbar_wait(tfull, nround & 1);
+        if (trc) trc[4 + 2 * r] = clock64();
+        tc_fence_after();
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
+        for (int c0 = 0; c0 < 64; c0 += 16) {
 #pragma unroll
-        for (int g = S - 1; g >= 0; --g) {                       // smallest weight first: acc = acc / 128 + G_g
-          if (g < glo || g > ghi) continue;
-          uint32_t v[16];
-          tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * BLK + cbase + c0), v);
-          tc_wait_ld();
+          for (int g = S - 1; g >= 0; --g) {                       // smallest weight first: acc = acc / 128 + G_g
+            if (g < glo || g > ghi) continue;
+            uint32_t v[16];
+            tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * BLK + cbase + c0), v);
+            tc_wait_ld();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) acc[c0 + j] = fma(acc[c0 + j], 0.0078125, (double)(int)v[j]);
+            for (int j = 0; j < 16; ++j) acc[c0 + j] = fma(acc[c0 + j], 0.0078125, (double)(int)v[j]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty)) : "memory");   // TMEM is free again
+      }
+      if (trc) trc[7] = clock64();
+      // stores in chunks of 8 columns: all loads of a chunk (column scales, old values of an accumulating block) are issued
+      // before its stores -- interleaved they would serialise on the memory latency
+#pragma unroll
+      for (int j0 = 0; j0 < 64; j0 += 8) {
+        const int c0 = cbase + j0;
+        if (rok && c0 < t.vc) {                                      // vc is a multiple of 16
+          double* o = t.out + (c0 >> 4) * TILE_D + (c0 & 15) * LDS + row;      // column c0 + j at o[j * LDS]
+          double sc[8], old[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) sc[j] = scale[t.sb + c0 + j];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) old[j] = t.accum ? o[j * LDS] : 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j * LDS] = fma(acc[j0 + j] * srow, sc[j], old[j]);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (trc && threadIdx.x == 64) trc[5 + 2 * r] = clock64();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(tempty)) : "memory");
+      if (trc) trc[8] = clock64();
     }
-    if (rok) {
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const int c = cbase + j;
-        if (c < t.vc) {
-          double* o = t.out + (c >> 4) * TILE_D + (c & 15) * LDS + row;
-          const double v = acc[j] * srow * scale[t.sb + c];
-          *o = t.accum ? *o + v : v;
-        }
-      }
-    }
-    if (trc && threadIdx.x == 64) trc[7] = clock64();
   }
   __syncthreads();
   if (warp == 1) {

@@ -73,7 +73,7 @@ struct OzPlan {
 cudaError_t oz_init_kernels();
 int oz_make_map(void* map128, const void* pool, size_t bytes);          // 0 on success
 void launch_oz_slice(int S, const OzJob* jobs, int njobs, int pass, unsigned long long* rowmax, double* scale, int8_t* pool, cudaStream_t st);
-void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, cudaStream_t st, long long* trace = nullptr);
+void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, int nctas, cudaStream_t st, long long* trace = nullptr);
 void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st);
 
 }  // namespace dsm

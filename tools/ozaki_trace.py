@@ -1,19 +1,20 @@
-"""Summarise DSMGP_OZAKI_TRACE (clock stamps of the INT8 block-product kernel): per tile nk + 7 stamps relative to the CTA start:
-setup done, first operands landed, round-0 MMAs issued, round-0 accumulators complete, round-0 epilogue done, round-1 complete, round-1 epilogue done."""
+"""Summarise DSMGP_OZAKI_TRACE / DSMGP_OZAKI_TRACE_SYRK (clock stamps of the persistent INT8 block-product kernel).
+Per block: nk, then SM-clock stamps relative to the moment its first MMA round may start (TMEM released by the previous block):
+[2] first operands landed, [3] round-0 MMAs issued, [4] round-0 accumulators complete, [5] round-1 MMAs issued, [6] round-1
+complete, [7] TMEM read by the epilogue, [8] stores issued."""
 import sys
 import numpy as np
 a = np.loadtxt(sys.argv[1])
 nk = a[:, 0]
 ghz = 1.965
-names = ["setup", "first_full", "r0_issued", "r0_done", "r0_epi", "r1_done", "r1_epi"]
-print("tiles", len(a), "mean nk", nk.mean())
+us_all = a[:, 1:] / ghz / 1e3
+print("blocks", len(a), "mean nk", nk.mean())
 for lo, hi in ((1, 8), (8, 16), (16, 32), (32, 64), (64, 200)):
     m = (nk >= lo) & (nk < hi)
     if not m.any():
         continue
-    s = a[m]
-    us = s[:, 1:] / ghz / 1e3
-    d = np.diff(np.concatenate([np.zeros((len(us), 1)), us], axis=1), axis=1)
-    print(f"nk in [{lo},{hi}): {m.sum()} tiles, mean nk {s[:,0].mean():.1f}; total {us[:, -1].mean():.1f} us; ideal MMA {s[:,0].mean()*36*72/ghz/1e3:.1f} us")
-    print("   cumulative us:", " ".join(f"{n}={v:.1f}" for n, v in zip(names, us.mean(0))))
-    print("   r0 mma span %.1f  r0 epilogue %.1f  r1 mma span %.1f  r1 epilogue %.1f" % ((us[:, 3] - us[:, 1]).mean(), (us[:, 4] - us[:, 3]).mean(), (us[:, 5] - us[:, 4]).mean(), (us[:, 6] - us[:, 5]).mean()))
+    u = us_all[m]
+    ideal = nk[m].mean() * 36 * 72 / ghz / 1e3
+    print(f"nk in [{lo},{hi}): {m.sum()} blocks, mean nk {nk[m].mean():.1f}; ideal MMA (S=8) {ideal:.1f} us")
+    print("   first operands %.1f | r0 issued %.1f | r0 done %.1f | r1 issued %.1f | r1 done %.1f | TMEM drained %.1f | stores issued %.1f" % tuple(u[:, i].mean() for i in (1, 2, 3, 4, 5, 6, 7)))
+    print("   occupancy of the MMA warp per block (start -> TMEM drained): %.1f us = %.0f %% of ideal" % (u[:, 6].mean(), 100 * ideal / u[:, 6].mean()))
