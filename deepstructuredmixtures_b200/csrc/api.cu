@@ -376,6 +376,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
           return a.J < c.J; });
         std::vector<int4> mt(mv.size());
         for (size_t i = 0; i < mv.size(); i++) mt[i] = make_int4(mv[i].slot, mv[i].I, mv[i].J, 0);
+        b.h_trtri3m = mt;
         CUDA_TRY(h, upload(&b.d_trtri3m_tasks, mt));
       }
       // back-substitution tasks (slot, J): level = distance from the bottom (a task depends on the tasks below it)
@@ -648,7 +649,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
     Batch& b = h->batches[bi];
     cudaEvent_t* ev = h->ev.data() + 8 * bi;
     const int nsl = b.s1 - b.s0;
-    h->oz_l21_ready = false;
+    h->oz_l21_ready = false; h->oz_inv_tiles_done = false;
     EV_RECORD(ev[0]);
     if (nsl == 0) { for (int k = 1; k < 8; k++) EV_RECORD(ev[k]); continue; }
     const LeafMeta* meta = h->d_meta.p + b.s0;
@@ -671,7 +672,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
       // 8-way 10.19 -> 9.57 ms, 4-way 18.95 -> 18.41 ms; neutral on the full 144-expert batch, which keeps the two launches and
       // their per-phase timings): DSMGP_FUSED_EVAL=0|1 overrides.
       const char* fe = getenv("DSMGP_FUSED_EVAL");
-      const bool fused = with_grad && !shr && b.n_trtri3 > 0 && !getenv("DSMGP_TRACE_FILE") &&
+      const bool fused = with_grad && !shr && b.n_trtri3 > 0 && !getenv("DSMGP_TRACE_FILE") && !(b.oz.active && b.oz.potrf) &&
                          (fe ? fe[0] == '1' : nsl * 3 < sms * 2);
       if (fused) {
         CUDA_TRY(h, cudaMemsetAsync(h->d_flags2.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
@@ -698,7 +699,14 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
         const char* trace_file = h->capturing ? nullptr : getenv("DSMGP_TRACE_FILE");
         if (trace_file) { cudaMalloc(&d_trace, (size_t)b.n_potrf2 * 64); cudaMemsetAsync(d_trace, 0, (size_t)b.n_potrf2 * 64, st); pa.trace = d_trace; }
         if (b.oz.active && b.oz.potrf && !trace_file && !h->capturing) {
-          const int32_t rc = oz_run_potrf(h, b, pa, sms, st);        // split factorisation, SYRK on the INT8 tensor cores
+          // split factorisation, SYRK on the INT8 tensor cores; on a gradient evaluation the inverse's tile-pipeline tasks
+          // ride behind the factorisation tiles of the two launches
+          Trtri3Args tinv{meta, h->d_F.p, h->d_W.p, h->d_WT.p, h->d_z.p, h->d_alpha.p, h->d_trpart.p, b.d_trpart_off,
+                          h->d_flags2.p, b.d_flag_off, h->d_apart.p, h->d_tpart.p, nullptr, 0,
+                          h->d_counter.p, h->d_counter.p + GERR, nullptr};
+          const bool inv_too = with_grad && !mask_all;
+          if (inv_too) CUDA_TRY(h, cudaMemsetAsync(h->d_flags2.p, 0, std::max<int64_t>(b.flag_ints, 1) * sizeof(int), st));
+          const int32_t rc = oz_run_potrf(h, b, pa, inv_too ? &tinv : nullptr, sms, st);
           if (rc != DSMGP_OK) return rc;
         } else
         launch_potrf2(pa, std::min(sms, b.n_potrf2), st);

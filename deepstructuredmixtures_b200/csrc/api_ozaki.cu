@@ -186,6 +186,14 @@ int32_t oz_plan(dsmgp_handle* h) {
       CUDA_TRY(h, upload(&b.oz.d_potrfA, pA)); CUDA_TRY(h, upload(&b.oz.d_potrfB, pB));
       CUDA_TRY(h, upload(&b.oz.d_kskip, kskip));
       b.oz.potrf = want_potrf && !pB.empty();
+      std::vector<int4> iA, iB;
+      for (const int4& tk : b.h_trtri3m) {
+        const std::vector<int>& ro = t.range_of[tk.x];
+        if (ro[tk.y] != ro[tk.z]) continue;
+        (kskip[tk.x] > 0 && tk.y >= kskip[tk.x] ? iB : iA).push_back(tk);
+      }
+      b.oz.n_invA = (int)iA.size(); b.oz.n_invB = (int)iB.size();
+      CUDA_TRY(h, upload(&b.oz.d_invA, iA)); CUDA_TRY(h, upload(&b.oz.d_invB, iB));
     }
     b.oz.n_parts = (int)parts.size();
     CUDA_TRY(h, upload(&b.oz.d_parts, parts));
@@ -234,12 +242,15 @@ static void traced_gemm(dsmgp_handle* h, int S, const OzTile* d_tiles, int n, co
 
 // The factorisation of one batch split at the root: block columns < mid, then A22 -= L21 L21^T as block products on the INT8
 // tensor cores, then block columns >= mid whose contractions start at mid.  The tile flags persist across the two launches.
-int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, int sms, cudaStream_t st) {
+int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Trtri3Args* inv, int sms, cudaStream_t st) {
   const int S = h->oz_S;
   OzTimer tm(st, h->capturing);
   Potrf2Args pa = full;
   pa.tasks = b.oz.d_potrfA; pa.ntasks = b.oz.n_potrfA;
-  launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  Trtri3Args ta{};
+  if (inv) { ta = *inv; ta.tasks = b.oz.d_invA; ta.ntasks = b.oz.n_invA; }
+  if (inv) launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
+  else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
   tm.mark("potrfA");
   CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
   launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
@@ -248,7 +259,11 @@ int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, int sms,
   traced_gemm(h, S, b.oz.d_syrk, b.oz.n_syrk, getenv("DSMGP_OZAKI_TRACE_SYRK"), st);
   tm.mark("syrk");
   pa.tasks = b.oz.d_potrfB; pa.ntasks = b.oz.n_potrfB; pa.counter = full.counter + 1; pa.kskip = b.oz.d_kskip;
-  launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  if (inv) {
+    ta.tasks = b.oz.d_invB; ta.ntasks = b.oz.n_invB;
+    launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
+    h->oz_inv_tiles_done = true;
+  } else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
   tm.mark("potrfB");
   tm.report("potrf");
   h->tm.launches += 5;
@@ -262,7 +277,7 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
   Trtri3Args ta = full;
   ta.tasks = b.oz.d_tasks; ta.ntasks = b.oz.n_tasks;
   OzTimer tm(st, h->capturing);
-  launch_trtri3_only(ta, std::max(1, std::min(sms, ta.ntasks)), st);
+  if (!h->oz_inv_tiles_done) launch_trtri3_only(ta, std::max(1, std::min(sms, ta.ntasks)), st);
   tm.mark("trtri3");
   const int S = h->oz_S;
   for (int li = 0; li < b.oz.n_levels; li++) {

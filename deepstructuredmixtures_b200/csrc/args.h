@@ -152,6 +152,7 @@ void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, 
 void launch_trtri3_only(const Trtri3Args& a, int nctas, cudaStream_t st);                      // without the block-column reduction
 void launch_alpha_reduce(const Trtri3Args& a, const int2* cols, int ncols, cudaStream_t st);
 void launch_eval2(const Potrf2Args& pa, const Trtri3Args& ta, int nctas, const int2* cols, int ncols, cudaStream_t st);
+void launch_eval2_only(const Potrf2Args& pa, const Trtri3Args& ta, int nctas, cudaStream_t st);      // without the block-column reduction
 void launch_untile(const double* Ft, int nkc, int n, double* out, cudaStream_t st);
 void launch_ov_count(const int64_t* obs, int64_t total, int* cntp, cudaStream_t st);
 void launch_ov_fill(const int64_t* obs, const int64_t* leaf_ptr, int L, const int64_t* poff, int* fill, int* plist, cudaStream_t st);

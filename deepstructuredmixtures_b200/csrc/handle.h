@@ -52,6 +52,7 @@ struct Batch {
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
   std::vector<int4> h_potrf2;                           // host copy of d_potrf2_tasks
+  std::vector<int4> h_trtri3m;                          // host copy of d_trtri3m_tasks
   std::vector<int4> h_trtri3;                           // host copy of d_trtri3_tasks (filtered by the INT8 split plan)
   OzPlan oz;                                            // split inverse on the INT8 tensor cores (api_ozaki.cu), DSMGP_OZAKI=1
 };
@@ -219,6 +220,7 @@ struct dsmgp_handle {
   // split inverse on the INT8 tensor cores: slice pool + its tensor map, T^T scratch, row scales
   DevBuf<int8_t> oz_pool; DevBuf<double> oz_scratch, oz_scale; DevBuf<unsigned long long> oz_rowmax;
   alignas(64) unsigned char oz_map[128]; int oz_S = 8;
+  bool oz_inv_tiles_done = false;         // the tile-pipeline part of the inverse ran inside the factorisation launches
   bool oz_l21_ready = false;              // the L21 slices of the current batch were made by the factorisation phase
   std::string err;
 
@@ -227,7 +229,7 @@ struct dsmgp_handle {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
       cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
       cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots); cudaFree(b.d_trtri3m_tasks);
-      cudaFree(b.oz.d_tasks); cudaFree(b.oz.d_parts); cudaFree(b.oz.d_potrfA); cudaFree(b.oz.d_potrfB); cudaFree(b.oz.d_kskip); cudaFree(b.oz.d_jobsL); cudaFree(b.oz.d_syrk);
+      cudaFree(b.oz.d_tasks); cudaFree(b.oz.d_parts); cudaFree(b.oz.d_potrfA); cudaFree(b.oz.d_potrfB); cudaFree(b.oz.d_kskip); cudaFree(b.oz.d_jobsL); cudaFree(b.oz.d_syrk); cudaFree(b.oz.d_invA); cudaFree(b.oz.d_invB);
       for (int l = 0; l < b.oz.n_levels; l++) { cudaFree(b.oz.levels[l].d_jobs1); cudaFree(b.oz.levels[l].d_jobs2); cudaFree(b.oz.levels[l].d_tiles1); cudaFree(b.oz.levels[l].d_tiles2); }
     }
     d_flags2.free();
@@ -282,5 +284,5 @@ int32_t standalone_device_check(std::string& err);
 // api_ozaki.cu
 int32_t oz_plan(dsmgp_handle* h);
 int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st);
-int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, int sms, cudaStream_t st);
+int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Trtri3Args* inv, int sms, cudaStream_t st);
 }  // namespace dsm

@@ -26,6 +26,10 @@ void launch_trtri3(const Trtri3Args& a, int nctas, const int2* cols, int ncols, 
   trtri3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a);
   alpha_reduce_kernel<<<ncols, BLK, 0, st>>>(a, cols, ncols);
 }
+void launch_eval2_only(const Potrf2Args& pa, const Trtri3Args& ta, int nctas, cudaStream_t st) {
+  Eval2Args a{pa, ta};
+  eval2_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a);
+}
 void launch_trtri3_only(const Trtri3Args& a, int nctas, cudaStream_t st) { trtri3_kernel<<<nctas, NTHREADS_PW, PIPE_SMEM_BYTES, st>>>(a); }
 void launch_alpha_reduce(const Trtri3Args& a, const int2* cols, int ncols, cudaStream_t st) { alpha_reduce_kernel<<<ncols, BLK, 0, st>>>(a, cols, ncols); }
 }  // namespace dsm

@@ -67,6 +67,9 @@ struct OzPlan {
   OzJob* d_jobsL = nullptr; int n_jobsL = 0;         // L21 blocks
   OzTile* d_syrk = nullptr; int n_syrk = 0;
   int l21_scale0 = 0, l21_nscale = 0;
+  // gradient evaluations: the tile-pipeline part of the inverse rides in the two factorisation launches (fused2.cuh):
+  // tiles of the first diagonal range (and of unsplit experts) behind launch A, tiles of the second range behind launch B
+  int4* d_invA = nullptr; int n_invA = 0; int4* d_invB = nullptr; int n_invB = 0;
 };
 
 // launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).
