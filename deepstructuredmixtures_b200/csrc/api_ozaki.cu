@@ -103,7 +103,8 @@ int32_t oz_plan(dsmgp_handle* h) {
     CUDA_TRY(h, upload(&b.oz.d_tasks, keep));
     std::vector<OzPart> parts;
     double flops = 0.0;
-    std::vector<OzJob> jL; std::vector<OzTile> tS;
+    std::vector<OzJob> jL, jT; std::vector<OzTile> tS, tT;
+    int64_t poolT = 0; int scaleT = 0;
     std::vector<int> kskip(b.s1 - b.s0, 0);
     int64_t l21_pool = max_pool; int l21_scale = (int)max_scale;
     for (int lv = maxdepth - 1; lv >= 0; lv--) {         // deepest level first
@@ -131,6 +132,26 @@ int32_t oz_plan(dsmgp_handle* h) {
         const int sB2 = scale; scale += J2 * BLK;
         double* T = h->oz_scratch.p + scratch; scratch += (int64_t)J1 * J2 * WBLK_D;
         if (lv == 0) kskip[sp.slot] = sp.mid;
+        if (lv == 0 && maxdepth == 1) {
+          // L21 = A21 X11^T.  Operand slices live in the (still unused) level region of the pool: A21 rows i over k < mid,
+          // X11 rows j over k <= j (stored transposed above the diagonal, W_J on it)
+          const int64_t qA = poolT; poolT += (int64_t)J2 * J1 * KB * S;
+          const int64_t qX = poolT; poolT += (int64_t)J1 * J1 * KB * S;
+          const int uA = scaleT; scaleT += J2 * BLK;
+          const int uX = scaleT; scaleT += J1 * BLK;
+          for (int c = 0; c < J2; c++)
+            for (int k = 0; k < J1; k++)
+              jT.push_back({fblk(sp.mid + c, k), 0, wid(sp.mid + c), BLK, uA + c * BLK, qA + ((int64_t)c * J1 + k) * KB * S});
+          for (int a = 0; a < J1; a++) {
+            for (int k = 0; k <= a; k++) {
+              if (k == a) jT.push_back({W + (int64_t)a * WBLK_D, 0, BLK, BLK, uX + a * BLK, qX + ((int64_t)a * J1 + k) * KB * S});
+              else jT.push_back({fblk(k, a), 1, BLK, BLK, uX + a * BLK, qX + ((int64_t)a * J1 + k) * KB * S});
+            }
+            for (int c = 0; c < J2; c++)
+              tT.push_back({(int)(qA + (int64_t)c * J1 * KB * S), (int)(qX + (int64_t)a * J1 * KB * S), 0, (a + 1) * KB, uA + c * BLK, uX + a * BLK,
+                            wid(sp.mid + c), BLK, const_cast<double*>(fblk(sp.mid + c, a)), 1.0, 0, 0});
+          }
+        }
         for (int a = 0; a < J1; a++) {                                       // a = Jb - lo
           const int Jb = sp.lo + a;
           for (int k = a; k < J1; k++) {                                     // X^T block (Jb, Kb), Kb >= Jb
@@ -186,6 +207,15 @@ int32_t oz_plan(dsmgp_handle* h) {
       CUDA_TRY(h, upload(&b.oz.d_potrfA, pA)); CUDA_TRY(h, upload(&b.oz.d_potrfB, pB));
       CUDA_TRY(h, upload(&b.oz.d_kskip, kskip));
       b.oz.potrf = want_potrf && !pB.empty();
+      {
+        const char* te = getenv("DSMGP_OZAKI_TRSM");
+        std::vector<int4> pA11;
+        for (const int4& tk : pA) if (!(kskip[tk.x] > 0 && tk.y >= kskip[tk.x])) pA11.push_back(tk);
+        std::stable_sort(tT.begin(), tT.end(), by_len);
+        b.oz.n_potrfA11 = (int)pA11.size(); b.oz.n_jobsT = (int)jT.size(); b.oz.n_tilesT = (int)tT.size(); b.oz.nscaleT = scaleT;
+        CUDA_TRY(h, upload(&b.oz.d_potrfA11, pA11)); CUDA_TRY(h, upload(&b.oz.d_jobsT, jT)); CUDA_TRY(h, upload(&b.oz.d_tilesT, tT));
+        b.oz.trsm = b.oz.potrf && !tT.empty() && !(te && te[0] == '0');
+      }
       std::vector<int4> iA, iB;
       for (const int4& tk : b.h_trtri3m) {
         const std::vector<int>& ro = t.range_of[tk.x];
@@ -249,9 +279,21 @@ int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Tr
   pa.tasks = b.oz.d_potrfA; pa.ntasks = b.oz.n_potrfA;
   Trtri3Args ta{};
   if (inv) { ta = *inv; ta.tasks = b.oz.d_invA; ta.ntasks = b.oz.n_invA; }
+  const bool gemm_panel = inv && b.oz.trsm;
+  if (gemm_panel) { pa.tasks = b.oz.d_potrfA11; pa.ntasks = b.oz.n_potrfA11; }
   if (inv) launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
   else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
   tm.mark("potrfA");
+  if (gemm_panel) {       // L21 = A21 X11^T in place of the panel tasks; their tile flags are set for the later launches
+    CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)b.oz.nscaleT * sizeof(unsigned long long), st));
+    launch_oz_slice(S, b.oz.d_jobsT, b.oz.n_jobsT, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_slice(S, b.oz.d_jobsT, b.oz.n_jobsT, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    tm.mark("sliceA21X11");
+    launch_oz_gemm(S, h->oz_map, b.oz.d_tilesT, b.oz.n_tilesT, h->oz_scale.p, num_sms(h->device), st);
+    launch_oz_setflags(b.oz.d_parts, b.oz.n_parts, full.flag_off, full.flags, st);
+    tm.mark("gemmL21");
+    h->tm.launches += 4;
+  }
   CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
   launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
   launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);

@@ -54,4 +54,8 @@ void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st) {
   oz::parts_kernel<<<nparts, BLK, 0, st>>>(a);
 }
 
+void launch_oz_setflags(const OzPart* parts, int n, const int64_t* flag_off, int* flags, cudaStream_t st) {
+  if (n > 0) oz::setflags_kernel<<<(n + 255) / 256, 256, 0, st>>>(parts, n, flag_off, flags);
+}
+
 }  // namespace dsm

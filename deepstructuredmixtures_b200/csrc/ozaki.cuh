@@ -337,5 +337,14 @@ __global__ void __launch_bounds__(BLK) parts_kernel(OzPartArgs a) {
   if (tid == 0) a.tpart[tile] = s_red[0] + s_red[1] + s_red[2] + s_red[3];
 }
 
+// Marks the factor tiles (I, J) of a part list as complete in a tile-flag array (the L21 tiles written by a GEMM instead of
+// panel tasks: the diagonal tasks of the second factorisation launch stream them for the forward solve).
+__global__ void setflags_kernel(const OzPart* __restrict__ parts, int n, const int64_t* __restrict__ flag_off, int* __restrict__ flags) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const OzPart p = parts[i];
+  flags[flag_off[p.slot] + (int64_t)p.I * (p.I + 1) / 2 + p.J] = 1;
+}
+
 }  // namespace oz
 }  // namespace dsm

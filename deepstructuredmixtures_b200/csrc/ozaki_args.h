@@ -70,6 +70,13 @@ struct OzPlan {
   // gradient evaluations: the tile-pipeline part of the inverse rides in the two factorisation launches (fused2.cuh):
   // tiles of the first diagonal range (and of unsplit experts) behind launch A, tiles of the second range behind launch B
   int4* d_invA = nullptr; int n_invA = 0; int4* d_invB = nullptr; int n_invB = 0;
+  // ... and with X11 at hand after launch A, the panel below it is a product as well:  L21 = A21 X11^T  (instead of panel
+  // tasks with a triangular solve): launch A then holds only the tiles of A11 (and the unsplit experts)
+  bool trsm = false;
+  int4* d_potrfA11 = nullptr; int n_potrfA11 = 0;
+  OzJob* d_jobsT = nullptr; int n_jobsT = 0;         // A21 blocks and X11 blocks
+  OzTile* d_tilesT = nullptr; int n_tilesT = 0;
+  int nscaleT = 0;
 };
 
 // launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).
@@ -78,5 +85,6 @@ int oz_make_map(void* map128, const void* pool, size_t bytes);          // 0 on 
 void launch_oz_slice(int S, const OzJob* jobs, int njobs, int pass, unsigned long long* rowmax, double* scale, int8_t* pool, cudaStream_t st);
 void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, int nctas, cudaStream_t st, long long* trace = nullptr);
 void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st);
+void launch_oz_setflags(const OzPart* parts, int n, const int64_t* flag_off, int* flags, cudaStream_t st);
 
 }  // namespace dsm
