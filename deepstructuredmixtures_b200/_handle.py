@@ -246,5 +246,12 @@ class Handle:
         self._ck(self._lib.dsmgp_get_timings(self._h, C.byref(t)))
         return {n: getattr(t, n) for n, _ in nat.Timings._fields_}
 
+    def int8_info(self) -> dict:
+        """The INT8 split path of the last evaluation (dsmgp_int8_info): op counts and CUDA-event times of its launches."""
+        o = np.zeros(8)
+        self._ck(self._lib.dsmgp_int8_info(self._h, nat.p_d(o), 8))
+        return {"batches": int(o[0]), "slices": int(o[1]), "int8_ops": o[2], "fp64_equiv_flops": o[3], "gemm_ms": o[4],
+                "slice_ms": o[5], "fp64_tile_ms": o[6], "pool_bytes": int(o[7])}
+
     def set_profiling(self, on: bool):
         self._ck(self._lib.dsmgp_set_profiling(self._h, 1 if on else 0))

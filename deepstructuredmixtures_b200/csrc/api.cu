@@ -193,7 +193,8 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     return DSMGP_ERR_OOM;
   }
   // streaming batches: cap the arena so that several batches pipeline well but each one still fills the GPU
-  if (!h->opts.keep_factors && h->opts.arena_bytes == 0) budget = std::min<int64_t>(budget, 48ll << 30);
+  // (24 GiB when the INT8 split path is on: its slice pool and scratch take ~3x the arena of a batch)
+  if (!h->opts.keep_factors && h->opts.arena_bytes == 0) budget = std::min<int64_t>(budget, (oz_enabled() ? 24ll : 48ll) << 30);
   h->batches.clear();
   {
     int s = 0;
@@ -633,6 +634,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
   const bool shr = !naive && !h->capturing && h->share.active && h->theta_global && (h->share.n_alias + h->share.n_prefix) > 0;
   #define EV_RECORD(e) do { if (!h->capturing) cudaEventRecord((e), st); } while (0)
   h->tm = dsmgp_timings{};
+  h->oz_segs.clear(); h->oz_ev_used = 0; h->oz_ksteps = 0.0;
   h->share_applied = shr;
   prepare_masks(h, with_grad ? leaf_scale : nullptr, with_grad, shr);
   const int* mask_all = (with_grad && h->use_mask) ? h->d_mask.p : nullptr;

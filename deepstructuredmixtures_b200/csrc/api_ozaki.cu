@@ -29,6 +29,12 @@ void collect_splits(int slot, int lo, int hi, int depth, int maxdepth, int min_n
 }
 }  // namespace
 
+// DSMGP_OZAKI=0 keeps every evaluation on the FP64 (DMMA) tile pipelines
+bool oz_enabled() {
+  const char* en = getenv("DSMGP_OZAKI");
+  return !(en && en[0] == '0');
+}
+
 int oz_env_slices() {
   const char* e = getenv("DSMGP_OZAKI_SLICES");
   const int s = e ? atoi(e) : 8;
@@ -38,8 +44,7 @@ int oz_env_slices() {
 // Builds the plan of every batch (sizes first, then the job / tile lists with final pointers).  Called at the end of
 // create; a handle without large experts, with several ranks' masks etc. simply keeps oz.active == false.
 int32_t oz_plan(dsmgp_handle* h) {
-  const char* en = getenv("DSMGP_OZAKI");
-  if (!en || en[0] != '1') return DSMGP_OK;
+  if (!oz_enabled()) return DSMGP_OK;
   const char* de = getenv("DSMGP_OZAKI_DEPTH");
   const char* me = getenv("DSMGP_OZAKI_MIN_NB");
   const int maxdepth = de ? std::max(1, std::min(4, atoi(de))) : 1;
@@ -83,10 +88,21 @@ int32_t oz_plan(dsmgp_handle* h) {
     max_l21_pool = std::max(max_l21_pool, lp); max_l21_scale = std::max(max_l21_scale, ls);
   }
   if (max_pool == 0) return DSMGP_OK;
+  {   // memory guard: the slice pool costs ~2.5x the factor arena of a batch; without room the FP64 pipelines stay in charge
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(h, cudaMemGetInfo(&free_b, &total_b));
+    free_b += g_cache.cached_bytes(h->device);
+    const double need = (double)(max_pool + max_l21_pool) * OZ_TILE_B + (double)max_scratch * 8 + (double)(max_scale + max_l21_scale) * 16;
+    if (need > 0.9 * (double)free_b) {
+      for (Batch& b : h->batches) b.oz.active = false;
+      return DSMGP_OK;
+    }
+  }
   CUDA_TRY(h, h->oz_pool.alloc((size_t)(max_pool + max_l21_pool) * OZ_TILE_B));
   CUDA_TRY(h, h->oz_scratch.alloc((size_t)max_scratch));
   CUDA_TRY(h, h->oz_scale.alloc((size_t)(max_scale + max_l21_scale)));
   CUDA_TRY(h, h->oz_rowmax.alloc((size_t)(max_scale + max_l21_scale)));
+  h->oz_pool_bytes = (int64_t)(max_pool + max_l21_pool) * OZ_TILE_B;
   if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return DSMGP_ERR_CUDA; }
   // pass 2: lists
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
@@ -190,6 +206,8 @@ int32_t oz_plan(dsmgp_handle* h) {
       auto by_len = [](const OzTile& x, const OzTile& y) { return (x.k1 - x.k0) > (y.k1 - y.k0); };
       std::stable_sort(t1.begin(), t1.end(), by_len);
       std::stable_sort(t2.begin(), t2.end(), by_len);
+      for (const OzTile& x : t1) L.ksteps1 += x.k1 - x.k0;
+      for (const OzTile& x : t2) L.ksteps2 += x.k1 - x.k0;
       L.n_jobs1 = (int)j1.size(); L.n_jobs2 = (int)j2.size(); L.n_tiles1 = (int)t1.size(); L.n_tiles2 = (int)t2.size(); L.n_scale = scale;
       CUDA_TRY(h, upload(&L.d_jobs1, j1)); CUDA_TRY(h, upload(&L.d_jobs2, j2));
       CUDA_TRY(h, upload(&L.d_tiles1, t1)); CUDA_TRY(h, upload(&L.d_tiles2, t2));
@@ -198,6 +216,8 @@ int32_t oz_plan(dsmgp_handle* h) {
     {   // factorisation phase of the root splits
       auto by_len = [](const OzTile& x, const OzTile& y) { return (x.k1 - x.k0) > (y.k1 - y.k0); };
       std::stable_sort(tS.begin(), tS.end(), by_len);
+      for (const OzTile& x : tS) b.oz.ksteps_syrk += x.k1 - x.k0;
+      for (const OzTile& x : tT) b.oz.ksteps_T += x.k1 - x.k0;
       b.oz.n_jobsL = (int)jL.size(); b.oz.n_syrk = (int)tS.size();
       b.oz.l21_scale0 = (int)max_scale; b.oz.l21_nscale = l21_scale - (int)max_scale;
       CUDA_TRY(h, upload(&b.oz.d_jobsL, jL)); CUDA_TRY(h, upload(&b.oz.d_syrk, tS));
@@ -231,6 +251,19 @@ int32_t oz_plan(dsmgp_handle* h) {
   }
   return DSMGP_OK;
 }
+
+// Always-on segment timing (two events per segment, no synchronisation): which part of an evaluation ran where.
+struct OzSegScope {
+  dsmgp_handle* h; cudaStream_t st; int idx = -1;
+  OzSegScope(dsmgp_handle* h_, int kind, cudaStream_t s) : h(h_), st(s) {
+    if (h->capturing) return;
+    auto ev = [&]() { if (h->oz_ev_used == h->oz_evs.size()) { cudaEvent_t e; cudaEventCreate(&e); h->oz_evs.push_back(e); } return h->oz_evs[h->oz_ev_used++]; };
+    cudaEvent_t a = ev(), b = ev();
+    cudaEventRecord(a, st);
+    h->oz_segs.push_back({kind, a, b}); idx = (int)h->oz_segs.size() - 1;
+  }
+  ~OzSegScope() { if (idx >= 0) cudaEventRecord(h->oz_segs[idx].b, st); }
+};
 
 // DSMGP_OZAKI_TIMING=1: CUDA-event time of every launch of the split phases, printed to stderr (synchronises: diagnostics only)
 struct OzTimer {
@@ -281,31 +314,51 @@ int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Tr
   if (inv) { ta = *inv; ta.tasks = b.oz.d_invA; ta.ntasks = b.oz.n_invA; }
   const bool gemm_panel = inv && b.oz.trsm;
   if (gemm_panel) { pa.tasks = b.oz.d_potrfA11; pa.ntasks = b.oz.n_potrfA11; }
-  if (inv) launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
-  else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  {
+    OzSegScope seg(h, 2, st);
+    if (inv) launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
+    else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  }
   tm.mark("potrfA");
   if (gemm_panel) {       // L21 = A21 X11^T in place of the panel tasks; their tile flags are set for the later launches
-    CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)b.oz.nscaleT * sizeof(unsigned long long), st));
-    launch_oz_slice(S, b.oz.d_jobsT, b.oz.n_jobsT, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-    launch_oz_slice(S, b.oz.d_jobsT, b.oz.n_jobsT, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    {
+      OzSegScope seg(h, 1, st);
+      CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)b.oz.nscaleT * sizeof(unsigned long long), st));
+      launch_oz_slice(S, b.oz.d_jobsT, b.oz.n_jobsT, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+      launch_oz_slice(S, b.oz.d_jobsT, b.oz.n_jobsT, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    }
     tm.mark("sliceA21X11");
-    launch_oz_gemm(S, h->oz_map, b.oz.d_tilesT, b.oz.n_tilesT, h->oz_scale.p, num_sms(h->device), st);
+    {
+      OzSegScope seg(h, 0, st);
+      launch_oz_gemm(S, h->oz_map, b.oz.d_tilesT, b.oz.n_tilesT, h->oz_scale.p, num_sms(h->device), st);
+      h->oz_ksteps += b.oz.ksteps_T;
+    }
     launch_oz_setflags(b.oz.d_parts, b.oz.n_parts, full.flag_off, full.flags, st);
     tm.mark("gemmL21");
     h->tm.launches += 4;
   }
-  CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
-  launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-  launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+  {
+    OzSegScope seg(h, 1, st);
+    CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
+    launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+  }
   tm.mark("sliceL21");
-  traced_gemm(h, S, b.oz.d_syrk, b.oz.n_syrk, getenv("DSMGP_OZAKI_TRACE_SYRK"), st);
+  {
+    OzSegScope seg(h, 0, st);
+    traced_gemm(h, S, b.oz.d_syrk, b.oz.n_syrk, getenv("DSMGP_OZAKI_TRACE_SYRK"), st);
+    h->oz_ksteps += b.oz.ksteps_syrk;
+  }
   tm.mark("syrk");
   pa.tasks = b.oz.d_potrfB; pa.ntasks = b.oz.n_potrfB; pa.counter = full.counter + 1; pa.kskip = b.oz.d_kskip;
-  if (inv) {
-    ta.tasks = b.oz.d_invB; ta.ntasks = b.oz.n_invB;
-    launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
-    h->oz_inv_tiles_done = true;
-  } else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  {
+    OzSegScope seg(h, 2, st);
+    if (inv) {
+      ta.tasks = b.oz.d_invB; ta.ntasks = b.oz.n_invB;
+      launch_eval2_only(pa, ta, std::max(1, std::min(sms, pa.ntasks + ta.ntasks)), st);
+      h->oz_inv_tiles_done = true;
+    } else launch_potrf2(pa, std::max(1, std::min(sms, pa.ntasks)), st);
+  }
   tm.mark("potrfB");
   tm.report("potrf");
   h->tm.launches += 5;
@@ -319,26 +372,40 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
   Trtri3Args ta = full;
   ta.tasks = b.oz.d_tasks; ta.ntasks = b.oz.n_tasks;
   OzTimer tm(st, h->capturing);
-  if (!h->oz_inv_tiles_done) launch_trtri3_only(ta, std::max(1, std::min(sms, ta.ntasks)), st);
+  if (!h->oz_inv_tiles_done) { OzSegScope seg(h, 2, st); launch_trtri3_only(ta, std::max(1, std::min(sms, ta.ntasks)), st); }
   tm.mark("trtri3");
   const int S = h->oz_S;
   for (int li = 0; li < b.oz.n_levels; li++) {
     const OzLevel& L = b.oz.levels[li];
-    CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)L.n_scale * sizeof(unsigned long long), st));
-    launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-    launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-    if (li == b.oz.n_levels - 1 && !h->oz_l21_ready) {      // root level: L21 not sliced by the factorisation phase
-      CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
-      launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-      launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    {
+      OzSegScope seg(h, 1, st);
+      CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)L.n_scale * sizeof(unsigned long long), st));
+      launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+      launch_oz_slice(S, L.d_jobs1, L.n_jobs1, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+      if (li == b.oz.n_levels - 1 && !h->oz_l21_ready) {      // root level: L21 not sliced by the factorisation phase
+        CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p + b.oz.l21_scale0, 0, (size_t)b.oz.l21_nscale * sizeof(unsigned long long), st));
+        launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+        launch_oz_slice(S, b.oz.d_jobsL, b.oz.n_jobsL, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+      }
     }
     tm.mark("slice1");
-    traced_gemm(h, S, L.d_tiles1, L.n_tiles1, (li == 0 && !h->capturing) ? getenv("DSMGP_OZAKI_TRACE") : nullptr, st);
+    {
+      OzSegScope seg(h, 0, st);
+      traced_gemm(h, S, L.d_tiles1, L.n_tiles1, (li == 0 && !h->capturing) ? getenv("DSMGP_OZAKI_TRACE") : nullptr, st);
+      h->oz_ksteps += L.ksteps1;
+    }
     tm.mark("gemm1");
-    launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
-    launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    {
+      OzSegScope seg(h, 1, st);
+      launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+      launch_oz_slice(S, L.d_jobs2, L.n_jobs2, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    }
     tm.mark("slice2");
-    launch_oz_gemm(S, h->oz_map, L.d_tiles2, L.n_tiles2, h->oz_scale.p, num_sms(h->device), st);
+    {
+      OzSegScope seg(h, 0, st);
+      launch_oz_gemm(S, h->oz_map, L.d_tiles2, L.n_tiles2, h->oz_scale.p, num_sms(h->device), st);
+      h->oz_ksteps += L.ksteps2;
+    }
     tm.mark("gemm2");
     h->tm.launches += 6;
   }
@@ -352,3 +419,22 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
 }
 
 }  // namespace dsm
+
+// out[0] batches on the split path, [1] slices S, [2] INT8 operations of the block products of the last evaluation
+// (2 * 128 * 128 * 32 per tcgen05.mma, S (S + 1) / 2 of them per k-step), [3] the FP64 flops they stand for, [4] / [5] / [6] CUDA-event
+// ms of the block-product launches / the slicing launches / the FP64 tile-pipeline launches of the last evaluation, [7] slice pool bytes
+extern "C" int32_t dsmgp_int8_info(dsmgp_handle* h, double* out, int32_t n) {
+  if (!h || !out || n < 8) return DSMGP_ERR_ARG;
+  cudaSetDevice(h->device);
+  int act = 0;
+  for (const Batch& b : h->batches) act += b.oz.active ? 1 : 0;
+  const int S = h->oz_S;
+  double ms[3] = {0, 0, 0};
+  cudaStreamSynchronize(h->stream);
+  for (const auto& sg : h->oz_segs) { float t = 0; if (cudaEventElapsedTime(&t, sg.a, sg.b) == cudaSuccess) ms[sg.kind] += t; }
+  out[0] = act; out[1] = S;
+  out[2] = h->oz_ksteps * (S * (S + 1) / 2) * 2.0 * BLK * BLK * OZ_KSTEP;
+  out[3] = h->oz_ksteps * 2.0 * BLK * BLK * OZ_KSTEP;
+  out[4] = ms[0]; out[5] = ms[1]; out[6] = ms[2]; out[7] = (double)h->oz_pool_bytes;
+  return DSMGP_OK;
+}

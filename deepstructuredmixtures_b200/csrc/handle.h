@@ -220,6 +220,11 @@ struct dsmgp_handle {
   // split inverse on the INT8 tensor cores: slice pool + its tensor map, T^T scratch, row scales
   DevBuf<int8_t> oz_pool; DevBuf<double> oz_scratch, oz_scale; DevBuf<unsigned long long> oz_rowmax;
   alignas(64) unsigned char oz_map[128]; int oz_S = 8;
+  // measured segments of the last evaluation (CUDA events, read by dsmgp_int8_info): 0 block products, 1 slicing, 2 FP64 tile launches
+  struct OzSeg { int kind; cudaEvent_t a, b; };
+  std::vector<OzSeg> oz_segs; std::vector<cudaEvent_t> oz_evs; size_t oz_ev_used = 0;
+  double oz_ksteps = 0.0;                 // k-steps of all block products of the last evaluation
+  int64_t oz_pool_bytes = 0;
   bool oz_inv_tiles_done = false;         // the tile-pipeline part of the inverse ran inside the factorisation launches
   bool oz_l21_ready = false;              // the L21 slices of the current batch were made by the factorisation phase
   std::string err;
@@ -249,6 +254,7 @@ struct dsmgp_handle {
     if (pin_rows) cudaFreeHost(pin_rows);
     if (pin_scal) cudaFreeHost(pin_scal);
     for (auto& e : ev) if (e) cudaEventDestroy(e);
+    for (auto& e : oz_evs) if (e) cudaEventDestroy(e);
     if (stream) cudaStreamDestroy(stream);
   }
 };
@@ -282,6 +288,7 @@ int32_t check_pd(dsmgp_handle* h);
 std::vector<int4> build_potrf2_tasks(const dsmgp_handle* h, const Batch& b, const std::vector<char>& keep, int sms);
 int32_t standalone_device_check(std::string& err);
 // api_ozaki.cu
+bool oz_enabled();
 int32_t oz_plan(dsmgp_handle* h);
 int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st);
 int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Trtri3Args* inv, int sms, cudaStream_t st);

@@ -52,6 +52,7 @@ struct OzLevel {
   OzJob* d_jobs1 = nullptr; int n_jobs1 = 0; OzTile* d_tiles1 = nullptr; int n_tiles1 = 0;     // stage 1: T^T = X11^T L21^T
   OzJob* d_jobs2 = nullptr; int n_jobs2 = 0; OzTile* d_tiles2 = nullptr; int n_tiles2 = 0;     // stage 2: X21^T = -T^T X22^T
   int n_scale = 0;
+  double ksteps1 = 0, ksteps2 = 0;                   // sum over the block products of their k-steps (for the op counts)
 };
 struct OzPlan {
   bool active = false;
@@ -77,6 +78,7 @@ struct OzPlan {
   OzJob* d_jobsT = nullptr; int n_jobsT = 0;         // A21 blocks and X11 blocks
   OzTile* d_tilesT = nullptr; int n_tilesT = 0;
   int nscaleT = 0;
+  double ksteps_syrk = 0, ksteps_T = 0;
 };
 
 // launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define DSMGP_VERSION 200
+#define DSMGP_VERSION 201
 
 typedef struct dsmgp_handle dsmgp_handle;
 
@@ -298,6 +298,15 @@ typedef struct {
 } dsmgp_timings;
 int32_t dsmgp_get_timings(const dsmgp_handle* h, dsmgp_timings* t);
 int32_t dsmgp_set_profiling(dsmgp_handle* h, int32_t on); /* per-phase CUDA events (adds syncs) */
+
+/* The INT8 split path of the last evaluation (csrc/api_ozaki.cu; no reference counterpart -- it replaces the BLAS-3 part of
+ * LAPACK potrf!/trtri that gaussianprocess.jl:99-101,219-226 call): experts of >= 1024 observations are split at the middle
+ * block row; the products L21 = A21 X11^T, A22 -= L21 L21^T, T = L21 X11, X21 = -X22 T run as error-free INT8 slice products
+ * (Ozaki scheme, 8 slices of 7 bits, exact int32 accumulation in TMEM) on the tcgen05 tensor cores, the diagonal ranges stay
+ * on the FP64 tile pipelines.  DSMGP_OZAKI=0 in the environment turns the path off.
+ * out[0] batches on the split path, [1] slices, [2] INT8 operations of the block products, [3] the FP64 flops they stand for,
+ * [4] / [5] / [6] CUDA-event ms of the block-product / slicing / FP64 tile-pipeline launches, [7] slice pool bytes.  n >= 8. */
+int32_t dsmgp_int8_info(dsmgp_handle* h, double* out, int32_t n);
 
 #ifdef __cplusplus
 }
