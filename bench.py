@@ -46,6 +46,16 @@ def fp64_peaks():
             "source": os.path.relpath(files[-1], ROOT)}
 
 
+def int8_peak():
+    """INT8 tcgen05 issue rate measured on this pool (tools/ozaki_proto.cu with OZAKI_RATE=1: 8192 back-to-back kind::i8 MMAs per SM
+    from shared memory): the 128 x 256 x 32 shape is the tensor roof, 128 x 128 x 32 the shape the block products use."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "int8_peaks_r02.json")))
+        return float(d["int8_m128_n256_tops"]), float(d["int8_m128_n128_tops"]), "profiles/int8_peaks_r02.json"
+    except Exception:
+        return 4500.0, 4233.0, "fallback: nominal 4.5 POP/s dense INT8 (profiles/int8_peaks_r02.json missing)"
+
+
 def hbm_peak():
     try:
         return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
@@ -348,8 +358,26 @@ def main():
             # small shards run the factorisation and the inverse as ONE persistent launch (csrc/fused2.cuh): one phase, one rate
             dom = "eval2_kernel"
             ach = potrf_tf = inv_tf = (potrf_fl + inv_fl) * args.steps / ((phase["potrf_ms"] + phase["inverse_ms"]) * 1e-3) * 1e-12 / world
+        # INT8 split path (csrc/api_ozaki.cu): the GEMM-shaped 3/4 of the factorisation and the inverse run as error-free INT8
+        # slice products on the tcgen05 tensor cores; the per-phase FP64 rates above then mix two engines and are reported as
+        # FP64-EQUIVALENT rates (they may exceed the FP64 roof).  The dominant kernel is the block-product kernel.
+        i8 = H.int8_info()
+        int8 = None
+        if i8["batches"] > 0 and i8["gemm_ms"] > 0:
+            pk8, pk8_shape, pk8_src = int8_peak()
+            fp64_part = max(potrf_fl + inv_fl - i8["fp64_equiv_flops"] * world, 0.0) / world     # per GPU, last evaluation
+            int8 = {"slices": i8["slices"], "gemm_ms": i8["gemm_ms"], "slice_ms": i8["slice_ms"], "fp64_tile_ms": i8["fp64_tile_ms"],
+                    "int8_tops": i8["int8_ops"] / (i8["gemm_ms"] * 1e-3) * 1e-12,
+                    "gemm_fp64_equiv_tflops": i8["fp64_equiv_flops"] / (i8["gemm_ms"] * 1e-3) * 1e-12,
+                    "fp64_tile_tflops": fp64_part / (i8["fp64_tile_ms"] * 1e-3) * 1e-12 if i8["fp64_tile_ms"] > 0 else None,
+                    "share_of_flops_on_int8": i8["fp64_equiv_flops"] * world / (potrf_fl + inv_fl) if potrf_fl + inv_fl > 0 else None,
+                    "pool_gb": i8["pool_bytes"] * 1e-9,
+                    "what": "rank 0, last timed evaluation, CUDA events around the launches: block products (oz::gemm_kernel, tcgen05 kind::i8, "
+                            "TMEM accumulators, TMA loads), slicing (oz::slice_kernel), FP64 tile pipelines (eval2_kernel, DMMA)"}
+            if i8["gemm_ms"] >= i8["fp64_tile_ms"]:
+                dom = "oz::gemm_kernel"
         # DRAM bytes per launch from `ncu --set full` (profiles/ncu_full_*_r01e.csv); only known for the profiled config
-        traffic, traffic_src = ncu_traffic_gb(dom, args.workload, world)
+        traffic, traffic_src = ncu_traffic_gb("oz_gemm_kernel" if dom == "oz::gemm_kernel" else dom, args.workload, world)
         pk = fp64_peaks()
         hbm, hbm_src = hbm_peak()
         ns_local = int(np.sum(H.leaf_owner() == 0))
@@ -376,9 +404,28 @@ def main():
                          "gram_frac_hbm": gram_gbs / hbm, "hbm_peak_source": hbm_src,
                          "gram_bound": "FP64 ALU (D exp per element)" if "ard" in w["kernel"] else "HBM write"},
             "sharing": sharing,
+            "int8_split": int8,
             "clocks": clocks_summary(samples),
             "host": {"tree_build_s": t_tree, "create_upload_s": t_create},
         }
+        if dom == "oz::gemm_kernel":
+            fp64_roof = dict(line["roofline"])
+            line["roofline"] = {
+                "bound": "tensor", "kernel": "oz::gemm_kernel<%d>" % int8["slices"], "achieved": int8["int8_tops"], "peak": pk8,
+                "unit": "TFLOP/s", "frac": int8["int8_tops"] / pk8, "ops": "INT8 multiply-adds counted as 2 operations (TOP/s)",
+                "frac_of_issue_rate_of_the_shape_used": int8["int8_tops"] / pk8_shape,
+                "traffic": traffic, "traffic_unit": "GB per launch (ncu dram read+write, one of the four block-product launches)",
+                "traffic_source": traffic_src,
+                "algorithmic": "operations per evaluation = 2 * 128 * 128 * 32 per tcgen05.mma x S (S + 1) / 2 slice pairs x the k-steps of all "
+                               "block products (L21 = A21 X11^T, A22 -= L21 L21^T, T = L21 X11, X21 = -X22 T of every expert with >= 8 block rows); "
+                               "achieved = those operations / the CUDA-event time of the four launches; per GPU",
+                "peak_source": f"tcgen05 kind::i8 128x256x32 issue rate measured on this pool ({pk8_src}); the 128x128x32 shape used (TMEM holds "
+                               f"four 128-column accumulators) issues at {pk8_shape:.0f}",
+                "fp64_equivalent_tflops_of_the_block_products": int8["gemm_fp64_equiv_tflops"],
+                "fp64_phases": {k: fp64_roof[k] for k in ("potrf_tflops", "inverse_tflops", "gram_gbs", "gram_frac_hbm", "hbm_peak_source", "gram_bound")},
+                "fp64_roof_dgemm_tflops": pk["dgemm"],
+                "note": "potrf_tflops / inverse_tflops are FP64-equivalent rates of phases that mix the INT8 products with the FP64 (DMMA) tile "
+                        "pipelines; with DSMGP_OZAKI=0 every flop runs on DMMA (profiles/bench_r02_cfg3_1gpu_fp64.json: 0.84 of the DGEMM roof)"}
         if world == 1 and keep and not args.no_predict:
             # update! + predict (common.jl:323-334, 294-307) on T fresh test points: every point is routed to one leaf
             # per sum-node branch; device time of predict_kernel and wall time of the public call (routing, H2D of the

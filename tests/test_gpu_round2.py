@@ -246,6 +246,9 @@ def test_shared_cholesky_equals_full_refactorisation(case, monkeypatch):
             "eps0_ard": dict(N=5000, D=2, V=3, K=3, M=200, eps=0.0, seed=8, kern=dsm.ArdSE(np.zeros(2), 0.0))}
     c = cfgs[case]
     monkeypatch.setenv("DSMGP_SHARE_MIN_FLOPS", "0")      # these models are small: take the continue branch however little it saves
+    # the sharing plan runs on the FP64 tile pipelines; the naive side must not take the INT8 split path (same arithmetic on
+    # both sides of a 1e-12 comparison; the split path has its own tests in test_gpu_ozaki.py)
+    monkeypatch.setenv("DSMGP_OZAKI", "0")
     x, y = synth(c["N"], c["D"], c["seed"], sorted1d=True)
     cfg = st.DSMGPConfig(None, c["kern"], -1.0, c["M"], c["K"], c["V"], 2, c["eps"], True)
     root = st.buildTree(x, y, cfg, np.random.default_rng(c["seed"]))
