@@ -365,12 +365,12 @@ def main():
         int8 = None
         if i8["batches"] > 0 and i8["gemm_ms"] > 0:
             pk8, pk8_shape, pk8_src = int8_peak()
-            fp64_part = max(potrf_fl + inv_fl - i8["fp64_equiv_flops"] * world, 0.0) / world     # per GPU, last evaluation
+            fp64_part = i8["fp64_tile_flops"]                     # rank 0: 2/3 r^3 per diagonal range of r rows
             int8 = {"slices": i8["slices"], "gemm_ms": i8["gemm_ms"], "slice_ms": i8["slice_ms"], "fp64_tile_ms": i8["fp64_tile_ms"],
                     "int8_tops": i8["int8_ops"] / (i8["gemm_ms"] * 1e-3) * 1e-12,
                     "gemm_fp64_equiv_tflops": i8["fp64_equiv_flops"] / (i8["gemm_ms"] * 1e-3) * 1e-12,
                     "fp64_tile_tflops": fp64_part / (i8["fp64_tile_ms"] * 1e-3) * 1e-12 if i8["fp64_tile_ms"] > 0 else None,
-                    "share_of_flops_on_int8": i8["fp64_equiv_flops"] * world / (potrf_fl + inv_fl) if potrf_fl + inv_fl > 0 else None,
+                    "share_of_flops_on_int8": 1.0 - fp64_part * world / (potrf_fl + inv_fl) if potrf_fl + inv_fl > 0 else None,
                     "pool_gb": i8["pool_bytes"] * 1e-9,
                     "what": "rank 0, last timed evaluation, CUDA events around the launches: block products (oz::gemm_kernel, tcgen05 kind::i8, "
                             "TMEM accumulators, TMA loads), slicing (oz::slice_kernel), FP64 tile pipelines (eval2_kernel, DMMA)"}

@@ -248,10 +248,10 @@ class Handle:
 
     def int8_info(self) -> dict:
         """The INT8 split path of the last evaluation (dsmgp_int8_info): op counts and CUDA-event times of its launches."""
-        o = np.zeros(8)
-        self._ck(self._lib.dsmgp_int8_info(self._h, nat.p_d(o), 8))
+        o = np.zeros(9)
+        self._ck(self._lib.dsmgp_int8_info(self._h, nat.p_d(o), 9))
         return {"batches": int(o[0]), "slices": int(o[1]), "int8_ops": o[2], "fp64_equiv_flops": o[3], "gemm_ms": o[4],
-                "slice_ms": o[5], "fp64_tile_ms": o[6], "pool_bytes": int(o[7])}
+                "slice_ms": o[5], "fp64_tile_ms": o[6], "pool_bytes": int(o[7]), "fp64_tile_flops": o[8]}
 
     def set_profiling(self, on: bool):
         self._ck(self._lib.dsmgp_set_profiling(self._h, 1 if on else 0))

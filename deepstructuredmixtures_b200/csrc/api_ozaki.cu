@@ -115,6 +115,15 @@ int32_t oz_plan(dsmgp_handle* h) {
       const std::vector<int>& ro = t.range_of[tk.x];
       if (ro[tk.y] == ro[tk.z]) keep.push_back(tk);
     }
+    for (int s = b.s0; s < b.s1; s++) {                 // rows of every diagonal range -> flops that stay on the tile pipelines
+      const LeafMeta& m = h->meta[s];
+      const std::vector<int>& ro = t.range_of[s - b.s0];
+      double rows = 0; int cur = ro.empty() ? -1 : ro[0];
+      for (int blk = 0; blk <= m.nb; blk++) {
+        if (blk == m.nb || ro[blk] != cur) { b.oz.tile_flops += 2.0 / 3.0 * rows * rows * rows; rows = 0; if (blk < m.nb) cur = ro[blk]; }
+        if (blk < m.nb) rows += std::min(BLK, m.n - blk * BLK > 0 ? m.n - blk * BLK : 0);
+      }
+    }
     b.oz.n_tasks = (int)keep.size();
     CUDA_TRY(h, upload(&b.oz.d_tasks, keep));
     std::vector<OzPart> parts;
@@ -422,7 +431,8 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
 
 // out[0] batches on the split path, [1] slices S, [2] INT8 operations of the block products of the last evaluation
 // (2 * 128 * 128 * 32 per tcgen05.mma, S (S + 1) / 2 of them per k-step), [3] the FP64 flops they stand for, [4] / [5] / [6] CUDA-event
-// ms of the block-product launches / the slicing launches / the FP64 tile-pipeline launches of the last evaluation, [7] slice pool bytes
+// ms of the block-product launches / the slicing launches / the FP64 tile-pipeline launches of the last evaluation, [7] slice pool bytes,
+// [8] (n >= 9) the factorisation + inverse flops that stay on the FP64 tile pipelines (2/3 r^3 per diagonal range of r rows)
 extern "C" int32_t dsmgp_int8_info(dsmgp_handle* h, double* out, int32_t n) {
   if (!h || !out || n < 8) return DSMGP_ERR_ARG;
   cudaSetDevice(h->device);
@@ -436,5 +446,6 @@ extern "C" int32_t dsmgp_int8_info(dsmgp_handle* h, double* out, int32_t n) {
   out[2] = h->oz_ksteps * (S * (S + 1) / 2) * 2.0 * BLK * BLK * OZ_KSTEP;
   out[3] = h->oz_ksteps * 2.0 * BLK * BLK * OZ_KSTEP;
   out[4] = ms[0]; out[5] = ms[1]; out[6] = ms[2]; out[7] = (double)h->oz_pool_bytes;
+  if (n >= 9) { out[8] = 0; for (const Batch& b : h->batches) if (b.oz.active) out[8] += b.oz.tile_flops; }
   return DSMGP_OK;
 }

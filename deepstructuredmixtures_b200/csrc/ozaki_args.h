@@ -60,6 +60,7 @@ struct OzPlan {
   OzLevel levels[4]; int n_levels = 0;             // deepest level first
   OzPart* d_parts = nullptr; int n_parts = 0;
   double gemm_flops = 0.0;
+  double tile_flops = 0.0;                         // factorisation + inverse flops left on the FP64 tile pipelines (2/3 r^3 per diagonal range)
   // right-looking split of the factorisation at the root split: columns < mid (launch A), A22 -= L21 L21^T on the INT8 tensor
   // cores, columns >= mid with the contraction starting at mid (launch B).  The L21 slices are reused by the inverse.
   bool potrf = false;

@@ -305,7 +305,8 @@ int32_t dsmgp_set_profiling(dsmgp_handle* h, int32_t on); /* per-phase CUDA even
  * (Ozaki scheme, 8 slices of 7 bits, exact int32 accumulation in TMEM) on the tcgen05 tensor cores, the diagonal ranges stay
  * on the FP64 tile pipelines.  DSMGP_OZAKI=0 in the environment turns the path off.
  * out[0] batches on the split path, [1] slices, [2] INT8 operations of the block products, [3] the FP64 flops they stand for,
- * [4] / [5] / [6] CUDA-event ms of the block-product / slicing / FP64 tile-pipeline launches, [7] slice pool bytes.  n >= 8. */
+ * [4] / [5] / [6] CUDA-event ms of the block-product / slicing / FP64 tile-pipeline launches, [7] slice pool bytes, [8] (when
+ * n >= 9) the factorisation + inverse flops left on the FP64 tile pipelines.  n >= 8. */
 int32_t dsmgp_int8_info(dsmgp_handle* h, double* out, int32_t n);
 
 #ifdef __cplusplus

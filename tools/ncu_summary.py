@@ -7,10 +7,12 @@ rows = list(csv.reader(io.StringIO(raw))); hdr, units, vals = rows[0], rows[1], 
 want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
         'launch__grid_size', 'lts__throughput.avg.pct_of_peak_sustained_elapsed', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed']
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed', 'sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed']
 print("metric,unit,value")
 for h, u, v in zip(hdr, units, vals):
-    if h in want: print(f"{h},{u},{v}")
+    if h in want or h.endswith('TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed'): print(f"{h},{u},{v}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src))); hdr = rows[1]; idx = {h: i for i, h in enumerate(hdr)}; data = rows[2:]
 cats = [h for h in hdr if h.startswith('stall_') and 'Not Issued' not in h]
