@@ -376,6 +376,11 @@ def main():
                             "TMEM accumulators, TMA loads), slicing (oz::slice_kernel), FP64 tile pipelines (eval2_kernel, DMMA)"}
             if i8["gemm_ms"] >= i8["fp64_tile_ms"]:
                 dom = "oz::gemm_kernel"
+            else:
+                # small shards: the chain-bound FP64 tile launches (factorisation + inverse of the diagonal ranges) take longer
+                # than the block products; their rate against the FP64 roof
+                dom = "eval2_kernel"
+                ach = int8["fp64_tile_tflops"]
         # DRAM bytes per launch from `ncu --set full` (profiles/ncu_full_*_r01e.csv); only known for the profiled config
         traffic, traffic_src = ncu_traffic_gb("oz_gemm_kernel" if dom == "oz::gemm_kernel" else dom, args.workload, world)
         pk = fp64_peaks()
