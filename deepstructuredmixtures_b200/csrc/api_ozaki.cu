@@ -103,7 +103,12 @@ int32_t oz_plan(dsmgp_handle* h) {
   CUDA_TRY(h, h->oz_scale.alloc((size_t)(max_scale + max_l21_scale)));
   CUDA_TRY(h, h->oz_rowmax.alloc((size_t)(max_scale + max_l21_scale)));
   h->oz_pool_bytes = (int64_t)(max_pool + max_l21_pool) * OZ_TILE_B;
-  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B) != 0) { h->err = "cuTensorMapEncodeTiled failed"; return DSMGP_ERR_CUDA; }
+  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B) != 0) {
+    // no tensor-map encoder in this driver: the FP64 pipelines stay in charge
+    for (Batch& b : h->batches) b.oz.active = false;
+    h->oz_pool.free(); h->oz_scratch.free(); h->oz_scale.free(); h->oz_rowmax.free(); h->oz_pool_bytes = 0;
+    return DSMGP_OK;
+  }
   // pass 2: lists
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
     Batch& b = h->batches[bi];

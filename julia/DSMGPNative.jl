@@ -263,4 +263,13 @@ function chol_continue!(A::Matrix{Float64}, ki::Int)
     return LinearAlgebra.LowerTriangular(A), Int(info[])
 end
 
+# dsmgp_int8_info: what the last evaluation ran on the INT8 tensor cores (csrc/api_ozaki.cu; `ENV["DSMGP_OZAKI"] = "0"` before
+# `create` keeps every flop on the FP64 pipelines).  Returns (batches, slices, int8_ops, fp64_equiv_flops, gemm_ms, slice_ms, fp64_tile_ms,
+# pool_bytes, fp64_tile_flops).
+function int8_info(h::Handle)
+    o = zeros(Float64, 9)
+    check(ccall((:dsmgp_int8_info, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Int32), h.ptr, o, 9), h.ptr)
+    return o
+end
+
 end # module
