@@ -402,6 +402,7 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     CUDA_TRY(h, upload(&b.d_trpart_off, trp));
     CUDA_TRY(h, upload(&b.d_gpart_off, gp));
     CUDA_TRY(h, upload(&b.d_trtri_tasks, tt));
+    b.h_lauum = lt;
     CUDA_TRY(h, upload(&b.d_lauum_tasks, lt));
     maxF = std::max(maxF, b.f_doubles); maxW = std::max(maxW, b.w_doubles);
     maxTr = std::max(maxTr, tro); maxG = std::max(maxG, go);
@@ -651,7 +652,7 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
     Batch& b = h->batches[bi];
     cudaEvent_t* ev = h->ev.data() + 8 * bi;
     const int nsl = b.s1 - b.s0;
-    h->oz_l21_ready = false; h->oz_inv_tiles_done = false;
+    h->oz_l21_ready = false; h->oz_inv_tiles_done = false; h->oz_x_complete = false;
     EV_RECORD(ev[0]);
     if (nsl == 0) { for (int k = 1; k < 8; k++) EV_RECORD(ev[k]); continue; }
     const LeafMeta* meta = h->d_meta.p + b.s0;
@@ -750,9 +751,14 @@ int32_t dsm::run_pipeline(dsmgp_handle* h, bool with_grad, const double* leaf_sc
     if (lau) {
       LauumArgs la{meta, h->d_F.p, h->d_WT.p, h->d_xg.p, h->d_alpha.p, h->d_prm.p, b.d_lauum_tasks, b.n_lauum,
                    h->d_counter.p + 1, h->d_gpart.p, b.d_gpart_off, (int)h->D, h->d_counter.p + GERR,
-                   mask_all ? mask_all + b.s0 : nullptr};
-      launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
-      h->tm.launches++;
+                   mask_all ? mask_all + b.s0 : nullptr, nullptr, nullptr};
+      if (b.oz.active && b.oz.lauum && h->oz_x_complete) {      // contraction of the split experts on the INT8 tensor cores
+        const int32_t rc = oz_run_lauum(h, b, la, sms, st);
+        if (rc != DSMGP_OK) return rc;
+      } else {
+        launch_lauum3(la, std::max(1, std::min(sms, b.n_lauum)), st);
+        h->tm.launches++;
+      }
     }
     EV_RECORD(ev[6]);
     RowsArgs ra{meta, scal, scal, h->d_prm.p, h->d_trpart.p, b.d_trpart_off, h->d_gpart.p, b.d_gpart_off,

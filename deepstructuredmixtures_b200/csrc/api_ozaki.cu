@@ -56,6 +56,13 @@ int32_t oz_plan(dsmgp_handle* h) {
   int64_t max_pool = 0, max_scratch = 0, max_scale = 0, max_l21_pool = 0, max_l21_scale = 0;
   const char* pe = getenv("DSMGP_OZAKI_POTRF");
   const bool want_potrf = !(pe && pe[0] == '0');
+  const char* le = getenv("DSMGP_OZAKI_LAUUM");
+  bool lauum_kernels = false;
+  for (int k = 0; k < h->nk; k++) {
+    const int ty = h->kernels[k].type;
+    lauum_kernels |= ty == DSMGP_ISO_SE || ty == DSMGP_ARD_LINEAR || (ty == DSMGP_ARD_SE && !h->opts.as_written_grads);
+  }
+  const bool want_lauum = lauum_kernels && !(le && le[0] == '0');
   // pass 1: splits and sizes
   for (size_t bi = 0; bi < h->batches.size(); bi++) {
     Batch& b = h->batches[bi];
@@ -81,6 +88,12 @@ int32_t oz_plan(dsmgp_handle* h) {
         scale += 2 * (J1 + J2) * BLK;
       }
       max_pool = std::max(max_pool, pool); max_scratch = std::max(max_scratch, scratch); max_scale = std::max(max_scale, scale);
+    }
+    {   // LAUUM on the split path: every F^-1 tile of the split experts goes through the scratch
+      int64_t sc = 0;
+      for (int s = b.s0; s < b.s1; s++)
+        if (t.range_of[s - b.s0].back() != t.range_of[s - b.s0].front()) sc += (int64_t)h->meta[s].nb * (h->meta[s].nb + 1) / 2 * WBLK_D;
+      if (want_lauum) max_scratch = std::max(max_scratch, sc);
     }
     // the L21 slices of the root splits live in their own region: the factorisation phase makes them, the inverse reuses them
     int64_t lp = 0, ls = 0;
@@ -259,6 +272,49 @@ int32_t oz_plan(dsmgp_handle* h) {
       b.oz.n_invA = (int)iA.size(); b.oz.n_invB = (int)iB.size();
       CUDA_TRY(h, upload(&b.oz.d_invA, iA)); CUDA_TRY(h, upload(&b.oz.d_invB, iB));
     }
+    if (want_lauum && !b.h_lauum.empty()) {
+      // operand X^T of every split expert: row blocks Jb, k blocks Kb >= Jb (upper block triangle; W_J^T on the diagonal)
+      const int KB = OZ_KSTEPS_PER_BLK;
+      std::vector<OzJob> jX; std::vector<OzTile> tW;
+      std::vector<int64_t> pre(b.s1 - b.s0, -1), poolX(b.s1 - b.s0, 0);
+      std::vector<int> scaleX(b.s1 - b.s0, 0);
+      int64_t pool = 0, wblk = 0; int scale = 0;
+      for (int s = b.s0; s < b.s1; s++) {
+        const int sl = s - b.s0;
+        const LeafMeta& m = h->meta[s];
+        if (t.range_of[sl].back() == t.range_of[sl].front()) continue;         // unsplit: contracted by lauum3 itself
+        const bool leaf_lauum = m.ktype == DSMGP_ISO_SE || m.ktype == DSMGP_ARD_LINEAR || (m.ktype == DSMGP_ARD_SE && !h->opts.as_written_grads);
+        if (!leaf_lauum) continue;
+        const int nb = m.nb;
+        const double* F = h->d_F.p + m.foff; const double* WT = h->d_WT.p + m.woff;
+        auto wid = [&](int blk) { const int w = m.np - blk * BLK; return w < BLK ? w : BLK; };
+        poolX[sl] = pool; pool += (int64_t)nb * nb * KB * S;
+        scaleX[sl] = scale; scale += nb * BLK;
+        pre[sl] = wblk; wblk += (int64_t)nb * (nb + 1) / 2;
+        for (int Jb = 0; Jb < nb; Jb++)
+          for (int Kb = Jb; Kb < nb; Kb++)
+            jX.push_back({Kb == Jb ? WT + (int64_t)Jb * WBLK_D : F + tile_off(Jb, Kb * (BLK / KC), m.nkc), 0, wid(Jb), wid(Kb), scaleX[sl] + Jb * BLK,
+                          poolX[sl] + ((int64_t)Jb * nb + Kb) * KB * S});
+      }
+      const int64_t need_pool = pool; const int need_scale = scale;
+      if (need_pool > 0 && need_pool <= max_pool && need_scale <= (int)max_scale) {
+        for (const int4& tk : b.h_lauum) {
+          if (pre[tk.x] < 0) continue;
+          const LeafMeta& m = h->meta[b.s0 + tk.x];
+          const int nb = m.nb, I = tk.y, J = tk.z;
+          auto wid = [&](int blk) { const int w = m.np - blk * BLK; return w < BLK ? w : BLK; };
+          const int kend = (nb - 1) * KB + (wid(nb - 1) + OZ_KSTEP - 1) / OZ_KSTEP;
+          tW.push_back({(int)(poolX[tk.x] + (int64_t)I * nb * KB * S), (int)(poolX[tk.x] + (int64_t)J * nb * KB * S), I * KB, kend,
+                        scaleX[tk.x] + I * BLK, scaleX[tk.x] + J * BLK, wid(I), wid(J), h->oz_scratch.p + (pre[tk.x] + tk.w) * (int64_t)WBLK_D, -1.0, 0, 0});
+        }
+        auto by_len = [](const OzTile& x, const OzTile& y) { return (x.k1 - x.k0) > (y.k1 - y.k0); };
+        std::stable_sort(tW.begin(), tW.end(), by_len);
+        for (const OzTile& x : tW) b.oz.ksteps_W += x.k1 - x.k0;
+        b.oz.n_jobsX = (int)jX.size(); b.oz.n_tilesW = (int)tW.size(); b.oz.nscaleX = need_scale;
+        CUDA_TRY(h, upload(&b.oz.d_jobsX, jX)); CUDA_TRY(h, upload(&b.oz.d_tilesW, tW)); CUDA_TRY(h, upload(&b.oz.d_pre_base, pre));
+        b.oz.lauum = !tW.empty();
+      }
+    }
     b.oz.n_parts = (int)parts.size();
     CUDA_TRY(h, upload(&b.oz.d_parts, parts));
     b.oz.gemm_flops = flops;
@@ -380,6 +436,34 @@ int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Tr
   return DSMGP_OK;
 }
 
+// LAUUM of one batch: X^T of the split experts is sliced once, F^-1_IJ = sum_{K >= I} X_KI^T X_KJ of all their tiles are block
+// products (stored negated in the scratch), and lauum3_kernel runs its dK-trace epilogue on them -- and the whole tile, contraction
+// included, for the unsplit experts (pre_base < 0).
+int32_t oz_run_lauum(dsmgp_handle* h, Batch& b, const LauumArgs& full, int sms, cudaStream_t st) {
+  const int S = h->oz_S;
+  OzTimer tm(st, h->capturing);
+  {
+    OzSegScope seg(h, 1, st);
+    CUDA_TRY(h, cudaMemsetAsync(h->oz_rowmax.p, 0, (size_t)b.oz.nscaleX * sizeof(unsigned long long), st));
+    launch_oz_slice(S, b.oz.d_jobsX, b.oz.n_jobsX, 0, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+    launch_oz_slice(S, b.oz.d_jobsX, b.oz.n_jobsX, 1, h->oz_rowmax.p, h->oz_scale.p, h->oz_pool.p, st);
+  }
+  tm.mark("sliceXT");
+  {
+    OzSegScope seg(h, 0, st);
+    launch_oz_gemm(S, h->oz_map, b.oz.d_tilesW, b.oz.n_tilesW, h->oz_scale.p, num_sms(h->device), st);
+    h->oz_ksteps += b.oz.ksteps_W;
+  }
+  tm.mark("gemmW");
+  LauumArgs la = full;
+  la.pre = h->oz_scratch.p; la.pre_base = b.oz.d_pre_base;
+  launch_lauum3(la, std::max(1, std::min(sms, la.ntasks)), st);
+  tm.mark("lauum3 traces");
+  tm.report("lauum");
+  h->tm.launches += 4;
+  return DSMGP_OK;
+}
+
 // The inverse of one batch: restricted tile pipeline, then per level  slice -> GEMM 1 -> slice -> GEMM 2,  then the
 // partials of the GEMM-written tiles and the block-column reduction (alpha, tr(F^-1)).
 int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st) {
@@ -428,6 +512,7 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
   launch_alpha_reduce(full, b.d_trtri_tasks, b.n_trtri, st);
   tm.mark("parts+reduce");
   tm.report("inverse");
+  h->oz_x_complete = true;
   h->tm.launches += 3;
   return DSMGP_OK;
 }

@@ -73,6 +73,9 @@ struct LauumArgs {
   int D;
   int* gerr;
   const int* mask;          // per slot: 0 = skip this expert, or null
+  // F^-1 tiles already computed (INT8 block products, api_ozaki.cu): tile of task w of slot s = pre + (pre_base[s] + w) * WBLK_D, holding
+  // -F^-1_IJ in the factor-tile layout (rows of block I); pre_base[s] < 0: this expert's tiles are contracted here.  null: all are
+  const double* pre; const int64_t* pre_base;
 };
 
 struct RowsArgs {

@@ -51,6 +51,7 @@ struct Batch {
   int2* d_solve_tasks = nullptr; int n_solve = 0;       // back-substitution: (slot, J) by level from the bottom
   int64_t* d_flag_off = nullptr; int64_t flag_ints = 0;
   double potrf_flops = 0, gram_bytes = 0;
+  std::vector<int4> h_lauum;                            // host copy of d_lauum_tasks
   std::vector<int4> h_potrf2;                           // host copy of d_potrf2_tasks
   std::vector<int4> h_trtri3m;                          // host copy of d_trtri3m_tasks
   std::vector<int4> h_trtri3;                           // host copy of d_trtri3_tasks (filtered by the INT8 split plan)
@@ -225,6 +226,7 @@ struct dsmgp_handle {
   std::vector<OzSeg> oz_segs; std::vector<cudaEvent_t> oz_evs; size_t oz_ev_used = 0;
   double oz_ksteps = 0.0;                 // k-steps of all block products of the last evaluation
   int64_t oz_pool_bytes = 0;
+  bool oz_x_complete = false;             // the split inverse of the current batch ran (X^T complete, no masked experts)
   bool oz_inv_tiles_done = false;         // the tile-pipeline part of the inverse ran inside the factorisation launches
   bool oz_l21_ready = false;              // the L21 slices of the current batch were made by the factorisation phase
   std::string err;
@@ -234,7 +236,7 @@ struct dsmgp_handle {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
       cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
       cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots); cudaFree(b.d_trtri3m_tasks);
-      cudaFree(b.oz.d_tasks); cudaFree(b.oz.d_parts); cudaFree(b.oz.d_potrfA); cudaFree(b.oz.d_potrfB); cudaFree(b.oz.d_kskip); cudaFree(b.oz.d_jobsL); cudaFree(b.oz.d_syrk); cudaFree(b.oz.d_invA); cudaFree(b.oz.d_invB); cudaFree(b.oz.d_potrfA11); cudaFree(b.oz.d_jobsT); cudaFree(b.oz.d_tilesT);
+      cudaFree(b.oz.d_tasks); cudaFree(b.oz.d_parts); cudaFree(b.oz.d_potrfA); cudaFree(b.oz.d_potrfB); cudaFree(b.oz.d_kskip); cudaFree(b.oz.d_jobsL); cudaFree(b.oz.d_syrk); cudaFree(b.oz.d_invA); cudaFree(b.oz.d_invB); cudaFree(b.oz.d_potrfA11); cudaFree(b.oz.d_jobsT); cudaFree(b.oz.d_tilesT); cudaFree(b.oz.d_jobsX); cudaFree(b.oz.d_tilesW); cudaFree(b.oz.d_pre_base);
       for (int l = 0; l < b.oz.n_levels; l++) { cudaFree(b.oz.levels[l].d_jobs1); cudaFree(b.oz.levels[l].d_jobs2); cudaFree(b.oz.levels[l].d_tiles1); cudaFree(b.oz.levels[l].d_tiles2); }
     }
     d_flags2.free();
@@ -292,4 +294,5 @@ bool oz_enabled();
 int32_t oz_plan(dsmgp_handle* h);
 int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sms, cudaStream_t st);
 int32_t oz_run_potrf(dsmgp_handle* h, Batch& b, const Potrf2Args& full, const Trtri3Args* inv, int sms, cudaStream_t st);
+int32_t oz_run_lauum(dsmgp_handle* h, Batch& b, const LauumArgs& full, int sms, cudaStream_t st);
 }  // namespace dsm

@@ -111,11 +111,17 @@ struct Lauum3Gen {
     n0 = wi / KC; n1 = (m.np - k1) / KC; c = 0;
     h.kind = 0; h.ti = ti; h.slot = tk.x; h.I = I; h.J = J; h.wi = wi; h.wj = blk_width(m.np, J);
     h.n_c = 0; h.n_main = n0 + n1; h.pad0 = tk.w;
+    if (a.pre != nullptr && a.pre_base[tk.x] >= 0) {
+      // the tile arrives ready-made (-F^-1_IJ): two 16-column tiles per stage, no contraction
+      A0 = a.pre + (a.pre_base[tk.x] + tk.w) * (int64_t)WBLK_D;
+      n0 = 0; n1 = 0; h.n_main = 0; h.n_c = h.wj / 32;
+    }
   }
   __device__ __forceinline__ bool next(ChunkDesc& d) {
-    if (c >= n0 + n1) return false;
+    if (c >= n0 + n1 + h.n_c) return false;
     d.flag0 = nullptr; d.flag1 = nullptr; d.abytes = TILE_BYTES; d.bbytes = TILE_BYTES;
-    if (c < n0) { d.a = A0 + (int64_t)c * TILE_D; d.b = B0 + (int64_t)c * TILE_D; }
+    if (h.n_c > 0) { d.a = A0 + (int64_t)(2 * c) * TILE_D; d.b = A0 + (int64_t)(2 * c + 1) * TILE_D; }
+    else if (c < n0) { d.a = A0 + (int64_t)c * TILE_D; d.b = B0 + (int64_t)c * TILE_D; }
     else { d.a = A1 + (int64_t)(c - n0) * TILE_D; d.b = B1 + (int64_t)(c - n0) * TILE_D; }
     c++;
     return true;
@@ -177,6 +183,14 @@ __global__ void __launch_bounds__(NTHREADS_PW, 1) lauum3_kernel(LauumArgs a) {
     const bool active = r0 < wi;
     Acc2 acc;
     acc2_zero(acc);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {                      // ready-made tile: acc = -(-F^-1_IJ)
+      if (e < hd.n_c) {
+        if (e > 0) st = p.wait();
+        if (active) { acc2_sub_tile(acc, p.A(st), r0, 2 * e); acc2_sub_tile(acc, p.B(st), r0, 2 * e + 1); }
+        p.release();
+      }
+    }
     for (int c = 0; c < hd.n_main; c++) {
       if (c > 0) st = p.wait();
       // K = I block: the A operand is W_I^T (zero for k < row): chunk c is all zero for slabs > c

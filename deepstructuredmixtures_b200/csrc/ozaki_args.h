@@ -80,6 +80,11 @@ struct OzPlan {
   OzTile* d_tilesT = nullptr; int n_tilesT = 0;
   int nscaleT = 0;
   double ksteps_syrk = 0, ksteps_T = 0;
+  // LAUUM contraction F^-1_IJ = sum_{K >= I} X_KI^T X_KJ of the split experts as block products on X^T (slices in the level region of
+  // the pool, tiles into the scratch); lauum3_kernel then only runs its dK-trace epilogue on them
+  bool lauum = false;
+  OzJob* d_jobsX = nullptr; int n_jobsX = 0; OzTile* d_tilesW = nullptr; int n_tilesW = 0; int nscaleX = 0; double ksteps_W = 0;
+  int64_t* d_pre_base = nullptr;
 };
 
 // launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).
