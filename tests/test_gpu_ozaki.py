@@ -121,17 +121,17 @@ def test_model_split_path_equals_fp64_pipelines(mixture, monkeypatch):
 
 
 def test_split_path_switches(monkeypatch):
-    """DSMGP_OZAKI_SLICES=7, DSMGP_OZAKI_DEPTH=2, DSMGP_OZAKI_POTRF=0 and DSMGP_OZAKI_TRSM=0 are all valid configurations of the
-    path: same results within the bounds of their slice count."""
+    """DSMGP_OZAKI_SLICES=7, DSMGP_OZAKI_DEPTH=2, DSMGP_OZAKI_POTRF=0, DSMGP_OZAKI_TRSM=0 and DSMGP_OZAKI_LAUUM=0 are all valid
+    configurations of the path: same results within the bounds of their slice count (true gradients: the LAUUM pass runs)."""
     import deepstructuredmixtures_b200 as dsm
     kern = dsm.ArdSE([0.1, -0.3, 0.4], 0.2)
-    gp0, x, y = _gp(3300, 3, 77, kern, monkeypatch, False)
+    gp0, x, y = _gp(3300, 3, 77, kern, monkeypatch, False, as_written=False)
     ref = (gp0.mll(), dsm.grad_mll(gp0).copy())
     dsm.model._model_of(gp0).close()
     for name, val, tol in (("DSMGP_OZAKI_SLICES", "7", 1e-8), ("DSMGP_OZAKI_DEPTH", "2", 1e-10), ("DSMGP_OZAKI_POTRF", "0", 1e-10),
-                           ("DSMGP_OZAKI_TRSM", "0", 1e-10)):
+                           ("DSMGP_OZAKI_TRSM", "0", 1e-10), ("DSMGP_OZAKI_LAUUM", "0", 1e-10)):
         monkeypatch.setenv(name, val)
-        gp, _, _ = _gp(3300, 3, 77, kern, monkeypatch, True)
+        gp, _, _ = _gp(3300, 3, 77, kern, monkeypatch, True, as_written=False)
         lml, g = gp.mll(), dsm.grad_mll(gp)
         assert dsm.model._model_of(gp).handle.int8_info()["batches"] > 0
         e = max(abs(lml - ref[0]) / abs(ref[0]), float(np.abs(g - ref[1]).max() / np.abs(ref[1]).max()))
