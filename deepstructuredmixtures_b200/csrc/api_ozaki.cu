@@ -116,7 +116,8 @@ int32_t oz_plan(dsmgp_handle* h) {
   CUDA_TRY(h, h->oz_scale.alloc((size_t)(max_scale + max_l21_scale)));
   CUDA_TRY(h, h->oz_rowmax.alloc((size_t)(max_scale + max_l21_scale)));
   h->oz_pool_bytes = (int64_t)(max_pool + max_l21_pool) * OZ_TILE_B;
-  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B) != 0) {
+  if (oz_make_map(h->oz_map, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B, 32 * oz_round_slices(S, 0)) != 0 ||
+      oz_make_map(h->oz_map + 128, h->oz_pool.p, (size_t)(max_pool + max_l21_pool) * OZ_TILE_B, 32 * oz_round_slices(S, 1)) != 0) {
     // no tensor-map encoder in this driver: the FP64 pipelines stay in charge
     for (Batch& b : h->batches) b.oz.active = false;
     h->oz_pool.free(); h->oz_scratch.free(); h->oz_scale.free(); h->oz_rowmax.free(); h->oz_pool_bytes = 0;
@@ -351,8 +352,14 @@ struct OzTimer {
 };
 
 // optional clock stamps of one GEMM launch (DSMGP_OZAKI_TRACE / DSMGP_OZAKI_TRACE_SYRK = file): tools/ozaki_trace.py
+static int oz_ctas(const dsmgp_handle* h) {      // DSMGP_OZAKI_CTAS: experiment (per-SM operand delivery against the number of active SMs)
+  const char* e = getenv("DSMGP_OZAKI_CTAS");
+  const int n = num_sms(h->device);
+  return e ? std::max(1, std::min(n, atoi(e))) : n;
+}
+
 static void traced_gemm(dsmgp_handle* h, int S, const OzTile* d_tiles, int n, const char* file, cudaStream_t st) {
-  const int nctas = num_sms(h->device);
+  const int nctas = oz_ctas(h);
   if (!file) { launch_oz_gemm(S, h->oz_map, d_tiles, n, h->oz_scale.p, nctas, st); return; }
   long long* d_trace = nullptr;
   cudaMalloc(&d_trace, (size_t)n * 128); cudaMemsetAsync(d_trace, 0, (size_t)n * 128, st);

@@ -220,7 +220,7 @@ struct dsmgp_handle {
   DevBuf<double> d_comm_buf;              // device staging for the prediction all-reduce
   // split inverse on the INT8 tensor cores: slice pool + its tensor map, T^T scratch, row scales
   DevBuf<int8_t> oz_pool; DevBuf<double> oz_scratch, oz_scale; DevBuf<unsigned long long> oz_rowmax;
-  alignas(64) unsigned char oz_map[128]; int oz_S = 8;
+  alignas(64) unsigned char oz_map[256]; int oz_S = 8;     // tensor maps of the two rounds' boxes
   // measured segments of the last evaluation (CUDA events, read by dsmgp_int8_info): 0 block products, 1 slicing, 2 FP64 tile launches
   struct OzSeg { int kind; cudaEvent_t a, b; };
   std::vector<OzSeg> oz_segs; std::vector<cudaEvent_t> oz_evs; size_t oz_ev_used = 0;

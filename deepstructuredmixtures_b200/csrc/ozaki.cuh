@@ -145,8 +145,8 @@ constexpr int OZ_THREADS = 64 + 256;      // producer warp, MMA warp, 8 epilogue
 // values of an accumulating block, stores) overlaps the MMAs of the next block.
 template <int S>
 __global__ void __launch_bounds__(OZ_THREADS, 1)
-gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ tiles, int ntiles, const double* __restrict__ scale,
-            long long* __restrict__ trace) {
+gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const OzTile* __restrict__ tiles, int ntiles,
+            const double* __restrict__ scale, long long* __restrict__ trace) {
   using C = Cfg<S>;
   constexpr int RING = C::NST * C::STAGE;                     // bytes of the operand ring
   constexpr int MAXST = 8;
@@ -164,7 +164,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
     mbar_init(tfull, 1); mbar_init(tempty, 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async;" ::: "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map0)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map1)) : "memory");
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tptr)), "r"(512u) : "memory");
@@ -196,11 +197,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map, const OzTile* __restrict__ 
             if (it[r] >= nst) mbar_wait(&empty[st], ((it[r] / nst) - 1) & 1);
             uint8_t* dst = ring + st * stage;
             mbar_expect_tx(&full[st], stage);
-            const int rowA = (t.a_tile + ks * S) * 32, rowB = (t.b_tile + ks * S) * 32;   // tensor-map rows = 128-byte core matrices
-            for (int s = 0; s < nsl; ++s) {
-              tma_load_2d(dst + s * OZ_TILE_B, &map, 0, rowA + s * 32, &full[st]);
-              tma_load_2d(dst + (nsl + s) * OZ_TILE_B, &map, 0, rowB + s * 32, &full[st]);
-            }
+            // tensor-map rows = 128-byte core matrices; the box of round r's map covers the nsl slice tiles of a k-step at once
+            const int rowA = (t.a_tile + ks * S) * 32, rowB = (t.b_tile + ks * S) * 32;
+            const CUtensorMap* map = (r == 0) ? &map0 : &map1;
+            tma_load_2d(dst, map, 0, rowA, &full[st]);
+            tma_load_2d(dst + nsl * OZ_TILE_B, map, 0, rowB, &full[st]);
           }
         }
       }

@@ -89,9 +89,10 @@ struct OzPlan {
 
 // launchers (k_ozaki.cu).  `map` is the CUtensorMap of the slice pool (128 opaque bytes, built by oz_make_map).
 cudaError_t oz_init_kernels();
-int oz_make_map(void* map128, const void* pool, size_t bytes);          // 0 on success
+int oz_make_map(void* map128, const void* pool, size_t bytes, int box_rows);          // 0 on success
+int oz_round_slices(int S, int r);                                        // slices round r of the block-product kernel loads per operand
 void launch_oz_slice(int S, const OzJob* jobs, int njobs, int pass, unsigned long long* rowmax, double* scale, int8_t* pool, cudaStream_t st);
-void launch_oz_gemm(int S, const void* map128, const OzTile* tiles, int ntiles, const double* scale, int nctas, cudaStream_t st, long long* trace = nullptr);
+void launch_oz_gemm(int S, const void* maps256, const OzTile* tiles, int ntiles, const double* scale, int nctas, cudaStream_t st, long long* trace = nullptr);
 void launch_oz_parts(const OzPartArgs& a, int nparts, cudaStream_t st);
 void launch_oz_setflags(const OzPart* parts, int n, const int64_t* flag_off, int* flags, cudaStream_t st);
 
