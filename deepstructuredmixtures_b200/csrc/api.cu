@@ -459,7 +459,10 @@ static int32_t plan_and_alloc(dsmgp_handle* h, const double* x, const int64_t* l
     CUDA_TRY(h, cudaMemset(h->d_alpha.p, 0, voff * sizeof(double)));
     if (ns) {
       double* d_x = nullptr; int64_t* d_obs = nullptr; int64_t* d_obs_off = nullptr;
-      CUDA_TRY(h, cudaMalloc(&d_x, (size_t)h->N * h->D * sizeof(double)));
+      if (cudaMalloc(&d_x, (size_t)h->N * h->D * sizeof(double)) == cudaErrorMemoryAllocation) {     // cached buffers may hold the memory
+        cudaGetLastError(); g_cache.release_all();
+        CUDA_TRY(h, cudaMalloc(&d_x, (size_t)h->N * h->D * sizeof(double)));
+      }
       CUDA_TRY(h, cudaMemcpy(d_x, x, (size_t)h->N * h->D * sizeof(double), cudaMemcpyHostToDevice));
       CUDA_TRY(h, upload(&d_obs, obs));
       CUDA_TRY(h, upload(&d_obs_off, obs_off));

@@ -85,10 +85,14 @@ struct BufCache {
     ents.erase(ents.begin() + best);
     return p;
   }
+  static constexpr size_t MAX_CACHED = size_t(48) << 30;     // per device: allocations outside DevBuf (CUB, torch, small uploads) need room too
   bool give(void* p, size_t bytes, int dev) {
     if (bytes < MIN_BYTES) return false;
     std::lock_guard<std::mutex> g(mu);
     if (ents.size() >= 64) return false;
+    size_t held = 0;
+    for (auto& e : ents) if (e.dev == dev) held += e.bytes;
+    if (held + bytes > MAX_CACHED) return false;
     ents.push_back({p, bytes, dev});
     return true;
   }
@@ -270,6 +274,11 @@ inline cudaError_t upload(T** dptr, const std::vector<T>& v) {
   *dptr = nullptr;
   if (v.empty()) return cudaSuccess;
   cudaError_t e = cudaMalloc(dptr, v.size() * sizeof(T));
+  if (e == cudaErrorMemoryAllocation) {          // the buffers cached from destroyed handles may hold the memory: drop them, retry once
+    cudaGetLastError();
+    g_cache.release_all();
+    e = cudaMalloc(dptr, v.size() * sizeof(T));
+  }
   if (e) return e;
   return cudaMemcpy(*dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
