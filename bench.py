@@ -410,6 +410,9 @@ def main():
                          "gram_bound": "FP64 ALU (D exp per element)" if "ard" in w["kernel"] else "HBM write"},
             "sharing": sharing,
             "int8_split": int8,
+            "dtype_note": ("FP64 in, FP64 out.  75 % of the factorisation / inverse flops are computed as error-free INT8 slice products of the "
+                           "FP64 operands (Ozaki scheme, 8 slices of 7 bits, exact int32 accumulation; measured error below cuBLAS DGEMM's), "
+                           "the rest on FP64 DMMA; DSMGP_OZAKI=0 runs everything on DMMA") if int8 else None,
             "clocks": clocks_summary(samples),
             "host": {"tree_build_s": t_tree, "create_upload_s": t_create},
         }
