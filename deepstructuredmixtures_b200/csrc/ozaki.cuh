@@ -125,9 +125,13 @@ __global__ void __launch_bounds__(256) slice_kernel(const OzJob* __restrict__ jo
         uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
         for (int q = 0; q < 16; q++) {
-          const double r = rint(v[q]);
+          // rint and double -> int in one FP64 add: |v| <= 64.5, so v + 1.5 * 2^52 holds rint(v) (nearest-even, like rint) in the
+          // low mantissa bits as a two's-complement integer.  The conversion instructions (F2F.F64 round, F2I) run at a quarter
+          // of the FP64 add rate and made this kernel conversion-bound (sm throughput 85 % at 4.1 TB/s).
+          const double t = v[q] + 6755399441055744.0;
+          const double r = t - 6755399441055744.0;
           v[q] = (v[q] - r) * 128.0;
-          w[q >> 2] |= ((uint32_t)(uint8_t)(int8_t)(int)r) << ((q & 3) * 8);
+          w[q >> 2] |= ((uint32_t)__double2loint(t) & 0xFFu) << ((q & 3) * 8);
         }
         *reinterpret_cast<uint4*>(dst + (int64_t)s * OZ_TILE_B) = make_uint4(w[0], w[1], w[2], w[3]);
       }
