@@ -282,7 +282,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CU
             tc_ld16(tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - glo) * BLK + cbase + c0), v);
             tc_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 16; ++j) acc[c0 + j] = fma(acc[c0 + j], 0.0078125, (double)(int)v[j]);
+            for (int j = 0; j < 16; ++j) {
+              // int32 -> FP64 without I2F (quarter-rate conversion unit): the bits of 2^52 + (x + 2^31), minus that offset -- exact
+              const double gx = __hiloint2double(0x43300000, (int)(v[j] ^ 0x80000000u)) - 4503601774854144.0;
+              acc[c0 + j] = fma(acc[c0 + j], 0.0078125, gx);
+            }
           }
         }
         tc_fence_before();
