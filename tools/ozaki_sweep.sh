@@ -1,9 +1,6 @@
 #!/bin/bash
-# ms per evaluation of the bench workloads with the INT8 split path off / on (and its minimum expert size)
-for wl in cfg2 cfg3b cfg4; do
-for cfg in "0 8" "1 8" "1 12" "1 16"; do
-  set -- $cfg
-  DSMGP_OZAKI=$1 DSMGP_OZAKI_MIN_NB=$2 python bench.py --workload $wl --steps 3 --warmup 3 --no-cpu-baseline --no-sub-records --no-predict 2>/dev/null | tail -1 | python -c "
-import json,sys; d=json.loads(sys.stdin.read()); p=d['phases_ms_per_step']; print('$wl ozaki $1 min_nb $2: potrf %.3f inverse %.3f grad %.3f total %.3f' % (p['potrf_ms'], p['inverse_ms'], p['grad_ms'], d['ms_per_step']))"
-done
+# ms per evaluation of cfg3 against the smallest expert (block rows) that takes the INT8 split path
+for nb in 6 8 10 12 16; do
+  DSMGP_OZAKI_MIN_NB=$nb python bench.py --workload cfg3 --steps 4 --warmup 3 --no-cpu-baseline --no-sub-records --no-predict 2>/dev/null | tail -1 | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); p=d['phases_ms_per_step']; i=d['int8_split']; print('min_nb $nb: total %.3f  potrf %.3f inverse %.3f | gemm %.2f slice %.2f fp64 tile %.2f' % (d['ms_per_step'], p['potrf_ms'], p['inverse_ms'], i['gemm_ms'], i['slice_ms'], i['fp64_tile_ms']))"
 done
