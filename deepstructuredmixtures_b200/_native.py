@@ -64,7 +64,7 @@ EXPORTS = [
     "dsmgp_finetune_eval", "dsmgp_train", "dsmgp_eval_local_dev", "dsmgp_eval_finish_dev", "dsmgp_leaf_rows", "dsmgp_leaf_owner",
     "dsmgp_update_weights", "dsmgp_predict", "dsmgp_predict_local", "dsmgp_predict_finish", "dsmgp_leaf_predict", "dsmgp_leaf_alpha", "dsmgp_leaf_factor",
     "dsmgp_leaf_info", "dsmgp_kernelmatrix", "dsmgp_overlap", "dsmgp_release_cache", "dsmgp_chol_continue", "dsmgp_chol_delete_rows", "dsmgp_potrf",
-    "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling", "dsmgp_int8_info",
+    "dsmgp_host_tree_eval", "dsmgp_host_shard", "dsmgp_get_timings", "dsmgp_set_profiling", "dsmgp_int8_info", "dsmgp_host_split_plan",
     "dsmgp_set_sharing", "dsmgp_get_sharing", "dsmgp_infer", "dsmgp_reset_weights", "dsmgp_comm_unique_id", "dsmgp_comm_init", "dsmgp_host_sharing_plan",
     "dsmgp_part_create", "dsmgp_part_destroy", "dsmgp_part_size", "dsmgp_part_range", "dsmgp_part_sorted_column", "dsmgp_part_split",
     "dsmgp_part_rows", "dsmgp_overlap_csr", "dsmgp_chol_delete_rows_batched",
@@ -142,6 +142,7 @@ def lib() -> C.CDLL:
         "dsmgp_get_timings": (I32, [P, C.POINTER(Timings)]),
         "dsmgp_set_profiling": (I32, [P, I32]),
         "dsmgp_int8_info": (I32, [P, pd, I32]),
+        "dsmgp_host_split_plan": (I32, [I64, I32, I32, pi32, pi32, pd]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)

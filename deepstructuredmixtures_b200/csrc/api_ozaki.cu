@@ -530,6 +530,26 @@ int32_t oz_run_inverse(dsmgp_handle* h, Batch& b, const Trtri3Args& full, int sm
 // (2 * 128 * 128 * 32 per tcgen05.mma, S (S + 1) / 2 of them per k-step), [3] the FP64 flops they stand for, [4] / [5] / [6] CUDA-event
 // ms of the block-product launches / the slicing launches / the FP64 tile-pipeline launches of the last evaluation, [7] slice pool bytes,
 // [8] (n >= 9) the factorisation + inverse flops that stay on the FP64 tile pipelines (2/3 r^3 per diagonal range of r rows)
+extern "C" int32_t dsmgp_host_split_plan(int64_t n, int32_t depth, int32_t min_nb, int32_t* range_of, int32_t* n_ranges, double* share_int8) {
+  if (n <= 0 || !range_of || !n_ranges) return DSMGP_ERR_ARG;
+  if (depth <= 0) { const char* de = getenv("DSMGP_OZAKI_DEPTH"); depth = de ? std::max(1, std::min(4, atoi(de))) : 1; }
+  if (min_nb <= 0) { const char* me = getenv("DSMGP_OZAKI_MIN_NB"); min_nb = me ? std::max(2, atoi(me)) : 8; }
+  const int64_t np = (n + PAD - 1) / PAD * PAD;
+  const int nb = (int)((np + BLK - 1) / BLK);
+  std::vector<std::vector<Split>> levels(depth);
+  std::vector<int> ro(nb, 0);
+  int nr = 0;
+  collect_splits(0, 0, nb, 0, depth, min_nb, levels, ro, nr);
+  double rest = 0.0, rows = 0.0;
+  for (int b = 0; b <= nb; b++) {
+    if (b == nb || (b > 0 && ro[b] != ro[b - 1])) { rest += (rows / (double)n) * (rows / (double)n) * (rows / (double)n); rows = 0.0; }
+    if (b < nb) { range_of[b] = ro[b]; rows += (double)std::max<int64_t>(0, std::min<int64_t>(BLK, n - (int64_t)b * BLK)); }
+  }
+  *n_ranges = nr;
+  if (share_int8) *share_int8 = 1.0 - rest;
+  return DSMGP_OK;
+}
+
 extern "C" int32_t dsmgp_int8_info(dsmgp_handle* h, double* out, int32_t n) {
   if (!h || !out || n < 8) return DSMGP_ERR_ARG;
   cudaSetDevice(h->device);

@@ -286,6 +286,11 @@ int32_t dsmgp_host_sharing_plan(int64_t L, const int64_t* leaf_ptr, const int64_
                                 const double* overlap, double tau, int32_t* kind, int32_t* source, int32_t* blocks);
 /* LPT bin packing of leaves by n^3 onto `world` ranks (deterministic). */
 int32_t dsmgp_host_shard(int64_t L, const int64_t* leaf_ptr, int32_t world, int32_t* owner);
+/* The diagonal ranges the INT8 split path (csrc/api_ozaki.cu) gives an expert of n observations: range_of[b] for its
+ * ceil(n_padded / 128) block rows (n_padded = n rounded up to 64; at least that many entries), ranges numbered from 0 in
+ * row order; *share_int8 = the fraction of the factorisation + inverse flops (2/3 n^3) that runs as INT8 block products
+ * (1 - sum over the ranges of (rows / n)^3).  depth / min_nb <= 0: the library defaults (environment included). */
+int32_t dsmgp_host_split_plan(int64_t n, int32_t depth, int32_t min_nb, int32_t* range_of, int32_t* n_ranges, double* share_int8);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 typedef struct {
