@@ -272,4 +272,14 @@ function int8_info(h::Handle)
     return o
 end
 
+# dsmgp_host_split_plan (host-only): the diagonal ranges of an expert of n observations on the INT8 split path and the share of its
+# factorisation + inverse flops that runs as INT8 block products.
+function split_plan(n::Integer; depth::Integer=0, min_nb::Integer=0)
+    nb = cld(cld(n, 64) * 64, 128)
+    ro = zeros(Int32, nb); nr = Ref{Int32}(0); share = Ref{Float64}(0.0)
+    rc = ccall((:dsmgp_host_split_plan, LIB), Int32, (Int64, Int32, Int32, Ptr{Int32}, Ref{Int32}, Ref{Float64}), n, depth, min_nb, ro, nr, share)
+    rc == 0 || error("dsmgp_host_split_plan failed: $rc")
+    return ro, Int(nr[]), share[]
+end
+
 end # module
