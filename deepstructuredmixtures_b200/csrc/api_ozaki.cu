@@ -35,6 +35,33 @@ bool oz_enabled() {
   return !(en && en[0] == '0');
 }
 
+// All device lists of one batch's plan go into ONE allocation (one cudaMalloc + one copy at create, one cudaFree at destroy:
+// twenty small allocations per batch cost more than the plan itself in a create / evaluate / destroy cycle).
+struct PlanBlob {
+  std::vector<unsigned char> host;
+  struct Fix { void** dst; size_t off; };
+  std::vector<Fix> fixes;
+  template <typename T>
+  void add(T** dptr, const std::vector<T>& v) {
+    *dptr = nullptr;
+    if (v.empty()) return;
+    const size_t off = (host.size() + 255) & ~size_t(255);
+    host.resize(off + v.size() * sizeof(T));
+    memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+    fixes.push_back({reinterpret_cast<void**>(dptr), off});
+  }
+  cudaError_t commit(void** base) {
+    *base = nullptr;
+    if (host.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc(base, host.size());
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); g_cache.release_all(); e = cudaMalloc(base, host.size()); }
+    if (e) return e;
+    if ((e = cudaMemcpy(*base, host.data(), host.size(), cudaMemcpyHostToDevice))) return e;
+    for (const Fix& f : fixes) *f.dst = static_cast<unsigned char*>(*base) + f.off;
+    return cudaSuccess;
+  }
+};
+
 int oz_env_slices() {
   const char* e = getenv("DSMGP_OZAKI_SLICES");
   const int s = e ? atoi(e) : 8;
@@ -128,6 +155,7 @@ int32_t oz_plan(dsmgp_handle* h) {
     Batch& b = h->batches[bi];
     if (!b.oz.active) continue;
     Tmp& t = tmp[bi];
+    PlanBlob blob;
     // tile-pipeline tasks restricted to the leaf ranges (order of the full list kept: still topological)
     std::vector<int4> keep;
     for (const int4& tk : b.h_trtri3) {
@@ -144,7 +172,7 @@ int32_t oz_plan(dsmgp_handle* h) {
       }
     }
     b.oz.n_tasks = (int)keep.size();
-    CUDA_TRY(h, upload(&b.oz.d_tasks, keep));
+    blob.add(&b.oz.d_tasks, keep);
     std::vector<OzPart> parts;
     double flops = 0.0;
     std::vector<OzJob> jL, jT; std::vector<OzTile> tS, tT;
@@ -153,7 +181,7 @@ int32_t oz_plan(dsmgp_handle* h) {
     int64_t l21_pool = max_pool; int l21_scale = (int)max_scale;
     for (int lv = maxdepth - 1; lv >= 0; lv--) {         // deepest level first
       if (t.levels[lv].empty()) continue;
-      OzLevel L;
+      OzLevel& L = b.oz.levels[b.oz.n_levels++];
       std::vector<OzJob> j1, j2; std::vector<OzTile> t1, t2;
       int64_t pool = 0, scratch = 0; int scale = 0;
       for (const Split& sp : t.levels[lv]) {
@@ -237,9 +265,8 @@ int32_t oz_plan(dsmgp_handle* h) {
       for (const OzTile& x : t1) L.ksteps1 += x.k1 - x.k0;
       for (const OzTile& x : t2) L.ksteps2 += x.k1 - x.k0;
       L.n_jobs1 = (int)j1.size(); L.n_jobs2 = (int)j2.size(); L.n_tiles1 = (int)t1.size(); L.n_tiles2 = (int)t2.size(); L.n_scale = scale;
-      CUDA_TRY(h, upload(&L.d_jobs1, j1)); CUDA_TRY(h, upload(&L.d_jobs2, j2));
-      CUDA_TRY(h, upload(&L.d_tiles1, t1)); CUDA_TRY(h, upload(&L.d_tiles2, t2));
-      b.oz.levels[b.oz.n_levels++] = L;
+      blob.add(&L.d_jobs1, j1); blob.add(&L.d_jobs2, j2);
+      blob.add(&L.d_tiles1, t1); blob.add(&L.d_tiles2, t2);
     }
     {   // factorisation phase of the root splits
       auto by_len = [](const OzTile& x, const OzTile& y) { return (x.k1 - x.k0) > (y.k1 - y.k0); };
@@ -248,12 +275,12 @@ int32_t oz_plan(dsmgp_handle* h) {
       for (const OzTile& x : tT) b.oz.ksteps_T += x.k1 - x.k0;
       b.oz.n_jobsL = (int)jL.size(); b.oz.n_syrk = (int)tS.size();
       b.oz.l21_scale0 = (int)max_scale; b.oz.l21_nscale = l21_scale - (int)max_scale;
-      CUDA_TRY(h, upload(&b.oz.d_jobsL, jL)); CUDA_TRY(h, upload(&b.oz.d_syrk, tS));
+      blob.add(&b.oz.d_jobsL, jL); blob.add(&b.oz.d_syrk, tS);
       std::vector<int4> pA, pB;
       for (const int4& tk : b.h_potrf2) (kskip[tk.x] > 0 && tk.z >= kskip[tk.x] ? pB : pA).push_back(tk);
       b.oz.n_potrfA = (int)pA.size(); b.oz.n_potrfB = (int)pB.size();
-      CUDA_TRY(h, upload(&b.oz.d_potrfA, pA)); CUDA_TRY(h, upload(&b.oz.d_potrfB, pB));
-      CUDA_TRY(h, upload(&b.oz.d_kskip, kskip));
+      blob.add(&b.oz.d_potrfA, pA); blob.add(&b.oz.d_potrfB, pB);
+      blob.add(&b.oz.d_kskip, kskip);
       b.oz.potrf = want_potrf && !pB.empty();
       {
         const char* te = getenv("DSMGP_OZAKI_TRSM");
@@ -261,7 +288,7 @@ int32_t oz_plan(dsmgp_handle* h) {
         for (const int4& tk : pA) if (!(kskip[tk.x] > 0 && tk.y >= kskip[tk.x])) pA11.push_back(tk);
         std::stable_sort(tT.begin(), tT.end(), by_len);
         b.oz.n_potrfA11 = (int)pA11.size(); b.oz.n_jobsT = (int)jT.size(); b.oz.n_tilesT = (int)tT.size(); b.oz.nscaleT = scaleT;
-        CUDA_TRY(h, upload(&b.oz.d_potrfA11, pA11)); CUDA_TRY(h, upload(&b.oz.d_jobsT, jT)); CUDA_TRY(h, upload(&b.oz.d_tilesT, tT));
+        blob.add(&b.oz.d_potrfA11, pA11); blob.add(&b.oz.d_jobsT, jT); blob.add(&b.oz.d_tilesT, tT);
         b.oz.trsm = b.oz.potrf && !tT.empty() && !(te && te[0] == '0');
       }
       std::vector<int4> iA, iB;
@@ -271,7 +298,7 @@ int32_t oz_plan(dsmgp_handle* h) {
         (kskip[tk.x] > 0 && tk.y >= kskip[tk.x] ? iB : iA).push_back(tk);
       }
       b.oz.n_invA = (int)iA.size(); b.oz.n_invB = (int)iB.size();
-      CUDA_TRY(h, upload(&b.oz.d_invA, iA)); CUDA_TRY(h, upload(&b.oz.d_invB, iB));
+      blob.add(&b.oz.d_invA, iA); blob.add(&b.oz.d_invB, iB);
     }
     if (want_lauum && !b.h_lauum.empty()) {
       // operand X^T of every split expert: row blocks Jb, k blocks Kb >= Jb (upper block triangle; W_J^T on the diagonal)
@@ -312,12 +339,13 @@ int32_t oz_plan(dsmgp_handle* h) {
         std::stable_sort(tW.begin(), tW.end(), by_len);
         for (const OzTile& x : tW) b.oz.ksteps_W += x.k1 - x.k0;
         b.oz.n_jobsX = (int)jX.size(); b.oz.n_tilesW = (int)tW.size(); b.oz.nscaleX = need_scale;
-        CUDA_TRY(h, upload(&b.oz.d_jobsX, jX)); CUDA_TRY(h, upload(&b.oz.d_tilesW, tW)); CUDA_TRY(h, upload(&b.oz.d_pre_base, pre));
+        blob.add(&b.oz.d_jobsX, jX); blob.add(&b.oz.d_tilesW, tW); blob.add(&b.oz.d_pre_base, pre);
         b.oz.lauum = !tW.empty();
       }
     }
     b.oz.n_parts = (int)parts.size();
-    CUDA_TRY(h, upload(&b.oz.d_parts, parts));
+    blob.add(&b.oz.d_parts, parts);
+    CUDA_TRY(h, blob.commit(&b.oz.d_blob));
     b.oz.gemm_flops = flops;
   }
   return DSMGP_OK;

@@ -240,8 +240,7 @@ struct dsmgp_handle {
       cudaFree(b.d_tile_off); cudaFree(b.d_trpart_off); cudaFree(b.d_gpart_off);
       cudaFree(b.d_trtri_tasks); cudaFree(b.d_lauum_tasks); cudaFree(b.d_potrf2_tasks); cudaFree(b.d_trtri3_tasks); cudaFree(b.d_solve_tasks); cudaFree(b.d_flag_off);
       cudaFree(b.d_potrf2_A); cudaFree(b.d_potrf2_B); cudaFree(b.d_prefix_slots); cudaFree(b.d_trtri3m_tasks);
-      cudaFree(b.oz.d_tasks); cudaFree(b.oz.d_parts); cudaFree(b.oz.d_potrfA); cudaFree(b.oz.d_potrfB); cudaFree(b.oz.d_kskip); cudaFree(b.oz.d_jobsL); cudaFree(b.oz.d_syrk); cudaFree(b.oz.d_invA); cudaFree(b.oz.d_invB); cudaFree(b.oz.d_potrfA11); cudaFree(b.oz.d_jobsT); cudaFree(b.oz.d_tilesT); cudaFree(b.oz.d_jobsX); cudaFree(b.oz.d_tilesW); cudaFree(b.oz.d_pre_base);
-      for (int l = 0; l < b.oz.n_levels; l++) { cudaFree(b.oz.levels[l].d_jobs1); cudaFree(b.oz.levels[l].d_jobs2); cudaFree(b.oz.levels[l].d_tiles1); cudaFree(b.oz.levels[l].d_tiles2); }
+      cudaFree(b.oz.d_blob);
     }
     d_flags2.free();
     oz_pool.free(); oz_scratch.free(); oz_scale.free(); oz_rowmax.free();

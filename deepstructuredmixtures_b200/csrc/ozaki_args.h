@@ -56,6 +56,7 @@ struct OzLevel {
 };
 struct OzPlan {
   bool active = false;
+  void* d_blob = nullptr;                          // ONE device allocation that holds every list below
   int4* d_tasks = nullptr; int n_tasks = 0;        // tile-pipeline tasks restricted to the diagonal ranges
   OzLevel levels[4]; int n_levels = 0;             // deepest level first
   OzPart* d_parts = nullptr; int n_parts = 0;
